@@ -1,0 +1,96 @@
+// Shared helpers for the sm_100a kernels behind include/dmu_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/dmu_b200.h"
+
+namespace dmu {
+
+// thread-local error text returned by dmu_last_error()
+char* err_buf();
+int fail(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+#define DMU_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) return dmu::fail(__VA_ARGS__); \
+    } while (0)
+
+inline cudaStream_t as_stream(dmu_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();
+
+// ---- dtype helpers -------------------------------------------------------
+__device__ __forceinline__ float ld_as_float(const void* base, int64_t idx, int dtype) {
+    if (dtype == DMU_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+    return reinterpret_cast<const float*>(base)[idx];
+}
+__device__ __forceinline__ void st_from_float(void* base, int64_t idx, int dtype, float v) {
+    if (dtype == DMU_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(base)[idx] = v;
+}
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int kVec = 4;  // elements per 16 B
+    static constexpr int kCode = DMU_F32;
+    __device__ static __forceinline__ float to_f(float v) { return v; }
+    __device__ static __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int kVec = 8;
+    static constexpr int kCode = DMU_BF16;
+    __device__ static __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ static __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// 16-byte vector of T <-> float[kVec]
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* p, float* out) {
+    if constexpr (sizeof(T) == 4) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else {
+        uint4 v = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __bfloat1622float2(h[i]);
+            out[2 * i] = f.x; out[2 * i + 1] = f.y;
+        }
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store_vec(T* p, const float* in) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+    } else {
+        uint4 v;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = v;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+inline bool is_nhwc(const dmu_tensor4& t) { return t.sc == 1; }
+
+}  // namespace dmu

@@ -1,0 +1,503 @@
+// GroupNorm(+SiLU) forward/backward, channel sums, activations, sinusoidal
+// embedding, parameter repack and the fused Adam+EMA update.
+// All HBM-bound: 128-bit accesses on NHWC rows, warp-shuffle / smem reductions,
+// fp32 statistics.  Call sites: see include/dmu_b200.h.
+#include "common.cuh"
+
+namespace dmu {
+
+constexpr int kMaxC = 1024;  // channels per pixel supported by the smem-staged kernels
+
+// one CTA handles pixels [p0, p1) of image n; thread -> (vector v of kVec channels, pixel lane)
+struct RowMap {
+    int V, lanes, v, lane; bool active;
+    __device__ RowMap(int C, int kVec) {
+        V = C / kVec;
+        lanes = blockDim.x / V;
+        v = threadIdx.x % V;
+        lane = threadIdx.x / V;
+        active = lane < lanes;
+    }
+};
+
+__device__ __forceinline__ void chunk_range(int HW, int& p0, int& p1) {
+    const int per = (HW + gridDim.x - 1) / gridDim.x;
+    p0 = blockIdx.x * per;
+    p1 = min(HW, p0 + per);
+}
+
+__device__ __forceinline__ int64_t pix_off(const dmu_tensor4& t, int n, int p, int W) {
+    return (int64_t)n * t.sn + (int64_t)(p / W) * t.sh + (int64_t)(p % W) * t.sw;
+}
+
+// ------------------------------------------------------------------ stats
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(dmu_gn_params P) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s_sum[kMaxC], s_sq[kMaxC];
+    const int n = blockIdx.y, HW = P.H * P.W, C = P.C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_sum[c] = 0.f; s_sq[c] = 0.f; }
+    __syncthreads();
+    RowMap m(C, kVec);
+    int p0, p1; chunk_range(HW, p0, p1);
+    if (m.active) {
+        float a[kVec], q[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { a[i] = 0.f; q[i] = 0.f; }
+        const T* base = reinterpret_cast<const T*>(P.x.ptr);
+        for (int p = p0 + m.lane; p < p1; p += m.lanes) {
+            float v[kVec];
+            load_vec<T>(base + pix_off(P.x, n, p, P.W) + m.v * kVec, v);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) { a[i] += v[i]; q[i] += v[i] * v[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { atomicAdd(&s_sum[m.v * kVec + i], a[i]); atomicAdd(&s_sq[m.v * kVec + i], q[i]); }
+    }
+    __syncthreads();
+    const int cpg = C / P.G;
+    for (int g = threadIdx.x; g < P.G; g += blockDim.x) {
+        float a = 0.f, q = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += s_sum[c]; q += s_sq[c]; }
+        atomicAdd(&P.sums[((int64_t)n * P.G + g) * 2 + 0], a);
+        atomicAdd(&P.sums[((int64_t)n * P.G + g) * 2 + 1], q);
+    }
+}
+
+// per-channel mean / rstd*gamma / beta staged in smem for image n
+__device__ __forceinline__ void stage_affine(const dmu_gn_params& P, int n, float* s_mean, float* s_scale, float* s_beta, float* s_rstd) {
+    const int cpg = P.C / P.G;
+    const float cnt = (float)cpg * (float)P.H * (float)P.W;
+    for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float su = P.sums[((int64_t)n * P.G + g) * 2 + 0], sq = P.sums[((int64_t)n * P.G + g) * 2 + 1];
+        const float mean = su / cnt;
+        const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + P.eps);
+        s_mean[c] = mean;
+        s_scale[c] = rstd * P.gamma[c];
+        s_beta[c] = P.beta[c];
+        if (s_rstd) s_rstd[c] = rstd;
+    }
+}
+
+// ------------------------------------------------------------------ apply
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(dmu_gn_params P) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC];
+    const int n = blockIdx.y, HW = P.H * P.W;
+    stage_affine(P, n, s_mean, s_scale, s_beta, nullptr);
+    __syncthreads();
+    RowMap m(P.C, kVec);
+    if (!m.active) return;
+    int p0, p1; chunk_range(HW, p0, p1);
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr);
+    T* yb = reinterpret_cast<T*>(P.y.ptr);
+    float mu[kVec], sc[kVec], be[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { mu[i] = s_mean[m.v * kVec + i]; sc[i] = s_scale[m.v * kVec + i]; be[i] = s_beta[m.v * kVec + i]; }
+    for (int p = p0 + m.lane; p < p1; p += m.lanes) {
+        float v[kVec];
+        load_vec<T>(xb + pix_off(P.x, n, p, P.W) + m.v * kVec, v);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            float u = (v[i] - mu[i]) * sc[i] + be[i];
+            v[i] = P.silu ? u / (1.f + expf(-u)) : u;
+        }
+        store_vec<T>(yb + pix_off(P.y, n, p, P.W) + m.v * kVec, v);
+    }
+}
+
+// du = dy * act'(u)
+__device__ __forceinline__ float act_grad(float u, float dy, int silu) {
+    if (!silu) return dy;
+    const float s = 1.f / (1.f + expf(-u));
+    return dy * (s * (1.f + u * (1.f - s)));
+}
+
+// ------------------------------------------------------------------ bwd reduce
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(dmu_gn_params P) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
+    __shared__ float s_a[kMaxC], s_b[kMaxC];
+    const int n = blockIdx.y, HW = P.H * P.W, C = P.C;
+    stage_affine(P, n, s_mean, s_scale, s_beta, s_rstd);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_a[c] = 0.f; s_b[c] = 0.f; }
+    __syncthreads();
+    RowMap m(C, kVec);
+    int p0, p1; chunk_range(HW, p0, p1);
+    if (m.active) {
+        float a[kVec], b[kVec], mu[kVec], sc[kVec], be[kVec], rs[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            a[i] = 0.f; b[i] = 0.f;
+            mu[i] = s_mean[m.v * kVec + i]; sc[i] = s_scale[m.v * kVec + i]; be[i] = s_beta[m.v * kVec + i]; rs[i] = s_rstd[m.v * kVec + i];
+        }
+        const T* xb = reinterpret_cast<const T*>(P.x.ptr);
+        const T* dyb = reinterpret_cast<const T*>(P.y.ptr);
+        for (int p = p0 + m.lane; p < p1; p += m.lanes) {
+            float xv[kVec], dv[kVec];
+            load_vec<T>(xb + pix_off(P.x, n, p, P.W) + m.v * kVec, xv);
+            load_vec<T>(dyb + pix_off(P.y, n, p, P.W) + m.v * kVec, dv);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) {
+                const float d = xv[i] - mu[i];
+                const float du = act_grad(d * sc[i] + be[i], dv[i], P.silu);
+                a[i] += du;
+                b[i] += du * (d * rs[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { atomicAdd(&s_a[m.v * kVec + i], a[i]); atomicAdd(&s_b[m.v * kVec + i], b[i]); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&P.red[((int64_t)n * C + c) * 2 + 0], s_a[c]);
+        atomicAdd(&P.red[((int64_t)n * C + c) * 2 + 1], s_b[c]);
+        if (P.dbeta) atomicAdd(&P.dbeta[c], s_a[c]);
+        if (P.dgamma) atomicAdd(&P.dgamma[c], s_b[c]);
+    }
+}
+
+// ------------------------------------------------------------------ bwd apply
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dmu_gn_params P) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
+    __shared__ float s_A[kMaxC], s_B[kMaxC];  // per channel: group sums / cnt
+    const int n = blockIdx.y, HW = P.H * P.W, C = P.C;
+    stage_affine(P, n, s_mean, s_scale, s_beta, s_rstd);
+    const int cpg = C / P.G;
+    const float inv_cnt = 1.f / ((float)cpg * (float)HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g0 = (c / cpg) * cpg;
+        float A = 0.f, B = 0.f;
+        for (int k = g0; k < g0 + cpg; ++k) {
+            const float gam = P.gamma[k];
+            A += gam * P.red[((int64_t)n * C + k) * 2 + 0];
+            B += gam * P.red[((int64_t)n * C + k) * 2 + 1];
+        }
+        s_A[c] = A * inv_cnt;
+        s_B[c] = B * inv_cnt;
+    }
+    __syncthreads();
+    RowMap m(C, kVec);
+    if (!m.active) return;
+    int p0, p1; chunk_range(HW, p0, p1);
+    float mu[kVec], sc[kVec], be[kVec], rs[kVec], A[kVec], B[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const int c = m.v * kVec + i;
+        mu[i] = s_mean[c]; sc[i] = s_scale[c]; be[i] = s_beta[c]; rs[i] = s_rstd[c]; A[i] = s_A[c]; B[i] = s_B[c];
+    }
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr);
+    const T* dyb = reinterpret_cast<const T*>(P.y.ptr);
+    T* dxb = reinterpret_cast<T*>(P.dx.ptr);
+    const T* a0 = reinterpret_cast<const T*>(P.add0.ptr);
+    const T* a1 = reinterpret_cast<const T*>(P.add1.ptr);
+    for (int p = p0 + m.lane; p < p1; p += m.lanes) {
+        float xv[kVec], dv[kVec], o[kVec];
+        load_vec<T>(xb + pix_off(P.x, n, p, P.W) + m.v * kVec, xv);
+        load_vec<T>(dyb + pix_off(P.y, n, p, P.W) + m.v * kVec, dv);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const float d = xv[i] - mu[i];
+            const float xhat = d * rs[i];
+            const float du = act_grad(d * sc[i] + be[i], dv[i], P.silu);
+            // sc = rstd*gamma
+            o[i] = du * sc[i] - rs[i] * (A[i] + xhat * B[i]);
+        }
+        if (a0) {
+            float t[kVec];
+            load_vec<T>(a0 + pix_off(P.add0, n, p, P.W) + m.v * kVec, t);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) o[i] += t[i];
+        }
+        if (a1) {
+            float t[kVec];
+            load_vec<T>(a1 + pix_off(P.add1, n, p, P.W) + m.v * kVec, t);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) o[i] += t[i];
+        }
+        store_vec<T>(dxb + pix_off(P.dx, n, p, P.W) + m.v * kVec, o);
+    }
+}
+
+// ------------------------------------------------------------------ column sums
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(dmu_tensor4 X, int H, int W, int C, float* out_nc, int64_t pitch,
+                                                     float* out_c, float scale) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s[kMaxC];
+    const int n = blockIdx.y, HW = H * W;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s[c] = 0.f;
+    __syncthreads();
+    RowMap m(C, kVec);
+    if (m.active) {
+        float a[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) a[i] = 0.f;
+        const T* xb = reinterpret_cast<const T*>(X.ptr);
+        for (int p = m.lane; p < HW; p += m.lanes) {
+            float v[kVec];
+            load_vec<T>(xb + pix_off(X, n, p, W) + m.v * kVec, v);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) a[i] += v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) atomicAdd(&s[m.v * kVec + i], a[i]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = s[c] * scale;
+        if (out_nc) out_nc[(int64_t)n * pitch + c] = v;
+        if (out_c) atomicAdd(&out_c[c], v);
+    }
+}
+
+// ------------------------------------------------------------------ activations (fp32 rows)
+__device__ __forceinline__ float act_f(float x, int kind) {
+    if (kind == 0) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    if (kind == 1) return x / (1.f + expf(-x));
+    return logf(x);
+}
+__device__ __forceinline__ float act_df(float x, int kind) {
+    if (kind == 0) {
+        const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+        const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+        return cdf + x * pdf;
+    }
+    if (kind == 1) {
+        const float s = 1.f / (1.f + expf(-x));
+        return s * (1.f + x * (1.f - s));
+    }
+    return 1.f / x;
+}
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int kind) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = act_f(x[i], kind);
+}
+__global__ void act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t n, int kind) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dx[i] = dy[i] * act_df(x[i], kind);
+}
+
+__global__ void sinusoidal_kernel(const void* t, int t_is_float, float* emb, int64_t batch, int dim, float neg_k) {
+    const int half = dim / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < batch * half; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / half;
+        const int j = (int)(i % half);
+        const float tv = t_is_float ? reinterpret_cast<const float*>(t)[b] : (float)reinterpret_cast<const int64_t*>(t)[b];
+        const float f = expf(__fmul_rn((float)j, neg_k));
+        const float a = __fmul_rn(tv, f);
+        emb[b * dim + j] = sinf(a);
+        emb[b * dim + half + j] = cosf(a);
+    }
+}
+
+// ------------------------------------------------------------------ repack
+__global__ void repack_kernel(const dmu_repack_desc* __restrict__ descs) {
+    const dmu_repack_desc d = descs[blockIdx.y];
+    const int64_t RS = (int64_t)d.R * d.S;
+    const int64_t total = (int64_t)d.O * d.I * RS;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // i enumerates the destination [O][R][S][I]
+        const int64_t ci = i % d.I;
+        const int64_t rs = (i / d.I) % RS;
+        const int64_t o = i / (d.I * RS);
+        int64_t src;
+        if (d.kind == 0) src = (o * d.I + ci) * RS + rs;        // OIHW
+        else if (d.kind == 1) src = (ci * d.O + o) * RS + rs;   // IOHW (ConvTranspose2d)
+        else src = i;
+        st_from_float(d.dst, i, d.dst_dtype, d.src[src]);
+    }
+}
+
+__global__ void copy4_kernel(dmu_tensor4 S, dmu_tensor4 D, int N, int H, int W, int C) {
+    const int64_t total = (int64_t)N * H * W * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int w = (int)((i / C) % W);
+        const int h = (int)((i / ((int64_t)C * W)) % H);
+        const int n = (int)(i / ((int64_t)C * W * H));
+        const float v = ld_as_float(S.ptr, n * S.sn + h * S.sh + w * S.sw + c * S.sc, S.dtype);
+        st_from_float(D.ptr, n * D.sn + h * D.sh + w * D.sw + c * D.sc, D.dtype, v);
+    }
+}
+
+// ------------------------------------------------------------------ Adam + EMA
+__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, float* __restrict__ ema, int64_t n, float lr, float b1,
+                                                       float b2, float eps, float wd, float bc1, float bc2_sqrt, float decay, float gscale) {
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < n) {
+            float4 pv = *reinterpret_cast<float4*>(p + i), gv = *reinterpret_cast<const float4*>(g + i);
+            float4 mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+            float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float gr = gp[k] * gscale + wd * pp[k];
+                mp[k] = b1 * mp[k] + (1.f - b1) * gr;
+                vp[k] = b2 * vp[k] + (1.f - b2) * gr * gr;
+                const float denom = sqrtf(vp[k]) / bc2_sqrt + eps;
+                pp[k] -= (lr / bc1) * (mp[k] / denom);
+            }
+            *reinterpret_cast<float4*>(p + i) = pv;
+            *reinterpret_cast<float4*>(m + i) = mv;
+            *reinterpret_cast<float4*>(v + i) = vv;
+            if (ema) {
+                float4 ev = *reinterpret_cast<float4*>(ema + i);
+                ev.x = decay * ev.x + (1.f - decay) * pv.x; ev.y = decay * ev.y + (1.f - decay) * pv.y;
+                ev.z = decay * ev.z + (1.f - decay) * pv.z; ev.w = decay * ev.w + (1.f - decay) * pv.w;
+                *reinterpret_cast<float4*>(ema + i) = ev;
+            }
+        } else {
+            for (int64_t j = i; j < n; ++j) {
+                float gr = g[j] * gscale + wd * p[j];
+                m[j] = b1 * m[j] + (1.f - b1) * gr;
+                v[j] = b2 * v[j] + (1.f - b2) * gr * gr;
+                const float denom = sqrtf(v[j]) / bc2_sqrt + eps;
+                p[j] -= (lr / bc1) * (m[j] / denom);
+                if (ema) ema[j] = decay * ema[j] + (1.f - decay) * p[j];
+            }
+        }
+    }
+}
+
+static int gn_check(const dmu_gn_params* p, const char* who, bool need_y, bool need_dx) {
+    DMU_REQUIRE(p, "%s: null params", who);
+    DMU_REQUIRE(p->x.ptr && p->sums && p->gamma && p->beta, "%s: null pointer", who);
+    DMU_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->G > 0, "%s: non-positive dims", who);
+    DMU_REQUIRE(p->C % p->G == 0, "%s: C=%d not divisible by G=%d", who, p->C, p->G);
+    DMU_REQUIRE(p->C <= kMaxC, "%s: C=%d exceeds %d", who, p->C, kMaxC);
+    DMU_REQUIRE(p->x.sc == 1, "%s: x must be NHWC (sc == 1)", who);
+    const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
+    DMU_REQUIRE(p->C % vec == 0 && p->x.sw % vec == 0 && p->x.sh % vec == 0 && p->x.sn % vec == 0, "%s: C and pitches must be multiples of %d", who, vec);
+    DMU_REQUIRE(p->C / vec <= 256, "%s: C too large for one CTA row", who);
+    if (need_y) {
+        DMU_REQUIRE(p->y.ptr && p->y.sc == 1 && p->y.dtype == p->x.dtype, "%s: y must be NHWC of x's dtype", who);
+        DMU_REQUIRE(p->y.sw % vec == 0 && p->y.sh % vec == 0 && p->y.sn % vec == 0, "%s: y pitches must be multiples of %d", who, vec);
+    }
+    if (need_dx) {
+        DMU_REQUIRE(p->dx.ptr && p->dx.sc == 1 && p->dx.dtype == p->x.dtype && p->red, "%s: dx/red missing or wrong dtype", who);
+        DMU_REQUIRE(p->dx.sw % vec == 0 && p->dx.sh % vec == 0 && p->dx.sn % vec == 0, "%s: dx pitches must be multiples of %d", who, vec);
+        if (p->add0.ptr) DMU_REQUIRE(p->add0.sc == 1 && p->add0.dtype == p->x.dtype && p->add0.sw % vec == 0 && p->add0.sn % vec == 0, "%s: add0 layout", who);
+        if (p->add1.ptr) DMU_REQUIRE(p->add1.sc == 1 && p->add1.dtype == p->x.dtype && p->add1.sw % vec == 0 && p->add1.sn % vec == 0, "%s: add1 layout", who);
+    }
+    return 0;
+}
+
+// pixel chunks per image so that the grid is about 4 waves of the SM count
+static dim3 gn_grid(int N, int HW, int C, int vec) {
+    const int lanes = 256 / (C / vec);
+    int chunks = (HW + lanes * 4 - 1) / (lanes * 4);  // >= 4 pixels per lane
+    const int want = (sm_count() * 4 + N - 1) / N;
+    if (chunks > want) chunks = want;
+    if (chunks < 1) chunks = 1;
+    return dim3(chunks, N);
+}
+
+}  // namespace dmu
+
+using namespace dmu;
+
+#define DISPATCH_T(dtype, KERNEL, grid, block, stream, ...)                                     \
+    do {                                                                                        \
+        if ((dtype) == DMU_BF16) KERNEL<__nv_bfloat16><<<grid, block, 0, stream>>>(__VA_ARGS__); \
+        else KERNEL<float><<<grid, block, 0, stream>>>(__VA_ARGS__);                             \
+    } while (0)
+
+extern "C" {
+
+int dmu_gn_stats(const dmu_gn_params* p, dmu_stream_t stream) {
+    if (int e = gn_check(p, "dmu_gn_stats", false, false)) return e;
+    const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
+    DISPATCH_T(p->x.dtype, gn_stats_kernel, gn_grid(p->N, p->H * p->W, p->C, vec), 256, as_stream(stream), *p);
+    return check_launch("dmu_gn_stats");
+}
+int dmu_gn_apply(const dmu_gn_params* p, dmu_stream_t stream) {
+    if (int e = gn_check(p, "dmu_gn_apply", true, false)) return e;
+    const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
+    DISPATCH_T(p->x.dtype, gn_apply_kernel, gn_grid(p->N, p->H * p->W, p->C, vec), 256, as_stream(stream), *p);
+    return check_launch("dmu_gn_apply");
+}
+int dmu_gn_bwd_reduce(const dmu_gn_params* p, dmu_stream_t stream) {
+    if (int e = gn_check(p, "dmu_gn_bwd_reduce", true, false)) return e;
+    DMU_REQUIRE(p->red, "dmu_gn_bwd_reduce: red workspace missing");
+    const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
+    DISPATCH_T(p->x.dtype, gn_bwd_reduce_kernel, gn_grid(p->N, p->H * p->W, p->C, vec), 256, as_stream(stream), *p);
+    return check_launch("dmu_gn_bwd_reduce");
+}
+int dmu_gn_bwd_apply(const dmu_gn_params* p, dmu_stream_t stream) {
+    if (int e = gn_check(p, "dmu_gn_bwd_apply", true, true)) return e;
+    const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
+    DISPATCH_T(p->x.dtype, gn_bwd_apply_kernel, gn_grid(p->N, p->H * p->W, p->C, vec), 256, as_stream(stream), *p);
+    return check_launch("dmu_gn_bwd_apply");
+}
+
+int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out_nc, int64_t pitch, float* out_c,
+               float scale, dmu_stream_t stream) {
+    DMU_REQUIRE(x && x->ptr, "dmu_colsum: null input");
+    DMU_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= kMaxC, "dmu_colsum: bad dims");
+    const int vec = x->dtype == DMU_BF16 ? 8 : 4;
+    DMU_REQUIRE(x->sc == 1 && C % vec == 0 && x->sw % vec == 0 && x->sn % vec == 0 && C / vec <= 256, "dmu_colsum: needs NHWC, C multiple of %d", vec);
+    DISPATCH_T(x->dtype, colsum_kernel, dim3(1, N), 256, as_stream(stream), *x, H, W, C, out_nc, pitch, out_c, scale);
+    return check_launch("dmu_colsum");
+}
+
+int dmu_act_fwd(const float* x, float* y, int64_t n, int32_t kind, dmu_stream_t stream) {
+    DMU_REQUIRE(x && y && n >= 0 && kind >= 0 && kind <= 2, "dmu_act_fwd: bad arguments");
+    if (n == 0) return 0;
+    int grid = (int)((n + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
+    act_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, y, n, kind);
+    return check_launch("dmu_act_fwd");
+}
+int dmu_act_bwd(const float* x, const float* dy, float* dx, int64_t n, int32_t kind, dmu_stream_t stream) {
+    DMU_REQUIRE(x && dy && dx && n >= 0 && kind >= 0 && kind <= 2, "dmu_act_bwd: bad arguments");
+    if (n == 0) return 0;
+    int grid = (int)((n + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
+    act_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, dy, dx, n, kind);
+    return check_launch("dmu_act_bwd");
+}
+
+int dmu_sinusoidal_embedding(const void* t, int32_t t_is_float, float* emb, int64_t batch, int32_t dim, dmu_stream_t stream) {
+    DMU_REQUIRE(t && emb && batch >= 0, "dmu_sinusoidal_embedding: bad arguments");
+    DMU_REQUIRE(dim >= 4 && dim % 2 == 0, "dmu_sinusoidal_embedding: dim must be even and >= 4 (embeddings.py:34 divides by half-1)");
+    if (batch == 0) return 0;
+    const int half = dim / 2;
+    const float neg_k = (float)(-(log(10000.0) / (double)(half - 1)));
+    int grid = (int)((batch * half + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
+    sinusoidal_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, t_is_float, emb, batch, dim, neg_k);
+    return check_launch("dmu_sinusoidal_embedding");
+}
+
+int dmu_repack_weights(const dmu_repack_desc* descs_device, int32_t n_desc, int64_t max_numel, dmu_stream_t stream) {
+    DMU_REQUIRE(descs_device && n_desc > 0 && max_numel > 0, "dmu_repack_weights: bad arguments");
+    int gx = (int)((max_numel + 255) / 256); if (gx > 64) gx = 64;
+    repack_kernel<<<dim3(gx, n_desc), 256, 0, as_stream(stream)>>>(descs_device);
+    return check_launch("dmu_repack_weights");
+}
+
+int dmu_copy4(const dmu_tensor4* src, const dmu_tensor4* dst, int32_t N, int32_t H, int32_t W, int32_t C, dmu_stream_t stream) {
+    DMU_REQUIRE(src && dst && src->ptr && dst->ptr, "dmu_copy4: null tensor");
+    DMU_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "dmu_copy4: bad dims");
+    const int64_t total = (int64_t)N * H * W * C;
+    int grid = (int)((total + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8;
+    copy4_kernel<<<grid, 256, 0, as_stream(stream)>>>(*src, *dst, N, H, W, C);
+    return check_launch("dmu_copy4");
+}
+
+int dmu_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int64_t step, float ema_decay, float grad_scale, dmu_stream_t stream) {
+    DMU_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "dmu_adam_ema: bad arguments");
+    if (n == 0) return 0;
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    int grid = (int)((n / 4 + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8; if (grid < 1) grid = 1;
+    adam_ema_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, ema_decay, grad_scale);
+    return check_launch("dmu_adam_ema");
+}
+
+}  // extern "C"

@@ -1,0 +1,384 @@
+// Fused per-step updates and loss: one launch each, 128-bit HBM accesses.
+// Arithmetic mirrors the reference's unfused torch expressions operation by
+// operation (explicit _rn intrinsics, no FMA contraction) so that results are
+// bit-comparable with the oracle.  See include/dmu_b200.h for the call sites.
+#include "common.cuh"
+
+namespace dmu {
+
+static thread_local char g_err[512] = {0};
+char* err_buf() { return g_err; }
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// grid for a memory-bound elementwise kernel: a multiple of the SM count
+static inline int ew_grid(int64_t work_items, int threads, int max_waves = 8) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count() * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+#define SQRT(a) __fsqrt_rn((a))
+
+// Generic driver: each sample b has per-sample coefficients computed once per
+// thread-chunk; the functor maps (coeffs, element index) -> output.
+template <class F>
+__global__ void __launch_bounds__(256) per_sample_kernel(F f, int64_t batch, int64_t inner) {
+    const int64_t total = batch * inner;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    const bool vec_ok = (inner % 4) == 0;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += stride) {
+        if (vec_ok) {
+            f.vec4(i / inner, i);
+        } else {
+            for (int k = 0; k < 4 && i + k < total; ++k) f.one((i + k) / inner, i + k);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ q_sample
+struct QSample {
+    const float* x0; const float* noise; const int64_t* t; const float* acp; float* out;
+    __device__ __forceinline__ void coef(int64_t b, float& a, float& s) const {
+        float c = acp[t[b]];
+        a = SQRT(c);
+        s = SQRT(SUB(1.f, c));
+    }
+    __device__ __forceinline__ void one(int64_t b, int64_t i) const {
+        float a, s; coef(b, a, s);
+        out[i] = ADD(MUL(a, x0[i]), MUL(s, noise[i]));
+    }
+    __device__ __forceinline__ void vec4(int64_t b, int64_t i) const {
+        float a, s; coef(b, a, s);
+        float4 x = *reinterpret_cast<const float4*>(x0 + i);
+        float4 n = *reinterpret_cast<const float4*>(noise + i);
+        float4 o;
+        o.x = ADD(MUL(a, x.x), MUL(s, n.x)); o.y = ADD(MUL(a, x.y), MUL(s, n.y));
+        o.z = ADD(MUL(a, x.z), MUL(s, n.z)); o.w = ADD(MUL(a, x.w), MUL(s, n.w));
+        *reinterpret_cast<float4*>(out + i) = o;
+    }
+};
+
+// ------------------------------------------------------------------ DDPM posterior step
+struct DdpmStep {
+    const float* x; const float* eps; const float* noise; const int64_t* t;
+    const float* betas; const float* alphas; const float* acp; float* out;
+    struct C { float inv_sqrt_alpha, k_eps, sd; bool add; };
+    __device__ __forceinline__ C coef(int64_t b) const {
+        const int64_t tb = t[b];
+        const bool pos = t[0] > 0;  // ddpm.py:311,323: the whole batch follows t[0]
+        const float alpha = alphas[tb], ac = acp[tb], beta = betas[tb];
+        // ddpm.py:311 indexes acp[t-1]; python's negative index wraps for t == 0 rows of a mixed batch
+        const float ac_prev = pos ? acp[tb > 0 ? tb - 1 : 0] : 1.f;
+        C c;
+        const float one_m = SUB(1.f, ac);
+        const float beta_tilde = MUL(DIV(SUB(1.f, ac_prev), one_m), beta);
+        c.inv_sqrt_alpha = __frcp_rn(SQRT(alpha));         // torch.pow(alpha, -0.5)
+        c.k_eps = DIV(beta, SQRT(one_m));
+        c.sd = SQRT(beta_tilde);
+        c.add = pos && noise != nullptr;
+        return c;
+    }
+    __device__ __forceinline__ float f(const C& c, float xv, float ev, float nv) const {
+        float mean = MUL(c.inv_sqrt_alpha, SUB(xv, MUL(c.k_eps, ev)));
+        return c.add ? ADD(mean, MUL(c.sd, nv)) : mean;
+    }
+    __device__ __forceinline__ void one(int64_t b, int64_t i) const {
+        C c = coef(b);
+        out[i] = f(c, x[i], eps[i], c.add ? noise[i] : 0.f);
+    }
+    __device__ __forceinline__ void vec4(int64_t b, int64_t i) const {
+        C c = coef(b);
+        float4 xv = *reinterpret_cast<const float4*>(x + i);
+        float4 ev = *reinterpret_cast<const float4*>(eps + i);
+        float4 nv = c.add ? *reinterpret_cast<const float4*>(noise + i) : make_float4(0, 0, 0, 0);
+        float4 o;
+        o.x = f(c, xv.x, ev.x, nv.x); o.y = f(c, xv.y, ev.y, nv.y);
+        o.z = f(c, xv.z, ev.z, nv.z); o.w = f(c, xv.w, ev.w, nv.w);
+        *reinterpret_cast<float4*>(out + i) = o;
+    }
+};
+
+// ------------------------------------------------------------------ DDIM step
+struct DdimStep {
+    const float* x; const float* eps; const float* noise; const int64_t* idx;
+    const float* a; const float* ap; const float* sg; const float* s1m; float* out;
+    struct C { float r, sqrt_a, dir, sqrt_ap, sigma; };
+    __device__ __forceinline__ C coef(int64_t b) const {
+        const int64_t i = idx[b];
+        C c;
+        c.r = s1m[i];
+        c.sqrt_a = SQRT(a[i]);
+        c.sigma = sg[i];
+        c.dir = SQRT(SUB(SUB(1.f, ap[i]), MUL(c.sigma, c.sigma)));
+        c.sqrt_ap = SQRT(ap[i]);
+        return c;
+    }
+    __device__ __forceinline__ float f(const C& c, float xv, float ev, float nv) const {
+        float x0 = DIV(SUB(xv, MUL(c.r, ev)), c.sqrt_a);
+        x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        float v = ADD(MUL(c.sqrt_ap, x0), MUL(c.dir, ev));
+        if (noise != nullptr) {
+            float z = fminf(fmaxf(nv, -3.f), 3.f);
+            v = ADD(v, MUL(c.sigma, z));
+        }
+        return v;
+    }
+    __device__ __forceinline__ void one(int64_t b, int64_t i) const {
+        C c = coef(b);
+        out[i] = f(c, x[i], eps[i], noise ? noise[i] : 0.f);
+    }
+    __device__ __forceinline__ void vec4(int64_t b, int64_t i) const {
+        C c = coef(b);
+        float4 xv = *reinterpret_cast<const float4*>(x + i);
+        float4 ev = *reinterpret_cast<const float4*>(eps + i);
+        float4 nv = noise ? *reinterpret_cast<const float4*>(noise + i) : make_float4(0, 0, 0, 0);
+        float4 o;
+        o.x = f(c, xv.x, ev.x, nv.x); o.y = f(c, xv.y, ev.y, nv.y);
+        o.z = f(c, xv.z, ev.z, nv.z); o.w = f(c, xv.w, ev.w, nv.w);
+        *reinterpret_cast<float4*>(out + i) = o;
+    }
+};
+
+// ------------------------------------------------------------------ x + a*g + b*z  (Langevin / renoise)
+struct Axpbz {
+    const float* x; const float* g; const float* z; float* out;
+    const float* sigmas; int64_t k; float beta;   // score form (coefficients from device sigma)
+    const float* acp; int64_t t;                  // renoise form
+    float a_host, b_host; int mode;               // 0 host scalars (x + a g + b z), 1 score, 2 renoise (a x + b z)
+    __device__ __forceinline__ void coef(float& a, float& b) const {
+        if (mode == 0) { a = a_host; b = b_host; }
+        else if (mode == 1) {
+            float s = MUL(sigmas[k], beta);
+            a = MUL(MUL(s, s), 2.f);
+            b = SQRT(MUL(a, 2.f));
+        } else {
+            float an = acp[t - 1], ac = acp[t];
+            a = SQRT(DIV(an, ac));
+            b = MUL(SQRT(DIV(SUB(1.f, an), SUB(1.f, ac))), SQRT(SUB(1.f, DIV(ac, an))));
+        }
+    }
+    __device__ __forceinline__ float f(float a, float b, float xv, float gv, float zv) const {
+        if (mode == 2) return ADD(MUL(a, xv), MUL(b, zv));
+        return ADD(ADD(xv, MUL(a, gv)), MUL(b, zv));
+    }
+    __device__ __forceinline__ void one(int64_t, int64_t i) const {
+        float a, b; coef(a, b);
+        out[i] = f(a, b, x[i], g ? g[i] : 0.f, z[i]);
+    }
+    __device__ __forceinline__ void vec4(int64_t, int64_t i) const {
+        float a, b; coef(a, b);
+        float4 xv = *reinterpret_cast<const float4*>(x + i);
+        float4 gv = g ? *reinterpret_cast<const float4*>(g + i) : make_float4(0, 0, 0, 0);
+        float4 zv = *reinterpret_cast<const float4*>(z + i);
+        float4 o;
+        o.x = f(a, b, xv.x, gv.x, zv.x); o.y = f(a, b, xv.y, gv.y, zv.y);
+        o.z = f(a, b, xv.z, gv.z, zv.z); o.w = f(a, b, xv.w, gv.w, zv.w);
+        *reinterpret_cast<float4*>(out + i) = o;
+    }
+};
+
+struct ScaleAdd {
+    const float* x; const float* z; const float* a; const float* c; float* out;
+    __device__ __forceinline__ float f(int64_t b, float xv, float zv) const {
+        const float t = MUL(c[b], zv);
+        return a ? ADD(MUL(a[b], xv), t) : ADD(xv, t);
+    }
+    __device__ __forceinline__ void one(int64_t b, int64_t i) const { out[i] = f(b, x[i], z[i]); }
+    __device__ __forceinline__ void vec4(int64_t b, int64_t i) const {
+        float4 xv = *reinterpret_cast<const float4*>(x + i);
+        float4 zv = *reinterpret_cast<const float4*>(z + i);
+        float4 o;
+        o.x = f(b, xv.x, zv.x); o.y = f(b, xv.y, zv.y); o.z = f(b, xv.z, zv.z); o.w = f(b, xv.w, zv.w);
+        *reinterpret_cast<float4*>(out + i) = o;
+    }
+};
+
+template <class F>
+static int launch_per_sample(const F& f, int64_t batch, int64_t inner, cudaStream_t s, const char* what) {
+    if (batch * inner == 0) return 0;
+    const int threads = 256;
+    int grid = ew_grid((batch * inner + 3) / 4, threads);
+    per_sample_kernel<F><<<grid, threads, 0, s>>>(f, batch, inner);
+    return check_launch(what);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------ loss
+// pass 1: per-block partial sums (fixed order) + optional gradient; pass 2: one block reduces in order.
+__global__ void __launch_bounds__(256) loss_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                           const float* __restrict__ w, float wm, float wl, float wh, float delta,
+                                                           float* __restrict__ dpred, float* __restrict__ partials,
+                                                           int64_t batch, int64_t inner, float inv_n) {
+    const int64_t total = batch * inner;
+    float acc = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = pred[i] - target[i];
+        const float ad = fabsf(d);
+        float l = 0.f, g = 0.f;
+        if (wm != 0.f) { l += wm * (d * d); g += wm * 2.f * d; }
+        if (wl != 0.f) { l += wl * ad; g += wl * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)); }
+        if (wh != 0.f) {
+            // F.smooth_l1_loss(beta=delta): 0.5 d^2/beta if |d| < beta else |d| - 0.5 beta
+            if (ad < delta) { l += wh * (0.5f * d * d / delta); g += wh * (d / delta); }
+            else { l += wh * (ad - 0.5f * delta); g += wh * (d > 0.f ? 1.f : -1.f); }
+        }
+        const float wb = w ? w[i / inner] : 1.f;
+        acc += wb * l;
+        if (dpred) dpred[i] = wb * g * inv_n;
+    }
+    __shared__ float sm[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += sm[i];
+        partials[blockIdx.x] = s;
+    }
+}
+__global__ void loss_final_kernel(const float* __restrict__ partials, int n, float inv_n, float* __restrict__ loss) {
+    __shared__ double sm[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partials[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sm[i];
+        *loss = (float)(s * (double)inv_n);
+    }
+}
+
+static int loss_grid(int64_t numel) { return ew_grid(numel, 256, 4); }
+
+}  // namespace dmu
+
+using namespace dmu;
+
+extern "C" {
+
+int dmu_abi_version(void) { return DMU_ABI_VERSION; }
+const char* dmu_last_error(void) { return err_buf(); }
+
+int dmu_sizeof(const char* name) {
+    auto eq = [](const char* a, const char* b) { while (*a && *a == *b) { ++a; ++b; } return *a == *b; };
+    if (eq(name, "dmu_tensor4")) return (int)sizeof(dmu_tensor4);
+    if (eq(name, "dmu_conv_params")) return (int)sizeof(dmu_conv_params);
+    if (eq(name, "dmu_wgrad_params")) return (int)sizeof(dmu_wgrad_params);
+    if (eq(name, "dmu_gn_params")) return (int)sizeof(dmu_gn_params);
+    if (eq(name, "dmu_attn_params")) return (int)sizeof(dmu_attn_params);
+    if (eq(name, "dmu_repack_desc")) return (int)sizeof(dmu_repack_desc);
+    return -1;
+}
+
+int dmu_q_sample(const float* x0, const float* noise, const int64_t* t, const float* acp, float* out,
+                 int64_t batch, int64_t inner, dmu_stream_t stream) {
+    DMU_REQUIRE(x0 && noise && t && acp && out, "dmu_q_sample: null pointer");
+    DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_q_sample: negative size");
+    DMU_REQUIRE(aligned16(x0) && aligned16(noise) && aligned16(out), "dmu_q_sample: buffers must be 16-byte aligned");
+    QSample f{x0, noise, t, acp, out};
+    return launch_per_sample(f, batch, inner, as_stream(stream), "dmu_q_sample");
+}
+
+int dmu_ddpm_step(const float* x, const float* eps, const float* noise, const int64_t* t, const float* betas,
+                  const float* alphas, const float* acp, float* out, int64_t batch, int64_t inner, dmu_stream_t stream) {
+    DMU_REQUIRE(x && eps && t && betas && alphas && acp && out, "dmu_ddpm_step: null pointer");
+    DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_ddpm_step: negative size");
+    DMU_REQUIRE(aligned16(x) && aligned16(eps) && aligned16(out) && aligned16(noise), "dmu_ddpm_step: buffers must be 16-byte aligned");
+    DdpmStep f{x, eps, noise, t, betas, alphas, acp, out};
+    return launch_per_sample(f, batch, inner, as_stream(stream), "dmu_ddpm_step");
+}
+
+int dmu_ddim_step(const float* x, const float* eps, const float* noise, const int64_t* idx, const float* a,
+                  const float* ap, const float* sg, const float* s1m, float* out, int64_t batch, int64_t inner,
+                  dmu_stream_t stream) {
+    DMU_REQUIRE(x && eps && idx && a && ap && sg && s1m && out, "dmu_ddim_step: null pointer");
+    DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_ddim_step: negative size");
+    DMU_REQUIRE(aligned16(x) && aligned16(eps) && aligned16(out) && aligned16(noise), "dmu_ddim_step: buffers must be 16-byte aligned");
+    DdimStep f{x, eps, noise, idx, a, ap, sg, s1m, out};
+    return launch_per_sample(f, batch, inner, as_stream(stream), "dmu_ddim_step");
+}
+
+int dmu_langevin_score_step(const float* x, const float* score, const float* noise, const float* sigmas, int64_t k,
+                            float beta, float* out, int64_t n, dmu_stream_t stream) {
+    DMU_REQUIRE(x && score && noise && sigmas && out, "dmu_langevin_score_step: null pointer");
+    DMU_REQUIRE(n >= 0 && k >= 0, "dmu_langevin_score_step: negative size/index");
+    DMU_REQUIRE(aligned16(x) && aligned16(score) && aligned16(noise) && aligned16(out), "dmu_langevin_score_step: alignment");
+    Axpbz f{x, score, noise, out, sigmas, k, beta, nullptr, 0, 0.f, 0.f, 1};
+    return launch_per_sample(f, 1, n, as_stream(stream), "dmu_langevin_score_step");
+}
+
+int dmu_langevin_energy_step(const float* x, const float* grad, const float* noise, float step, float sqrt_2step,
+                             float* out, int64_t n, dmu_stream_t stream) {
+    DMU_REQUIRE(x && grad && noise && out, "dmu_langevin_energy_step: null pointer");
+    DMU_REQUIRE(n >= 0, "dmu_langevin_energy_step: negative size");
+    DMU_REQUIRE(aligned16(x) && aligned16(grad) && aligned16(noise) && aligned16(out), "dmu_langevin_energy_step: alignment");
+    Axpbz f{x, grad, noise, out, nullptr, 0, 0.f, nullptr, 0, -step, sqrt_2step, 0};
+    return launch_per_sample(f, 1, n, as_stream(stream), "dmu_langevin_energy_step");
+}
+
+int dmu_energy_renoise(const float* x, const float* noise, const float* acp, int64_t t, float* out, int64_t n,
+                       dmu_stream_t stream) {
+    DMU_REQUIRE(x && noise && acp && out, "dmu_energy_renoise: null pointer");
+    DMU_REQUIRE(t >= 1, "dmu_energy_renoise: t must be >= 1 (energy_based.py:240)");
+    DMU_REQUIRE(aligned16(x) && aligned16(noise) && aligned16(out), "dmu_energy_renoise: alignment");
+    Axpbz f{x, nullptr, noise, out, nullptr, 0, 0.f, acp, t, 0.f, 0.f, 2};
+    return launch_per_sample(f, 1, n, as_stream(stream), "dmu_energy_renoise");
+}
+
+int dmu_zero(void* ptr, int64_t nbytes, dmu_stream_t stream) {
+    DMU_REQUIRE(ptr && nbytes >= 0, "dmu_zero: bad arguments");
+    if (nbytes == 0) return 0;
+    cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)nbytes, as_stream(stream));
+    if (e != cudaSuccess) return fail("dmu_zero: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int dmu_scale_add(const float* x, const float* z, const float* a, const float* c, float* out, int64_t batch, int64_t inner,
+                  dmu_stream_t stream) {
+    DMU_REQUIRE(x && z && c && out, "dmu_scale_add: null pointer");
+    DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_scale_add: negative size");
+    DMU_REQUIRE(aligned16(x) && aligned16(z) && aligned16(out), "dmu_scale_add: buffers must be 16-byte aligned");
+    ScaleAdd f{x, z, a, c, out};
+    return launch_per_sample(f, batch, inner, as_stream(stream), "dmu_scale_add");
+}
+
+int64_t dmu_loss_workspace_floats(int64_t numel) { return (int64_t)loss_grid(numel > 0 ? numel : 1); }
+
+int dmu_diffusion_loss(const float* pred, const float* target, const float* w, float wm, float wl, float wh, float delta,
+                       float* loss, float* dpred, float* partials, int64_t batch, int64_t inner, dmu_stream_t stream) {
+    DMU_REQUIRE(pred && target && loss && partials, "dmu_diffusion_loss: null pointer");
+    DMU_REQUIRE(batch > 0 && inner > 0, "dmu_diffusion_loss: empty input (mean of zero elements)");
+    const int64_t n = batch * inner;
+    const int grid = loss_grid(n);
+    const float inv_n = (float)(1.0 / (double)n);
+    loss_partial_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, target, w, wm, wl, wh, delta, dpred, partials, batch, inner, inv_n);
+    if (int e = check_launch("dmu_diffusion_loss/partial")) return e;
+    loss_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, grid, inv_n, loss);
+    return check_launch("dmu_diffusion_loss/final");
+}
+
+}  // extern "C"

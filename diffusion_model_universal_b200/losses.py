@@ -1,0 +1,92 @@
+"""DiffusionLoss — host mirror of utils/losses.py:8-181 over one fused kernel.
+
+The [B]-sized time weights are computed with the reference's own torch
+expressions (bit-identical on the same device); the
+per-element work — difference, mse/l1/huber mix, weighting, mean and the
+gradient w.r.t. the prediction — is a single pass of ``dmu_diffusion_loss``.
+"""
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+
+class DiffusionLoss:
+    LOSS_TYPES = ("mse", "l1", "huber", "hybrid")
+
+    def __init__(self, loss_type: str = "mse", loss_config: Optional[Dict] = None):
+        self.loss_type = loss_type.lower()
+        self.loss_config = loss_config or {}
+        if self.loss_type not in self.LOSS_TYPES:
+            raise ValueError(f"Unsupported loss type: {loss_type}")
+        c = self.loss_config
+        self.mse_weight = c.get("mse_weight", 1.0)
+        self.l1_weight = c.get("l1_weight", 0.0)
+        self.huber_weight = c.get("huber_weight", 0.0)
+        self.huber_delta = c.get("huber_delta", 1.0)
+        self.use_hybrid = c.get("use_hybrid", False)
+        if self.use_hybrid:
+            w = c.get("hybrid_weights", {})
+            self.hybrid_weights = {"mse": w.get("mse", 1.0), "l1": w.get("l1", 0.0), "huber": w.get("huber", 0.0)}
+        self.use_time_weighting = c.get("use_time_weighting", True)
+        self.time_weight_type = c.get("time_weight_type", "snr")
+        self.time_weight_params = c.get("time_weight_params", {"min_weight": 0.1, "max_weight": 1.0})
+        self.perceptual_weight = c.get("perceptual_weight", 0.0)
+        self.adversarial_weight = c.get("adversarial_weight", 0.0)
+        if self.perceptual_weight > 0:
+            raise NotImplementedError("perceptual (VGG16) term is outside the hot path (weight 0.0 in every shipped config)")
+
+    def coefficients(self):
+        """(w_mse, w_l1, w_huber) the way losses.py:105-131 resolves them."""
+        if self.use_hybrid:
+            hw = self.hybrid_weights
+            return tuple(float(v) if v > 0 else 0.0 for v in (hw["mse"], hw["l1"], hw["huber"]))
+        if self.loss_type == "mse":
+            return (float(self.mse_weight), 0.0, 0.0)
+        if self.loss_type == "l1":
+            return (0.0, float(self.l1_weight), 0.0)
+        if self.loss_type == "huber":
+            return (0.0, 0.0, float(self.huber_weight))
+        raise ValueError(f"Unsupported single loss type: {self.loss_type}")  # 'hybrid' without use_hybrid, losses.py:113-114
+
+    def _get_time_weights(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """losses.py:133-181, returned flat [B]."""
+        lo, hi = self.time_weight_params["min_weight"], self.time_weight_params["max_weight"]
+        if self.time_weight_type == "snr":
+            betas = torch.linspace(1e-4, 2e-2, timesteps.max().item() + 1, device=timesteps.device)
+            acp = torch.cumprod(1 - betas, dim=0).index_select(0, timesteps)
+            snr = acp / (1 - acp)
+            w = (snr / snr.max()).clamp(min=1e-5)
+        elif self.time_weight_type == "linear":
+            w = 1 - (timesteps.float() / timesteps.max())
+        elif self.time_weight_type == "inverse":
+            w = 1 / (timesteps.float() + 1)
+        else:
+            w = torch.ones_like(timesteps, dtype=torch.float)
+        return lo + (hi - lo) * ((w - w.min()) / (w.max() - w.min() + 1e-5))
+
+    def __call__(self, pred: torch.Tensor, target: torch.Tensor, timesteps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        w = None
+        if self.use_time_weighting and timesteps is not None:
+            w = self._get_time_weights(timesteps).float().contiguous()
+        wm, wl, wh = self.coefficients()
+        return _LossFn.apply(pred, target, w, wm, wl, wh, float(self.huber_delta))
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, w, wm, wl, wh, delta):
+        need = pred.requires_grad
+        loss, dpred = ops.diffusion_loss(pred.contiguous().float(), target.contiguous().float(), w, wm, wl, wh, delta, need)
+        ctx.dpred = dpred
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d = ctx.dpred
+        if d is None:
+            return (None,) * 7
+        # g is the scalar upstream gradient (1.0 for loss.backward()); keep it on device, no sync
+        return (d * g, None, None, None, None, None, None)

@@ -1,0 +1,187 @@
+"""Tensor-level wrappers over the C ABI (include/dmu_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; all
+arithmetic happens in libdmu_b200.so.  Every wrapper requires CUDA tensors and
+raises otherwise — there is no fallback path.
+"""
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _abi
+from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("diffusion_model_universal_b200 runs on CUDA (sm_100a) only: got a CPU tensor. "
+                               "Move the model and inputs to a B200 device; there is no CPU fallback.")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous float32 tensor")
+    return t
+
+
+def t4_nchw(t: torch.Tensor) -> Tensor4:
+    """Describe a contiguous [N,C,H,W] tensor."""
+    n, c, h, w = t.shape
+    assert t.is_contiguous()
+    return Tensor4(t.data_ptr(), c * h * w, w, 1, h * w, dtype_code(t), 0)
+
+
+def t4_nhwc(t: torch.Tensor, c0: int = 0, c: int = None) -> Tensor4:
+    """Describe channels [c0, c0+c) of a contiguous [N,H,W,Ctot] tensor."""
+    n, h, w, ct = t.shape
+    assert t.is_contiguous()
+    return Tensor4(t.data_ptr() + c0 * t.element_size(), h * w * ct, w * ct, ct, 1, dtype_code(t), 0)
+
+
+def t4_rows(t: torch.Tensor) -> Tensor4:
+    """[M, C] row matrix as an N=M, H=W=1 tensor."""
+    m, c = t.shape
+    assert t.stride(1) == 1
+    p = t.stride(0)
+    return Tensor4(t.data_ptr(), p, p, p, 1, dtype_code(t), 0)
+
+
+# ------------------------------------------------------------------ process updates
+def q_sample(x0, t, noise, alphas_cumprod):
+    """models/ddpm.py:286-296."""
+    _need_cuda(x0, t, noise, alphas_cumprod)
+    x0, noise = _f32c(x0, "x0"), _f32c(noise, "noise")
+    out = torch.empty_like(x0)
+    b = x0.shape[0]
+    check(_abi.lib().dmu_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
+                                  b, x0.numel() // max(b, 1), _stream()), "q_sample")
+    return out
+
+
+def ddpm_step(x, eps, t, noise, betas, alphas, alphas_cumprod, out=None):
+    """models/ddpm.py:306-329 after the eps prediction (noise=None only when t == 0)."""
+    _need_cuda(x, eps, t)
+    x, eps = _f32c(x, "x"), _f32c(eps, "eps")
+    if noise is not None:
+        _f32c(noise, "noise")
+    if t.dtype != torch.int64:
+        raise TypeError("t must be int64")
+    out = torch.empty_like(x) if out is None else out
+    b = x.shape[0]
+    check(_abi.lib().dmu_ddpm_step(x.data_ptr(), eps.data_ptr(), noise.data_ptr() if noise is not None else None, t.data_ptr(),
+                                   betas.data_ptr(), alphas.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
+                                   b, x.numel() // max(b, 1), _stream()), "ddpm_step")
+    return out
+
+
+def ddim_step(x, eps, idx, noise, alphas, alphas_prev, sigmas, sqrt_one_minus_alphas, out=None):
+    """models/ddim.py:97-124 after the eps prediction; idx indexes the S-entry tables."""
+    _need_cuda(x, eps, idx)
+    x, eps = _f32c(x, "x"), _f32c(eps, "eps")
+    if idx.dtype != torch.int64:
+        raise TypeError("idx must be int64")
+    out = torch.empty_like(x) if out is None else out
+    b = x.shape[0]
+    check(_abi.lib().dmu_ddim_step(x.data_ptr(), eps.data_ptr(), noise.data_ptr() if noise is not None else None, idx.data_ptr(),
+                                   alphas.data_ptr(), alphas_prev.data_ptr(), sigmas.data_ptr(), sqrt_one_minus_alphas.data_ptr(),
+                                   out.data_ptr(), b, x.numel() // max(b, 1), _stream()), "ddim_step")
+    return out
+
+
+def langevin_score_step(x, score, noise, sigmas, k: int, beta: float, out=None):
+    """models/score_based.py:236-245."""
+    _need_cuda(x, score, noise, sigmas)
+    out = torch.empty_like(x) if out is None else out
+    check(_abi.lib().dmu_langevin_score_step(_f32c(x, "x").data_ptr(), _f32c(score, "score").data_ptr(), _f32c(noise, "noise").data_ptr(),
+                                             sigmas.data_ptr(), k, beta, out.data_ptr(), x.numel(), _stream()), "langevin_score_step")
+    return out
+
+
+def langevin_energy_step(x, grad, noise, step_size: float, out=None):
+    """models/energy_based.py:271-273 (math.sqrt repair)."""
+    _need_cuda(x, grad, noise)
+    out = torch.empty_like(x) if out is None else out
+    check(_abi.lib().dmu_langevin_energy_step(_f32c(x, "x").data_ptr(), _f32c(grad, "grad").data_ptr(), _f32c(noise, "noise").data_ptr(),
+                                              step_size, math.sqrt(2 * step_size), out.data_ptr(), x.numel(), _stream()), "langevin_energy_step")
+    return out
+
+
+def energy_renoise(x, noise, alphas_cumprod, t: int, out=None):
+    """models/energy_based.py:240-246."""
+    _need_cuda(x, noise, alphas_cumprod)
+    out = torch.empty_like(x) if out is None else out
+    check(_abi.lib().dmu_energy_renoise(_f32c(x, "x").data_ptr(), _f32c(noise, "noise").data_ptr(), alphas_cumprod.data_ptr(), t,
+                                        out.data_ptr(), x.numel(), _stream()), "energy_renoise")
+    return out
+
+
+def scale_add(x, z, a, c, out=None):
+    """out[b] = a[b]*x[b] + c[b]*z[b] (a None = 1): score_based.py:200-201, losses.py:240."""
+    _need_cuda(x, z, c)
+    x, z = _f32c(x, "x"), _f32c(z, "z")
+    out = torch.empty_like(x) if out is None else out
+    b = x.shape[0]
+    c = c.float().contiguous()
+    a = a.float().contiguous() if a is not None else None
+    check(_abi.lib().dmu_scale_add(x.data_ptr(), z.data_ptr(), a.data_ptr() if a is not None else None, c.data_ptr(), out.data_ptr(),
+                                   b, x.numel() // max(b, 1), _stream()), "scale_add")
+    return out
+
+
+def diffusion_loss(pred, target, w, wm, wl, wh, delta, want_grad: bool):
+    """utils/losses.py:74-131 given per-sample weights w [B] (or None).  Returns (loss 0-dim, dpred or None)."""
+    _need_cuda(pred, target, w)
+    pred, target = _f32c(pred, "pred"), _f32c(target, "target")
+    b = pred.shape[0]
+    n = pred.numel()
+    loss = torch.empty((), device=pred.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred) if want_grad else None
+    part = torch.empty(_abi.lib().dmu_loss_workspace_floats(n), device=pred.device, dtype=torch.float32)
+    check(_abi.lib().dmu_diffusion_loss(pred.data_ptr(), target.data_ptr(), w.data_ptr() if w is not None else None,
+                                        wm, wl, wh, delta, loss.data_ptr(), dpred.data_ptr() if want_grad else None,
+                                        part.data_ptr(), b, n // b, _stream()), "diffusion_loss")
+    return loss, dpred
+
+
+# ------------------------------------------------------------------ UNet primitives (used by tests; the engine builds structs directly)
+def conv2d_raw(p: ConvParams):
+    check(_abi.lib().dmu_conv2d(C.byref(p), _stream()), "conv2d")
+
+
+def wgrad_raw(p: WgradParams):
+    check(_abi.lib().dmu_conv2d_wgrad(C.byref(p), _stream()), "conv2d_wgrad")
+
+
+def copy4(src: Tensor4, dst: Tensor4, n, h, w, c):
+    check(_abi.lib().dmu_copy4(C.byref(src), C.byref(dst), n, h, w, c, _stream()), "copy4")
+
+
+def nchw_to_nhwc(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    _need_cuda(x)
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), device=x.device, dtype=dtype or x.dtype)
+    copy4(t4_nchw(x.contiguous()), t4_nhwc(out), n, h, w, c)
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), device=x.device, dtype=dtype or x.dtype)
+    copy4(t4_nhwc(x.contiguous()), t4_nchw(out), n, h, w, c)
+    return out

@@ -1,0 +1,796 @@
+"""UNet denoiser: parameter containers + the CUDA execution engine.
+
+Host-side mirror of the reference network (models/ddpm.py:32-135,
+models/layers/{residual,attention,embeddings}.py).  The ``nn.Module`` tree
+below only *holds parameters* — same names, shapes, registration order and
+default initialisation as the reference, so ``state_dict()`` is interchangeable
+ — its ``forward`` never touches ATen: it hands raw pointers to
+a recorded plan of libdmu_b200.so launches (include/dmu_b200.h).
+
+Data layout in HBM:
+  * activations: NHWC, compute dtype (fp32 or bf16), one arena per plan;
+    ``torch.cat`` of the up path never happens — producers write straight into
+    channel slices of the consumer's buffer (row pitch != C);
+  * parameters: one flat fp32 arena (the nn.Parameters are views into it),
+    conv filters additionally repacked to [O][R][S][I] in the compute dtype;
+  * gradients: flat fp32 arena with the same offsets (``param.grad`` views).
+"""
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _abi, ops
+from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, RepackDesc
+
+
+def gn_groups(channels: int, num_groups: int = 32) -> int:
+    """residual.py:22-29 group-count rule."""
+    g = min(num_groups, channels)
+    while channels % g != 0 and g > 1:
+        g -= 1
+    return g
+
+
+# ============================================================================
+# Parameter containers (never executed by ATen)
+# ============================================================================
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: executed by the dmu_b200 engine, not by ATen")
+
+
+class TransformerPositionalEmbedding(_Holder):
+    """embeddings.py:11-39 (no parameters)."""
+
+    def __init__(self, dimension: int):
+        super().__init__()
+        self.dimension = dimension
+
+
+class TimeEmbedding(_Holder):
+    """embeddings.py:41-64."""
+
+    def __init__(self, base_dim: int, output_dim: int):
+        super().__init__()
+        self.positional_encoding = nn.Sequential(
+            TransformerPositionalEmbedding(base_dim), nn.Linear(base_dim, output_dim), nn.GELU(), nn.Linear(output_dim, output_dim))
+        for layer in self.positional_encoding:
+            if isinstance(layer, nn.Linear):
+                nn.init.xavier_uniform_(layer.weight)
+                nn.init.zeros_(layer.bias)
+
+
+class ResidualBlock(_Holder):
+    """residual.py:11-52."""
+
+    def __init__(self, in_channels, out_channels, time_emb_channels, num_groups=32):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.norm1 = nn.GroupNorm(gn_groups(in_channels, num_groups), in_channels)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1)
+        self.time_mlp = nn.Linear(time_emb_channels, out_channels)
+        self.norm2 = nn.GroupNorm(gn_groups(out_channels, num_groups), out_channels)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1) if in_channels != out_channels else nn.Identity()
+        nn.init.zeros_(self.time_mlp.weight)
+        nn.init.zeros_(self.time_mlp.bias)
+        nn.init.zeros_(self.conv2.weight)
+        nn.init.zeros_(self.conv2.bias)
+
+
+class SelfAttentionBlock(_Holder):
+    """attention.py:10-27."""
+
+    def __init__(self, in_channels, embedding_dim, num_heads=4, num_groups=32):
+        super().__init__()
+        self.num_heads = num_heads
+        self.query_projection = nn.Linear(in_channels, embedding_dim)
+        self.key_projection = nn.Linear(in_channels, embedding_dim)
+        self.value_projection = nn.Linear(in_channels, embedding_dim)
+        self.final_projection = nn.Linear(embedding_dim, embedding_dim)
+        self.norm = nn.GroupNorm(num_groups, embedding_dim)
+
+
+class _Stage(_Holder):
+    """ConvDownBlock / ConvUpBlock / AttentionDownBlock / AttentionUpBlock (residual.py:70-255)."""
+
+    def __init__(self, in_channels, out_channels, temb, attn: bool, up: bool):
+        super().__init__()
+        self.res_blocks = nn.ModuleList(
+            [ResidualBlock(in_channels if i == 0 else out_channels, out_channels, temb) for i in range(2)])
+        if attn:
+            self.attention_blocks = nn.ModuleList([SelfAttentionBlock(out_channels, out_channels, 4) for _ in range(2)])
+        if up:
+            self.upsample = nn.ConvTranspose2d(out_channels, out_channels, kernel_size=4, stride=2, padding=1)
+        else:
+            self.downsample = nn.Conv2d(out_channels, out_channels, kernel_size=4, stride=2, padding=1)
+        self.has_attn = attn
+
+
+def down_plan(Cm):
+    return [(False, Cm, Cm), (False, Cm, Cm), (False, Cm, 2 * Cm), (True, 2 * Cm, 2 * Cm), (False, 2 * Cm, 4 * Cm)]
+
+
+def up_plan(Cm):
+    return [(False, 8 * Cm, 4 * Cm), (True, 6 * Cm, 2 * Cm), (False, 4 * Cm, 2 * Cm), (False, 3 * Cm, Cm), (False, 2 * Cm, Cm)]
+
+
+class UNet(nn.Module):
+    """models/ddpm.py:32-135 — same constructor, same state_dict, CUDA-only forward."""
+
+    def __init__(self, in_channels: int, model_channels: int, out_channels: int, precision: str = "fp32", sigma_embed: bool = False):
+        super().__init__()
+        Cm = model_channels
+        self.in_channels, self.model_channels, self.out_channels = in_channels, Cm, out_channels
+        self.initial_conv = nn.Conv2d(in_channels, Cm, kernel_size=3, padding="same")
+        nn.init.kaiming_normal_(self.initial_conv.weight)
+        self.time_embedding = TimeEmbedding(Cm, Cm * 4)
+        self.down_blocks = nn.ModuleList([_Stage(ci, co, 4 * Cm, a, up=False) for a, ci, co in down_plan(Cm)])
+        self.bottleneck = nn.Sequential(ResidualBlock(4 * Cm, 4 * Cm, 4 * Cm), SelfAttentionBlock(4 * Cm, 4 * Cm, 4), ResidualBlock(4 * Cm, 4 * Cm, 4 * Cm))
+        self.up_blocks = nn.ModuleList([_Stage(ci, co, 4 * Cm, a, up=True) for a, ci, co in up_plan(Cm)])
+        self.output_conv = nn.Sequential(nn.GroupNorm(32, Cm), nn.SiLU(), nn.Conv2d(Cm, out_channels, kernel_size=3, padding=1))
+        if sigma_embed:  # models/score_based.py:57-61
+            self.time_embed = nn.Sequential(nn.Linear(1, Cm), nn.SiLU(), nn.Linear(Cm, Cm * 4))
+        self.sigma_embed = sigma_embed
+        self.precision = precision
+        self._engine = None
+
+    @property
+    def engine(self) -> "Engine":
+        if self._engine is None:
+            object.__setattr__(self, "_engine", Engine(self))
+        return self._engine
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """eps_theta(x, t): x fp32 [B,C,H,W] (NCHW), t [B] -> fp32 [B,C,H,W]."""
+        return self.engine.forward(x, t)
+
+
+# ============================================================================
+# Engine
+# ============================================================================
+class Buf:
+    """NHWC activation view: channels [0,C) of rows with `pitch` elements."""
+    __slots__ = ("addr", "N", "H", "W", "C", "pitch", "code", "esize", "grad", "root", "_written")
+
+    def __init__(self, addr, N, H, W, C, pitch, code, root=None):
+        self.addr, self.N, self.H, self.W, self.C, self.pitch, self.code = addr, N, H, W, C, pitch, code
+        self.esize = 2 if code == BF16 else 4
+        self.grad = None
+        self.root = root if root is not None else self   # channel slices share their parent's state
+        self._written = False
+
+    # "has some consumer already written this tensor's gradient buffer?" (shared by all slices of a buffer)
+    @property
+    def grad_written(self):
+        return self.grad is not None and self.grad.root._written
+
+    @grad_written.setter
+    def grad_written(self, v):
+        self.grad.root._written = v
+
+    def t4(self) -> Tensor4:
+        return Tensor4(self.addr, self.H * self.W * self.pitch, self.W * self.pitch, self.pitch, 1, self.code, 0)
+
+    def slice(self, c0, c) -> "Buf":
+        b = Buf(self.addr + c0 * self.esize, self.N, self.H, self.W, c, self.pitch, self.code, root=self.root)
+        if self.grad is not None:
+            b.grad = self.grad.slice(c0, c)
+        return b
+
+
+def _null_t4():
+    return Tensor4(None, 0, 0, 0, 0, 0, 0)
+
+
+def _nchw_t4(addr, Cc, H, W):
+    return Tensor4(addr, Cc * H * W, W, 1, H * W, F32, 0)
+
+
+def _rows_t4(addr, pitch, code=F32):
+    return Tensor4(addr, pitch, pitch, pitch, 1, code, 0)
+
+
+class _Bump:
+    def __init__(self, base=0):
+        self.base, self.off = base, 0
+
+    def take(self, nbytes, align=256):
+        self.off = (self.off + align - 1) // align * align
+        a = self.base + self.off
+        self.off += nbytes
+        return a
+
+
+class Plan:
+    """A recorded launch sequence for one (N, H, W, mode) problem."""
+
+    def __init__(self):
+        self.fwd, self.bwd = [], []
+        self.arena = None       # torch uint8 tensor keeping all plan buffers alive
+        self.stem = None        # ConvParams whose x.ptr is patched per call
+        self.temb_in = None     # (op index in fwd) first-op args patched per call
+        self.head = None        # ConvParams whose y.ptr is patched per call
+        self.head_dgrad = None  # ConvParams whose x.ptr (dout) is patched
+        self.head_wgrad = None  # WgradParams whose p.ptr (dout) is patched
+        self.stem_wgrad = None  # WgradParams whose q.ptr (input x) is patched
+        self.busy = False       # activations saved for a pending backward
+
+
+class Engine:
+    """Builds and runs launch plans for one UNet instance."""
+
+    def __init__(self, net: UNet):
+        self.net = net
+        self.code = BF16 if net.precision == "bf16" else F32
+        if net.precision not in ("fp32", "bf16"):
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {net.precision!r}")
+        self.tdtype = torch.bfloat16 if self.code == BF16 else torch.float32
+        self.esize = 2 if self.code == BF16 else 4
+        self.flat = None
+        self.gflat = None
+        self.plans = {}
+        self.frozen = False     # weights known unchanged: skip the repack launch
+        self.impl = 0           # conv implementation selector forwarded to the kernels (0 auto)
+        self._lib = None
+
+    # ------------------------------------------------------------------ parameters
+    def _arena_order(self):
+        """Arena order: time_mlp weights (block order) | time_mlp biases | per attention block q,k,v weights then
+        q,k,v biases | everything else in registration order.  Contiguity lets the 22 time projections run as one
+        GEMM and Q/K/V as one [3C, C] projection."""
+        named = OrderedDict(self.net.named_parameters())
+        res_prefixes = self.res_block_prefixes()
+        order = [p + "time_mlp.weight" for p in res_prefixes] + [p + "time_mlp.bias" for p in res_prefixes]
+        for ap in self.attn_block_prefixes():
+            order += [ap + n + ".weight" for n in ("query_projection", "key_projection", "value_projection")]
+            order += [ap + n + ".bias" for n in ("query_projection", "key_projection", "value_projection")]
+        seen = set(order)
+        order += [k for k in named if k not in seen]
+        return named, order
+
+    def res_block_prefixes(self):
+        out = []
+        for i in range(5):
+            out += [f"down_blocks.{i}.res_blocks.{j}." for j in range(2)]
+        out += ["bottleneck.0.", "bottleneck.2."]
+        for i in range(5):
+            out += [f"up_blocks.{i}.res_blocks.{j}." for j in range(2)]
+        return out
+
+    def attn_block_prefixes(self):
+        return ([f"down_blocks.3.attention_blocks.{j}." for j in range(2)] + ["bottleneck.1."] +
+                [f"up_blocks.1.attention_blocks.{j}." for j in range(2)])
+
+    def _flatten(self, device):
+        named, order = self._arena_order()
+        offs, total = {}, 0
+        for k in order:
+            n = named[k].numel()
+            offs[k] = (total, n)
+            total += (n + 3) // 4 * 4
+        flat = torch.zeros(total, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for k in order:
+                o, n = offs[k]
+                flat[o:o + n].copy_(named[k].detach().reshape(-1))
+                named[k].data = flat[o:o + n].view(named[k].shape)
+        self.flat, self.offs, self.total = flat, offs, total
+        self.named = named
+        self.gflat = torch.zeros(total, device=device, dtype=torch.float32)
+        # conv filter cache in the compute dtype, [O][R][S][I]
+        self.wc_off, wc_total, descs = {}, 0, []
+        for k, p in named.items():
+            if p.dim() == 4:
+                self.wc_off[k] = wc_total
+                wc_total += (p.numel() + 7) // 8 * 8
+        self.wcache = torch.zeros(max(wc_total, 8), device=device, dtype=self.tdtype)
+        max_numel = 1
+        for k, off in self.wc_off.items():
+            p = named[k]
+            is_t = k.endswith("upsample.weight")
+            O, I = (p.shape[1], p.shape[0]) if is_t else (p.shape[0], p.shape[1])
+            descs.append(RepackDesc(p.data_ptr(), self.wcache.data_ptr() + off * self.esize, O, I, p.shape[2], p.shape[3], 1 if is_t else 0, self.code))
+            max_numel = max(max_numel, p.numel())
+        arr = (RepackDesc * len(descs))(*descs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.repack_table = host.to(device)
+        self.repack_n, self.repack_max = len(descs), max_numel
+        self.plans = {}
+        self.device = device
+
+    def _params_in_arena(self):
+        if self.flat is None:
+            return False
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        p0 = self.net.initial_conv.weight
+        return p0.device == self.flat.device and lo <= p0.data_ptr() < hi and lo <= self.net.output_conv[2].bias.data_ptr() < hi
+
+    def prepare(self, device):
+        if self._lib is None:
+            self._lib = _abi.lib()
+        if not self._params_in_arena():
+            self._flatten(device)
+
+    def paddr(self, name):  # fp32 address of a parameter inside the flat arena
+        return self.flat.data_ptr() + self.offs[name][0] * 4
+
+    def gaddr(self, name):
+        return self.gflat.data_ptr() + self.offs[name][0] * 4
+
+    def waddr(self, name):  # repacked filter
+        return self.wcache.data_ptr() + self.wc_off[name] * self.esize
+
+    def repack(self, stream):
+        _abi.check(self._lib.dmu_repack_weights(self.repack_table.data_ptr(), self.repack_n, self.repack_max, stream), "repack_weights")
+
+    # ------------------------------------------------------------------ public entry points
+    def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        ops._need_cuda(x, t)
+        if x.dim() != 4 or x.shape[1] != self.net.in_channels:
+            raise ValueError(f"expected x of shape [B,{self.net.in_channels},H,W], got {tuple(x.shape)}")
+        if x.shape[2] % 32 != 0 or x.shape[3] % 32 != 0:
+            raise ValueError("UNet has five stride-2 stages: H and W must be multiples of 32")
+        if t.dim() != 1 or t.shape[0] != x.shape[0]:
+            raise ValueError("t must have shape [B]")
+        self.prepare(x.device)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.net.parameters()))
+        x = x.contiguous().float()
+        if t.dtype not in (torch.int64, torch.float32):
+            t = t.float() if t.is_floating_point() else t.long()
+        t = t.contiguous()
+        if need_grad:
+            params = [self.named[k] for k in self.offs]
+            return _UNetFn.apply(self, x, t, *params)
+        return self.run_forward(x, t, self.get_plan(x.shape, False))
+
+    def get_plan(self, shape, train: bool) -> Plan:
+        key = (tuple(shape), train)
+        lst = self.plans.setdefault(key, [])
+        for p in lst:
+            if not p.busy:
+                return p
+        p = self._build(shape[0], shape[2], shape[3], train)
+        lst.append(p)
+        return p
+
+    def _run(self, oplist, stream):
+        for fn, args in oplist:
+            rc = fn(*args, stream)
+            if rc != 0:
+                _abi.check(rc, fn.__name__)
+
+    def run_forward(self, x, t, plan: Plan) -> torch.Tensor:
+        stream = ops._stream()
+        if not self.frozen:
+            self.repack(stream)
+        out = torch.empty_like(x)
+        plan.stem.x.ptr = x.data_ptr()
+        plan.head.y.ptr = out.data_ptr()
+        fn, args = plan.fwd[plan.temb_in]
+        if self.net.sigma_embed:   # (sigma, log_sigma_out, n, kind)
+            plan.fwd[plan.temb_in] = (fn, (t.data_ptr(),) + tuple(args[1:]))
+        else:                      # (t, t_is_float, emb, batch, dim)
+            plan.fwd[plan.temb_in] = (fn, (t.data_ptr(), 1 if t.dtype == torch.float32 else 0) + tuple(args[2:]))
+        self._run(plan.fwd, stream)
+        return out
+
+    def run_backward(self, plan: Plan, x, dout):
+        """Fills the gradient arena; returns it (flat fp32, same offsets as the parameter arena)."""
+        stream = ops._stream()
+        g = self.gflat
+        # param.grad tensors handed out by an earlier backward are views of this arena.  If any is still installed
+        # (gradient accumulation, zero_grad(set_to_none=False)) detach it first so autograd's `grad += new` stays correct.
+        lo, hi = g.data_ptr(), g.data_ptr() + g.numel() * 4
+        for p in self.named.values():
+            if p.grad is not None and lo <= p.grad.data_ptr() < hi:
+                p.grad = p.grad.clone()
+        dout = dout.contiguous().float()
+        plan.head_dgrad.x.ptr = dout.data_ptr()
+        plan.head_wgrad.p.ptr = dout.data_ptr()
+        plan.stem_wgrad.q.ptr = x.data_ptr()
+        _abi.check(self._lib.dmu_zero(g.data_ptr(), g.numel() * 4, stream), "zero grads")
+        self._run(plan.bwd, stream)
+        return g
+
+    # ------------------------------------------------------------------ plan construction
+    def _build(self, N, H, W, train) -> Plan:
+        dry = _PlanBuilder(self, N, H, W, train, base=(0, 0, 0))
+        dry.build()
+        rnd = lambda v: (v + 255) // 256 * 256
+        n_main, n_stats, n_red = rnd(dry.bump.off), rnd(dry.stats.off + 4), rnd(dry.red.off + 4)
+        nbytes = n_main + n_stats + n_red + 256
+        arena = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+        base = rnd(arena.data_ptr())
+        real = _PlanBuilder(self, N, H, W, train, base=(base, base + n_main, base + n_main + n_stats))
+        plan = real.build()
+        plan.arena = arena
+        plan.nbytes = nbytes
+        return plan
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng: Engine, x, t, *params):
+        plan = eng.get_plan(x.shape, True)
+        plan.busy = True
+        out = eng.run_forward(x, t, plan)
+        ctx.eng, ctx.plan = eng, plan
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng, plan = ctx.eng, ctx.plan
+        (x,) = ctx.saved_tensors
+        try:
+            g = eng.run_backward(plan, x, dout)
+        finally:
+            plan.busy = False
+        grads = []
+        for k in eng.offs:
+            o, n = eng.offs[k]
+            p = eng.named[k]
+            grads.append(g[o:o + n].view(p.shape) if p.requires_grad else None)
+        return (None, None, None) + tuple(grads)
+
+
+class _PlanBuilder:
+    def __init__(self, eng: Engine, N, H, W, train, base):
+        self.e, self.N, self.H, self.W, self.train = eng, N, H, W, train
+        main_base, stats_base, red_base = base
+        self.bump = _Bump(main_base)        # activations, gradients of activations, fp32 rows
+        self.stats = _Bump(stats_base)      # GroupNorm (sum, sumsq) accumulators: zeroed by one launch per forward
+        self.red = _Bump(red_base)          # GroupNorm backward accumulators: zeroed by one launch per backward
+        self.plan = Plan()
+        self.lib = eng._lib
+        self.code, self.esize = eng.code, eng.esize
+        self.tape = []   # backward emitters, run in reverse
+
+    # ---- allocation helpers
+    def act(self, H, W, Cc, want_grad=True) -> Buf:
+        b = Buf(self.bump.take(self.N * H * W * Cc * self.esize), self.N, H, W, Cc, Cc, self.code)
+        if self.train and want_grad:
+            b.grad = Buf(self.bump.take(self.N * H * W * Cc * self.esize), self.N, H, W, Cc, Cc, self.code)
+        return b
+
+    def tmp(self, H, W, Cc) -> Buf:
+        return Buf(self.bump.take(self.N * H * W * Cc * self.esize), self.N, H, W, Cc, Cc, self.code)
+
+    def f32(self, n):
+        return self.bump.take(n * 4)
+
+    # ---- op emitters
+    def emit(self, lst, fn, *args):
+        lst.append((fn, args))
+
+    def gp(self, name):
+        """Gradient-arena address of a parameter."""
+        return self.e.gaddr(name)
+
+    def conv(self, lst, x: Tensor4, y: Tensor4, w, w_strides, w_code, dims, geom, bias=None, temb=None, temb_pitch=0, res=None, gather=0):
+        N, Hi, Wi, Ck, Ho, Wo, Cj = dims
+        R, S, stride, pad = geom
+        p = ConvParams(x, y, res if res is not None else _null_t4(), w, w_strides[0], w_strides[1], w_strides[2], bias, temb, temb_pitch,
+                       N, Hi, Wi, Ck, Ho, Wo, Cj, R, S, stride, pad, gather, w_code, self.e.impl, 0)
+        lst.append((self.lib.dmu_conv2d, (C.byref(p),)))
+        self.plan.keep.append(p)
+        return p
+
+    def wgrad(self, p4: Tensor4, q4: Tensor4, dw, dw_strides, dbias, dims, geom):
+        N, Hp, Wp, Ca, Hq, Wq, Cb = dims
+        R, S, stride, pad = geom
+        p = WgradParams(p4, q4, dw, dw_strides[0], dw_strides[1], dw_strides[2], dbias, N, Hp, Wp, Ca, Hq, Wq, Cb, R, S, stride, pad, self.e.impl)
+        self.plan.bwd.append((self.lib.dmu_conv2d_wgrad, (C.byref(p),)))
+        self.plan.keep.append(p)
+        return p
+
+    def gn(self, x: Buf, G, gamma_name, beta_name, silu: bool):
+        """Forward GroupNorm(+SiLU): returns (y, gn-record)."""
+        sums = self.stats.take(self.N * G * 2 * 4, 16)
+        y = self.act(x.H, x.W, x.C)
+        p = GnParams(x.t4(), y.t4(), _null_t4(), _null_t4(), _null_t4(), sums, self.e.paddr(gamma_name), self.e.paddr(beta_name),
+                     None, None, None, self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, 0)
+        self.plan.keep.append(p)
+        self.plan.fwd.append((self.lib.dmu_gn_stats, (C.byref(p),)))
+        self.plan.fwd.append((self.lib.dmu_gn_apply, (C.byref(p),)))
+        return y, (x, y, sums, G, gamma_name, beta_name, silu)
+
+    def gn_bwd(self, rec, dx: Buf, add0: Buf = None, add1: Buf = None):
+        """Backward of gn(): reads rec.y.grad, writes dx (+ addends)."""
+        x, y, sums, G, gname, bname, silu = rec
+        red = self.red.take(self.N * x.C * 2 * 4, 16)
+        p = GnParams(x.t4(), y.grad.t4(), dx.t4(), add0.t4() if add0 is not None else _null_t4(), add1.t4() if add1 is not None else _null_t4(),
+                     sums, self.e.paddr(gname), self.e.paddr(bname), red, self.gp(gname), self.gp(bname),
+                     self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, 0)
+        self.plan.keep.append(p)
+        self.plan.bwd.append((self.lib.dmu_gn_bwd_reduce, (C.byref(p),)))
+        self.plan.bwd.append((self.lib.dmu_gn_bwd_apply, (C.byref(p),)))
+
+    # ---- conv layer helpers (filters repacked [O][R][S][I])
+    def conv_layer(self, x: Buf, y: Buf, wname, bname, R, stride, pad, temb=None, temb_pitch=0, res: Buf = None):
+        Ci, Co = x.C, y.C
+        self.conv(self.plan.fwd, x.t4(), y.t4(), self.e.waddr(wname), (R * R * Ci, 1, Ci), self.code,
+                  (self.N, x.H, x.W, Ci, y.H, y.W, Co), (R, R, stride, pad), bias=self.e.paddr(bname), temb=temb, temb_pitch=temb_pitch,
+                  res=res.t4() if res is not None else None)
+
+    def conv_layer_bwd(self, x: Buf, y: Buf, wname, bname, R, stride, pad, dx: Buf, need_dx=True):
+        """dgrad into dx (plain write) and wgrad/dbias into the arena.  dy = y.grad."""
+        Ci, Co = x.C, y.C
+        dy = y.grad
+        if need_dx:
+            # dx[n,hi,wi,ci] = sum dy[n,(hi+pad-r)/s,..,co] w[co][r][s][ci]
+            self.conv(self.plan.bwd, dy.t4(), dx.t4(), self.e.waddr(wname), (1, R * R * Ci, Ci), self.code,
+                      (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad), gather=1)
+        self.wgrad(dy.t4(), x.t4(), self.gp(wname), (Ci * R * R, R * R, 1), self.gp(bname),
+                   (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad))
+
+    def linear(self, lst, x4: Tensor4, y4: Tensor4, M, I, O, w_addr, b_addr, res4=None, w_code=F32):
+        self.conv(lst, x4, y4, w_addr, (I, 1, 0), w_code, (M, 1, 1, I, 1, 1, O), (1, 1, 1, 0), bias=b_addr, res=res4)
+
+    def linear_bwd(self, x4, dy4, dx4, M, I, O, wname_addr, gw_addr, gb_addr, res4=None, need_dx=True):
+        if need_dx:
+            self.conv(self.plan.bwd, dy4, dx4, wname_addr, (1, I, 0), F32, (M, 1, 1, O, 1, 1, I), (1, 1, 1, 0), res=res4)
+        self.wgrad(dy4, x4, gw_addr, (I, 1, 0), gb_addr, (M, 1, 1, O, 1, 1, I), (1, 1, 1, 0))
+
+    # ---- blocks
+    def res_block(self, pfx, x: Buf, y: Buf, tp_addr, tp_pitch, extra_add: Buf = None):
+        """Forward ops of residual.py:54-68 writing into y; registers the backward emitter.
+        extra_add: an already-written gradient of x from another consumer (skip connection)."""
+        e = self.e
+        Ci, Co = x.C, y.C
+        a1, rec1 = self.gn(x, gn_groups(Ci), pfx + "norm1.weight", pfx + "norm1.bias", True)
+        h = self.act(x.H, x.W, Co)
+        self.conv_layer(a1, h, pfx + "conv1.weight", pfx + "conv1.bias", 3, 1, 1, temb=tp_addr, temb_pitch=tp_pitch)
+        a2, rec2 = self.gn(h, gn_groups(Co), pfx + "norm2.weight", pfx + "norm2.bias", True)
+        has_sc = Ci != Co
+        if has_sc:
+            sc = self.tmp(x.H, x.W, Co)
+            self.conv_layer(x, sc, pfx + "shortcut.weight", pfx + "shortcut.bias", 1, 1, 0)
+            self.conv_layer(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, res=sc)
+        else:
+            self.conv_layer(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, res=x)
+        if not self.train:
+            return
+
+        def bwd():
+            # conv2
+            self.conv_layer_bwd(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, a2.grad)
+            # norm2 + silu -> dh
+            self.gn_bwd(rec2, h.grad)
+            # time projection: per-image channel sums of dh
+            t4 = h.grad.t4()
+            self.plan.keep.append(t4)
+            self.plan.bwd.append((self.lib.dmu_colsum, (C.byref(t4), self.N, h.H, h.W, Co, self.dtproj + self.tp_off[pfx] * 4, self.tp_total, None, 1.0)))
+            # conv1
+            self.conv_layer_bwd(a1, h, pfx + "conv1.weight", pfx + "conv1.bias", 3, 1, 1, a1.grad)
+            # shortcut
+            if has_sc:
+                dxs = self.tmp(x.H, x.W, Ci)
+                scb = Buf(0, self.N, x.H, x.W, Co, Co, self.code)
+                scb.grad = y.grad
+                self.conv_layer_bwd(x, scb, pfx + "shortcut.weight", pfx + "shortcut.bias", 1, 1, 0, dxs)
+            else:
+                dxs = y.grad
+            prev = x.grad if x.grad_written else None
+            self.gn_bwd(rec1, x.grad, add0=dxs, add1=prev)
+            x.grad_written = True
+        self.tape.append(bwd)
+
+    def attn_block(self, pfx, x: Buf, y: Buf, heads=4):
+        """attention.py:36-68 writing GN(proj + x) into y."""
+        e = self.e
+        Cc, S = x.C, x.H * x.W
+        M = self.N * S
+        qkv = self.act(x.H, x.W, 3 * Cc)
+        wq, bq = e.paddr(pfx + "query_projection.weight"), e.paddr(pfx + "query_projection.bias")
+        self.linear(self.plan.fwd, _rows_t4(x.addr, x.pitch, self.code), _rows_t4(qkv.addr, 3 * Cc, self.code), M, Cc, 3 * Cc, wq, bq)
+        o = self.act(x.H, x.W, Cc)
+        lse = self.f32(self.N * heads * S)
+        ap = AttnParams(qkv.addr, 3 * Cc, o.addr, Cc, None, 0, None, 0, lse, self.N, S, Cc, heads, self.code, 0)
+        self.plan.keep.append(ap)
+        self.plan.fwd.append((self.lib.dmu_attn_fwd, (C.byref(ap),)))
+        z = self.act(x.H, x.W, Cc)
+        wf, bf = e.paddr(pfx + "final_projection.weight"), e.paddr(pfx + "final_projection.bias")
+        self.linear(self.plan.fwd, _rows_t4(o.addr, Cc, self.code), _rows_t4(z.addr, Cc, self.code), M, Cc, Cc, wf, bf,
+                    res4=_rows_t4(x.addr, x.pitch, self.code))
+        G = gn_groups(Cc)
+        sums = self.stats.take(self.N * G * 2 * 4, 16)
+        gp_ = GnParams(z.t4(), y.t4(), _null_t4(), _null_t4(), _null_t4(), sums, e.paddr(pfx + "norm.weight"), e.paddr(pfx + "norm.bias"),
+                       None, None, None, self.N, x.H, x.W, Cc, G, 0, 1e-5, 0)
+        self.plan.keep.append(gp_)
+        self.plan.fwd.append((self.lib.dmu_gn_stats, (C.byref(gp_),)))
+        self.plan.fwd.append((self.lib.dmu_gn_apply, (C.byref(gp_),)))
+        rec = (z, y, sums, G, pfx + "norm.weight", pfx + "norm.bias", False)
+        if not self.train:
+            return
+
+        def bwd():
+            self.gn_bwd(rec, z.grad)
+            dz4 = _rows_t4(z.grad.addr, Cc, self.code)
+            # final projection: do = dz Wf ; dWf += dz^T o
+            self.linear_bwd(_rows_t4(o.addr, Cc, self.code), dz4, _rows_t4(o.grad.addr, Cc, self.code), M, Cc, Cc, wf,
+                            self.gp(pfx + "final_projection.weight"), self.gp(pfx + "final_projection.bias"))
+            bp = AttnParams(qkv.addr, 3 * Cc, o.addr, Cc, o.grad.addr, Cc, qkv.grad.addr, 3 * Cc, lse, self.N, S, Cc, heads, self.code, 0)
+            self.plan.keep.append(bp)
+            self.plan.bwd.append((self.lib.dmu_attn_bwd, (C.byref(bp),)))
+            # qkv projection: dx = dqkv Wqkv + dz ; dWqkv += dqkv^T x
+            self.linear_bwd(_rows_t4(x.addr, x.pitch, self.code), _rows_t4(qkv.grad.addr, 3 * Cc, self.code),
+                            _rows_t4(x.grad.addr, x.grad.pitch, self.code), M, Cc, 3 * Cc, wq,
+                            self.gp(pfx + "query_projection.weight"), self.gp(pfx + "query_projection.bias"), res4=dz4)
+            x.grad_written = True
+        self.tape.append(bwd)
+
+    def stage(self, pfx, has_attn, x: Buf, Co) -> Buf:
+        """Two (ResBlock [, Attention]) pairs; returns the stage output before down/up-sampling."""
+        h = x
+        for j in range(2):
+            y = self.act(x.H, x.W, Co)
+            self.res_block(f"{pfx}res_blocks.{j}.", h, y, self.tproj + self.tp_off[f"{pfx}res_blocks.{j}."] * 4, self.tp_total)
+            h = y
+            if has_attn:
+                y2 = self.act(x.H, x.W, Co)
+                self.attn_block(f"{pfx}attention_blocks.{j}.", h, y2)
+                h = y2
+        return h
+
+    # ---- whole network
+    def build(self) -> Plan:
+        e, net, N, H, W = self.e, self.e.net, self.N, self.H, self.W
+        Cm = net.model_channels
+        plan = self.plan
+        plan.keep = []
+        lib = self.lib
+        T4 = 4 * Cm
+        # time-projection column offsets (arena order == res_block_prefixes order)
+        self.tp_off, off = {}, 0
+        for p in e.res_block_prefixes():
+            self.tp_off[p] = off
+            off += e.named[p + "time_mlp.weight"].shape[0]
+        self.tp_total = off
+
+        # -------- time embedding
+        plan.temb_in = len(plan.fwd)
+        if not net.sigma_embed:
+            emb = self.f32(N * Cm)
+            plan.fwd.append((lib.dmu_sinusoidal_embedding, (None, 0, emb, N, Cm)))   # t pointer patched per call
+            h1 = self.f32(N * T4)
+            te = "time_embedding.positional_encoding."
+            self.linear(plan.fwd, _rows_t4(emb, Cm), _rows_t4(h1, T4), N, Cm, T4, e.paddr(te + "1.weight"), e.paddr(te + "1.bias"))
+            g1 = self.f32(N * T4)
+            plan.fwd.append((lib.dmu_act_fwd, (h1, g1, N * T4, 0)))
+            temb = self.f32(N * T4)
+            self.linear(plan.fwd, _rows_t4(g1, T4), _rows_t4(temb, T4), N, T4, T4, e.paddr(te + "3.weight"), e.paddr(te + "3.bias"))
+        else:
+            # score_based.py:57-61,82-83: Linear(1,C) -> SiLU -> Linear(C,4C) on log(sigma)
+            ls = self.f32(N)
+            plan.fwd.append((lib.dmu_act_fwd, (None, ls, N, 2)))                      # sigma pointer patched per call
+            h1 = self.f32(N * Cm)
+            self.linear(plan.fwd, _rows_t4(ls, 1), _rows_t4(h1, Cm), N, 1, Cm, e.paddr("time_embed.0.weight"), e.paddr("time_embed.0.bias"))
+            g1 = self.f32(N * Cm)
+            plan.fwd.append((lib.dmu_act_fwd, (h1, g1, N * Cm, 1)))
+            temb = self.f32(N * T4)
+            self.linear(plan.fwd, _rows_t4(g1, Cm), _rows_t4(temb, T4), N, Cm, T4, e.paddr("time_embed.2.weight"), e.paddr("time_embed.2.bias"))
+        self.tproj = self.f32(N * self.tp_total)
+        first = e.res_block_prefixes()[0]
+        self.linear(plan.fwd, _rows_t4(temb, T4), _rows_t4(self.tproj, self.tp_total), N, T4, self.tp_total,
+                    e.paddr(first + "time_mlp.weight"), e.paddr(first + "time_mlp.bias"))
+        self.dtproj = self.f32(N * self.tp_total) if self.train else 0
+
+        # -------- stem (NCHW fp32 -> NHWC)
+        h0 = self.act(H, W, Cm)
+        plan.stem = self.conv(plan.fwd, _nchw_t4(None, net.in_channels, H, W), h0.t4(), e.waddr("initial_conv.weight"),
+                              (9 * net.in_channels, 1, net.in_channels), self.code, (N, H, W, net.in_channels, H, W, Cm), (3, 3, 1, 1),
+                              bias=e.paddr("initial_conv.bias"))
+
+        # -------- concat buffers of the up path: cat_k = [h part | skip part]
+        dplan, uplan = down_plan(Cm), up_plan(Cm)
+        cat = []
+        for k, (_, cin, _) in enumerate(uplan):
+            r = 1 << k  # spatial size factor: cat_0 at H/32
+            cat.append(self.act(H // 32 * r, W // 32 * r, cin))
+        # -------- down path
+        x = h0
+        skips = []
+        for i, (attn, ci, co) in enumerate(dplan):
+            pfx = f"down_blocks.{i}."
+            y = self.stage(pfx, attn, x, co)
+            kcat = 4 - i
+            hpart = uplan[kcat][1] - co
+            d = cat[kcat].slice(hpart, co)
+            self.conv_layer(y, d, pfx + "downsample.weight", pfx + "downsample.bias", 4, 2, 1)
+            if self.train:
+                def down_bwd(y=y, d=d, pfx=pfx):
+                    self.conv_layer_bwd(y, d, pfx + "downsample.weight", pfx + "downsample.bias", 4, 2, 1, y.grad)
+                    y.grad_written = True
+                self.tape.append(down_bwd)
+            skips.append(d)
+            x = d
+        # -------- bottleneck (writes into the h part of cat_0)
+        b0 = self.act(x.H, x.W, 4 * Cm)
+        self.res_block("bottleneck.0.", x, b0, self.tproj + self.tp_off["bottleneck.0."] * 4, self.tp_total)
+        b1 = self.act(x.H, x.W, 4 * Cm)
+        self.attn_block("bottleneck.1.", b0, b1)
+        b2 = cat[0].slice(0, 4 * Cm)
+        self.res_block("bottleneck.2.", b1, b2, self.tproj + self.tp_off["bottleneck.2."] * 4, self.tp_total)
+        # -------- up path
+        for k, (attn, ci, co) in enumerate(uplan):
+            pfx = f"up_blocks.{k}."
+            y = self.stage(pfx, attn, cat[k], co)
+            if k < 4:
+                u = cat[k + 1].slice(0, co)
+            else:
+                u = self.act(H, W, co)
+            # ConvTranspose2d 4x4 s2 p1 (residual.py:121,242): transposed gather, filters repacked [O][R][S][I]
+            self.conv(plan.fwd, y.t4(), u.t4(), e.waddr(pfx + "upsample.weight"), (16 * co, 1, co), self.code,
+                      (N, y.H, y.W, co, u.H, u.W, co), (4, 4, 2, 1), bias=e.paddr(pfx + "upsample.bias"), gather=1)
+            if self.train:
+                def up_bwd(y=y, u=u, pfx=pfx, co=co):
+                    du = u.grad
+                    # dgrad of a transposed conv is a strided conv over du
+                    self.conv(plan.bwd, du.t4(), y.grad.t4(), e.waddr(pfx + "upsample.weight"), (1, 16 * co, co), self.code,
+                              (N, u.H, u.W, co, y.H, y.W, co), (4, 4, 2, 1), gather=0)
+                    y.grad_written = True
+                    # dW[ci][co][r][s] (IOHW) += x[.., ci] * du[gathered, co]
+                    self.wgrad(y.t4(), du.t4(), self.gp(pfx + "upsample.weight"), (co * 16, 16, 1), None,
+                               (N, y.H, y.W, co, u.H, u.W, co), (4, 4, 2, 1))
+                    t4 = du.t4()
+                    plan.keep.append(t4)
+                    plan.bwd.append((lib.dmu_colsum, (C.byref(t4), N, u.H, u.W, co, None, 0, self.gp(pfx + "upsample.bias"), 1.0)))
+                self.tape.append(up_bwd)
+            x = u
+        # -------- head: GroupNorm -> SiLU -> conv3x3 -> NCHW fp32
+        a, rec = self.gn(x, 32, "output_conv.0.weight", "output_conv.0.bias", True)
+        plan.head = self.conv(plan.fwd, a.t4(), _nchw_t4(None, net.out_channels, H, W), e.waddr("output_conv.2.weight"), (9 * Cm, 1, Cm), self.code,
+                              (N, H, W, Cm, H, W, net.out_channels), (3, 3, 1, 1), bias=e.paddr("output_conv.2.bias"))
+        # one launch zeroes every GroupNorm statistics accumulator of the forward
+        plan.fwd.insert(0, (lib.dmu_zero, (self.stats.base, max(self.stats.off, 4))))
+        plan.temb_in += 1
+
+        if not self.train:
+            return plan
+
+        # ======================= backward =======================
+        Co = net.out_channels
+        dout4 = _nchw_t4(None, Co, H, W)
+        # head conv: da = dgrad(dout), dW, db
+        plan.head_dgrad = self.conv(plan.bwd, dout4, a.grad.t4(), e.waddr("output_conv.2.weight"), (1, 9 * Cm, Cm), self.code,
+                                    (N, H, W, Co, H, W, Cm), (3, 3, 1, 1), gather=1)
+        plan.head_wgrad = self.wgrad(_nchw_t4(None, Co, H, W), a.t4(), self.gp("output_conv.2.weight"), (Cm * 9, 9, 1), self.gp("output_conv.2.bias"),
+                                     (N, H, W, Co, H, W, Cm), (3, 3, 1, 1))
+        self.gn_bwd(rec, x.grad)
+        x.grad_written = True
+        for fn in reversed(self.tape):
+            fn()
+        # stem: wgrad only (the network input needs no gradient on this path)
+        plan.stem_wgrad = self.wgrad(h0.grad.t4(), _nchw_t4(None, net.in_channels, H, W), self.gp("initial_conv.weight"),
+                                     (net.in_channels * 9, 9, 1), self.gp("initial_conv.bias"), (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
+        # time projections (one GEMM for all 22 blocks), then the embedding MLP
+        dtemb = self.f32(N * T4)
+        self.linear_bwd(_rows_t4(temb, T4), _rows_t4(self.dtproj, self.tp_total), _rows_t4(dtemb, T4), N, T4, self.tp_total,
+                        e.paddr(first + "time_mlp.weight"), self.gp(first + "time_mlp.weight"), self.gp(first + "time_mlp.bias"))
+        if not net.sigma_embed:
+            te = "time_embedding.positional_encoding."
+            dg1 = self.f32(N * T4)
+            self.linear_bwd(_rows_t4(g1, T4), _rows_t4(dtemb, T4), _rows_t4(dg1, T4), N, T4, T4, e.paddr(te + "3.weight"),
+                            self.gp(te + "3.weight"), self.gp(te + "3.bias"))
+            dh1 = self.f32(N * T4)
+            plan.bwd.append((lib.dmu_act_bwd, (h1, dg1, dh1, N * T4, 0)))
+            self.linear_bwd(_rows_t4(emb, Cm), _rows_t4(dh1, T4), None, N, Cm, T4, e.paddr(te + "1.weight"),
+                            self.gp(te + "1.weight"), self.gp(te + "1.bias"), need_dx=False)
+        else:
+            dg1 = self.f32(N * Cm)
+            self.linear_bwd(_rows_t4(g1, Cm), _rows_t4(dtemb, T4), _rows_t4(dg1, Cm), N, Cm, T4, e.paddr("time_embed.2.weight"),
+                            self.gp("time_embed.2.weight"), self.gp("time_embed.2.bias"))
+            dh1 = self.f32(N * Cm)
+            plan.bwd.append((lib.dmu_act_bwd, (h1, dg1, dh1, N * Cm, 1)))
+            self.linear_bwd(_rows_t4(ls, 1), _rows_t4(dh1, Cm), None, N, 1, Cm, e.paddr("time_embed.0.weight"),
+                            self.gp("time_embed.0.weight"), self.gp("time_embed.0.bias"), need_dx=False)
+        # one launch zeroes every GroupNorm backward accumulator
+        plan.bwd.insert(0, (lib.dmu_zero, (self.red.base, max(self.red.off, 4))))
+        return plan

@@ -1,0 +1,245 @@
+/*
+ * dmu_b200.h — C ABI of the B200-native denoiser hot path.
+ *
+ * Drop-in boundary for ChristianLin0420/diffusion-model-universal's UNet
+ * denoiser path.  The reference is pure Python: the boundary
+ * it exposes is the class API `BaseDiffusion.forward / loss_function /
+ * generate_samples` (models/base_model.py:57-117).  That API is mirrored in
+ * Python by `diffusion_model_universal_b200/` and every arithmetic step
+ * behind it is one of the entry points below.  Each entry point names the
+ * reference call site(s) it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless
+ *    stated; the library neither allocates nor frees nor retains them.
+ *  - every call enqueues work on `stream` (a cudaStream_t) and returns
+ *    without synchronising.  Return value 0 = ok, non-zero = error; the
+ *    message is available from dmu_last_error() (thread-local).
+ *  - activations are 4-D tensors described by element strides (dmu_tensor4),
+ *    so NHWC-with-pitch (internal) and NCHW fp32 (API boundary) both work.
+ *  - dtype codes: DMU_F32 = 0, DMU_BF16 = 1.  Accumulation is always fp32.
+ */
+#ifndef DMU_B200_H
+#define DMU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMU_ABI_VERSION 1
+#define DMU_F32 0
+#define DMU_BF16 1
+
+typedef void* dmu_stream_t; /* cudaStream_t */
+
+typedef struct {
+    void* ptr;
+    int64_t sn, sh, sw, sc; /* element strides of (n, h, w, c) */
+    int32_t dtype;          /* DMU_F32 | DMU_BF16 */
+    int32_t _pad;
+} dmu_tensor4;
+
+int dmu_abi_version(void);
+const char* dmu_last_error(void);
+/* struct sizes, so a foreign-language binding can assert its mirror matches */
+int dmu_sizeof(const char* struct_name);
+
+/* ------------------------------------------------------------------ *
+ * Diffusion-process updates (fp32, any contiguous [B, inner] layout)  *
+ * ------------------------------------------------------------------ */
+
+/* models/ddpm.py:286-296 `_add_noise`:  out = sqrt(acp[t]) x0 + sqrt(1-acp[t]) noise */
+int dmu_q_sample(const float* x0, const float* noise, const int64_t* t, const float* alphas_cumprod,
+                 float* out, int64_t batch, int64_t inner, dmu_stream_t stream);
+
+/* models/ddpm.py:306-329 `_reverse_diffusion_step` after the eps prediction.
+ * `noise` is the randn_like draw of ddpm.py:324 (may be NULL when the caller
+ * knows t == 0).  The t[0] > 0 branch of ddpm.py:311,323 is taken on device
+ * from t[0]; no host sync.  out may alias x. */
+int dmu_ddpm_step(const float* x, const float* eps, const float* noise, const int64_t* t,
+                  const float* betas, const float* alphas, const float* alphas_cumprod,
+                  float* out, int64_t batch, int64_t inner, dmu_stream_t stream);
+
+/* models/ddim.py:97-124 `_ddim_sample` after the eps prediction; `idx`
+ * indexes the S-entry tables (repaired driver).  `noise`
+ * NULL <=> eta == 0 (ddim.py:117-121).  Clamps x0 to [-1,1], noise to [-3,3]. */
+int dmu_ddim_step(const float* x, const float* eps, const float* noise, const int64_t* idx,
+                  const float* ddim_alphas, const float* ddim_alphas_prev, const float* ddim_sigmas,
+                  const float* ddim_sqrt_one_minus_alphas,
+                  float* out, int64_t batch, int64_t inner, dmu_stream_t stream);
+
+/* models/score_based.py:236-245: step = 2 (sigma*beta)^2 ; out = x + step*score + sqrt(2 step)*noise.
+ * sigma is read from device memory (sigmas[k]) exactly like the reference's 0-dim tensor. */
+int dmu_langevin_score_step(const float* x, const float* score, const float* noise, const float* sigmas, int64_t k,
+                            float beta, float* out, int64_t n, dmu_stream_t stream);
+
+/* models/energy_based.py:271-273 (math.sqrt repair): out = x - step*grad + sqrt_2step*noise */
+int dmu_langevin_energy_step(const float* x, const float* grad, const float* noise, float step, float sqrt_2step,
+                             float* out, int64_t n, dmu_stream_t stream);
+
+/* models/energy_based.py:240-246: out = sqrt(a[t-1]/a[t]) x + sqrt((1-a[t-1])/(1-a[t])) sqrt(1-a[t]/a[t-1]) noise */
+int dmu_energy_renoise(const float* x, const float* noise, const float* alphas_cumprod, int64_t t,
+                       float* out, int64_t n, dmu_stream_t stream);
+
+/* out[b,i] = a[b]*x[b,i] + c[b]*z[b,i]  (a NULL = 1).  models/score_based.py:200-201 (x + sigma*noise) and the
+ * score-matching target -noise/sigma of utils/losses.py:240. */
+int dmu_scale_add(const float* x, const float* z, const float* a, const float* c, float* out,
+                  int64_t batch, int64_t inner, dmu_stream_t stream);
+
+/* utils/losses.py:74-131 `DiffusionLoss.__call__` minus the [B]-sized time
+ * weights (computed by the host with the reference's own torch ops and passed
+ * as `w`, NULL = unweighted):
+ *   loss = mean_b,i( w[b] * (wm d^2 + wl |d| + wh smooth_l1(d; delta)) ),  d = pred - target
+ * Writes the scalar to `loss` and, when dpred != NULL, d loss / d pred.
+ * `partials` is workspace of dmu_loss_workspace_floats(batch*inner) floats. */
+int64_t dmu_loss_workspace_floats(int64_t numel);
+int dmu_diffusion_loss(const float* pred, const float* target, const float* w,
+                       float wm, float wl, float wh, float delta,
+                       float* loss, float* dpred, float* partials,
+                       int64_t batch, int64_t inner, dmu_stream_t stream);
+
+/* ------------------------------------------------------------------ *
+ * UNet denoiser primitives                                            *
+ * ------------------------------------------------------------------ */
+
+/* Implicit-GEMM convolution (nn.Conv2d / nn.ConvTranspose2d / nn.Linear and
+ * their input gradients):  models/layers/residual.py:33,40,44,91,121,178,242,
+ * models/ddpm.py:49,90, models/layers/attention.py:21-24,
+ * models/layers/embeddings.py:55,57, residual.py:36 (time_mlp).
+ *
+ *   y[n,ho,wo,j] = bias[j] + temb[n,j] + res[n,ho,wo,j]
+ *                + sum_{r,s,k} x[n, hi, wi, k] * w[j*w_sn + k*w_sk + (r*S+s)*w_st]
+ *   gather 0 (conv):        hi = ho*stride - pad + r
+ *   gather 1 (transposed):  hi = (ho + pad - r) / stride   when divisible
+ *
+ * With the weight strides this one contraction covers fprop and dgrad of
+ * both layer kinds.  impl: 0 = auto, 1 = SIMT fp32-FMA kernel, 2 = tcgen05.
+ */
+typedef struct {
+    dmu_tensor4 x;       /* gathered input, channels K = Ck */
+    dmu_tensor4 y;       /* output, channels J = Cj */
+    dmu_tensor4 res;     /* optional residual added in the epilogue (ptr NULL = none) */
+    const void* w;       /* weights, dtype w_dtype */
+    int64_t w_sn, w_sk, w_st;
+    const float* bias;   /* [Cj] fp32 or NULL */
+    const float* temb;   /* [N, Cj] fp32 (row pitch temb_pitch) or NULL */
+    int64_t temb_pitch;
+    int32_t N, Hi, Wi, Ck;
+    int32_t Ho, Wo, Cj;
+    int32_t R, S, stride, pad;
+    int32_t gather;      /* 0 conv, 1 transposed */
+    int32_t w_dtype;
+    int32_t impl;
+    int32_t _pad;
+} dmu_conv_params;
+int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream);
+
+/* Weight gradient of the same contraction (autograd of the call sites above):
+ *   dw[a*dw_sa + b*dw_sb + (r*S+s)*dw_st] += sum_{n,po,qo} p[n,po,qo,a] * q[n, po*stride-pad+r, qo*stride-pad+s, b]
+ * p = tensor on the strided (small) grid, q = gathered tensor.  fp32 output,
+ * accumulated with atomics (caller zeroes dw).  Optionally also
+ * dbias[a] += sum p[.,.,.,a]. */
+typedef struct {
+    dmu_tensor4 p;
+    dmu_tensor4 q;
+    float* dw;
+    int64_t dw_sa, dw_sb, dw_st;
+    float* dbias;        /* [Ca] or NULL */
+    int32_t N, Hp, Wp, Ca;
+    int32_t Hq, Wq, Cb;
+    int32_t R, S, stride, pad;
+    int32_t impl;
+} dmu_wgrad_params;
+int dmu_conv2d_wgrad(const dmu_wgrad_params* p, dmu_stream_t stream);
+
+/* nn.GroupNorm (+ nn.SiLU): residual.py:31-32,38-39, attention.py:27,68, ddpm.py:88-89,
+ * energy_based.py:56-57,79-80.  NHWC tensors (sc == 1).
+ *  stats:   sums[n,g,0..1] += (sum x, sum x^2) over the group  (caller zeroes sums)
+ *  apply:   y = act((x - mean) * rstd * gamma + beta),  act = SiLU if silu else identity
+ *  bwd_reduce: red[n,c,0..1] += (sum_p du, sum_p du*xhat), du = dy * act'(u); dgamma/dbeta += over n
+ *  bwd_apply:  dx = rstd*(du*gamma - (A + xhat*Bq)/cnt) + add0 + add1
+ */
+typedef struct {
+    dmu_tensor4 x;       /* input of the norm */
+    dmu_tensor4 y;       /* output (apply) | dy (bwd) */
+    dmu_tensor4 dx;      /* bwd_apply output */
+    dmu_tensor4 add0, add1; /* optional addends for dx (ptr NULL = none) */
+    float* sums;         /* [N, G, 2] raw sums */
+    const float* gamma;  /* [C] */
+    const float* beta;   /* [C] */
+    float* red;          /* [N, C, 2] bwd workspace */
+    float* dgamma;       /* [C] accumulated */
+    float* dbeta;        /* [C] accumulated */
+    int32_t N, H, W, C, G;
+    int32_t silu;
+    float eps;
+    int32_t _pad;
+} dmu_gn_params;
+int dmu_gn_stats(const dmu_gn_params* p, dmu_stream_t stream);
+int dmu_gn_apply(const dmu_gn_params* p, dmu_stream_t stream);
+int dmu_gn_bwd_reduce(const dmu_gn_params* p, dmu_stream_t stream);
+int dmu_gn_bwd_apply(const dmu_gn_params* p, dmu_stream_t stream);
+
+/* Per-image and total channel sums of an NHWC tensor (bias / time_mlp grads):
+ *   out_nc[n*pitch + c] = sum_p x[n,p,c] (optional);  out_c[c] += sum_{n,p} x[n,p,c] (optional)
+ * scale multiplies both (1/HW gives the spatial mean of energy_based.py:83). */
+int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C,
+               float* out_nc, int64_t out_nc_pitch, float* out_c, float scale, dmu_stream_t stream);
+
+/* Multi-head self-attention core, attention.py:49-61.  qkv: [N, S, 3C] rows
+ * (pitch), heads*d = C; o: [N, S, C].  lse: [N, heads, S] fp32 (saved for bwd).
+ * bwd writes dqkv given do. */
+typedef struct {
+    const void* qkv; int64_t qkv_pitch;
+    void* o; int64_t o_pitch;
+    const void* d_o; int64_t do_pitch;
+    void* dqkv; int64_t dqkv_pitch;
+    float* lse;
+    int32_t N, S, C, heads;
+    int32_t dtype;
+    int32_t _pad;
+} dmu_attn_params;
+int dmu_attn_fwd(const dmu_attn_params* p, dmu_stream_t stream);
+int dmu_attn_bwd(const dmu_attn_params* p, dmu_stream_t stream);
+
+/* embeddings.py:24-39: emb[b, 0:half] = sin(t[b] f_i), emb[b, half:] = cos(t[b] f_i),
+ * f_i = exp(-i ln(1e4)/(half-1)).  t is int64 (t_is_float = 0) or fp32. */
+int dmu_sinusoidal_embedding(const void* t, int32_t t_is_float, float* emb, int64_t batch, int32_t dim, dmu_stream_t stream);
+
+/* Elementwise activations on fp32 rows: kind 0 = exact GELU (embeddings.py:56), 1 = SiLU (score_based.py:59),
+ * 2 = log (score_based.py:82).  bwd: dx = dy * act'(x). */
+int dmu_act_fwd(const float* x, float* y, int64_t n, int32_t kind, dmu_stream_t stream);
+int dmu_act_bwd(const float* x, const float* dy, float* dx, int64_t n, int32_t kind, dmu_stream_t stream);
+
+/* Layout / dtype repack of parameters into kernel-friendly caches (derived,
+ * never the stored format; SURVEY.md §8b "Ownership").  One launch for a
+ * whole table.  kind 0: OIHW -> [O][R][S][I];  kind 1: IOHW (ConvTranspose2d)
+ * -> [O][R][S][I];  kind 2: plain copy/cast ([O][I] Linear, vectors). */
+typedef struct {
+    const float* src;
+    void* dst;
+    int32_t O, I, R, S;
+    int32_t kind;
+    int32_t dst_dtype;
+} dmu_repack_desc;
+int dmu_repack_weights(const dmu_repack_desc* descs_device, int32_t n_desc, int64_t max_numel, dmu_stream_t stream);
+
+/* cudaMemsetAsync(ptr, 0, nbytes) on `stream` (zeroing of accumulation buffers inside a recorded plan). */
+int dmu_zero(void* ptr, int64_t nbytes, dmu_stream_t stream);
+
+/* Generic strided copy/cast between two 4-D tensors (tests, layout changes at the boundary). */
+int dmu_copy4(const dmu_tensor4* src, const dmu_tensor4* dst, int32_t N, int32_t H, int32_t W, int32_t C, dmu_stream_t stream);
+
+/* Fused Adam + EMA over a flat fp32 arena (SURVEY.md §8 f1;
+ * trainers/ddpm_trainer.py:139-143,463-480):  torch.optim.Adam semantics
+ * (no amsgrad, L2 weight decay), then ema = decay*ema + (1-decay)*p (ema NULL = skip). */
+int dmu_adam_ema(float* p, const float* g, float* m, float* v, float* ema,
+                 int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                 int64_t step, float ema_decay, float grad_scale, dmu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMU_B200_H */

@@ -1,0 +1,324 @@
+"""GPU parity of the UNet primitives (C ABI) against ATen fp32 on the same device."""
+
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 2e-5, torch.bfloat16: 6e-3}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    a, b = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = a, b
+
+
+def _mods():
+    from diffusion_model_universal_b200 import ops, _abi
+    return ops, _abi
+
+
+def _null():
+    from diffusion_model_universal_b200._abi import Tensor4
+    return Tensor4(None, 0, 0, 0, 0, 0, 0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _repack(w, transposed, dtype):
+    """OIHW (or IOHW for ConvTranspose2d) -> [O][R][S][I] via the library's own repack kernel."""
+    ops, _abi = _mods()
+    w = w.contiguous()
+    O, I = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
+    dst = torch.empty(O * w.shape[2] * w.shape[3] * I, device=w.device, dtype=dtype)
+    d = _abi.RepackDesc(w.data_ptr(), dst.data_ptr(), O, I, w.shape[2], w.shape[3], 1 if transposed else 0, ops.dtype_code(dst))
+    tab = torch.frombuffer(bytearray(bytes(d)), dtype=torch.uint8).cuda()
+    _abi.check(_abi.lib().dmu_repack_weights(tab.data_ptr(), 1, w.numel(), _stream()))
+    torch.cuda.synchronize()
+    return dst
+
+
+CONV_CASES = [
+    # N, H, W, Ci, Co, R, stride, pad, kind
+    (2, 32, 32, 64, 64, 3, 1, 1, "conv"),
+    (3, 16, 16, 64, 128, 3, 1, 1, "conv"),
+    (2, 8, 8, 192, 64, 3, 1, 1, "conv"),
+    (4, 4, 4, 128, 128, 3, 1, 1, "conv"),
+    (5, 1, 1, 512, 256, 3, 1, 1, "conv"),
+    (3, 2, 2, 384, 128, 3, 1, 1, "conv"),
+    (2, 8, 8, 64, 128, 1, 1, 0, "conv"),
+    (2, 32, 32, 64, 64, 4, 2, 1, "conv"),
+    (3, 2, 2, 256, 256, 4, 2, 1, "conv"),
+    (2, 16, 16, 64, 64, 4, 2, 1, "convT"),
+    (3, 1, 1, 256, 256, 4, 2, 1, "convT"),
+    (2, 12, 20, 24, 40, 3, 1, 1, "conv"),     # ragged: non-square, channel counts off the tile sizes
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_fprop_dgrad_wgrad(case, dtype):
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams, WgradParams
+    N, H, W, Ci, Co, R, stride, pad, kind = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(sum(v for v in case if isinstance(v, int)))
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev)
+    if kind == "conv":
+        w = (torch.randn(Co, Ci, R, R, generator=g) / math.sqrt(Ci * R * R)).to(dev)
+        Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+    else:
+        w = (torch.randn(Ci, Co, R, R, generator=g) / math.sqrt(Ci * R * R / 4)).to(dev)
+        Ho, Wo = (H - 1) * stride - 2 * pad + R, (W - 1) * stride - 2 * pad + R
+    bias = torch.randn(Co, generator=g).to(dev)
+    temb = torch.randn(N, Co + 8, generator=g).to(dev)     # pitched rows
+    res_full = torch.randn(N, Ho, Wo, Co + 16, generator=g).to(dev).to(dtype)   # residual read from a channel slice
+    xh = ops.nchw_to_nhwc(x, dtype)
+    xq, wq = xh.float().permute(0, 3, 1, 2), w
+    if dtype == torch.bfloat16:
+        wq = w.to(dtype).float()
+    wk = _repack(w, kind == "convT", dtype)
+    y_full = torch.zeros(N, Ho, Wo, Co + 24, device=dev, dtype=dtype)           # output written into a channel slice
+    code = ops.dtype_code(xh)
+    p = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(y_full, 8, Co), ops.t4_nhwc(res_full, 16, Co), wk.data_ptr(), R * R * Ci, 1, Ci,
+                   bias.data_ptr(), temb.data_ptr() + 4 * 4, Co + 8, N, H, W, Ci, Ho, Wo, Co, R, R, stride, pad,
+                   0 if kind == "conv" else 1, code, 1, 0)
+    ops.conv2d_raw(p)
+    if kind == "conv":
+        ref = F.conv2d(xq, wq, bias, stride=stride, padding=pad)
+    else:
+        ref = F.conv_transpose2d(xq, wq, bias, stride=stride, padding=pad)
+    ref = ref + temb[:, 4:4 + Co, None, None] + res_full[..., 16:16 + Co].float().permute(0, 3, 1, 2)
+    got = y_full[..., 8:8 + Co].float().permute(0, 3, 1, 2)
+    assert rel_l2(got, ref) < TOL[dtype], "fprop"
+    assert y_full[..., :8].abs().max() == 0 and y_full[..., 8 + Co:].abs().max() == 0, "wrote outside its channel slice"
+
+    # ---- dgrad: gradient w.r.t. x of the same layer
+    dy = torch.randn(N, Co, Ho, Wo, generator=g).to(dev)
+    dyh = ops.nchw_to_nhwc(dy, dtype)
+    dyq = dyh.float().permute(0, 3, 1, 2)
+    dx = torch.empty(N, H, W, Ci, device=dev, dtype=dtype)
+    p2 = ConvParams(ops.t4_nhwc(dyh), ops.t4_nhwc(dx), _null(), wk.data_ptr(), 1, R * R * Ci, Ci, None, None, 0,
+                    N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1 if kind == "conv" else 0, code, 1, 0)
+    ops.conv2d_raw(p2)
+    if kind == "conv":
+        dref = torch.nn.grad.conv2d_input((N, Ci, H, W), wq, dyq, stride=stride, padding=pad)
+    else:
+        dref = F.conv2d(dyq, wq, stride=stride, padding=pad)
+    assert rel_l2(dx.float().permute(0, 3, 1, 2), dref) < TOL[dtype], "dgrad"
+
+    # ---- wgrad (+ bias grad) in the parameter's own layout, accumulated onto existing content
+    dw = torch.ones_like(w)
+    db = torch.ones(Co, device=dev)
+    if kind == "conv":
+        p3 = WgradParams(ops.t4_nhwc(dyh), ops.t4_nhwc(xh), dw.data_ptr(), Ci * R * R, R * R, 1, db.data_ptr(),
+                         N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1)
+        wref = torch.nn.grad.conv2d_weight(xq, w.shape, dyq, stride=stride, padding=pad)
+    else:
+        p3 = WgradParams(ops.t4_nhwc(xh), ops.t4_nhwc(dyh), dw.data_ptr(), Co * R * R, R * R, 1, None,
+                         N, H, W, Ci, Ho, Wo, Co, R, R, stride, pad, 1)
+        wref = torch.nn.grad.conv2d_weight(dyq, (Ci, Co, R, R), xq, stride=stride, padding=pad)
+    ops.wgrad_raw(p3)
+    assert rel_l2(dw - 1, wref) < 5e-5, "wgrad"
+    if kind == "conv":
+        assert rel_l2(db - 1, dyq.sum(dim=(0, 2, 3))) < 5e-5, "dbias"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem_and_head_layouts(dtype):
+    """3-channel NCHW fp32 boundary tensors: stem fprop/wgrad, head fprop (small-N kernel)/dgrad/wgrad."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams, WgradParams
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(9)
+    N, H, W, Cm = 3, 32, 32, 64
+    x = torch.randn(N, 3, H, W, generator=g).to(dev)
+    w = (torch.randn(Cm, 3, 3, 3, generator=g) / 5).to(dev)
+    b = torch.randn(Cm, generator=g).to(dev)
+    wk = _repack(w, False, dtype)
+    code = ops.dtype_code(wk)
+    y = torch.empty(N, H, W, Cm, device=dev, dtype=dtype)
+    ops.conv2d_raw(ConvParams(ops.t4_nchw(x), ops.t4_nhwc(y), _null(), wk.data_ptr(), 27, 1, 3, b.data_ptr(), None, 0,
+                              N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 0, code, 1, 0))
+    wq = w.to(dtype).float()
+    assert rel_l2(y.float().permute(0, 3, 1, 2), F.conv2d(x, wq, b, padding=1)) < TOL[dtype]
+    dy = torch.randn(N, Cm, H, W, generator=g).to(dev)
+    dyh = ops.nchw_to_nhwc(dy, dtype)
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    ops.wgrad_raw(WgradParams(ops.t4_nhwc(dyh), ops.t4_nchw(x), dw.data_ptr(), 27, 9, 1, db.data_ptr(), N, H, W, Cm, H, W, 3, 3, 3, 1, 1, 1))
+    assert rel_l2(dw, torch.nn.grad.conv2d_weight(x, w.shape, dyh.float().permute(0, 3, 1, 2), padding=1)) < 5e-5
+    # head: Cm -> 3, NHWC in, NCHW fp32 out
+    a = torch.randn(N, Cm, H, W, generator=g).to(dev)
+    ah = ops.nchw_to_nhwc(a, dtype)
+    wh = (torch.randn(3, Cm, 3, 3, generator=g) / 24).to(dev)
+    bh = torch.randn(3, generator=g).to(dev)
+    whk = _repack(wh, False, dtype)
+    out = torch.empty(N, 3, H, W, device=dev)
+    ops.conv2d_raw(ConvParams(ops.t4_nhwc(ah), ops.t4_nchw(out), _null(), whk.data_ptr(), 9 * Cm, 1, Cm, bh.data_ptr(), None, 0,
+                              N, H, W, Cm, H, W, 3, 3, 3, 1, 1, 0, code, 1, 0))
+    aq, whq = ah.float().permute(0, 3, 1, 2), wh.to(dtype).float()
+    assert rel_l2(out, F.conv2d(aq, whq, bh, padding=1)) < TOL[dtype]
+    dout = torch.randn(N, 3, H, W, generator=g).to(dev)
+    da = torch.empty(N, H, W, Cm, device=dev, dtype=dtype)
+    ops.conv2d_raw(ConvParams(ops.t4_nchw(dout), ops.t4_nhwc(da), _null(), whk.data_ptr(), 1, 9 * Cm, Cm, None, None, 0,
+                              N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 1, code, 1, 0))
+    assert rel_l2(da.float().permute(0, 3, 1, 2), torch.nn.grad.conv2d_input(a.shape, whq, dout, padding=1)) < TOL[dtype]
+    dwh, dbh = torch.zeros_like(wh), torch.zeros_like(bh)
+    ops.wgrad_raw(WgradParams(ops.t4_nchw(dout), ops.t4_nhwc(ah), dwh.data_ptr(), Cm * 9, 9, 1, dbh.data_ptr(), N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 1))
+    assert rel_l2(dwh, torch.nn.grad.conv2d_weight(aq, wh.shape, dout, padding=1)) < 5e-5
+    assert rel_l2(dbh, dout.sum(dim=(0, 2, 3))) < 5e-5
+
+
+@pytest.mark.parametrize("M,I,O", [(128, 256, 3136), (7, 64, 256), (2048, 128, 384), (5, 1, 64)])
+def test_linear_via_conv(M, I, O):
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams, WgradParams
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + O)
+    x, w, b = torch.randn(M, I, generator=g).to(dev), (torch.randn(O, I, generator=g) / math.sqrt(I)).to(dev), torch.randn(O, generator=g).to(dev)
+    y = torch.empty(M, O, device=dev)
+    ops.conv2d_raw(ConvParams(ops.t4_rows(x), ops.t4_rows(y), _null(), w.data_ptr(), I, 1, 0, b.data_ptr(), None, 0,
+                              M, 1, 1, I, 1, 1, O, 1, 1, 1, 0, 0, 0, 1, 0))
+    assert rel_l2(y, F.linear(x, w, b)) < 2e-5
+    dy = torch.randn(M, O, generator=g).to(dev)
+    dx = torch.empty(M, I, device=dev)
+    ops.conv2d_raw(ConvParams(ops.t4_rows(dy), ops.t4_rows(dx), _null(), w.data_ptr(), 1, I, 0, None, None, 0,
+                              M, 1, 1, O, 1, 1, I, 1, 1, 1, 0, 0, 0, 1, 0))
+    assert rel_l2(dx, dy @ w) < 2e-5
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    ops.wgrad_raw(WgradParams(ops.t4_rows(dy), ops.t4_rows(x), dw.data_ptr(), I, 1, 0, db.data_ptr(), M, 1, 1, O, 1, 1, I, 1, 1, 1, 0, 1))
+    assert rel_l2(dw, dy.t() @ x) < 5e-5 and rel_l2(db, dy.sum(0)) < 5e-5
+
+
+@pytest.mark.parametrize("C_,G", [(64, 32), (128, 32), (192, 32), (256, 32), (384, 32), (512, 32), (32, 32), (16, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("silu", [1, 0])
+def test_groupnorm_fwd_bwd(C_, G, dtype, silu):
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import GnParams
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C_ + silu)
+    N, H, W = (3, 8, 8) if C_ > 128 else (2, 16, 16)
+    x = (torch.randn(N, C_, H, W, generator=g) * 2 + 0.5).to(dev)
+    gamma, beta = (1 + 0.2 * torch.randn(C_, generator=g)).to(dev), (0.1 * torch.randn(C_, generator=g)).to(dev)
+    xh = ops.nchw_to_nhwc(x, dtype)
+    xq = xh.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yh = torch.empty_like(xh)
+    sums = torch.zeros(N, G, 2, device=dev)
+    lib = _abi.lib()
+    p = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(yh), _null(), _null(), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                 None, None, None, N, H, W, C_, G, silu, 1e-5, 0)
+    _abi.check(lib.dmu_gn_stats(C.byref(p), _stream()))
+    _abi.check(lib.dmu_gn_apply(C.byref(p), _stream()))
+    gq, bq = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.group_norm(xq, G, gq, bq, eps=1e-5)
+    ref = F.silu(ref) if silu else ref
+    assert rel_l2(yh.float().permute(0, 3, 1, 2), ref) < TOL[dtype]
+    dy = torch.randn(N, C_, H, W, generator=g).to(dev)
+    dyh = ops.nchw_to_nhwc(dy, dtype)
+    add = torch.randn(N, H, W, C_, generator=g).to(dev).to(dtype)
+    dxh = torch.empty_like(xh)
+    red = torch.zeros(N, C_, 2, device=dev)
+    dgam, dbet = torch.zeros(C_, device=dev), torch.zeros(C_, device=dev)
+    p2 = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(dyh), ops.t4_nhwc(dxh), ops.t4_nhwc(add), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                  red.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), N, H, W, C_, G, silu, 1e-5, 0)
+    _abi.check(lib.dmu_gn_bwd_reduce(C.byref(p2), _stream()))
+    _abi.check(lib.dmu_gn_bwd_apply(C.byref(p2), _stream()))
+    ref.backward(dyh.float().permute(0, 3, 1, 2))
+    tol = 3e-5 if dtype == torch.float32 else 8e-3
+    assert rel_l2(dxh.float().permute(0, 3, 1, 2), xq.grad + add.float().permute(0, 3, 1, 2)) < tol
+    assert rel_l2(dgam, gq.grad) < 1e-4 and rel_l2(dbet, bq.grad) < 1e-4
+
+
+@pytest.mark.parametrize("N,S,C_,heads", [(3, 16, 128, 4), (2, 64, 128, 4), (5, 1, 256, 4), (4, 4, 128, 4), (2, 16, 64, 4), (3, 4, 32, 4)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_core(N, S, C_, heads, dtype):
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import AttnParams
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(S * C_)
+    qkv = torch.randn(N, S, 3 * C_, generator=g).to(dev).to(dtype)
+    o = torch.empty(N, S, C_, device=dev, dtype=dtype)
+    lse = torch.empty(N, heads, S, device=dev)
+    do = torch.randn(N, S, C_, generator=g).to(dev).to(dtype)
+    dqkv = torch.empty_like(qkv)
+    p = AttnParams(qkv.data_ptr(), 3 * C_, o.data_ptr(), C_, do.data_ptr(), C_, dqkv.data_ptr(), 3 * C_, lse.data_ptr(), N, S, C_, heads, ops.dtype_code(qkv), 0)
+    lib = _abi.lib()
+    _abi.check(lib.dmu_attn_fwd(C.byref(p), _stream()))
+    _abi.check(lib.dmu_attn_bwd(C.byref(p), _stream()))
+    d = C_ // heads
+    qr = qkv.float().clone().requires_grad_(True)
+    q, k, v = [z.reshape(N, S, heads, d).transpose(1, 2) for z in qr.split(C_, dim=-1)]
+    ref = torch.matmul(torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * d ** -0.5, dim=-1), v).transpose(1, 2).reshape(N, S, C_)
+    assert rel_l2(o, ref) < TOL[dtype]
+    ref.backward(do.float())
+    assert rel_l2(dqkv, qr.grad) < (5e-5 if dtype == torch.float32 else 1.5e-2)
+
+
+def test_small_fp32_ops():
+    ops, _abi = _mods()
+    from oracle.unet import sinusoidal_embedding
+    lib = _abi.lib()
+    dev = torch.device("cuda:0")
+    for dim in (32, 64):
+        t = torch.tensor([0, 1, 17, 500, 999], device=dev)
+        emb = torch.empty(5, dim, device=dev)
+        _abi.check(lib.dmu_sinusoidal_embedding(t.data_ptr(), 0, emb.data_ptr(), 5, dim, _stream()))
+        ref = sinusoidal_embedding(t.cpu(), dim)
+        assert (emb.cpu() - ref).abs().max() < 2e-5   # |arg| up to 1e3 rad: a few ulp of the argument
+        tf = t.float()
+        _abi.check(lib.dmu_sinusoidal_embedding(tf.data_ptr(), 1, emb.data_ptr(), 5, dim, _stream()))
+        assert (emb.cpu() - ref).abs().max() < 2e-5
+    x = torch.randn(1000, device=dev) * 3
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    dy = torch.randn_like(x)
+    for kind, fn in ((0, F.gelu), (1, F.silu), (2, torch.log)):
+        xi = x.abs() + 0.1 if kind == 2 else x
+        xr = xi.clone().requires_grad_(True)
+        _abi.check(lib.dmu_act_fwd(xi.data_ptr(), y.data_ptr(), 1000, kind, _stream()))
+        _abi.check(lib.dmu_act_bwd(xi.data_ptr(), dy.data_ptr(), dx.data_ptr(), 1000, kind, _stream()))
+        r = fn(xr)
+        r.backward(dy)
+        assert rel_l2(y, r) < 1e-6 and rel_l2(dx, xr.grad) < 1e-6, kind
+    # colsum
+    from diffusion_model_universal_b200 import ops
+    for dtype in (torch.float32, torch.bfloat16):
+        z = torch.randn(3, 8, 8, 192, device=dev).to(dtype)
+        nc = torch.zeros(3, 200, device=dev)
+        c = torch.ones(192, device=dev)
+        t4 = ops.t4_nhwc(z)
+        _abi.check(lib.dmu_colsum(C.byref(t4), 3, 8, 8, 192, nc.data_ptr(), 200, c.data_ptr(), 0.5, _stream()))
+        ref = z.float().sum(dim=(1, 2)) * 0.5
+        assert rel_l2(nc[:, :192], ref) < 1e-5 and rel_l2(c - 1, ref.sum(0)) < 1e-5
+
+
+def test_adam_ema_matches_torch():
+    ops, _abi = _mods()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    n = 10007
+    p0 = torch.randn(n, generator=g).to(dev)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
+    p, m, v, ema = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), p0.clone()
+    ema_ref = p0.clone()
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g).to(dev)
+        p_ref.grad = grad.clone()
+        opt.step()
+        ema_ref.mul_(0.999).add_(p_ref.detach(), alpha=0.001)
+        _abi.check(_abi.lib().dmu_adam_ema(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n,
+                                           2e-4, 0.9, 0.999, 1e-8, 0.0, step, 0.999, 1.0, _stream()))
+    assert rel_l2(p, p_ref) < 1e-6 and rel_l2(ema, ema_ref) < 1e-6
