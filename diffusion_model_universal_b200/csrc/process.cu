@@ -296,6 +296,7 @@ int dmu_sizeof(const char* name) {
 
 int dmu_q_sample(const float* x0, const float* noise, const int64_t* t, const float* acp, float* out,
                  int64_t batch, int64_t inner, dmu_stream_t stream) {
+    if (batch == 0 || inner == 0) return 0;  // empty batch: nothing to do (pointers may be NULL)
     DMU_REQUIRE(x0 && noise && t && acp && out, "dmu_q_sample: null pointer");
     DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_q_sample: negative size");
     DMU_REQUIRE(aligned16(x0) && aligned16(noise) && aligned16(out), "dmu_q_sample: buffers must be 16-byte aligned");
@@ -305,6 +306,7 @@ int dmu_q_sample(const float* x0, const float* noise, const int64_t* t, const fl
 
 int dmu_ddpm_step(const float* x, const float* eps, const float* noise, const int64_t* t, const float* betas,
                   const float* alphas, const float* acp, float* out, int64_t batch, int64_t inner, dmu_stream_t stream) {
+    if (batch == 0 || inner == 0) return 0;  // empty batch: nothing to do (pointers may be NULL)
     DMU_REQUIRE(x && eps && t && betas && alphas && acp && out, "dmu_ddpm_step: null pointer");
     DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_ddpm_step: negative size");
     DMU_REQUIRE(aligned16(x) && aligned16(eps) && aligned16(out) && aligned16(noise), "dmu_ddpm_step: buffers must be 16-byte aligned");
@@ -315,6 +317,7 @@ int dmu_ddpm_step(const float* x, const float* eps, const float* noise, const in
 int dmu_ddim_step(const float* x, const float* eps, const float* noise, const int64_t* idx, const float* a,
                   const float* ap, const float* sg, const float* s1m, float* out, int64_t batch, int64_t inner,
                   dmu_stream_t stream) {
+    if (batch == 0 || inner == 0) return 0;  // empty batch: nothing to do (pointers may be NULL)
     DMU_REQUIRE(x && eps && idx && a && ap && sg && s1m && out, "dmu_ddim_step: null pointer");
     DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_ddim_step: negative size");
     DMU_REQUIRE(aligned16(x) && aligned16(eps) && aligned16(out) && aligned16(noise), "dmu_ddim_step: buffers must be 16-byte aligned");
@@ -359,6 +362,7 @@ int dmu_zero(void* ptr, int64_t nbytes, dmu_stream_t stream) {
 
 int dmu_scale_add(const float* x, const float* z, const float* a, const float* c, float* out, int64_t batch, int64_t inner,
                   dmu_stream_t stream) {
+    if (batch == 0 || inner == 0) return 0;  // empty batch: nothing to do (pointers may be NULL)
     DMU_REQUIRE(x && z && c && out, "dmu_scale_add: null pointer");
     DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_scale_add: negative size");
     DMU_REQUIRE(aligned16(x) && aligned16(z) && aligned16(out), "dmu_scale_add: buffers must be 16-byte aligned");

@@ -182,12 +182,16 @@ def main():
         torch.manual_seed(8)
         x = torch.randn(1, 3, 32, 32)
         x_init = x.clone()
+        traj = []
         with torch.no_grad():
             for i in range(len(dm.ddim_timesteps) - 1, -1, -1):
                 tt = torch.full((1,), int(dm.ddim_timesteps[i]))
                 eps = dm.forward(x, tt)
                 x = dm._ddim_sample(x, torch.full((1,), i), None, pred_noise=eps)
-        ddim_out[eta] = {"final": x, "x_init": x_init}
+                traj.append(x.clone())
+        # traj[j] = state after processing table index 49-j (for teacher-forced per-step parity:
+        # a 50-step chain through a random-weight network amplifies 1e-6 differences to O(1))
+        ddim_out[eta] = {"final": x, "x_init": x_init, "traj": torch.stack(traj)}
     # single-step arithmetic with injected eps/noise
     dm = DDIM({**base_cfg, "ddim_sampling_steps": 50, "eta": 0.5})
     cases = {}

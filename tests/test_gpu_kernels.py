@@ -277,10 +277,10 @@ def test_small_fp32_ops():
         emb = torch.empty(5, dim, device=dev)
         _abi.check(lib.dmu_sinusoidal_embedding(t.data_ptr(), 0, emb.data_ptr(), 5, dim, _stream()))
         ref = sinusoidal_embedding(t.cpu(), dim)
-        assert (emb.cpu() - ref).abs().max() < 2e-5   # |arg| up to 1e3 rad: a few ulp of the argument
+        assert (emb.cpu() - ref).abs().max() < 1.5e-4   # |arg| up to 1e3 rad: 1 ulp of the frequency (CPU vs GPU expf) is 6e-5 rad
         tf = t.float()
         _abi.check(lib.dmu_sinusoidal_embedding(tf.data_ptr(), 1, emb.data_ptr(), 5, dim, _stream()))
-        assert (emb.cpu() - ref).abs().max() < 2e-5
+        assert (emb.cpu() - ref).abs().max() < 1.5e-4
     x = torch.randn(1000, device=dev) * 3
     y, dx = torch.empty_like(x), torch.empty_like(x)
     dy = torch.randn_like(x)
