@@ -14,6 +14,9 @@ from . import _abi
 from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, check
 
 
+LAUNCHES = 0   # kernels launched through this module / the engine (bench.py reports it as gpu_launches)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -23,6 +26,11 @@ def _need_cuda(*ts):
         if t is not None and not t.is_cuda:
             raise RuntimeError("diffusion_model_universal_b200 runs on CUDA (sm_100a) only: got a CPU tensor. "
                                "Move the model and inputs to a B200 device; there is no CPU fallback.")
+
+
+def _launched(n=1):
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def dtype_code(t: torch.Tensor) -> int:
@@ -68,6 +76,7 @@ def q_sample(x0, t, noise, alphas_cumprod):
     x0, noise = _f32c(x0, "x0"), _f32c(noise, "noise")
     out = torch.empty_like(x0)
     b = x0.shape[0]
+    _launched()
     check(_abi.lib().dmu_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
                                   b, x0.numel() // max(b, 1), _stream()), "q_sample")
     return out
@@ -83,6 +92,7 @@ def ddpm_step(x, eps, t, noise, betas, alphas, alphas_cumprod, out=None):
         raise TypeError("t must be int64")
     out = torch.empty_like(x) if out is None else out
     b = x.shape[0]
+    _launched()
     check(_abi.lib().dmu_ddpm_step(x.data_ptr(), eps.data_ptr(), noise.data_ptr() if noise is not None else None, t.data_ptr(),
                                    betas.data_ptr(), alphas.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
                                    b, x.numel() // max(b, 1), _stream()), "ddpm_step")
@@ -97,6 +107,7 @@ def ddim_step(x, eps, idx, noise, alphas, alphas_prev, sigmas, sqrt_one_minus_al
         raise TypeError("idx must be int64")
     out = torch.empty_like(x) if out is None else out
     b = x.shape[0]
+    _launched()
     check(_abi.lib().dmu_ddim_step(x.data_ptr(), eps.data_ptr(), noise.data_ptr() if noise is not None else None, idx.data_ptr(),
                                    alphas.data_ptr(), alphas_prev.data_ptr(), sigmas.data_ptr(), sqrt_one_minus_alphas.data_ptr(),
                                    out.data_ptr(), b, x.numel() // max(b, 1), _stream()), "ddim_step")
@@ -107,6 +118,7 @@ def langevin_score_step(x, score, noise, sigmas, k: int, beta: float, out=None):
     """models/score_based.py:236-245."""
     _need_cuda(x, score, noise, sigmas)
     out = torch.empty_like(x) if out is None else out
+    _launched()
     check(_abi.lib().dmu_langevin_score_step(_f32c(x, "x").data_ptr(), _f32c(score, "score").data_ptr(), _f32c(noise, "noise").data_ptr(),
                                              sigmas.data_ptr(), k, beta, out.data_ptr(), x.numel(), _stream()), "langevin_score_step")
     return out
@@ -116,6 +128,7 @@ def langevin_energy_step(x, grad, noise, step_size: float, out=None):
     """models/energy_based.py:271-273 (math.sqrt repair)."""
     _need_cuda(x, grad, noise)
     out = torch.empty_like(x) if out is None else out
+    _launched()
     check(_abi.lib().dmu_langevin_energy_step(_f32c(x, "x").data_ptr(), _f32c(grad, "grad").data_ptr(), _f32c(noise, "noise").data_ptr(),
                                               step_size, math.sqrt(2 * step_size), out.data_ptr(), x.numel(), _stream()), "langevin_energy_step")
     return out
@@ -125,6 +138,7 @@ def energy_renoise(x, noise, alphas_cumprod, t: int, out=None):
     """models/energy_based.py:240-246."""
     _need_cuda(x, noise, alphas_cumprod)
     out = torch.empty_like(x) if out is None else out
+    _launched()
     check(_abi.lib().dmu_energy_renoise(_f32c(x, "x").data_ptr(), _f32c(noise, "noise").data_ptr(), alphas_cumprod.data_ptr(), t,
                                         out.data_ptr(), x.numel(), _stream()), "energy_renoise")
     return out
@@ -138,6 +152,7 @@ def scale_add(x, z, a, c, out=None):
     b = x.shape[0]
     c = c.float().contiguous()
     a = a.float().contiguous() if a is not None else None
+    _launched()
     check(_abi.lib().dmu_scale_add(x.data_ptr(), z.data_ptr(), a.data_ptr() if a is not None else None, c.data_ptr(), out.data_ptr(),
                                    b, x.numel() // max(b, 1), _stream()), "scale_add")
     return out
@@ -152,6 +167,7 @@ def diffusion_loss(pred, target, w, wm, wl, wh, delta, want_grad: bool):
     loss = torch.empty((), device=pred.device, dtype=torch.float32)
     dpred = torch.empty_like(pred) if want_grad else None
     part = torch.empty(_abi.lib().dmu_loss_workspace_floats(n), device=pred.device, dtype=torch.float32)
+    _launched(2)
     check(_abi.lib().dmu_diffusion_loss(pred.data_ptr(), target.data_ptr(), w.data_ptr() if w is not None else None,
                                         wm, wl, wh, delta, loss.data_ptr(), dpred.data_ptr() if want_grad else None,
                                         part.data_ptr(), b, n // b, _stream()), "diffusion_loss")
@@ -160,14 +176,17 @@ def diffusion_loss(pred, target, w, wm, wl, wh, delta, want_grad: bool):
 
 # ------------------------------------------------------------------ UNet primitives (used by tests; the engine builds structs directly)
 def conv2d_raw(p: ConvParams):
+    _launched()
     check(_abi.lib().dmu_conv2d(C.byref(p), _stream()), "conv2d")
 
 
 def wgrad_raw(p: WgradParams):
+    _launched()
     check(_abi.lib().dmu_conv2d_wgrad(C.byref(p), _stream()), "conv2d_wgrad")
 
 
 def copy4(src: Tensor4, dst: Tensor4, n, h, w, c):
+    _launched()
     check(_abi.lib().dmu_copy4(C.byref(src), C.byref(dst), n, h, w, c, _stream()), "copy4")
 
 

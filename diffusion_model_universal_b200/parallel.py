@@ -1,0 +1,57 @@
+"""Data-parallel gradient exchange (SURVEY.md §8 a13 / e).
+
+The reference wraps the model in DDP but never triggers the reducer
+(trainers/ddpm_trainer.py:130-136 vs :543-547), so its ranks silently diverge.
+Here the flat gradient arena is averaged across ranks in buckets, each an
+asynchronous ``all_reduce`` (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU
+tests).  The arena is laid out [time MLPs | attention qkv | everything else in
+forward order]; the backward finishes gradients in roughly reverse forward
+order, so buckets are issued from the arena's tail towards its head and the
+first bucket (time MLP gradients, completed last) goes out at the very end.
+"""
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def bucket_ranges(total: int, bucket_elems: int) -> List[Tuple[int, int]]:
+    """[lo, hi) element ranges covering [0, total), issued tail-first."""
+    if total <= 0:
+        return []
+    bucket_elems = max(1, int(bucket_elems))
+    out, hi = [], total
+    while hi > 0:
+        lo = max(0, hi - bucket_elems)
+        out.append((lo, hi))
+        hi = lo
+    return out
+
+
+class GradAllReducer:
+    """Averages ``engine.gflat`` across the process group."""
+
+    def __init__(self, unet, bucket_mb: float = 16.0, group=None):
+        self.unet, self.group = unet, group
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def launch(self):
+        """Issue all buckets asynchronously; returns the work handles."""
+        if self.world == 1:
+            return []
+        g = self.unet.engine.gflat
+        works = []
+        for lo, hi in bucket_ranges(g.numel(), self.bucket_elems):
+            works.append(dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        return works
+
+    def finish(self, works) -> float:
+        """Wait for the buckets; returns the scale (1/world) the optimizer must apply to the summed gradients."""
+        for w in works:
+            w.wait()
+        return 1.0 / self.world
+
+    def allreduce(self) -> float:
+        return self.finish(self.launch())

@@ -327,6 +327,7 @@ class Engine:
         return self.wcache.data_ptr() + self.wc_off[name] * self.esize
 
     def repack(self, stream):
+        ops.LAUNCHES += 1
         _abi.check(self._lib.dmu_repack_weights(self.repack_table.data_ptr(), self.repack_n, self.repack_max, stream), "repack_weights")
 
     # ------------------------------------------------------------------ public entry points
@@ -360,6 +361,7 @@ class Engine:
         return p
 
     def _run(self, oplist, stream):
+        ops.LAUNCHES += len(oplist)
         for fn, args in oplist:
             rc = fn(*args, stream)
             if rc != 0:
