@@ -1,11 +1,548 @@
-// tcgen05 / TMA implicit-GEMM convolution (bf16 operands, fp32 TMEM accumulators).
-#include "common.cuh"
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulators in TMEM).
+//
+// fprop / dgrad  (dmu_conv2d, impl 2):   D[pixel, j] = sum_{tap, k} X[pixel shifted by tap, k] * W[j][tap][k]
+//   * M = 128 output pixels per CTA = one TMA box (64 channels x BW x BH x BN) of the NHWC input per (tap, 64-channel chunk);
+//     the box lands in shared memory as 128 rows x 128 bytes with the 128-byte swizzle, which IS the K-major UMMA
+//     operand layout: no im2col buffer, padding comes from TMA out-of-bounds zero fill (signed box coordinates).
+//   * stride-2 convolutions read one of four parity sub-lattices of the input (four tensor maps with doubled strides);
+//     transposed stride-2 convolutions run as four output-parity phases of 2x2 taps (blockIdx.z) - no zero insertion.
+//   * N = 64 or 128 output channels per CTA; weights [J][taps][K] come through a 2-D tensor map.
+//   * one elected thread issues TMA, one issues tcgen05.mma; an mbarrier ring of kStages connects them; the
+//     accumulator is read back with tcgen05.ld and the epilogue fuses + bias + temb[n, j] + residual -> bf16 NHWC.
+//
+// wgrad (dmu_conv2d_wgrad, impl 2):  dW[a][tap][b] += sum_pixels P[pixel, a] * Q[pixel shifted by tap, b]
+//   * the contraction runs over pixels, so both operands are MN-major (channels contiguous): the same TMA boxes
+//     (64 channels x 64 pixels) are consumed through MN-major UMMA descriptors; M = two (tap, 64-channel) blocks of Q,
+//     N = up to 128 channels of P; split over pixel ranges (blockIdx.z), fp32 atomics into the OIHW gradient.
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace dmu {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------ host helpers
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+int make_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box,
+                  const char* what) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    DMU_REQUIRE(enc, "%s: cuTensorMapEncodeTiled is not available from this driver", what);
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_elems[i] * 2;
+    }
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DMU_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed (CUresult %d; dims %llu %llu %llu %llu, box %u %u %u %u)", what, (int)r,
+                (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+                (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return 0;
+}
+
+static inline int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool nhwc_bf16_ok(const dmu_tensor4& t) {
+    return t.dtype == DMU_BF16 && t.sc == 1 && aligned16(t.ptr) && t.sw % 8 == 0 && t.sh % 8 == 0 && t.sn % 8 == 0;
+}
+
+constexpr int kMaxTaps = 16;
+constexpr int kMaxPhases = 4;
+
+struct Tap { int dh, dw, map, wk; };
+struct Phase { int tap0, ntaps, oph, opw, TH, TW; };
+struct Maps { CUtensorMap a[4]; CUtensorMap b; };
+
+// pixel-box geometry shared by both kernels: `pix` pixels per box
+struct Box { int BN, BH, BW, tiles_n, tiles_h, tiles_w; };
+static Box make_box(int N, int TH, int TW, int pix) {
+    Box b;
+    b.BW = pow2_ceil(TW) < pix ? pow2_ceil(TW) : pix;
+    b.BH = pow2_ceil(TH) < pix / b.BW ? pow2_ceil(TH) : pix / b.BW;
+    b.BN = pix / (b.BW * b.BH);
+    if (b.BN > N) b.BN = N;
+    b.tiles_w = (TW + b.BW - 1) / b.BW;
+    b.tiles_h = (TH + b.BH - 1) / b.BH;
+    b.tiles_n = (N + b.BN - 1) / b.BN;
+    return b;
+}
+
+// Tap table + tensor maps of a gather-0 ("convolution") read pattern: q = p*stride - pad + (r, s).
+// Tap (r, s) reads parity sub-lattice ((r-pad) mod stride, (s-pad) mod stride) at box shift (floor((r-pad)/stride), ...).
+static int build_gather0(const dmu_tensor4& x, int N, int Hi, int Wi, int C, int R, int S, int stride, int pad, const Box& b, Tap* taps,
+                         Maps* maps, int* map_h, int* map_w, const char* what) {
+    bool used[4] = {false, false, false, false};
+    for (int r = 0; r < R; ++r)
+        for (int s = 0; s < S; ++s) {
+            const int ah = floordiv(r - pad, stride), aw = floordiv(s - pad, stride);
+            const int ph = (r - pad) - ah * stride, pw = (s - pad) - aw * stride;
+            Tap& t = taps[r * S + s];
+            t.dh = ah; t.dw = aw; t.map = ph * stride + pw; t.wk = (r * S + s) * C;
+            used[t.map] = true;
+        }
+    for (int m = 0; m < stride * stride; ++m) {
+        map_h[m] = map_w[m] = 0;
+        if (!used[m]) continue;
+        const int ph = m / stride, pw = m % stride;
+        if (ph >= Hi || pw >= Wi) {  // empty sub-lattice (e.g. 1x1 input, stride 2): every tap on it is out of bounds
+            used[m] = false;
+            continue;
+        }
+        const int Hm = (Hi - ph + stride - 1) / stride, Wm = (Wi - pw + stride - 1) / stride;
+        map_h[m] = Hm; map_w[m] = Wm;
+        const uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wm, (uint64_t)Hm, (uint64_t)N};
+        const uint64_t str[4] = {1, (uint64_t)x.sw * stride, (uint64_t)x.sh * stride, (uint64_t)x.sn};
+        const uint32_t box[4] = {64, (uint32_t)b.BW, (uint32_t)b.BH, (uint32_t)b.BN};
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(x.ptr) + (int64_t)ph * x.sh + (int64_t)pw * x.sw;
+        if (int rc = make_map_bf16(&maps->a[m], base, 4, dims, str, box, what)) return rc;
+    }
+    return 0;
+}
+
+// ================================================================================================ fprop / dgrad kernel
+struct ConvArgs {
+    Tap taps[kMaxTaps];
+    Phase phases[kMaxPhases];
+    int map_h[4], map_w[4];      // extents of each A tensor map (to skip taps whose whole box is out of bounds)
+    int N, Ho, Wo, Ck, Cj, os;
+    int BN, BH, BW, tiles_h, tiles_w;
+    __nv_bfloat16* y; int64_t y_sn, y_sh, y_sw;
+    const __nv_bfloat16* res; int64_t r_sn, r_sh, r_sw;
+    const float* bias;
+    const float* temb; int64_t temb_pitch;
+};
+
+template <int NT>
+struct ConvCfg {
+    static constexpr int kStages = NT == 64 ? 4 : 3;
+    static constexpr int kABytes = 128 * 128;     // 128 pixels x 64 bf16
+    static constexpr int kBBytes = NT * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kSmem = kStages * kStageBytes + 1024;   // + alignment slack
+};
+
+template <int NT>
+__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
+    using Cfg = ConvCfg<NT>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
+    __shared__ uint32_t s_tmem, s_issued;
+
+    const Phase ph = P.phases[blockIdx.z];
+    const int tile = blockIdx.x;
+    const int tw0 = (tile % P.tiles_w) * P.BW;
+    const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
+    const int n0 = (tile / (P.tiles_w * P.tiles_h)) * P.BN;
+    if (th0 >= ph.TH || tw0 >= ph.TW) return;   // phase smaller than the grid's tile space (whole CTA leaves)
+    const int j0 = blockIdx.y * NT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = P.Ck >> 6;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&acc_bar, 2);
+        fence_mbar_init();
+        s_issued = 0;
+    }
+    if (warp == 1) tmem_alloc(&s_tmem, NT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    auto tap_live = [&](const Tap& t) {   // does the shifted box intersect its sub-lattice at all?
+        const int h = th0 + t.dh, w = tw0 + t.dw;
+        return h < P.map_h[t.map] && h + P.BH > 0 && w < P.map_w[t.map] && w + P.BW > 0;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------ TMA producer
+        const uint32_t a_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
+        int it = 0;
+        for (int ti = 0; ti < ph.ntaps; ++ti) {
+            const Tap t = P.taps[ph.tap0 + ti];
+            if (!tap_live(t)) continue;
+            for (int c = 0; c < chunks; ++c, ++it) {
+                const int st = it % kStages;
+                mbar_wait(&empty_bar[st], ((it / kStages) & 1) ^ 1);
+                uint8_t* sa = smem + st * Cfg::kStageBytes;
+                mbar_arrive_expect_tx(&full_bar[st], a_bytes + Cfg::kBBytes);
+                tma_load_4d(sa, &maps.a[t.map], &full_bar[st], c * 64, tw0 + t.dw, th0 + t.dh, n0);
+                tma_load_2d(sa + Cfg::kABytes, &maps.b, &full_bar[st], t.wk + c * 64, j0);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
+        int it = 0;
+        for (int ti = 0; ti < ph.ntaps; ++ti) {
+            const Tap t = P.taps[ph.tap0 + ti];
+            if (!tap_live(t)) continue;
+            for (int c = 0; c < chunks; ++c, ++it) {
+                const int st = it % kStages;
+                mbar_wait(&full_bar[st], (it / kStages) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
+                const uint64_t da = smem_desc_sw128(sa, 16, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
+                    umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                umma_commit(&empty_bar[st]);
+            }
+        }
+        s_issued = (uint32_t)it;
+        umma_commit(&acc_bar);      // arrival 1: all MMAs retired
+        mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------- epilogue: all 4 warps, thread = one output pixel (TMEM lane)
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    const bool have_acc = *reinterpret_cast<volatile uint32_t*>(&s_issued) != 0;
+    const int row = threadIdx.x;
+    const int wl = row % P.BW, hl = (row / P.BW) % P.BH, nl = row / (P.BW * P.BH);
+    const int n = n0 + nl, th = th0 + hl, tw = tw0 + wl;
+    const int ho = th * P.os + ph.oph, wo = tw * P.os + ph.opw;
+    const bool valid = nl < P.BN && n < P.N && th < ph.TH && tw < ph.TW && ho < P.Ho && wo < P.Wo;
+    __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0;
+    const __nv_bfloat16* rp = P.res ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
+    const float* tp = P.temb ? P.temb + (int64_t)n * P.temb_pitch + j0 : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < NT; c += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (valid) {
+            if (!have_acc) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (P.bias) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c + i));
+                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                }
+            }
+            if (tp) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(tp + c + i));
+                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                }
+            }
+            if (rp) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    float r[8];
+                    load_vec<__nv_bfloat16>(rp + c + i, r);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[i + k] += r[k];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp + c + i, v + i);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, NT);
+}
+
+static int conv_supported(const dmu_conv_params* p) {
+    if (!p || !p->x.ptr || !p->y.ptr || !p->w) return 0;
+    if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y)) return 0;
+    if (p->res.ptr && !nhwc_bf16_ok(p->res)) return 0;
+    if (p->Ck % 64 != 0 || p->Cj % 64 != 0) return 0;
+    if (p->w_sk != 1 || p->w_st != p->Ck || p->w_sn != (int64_t)p->R * p->S * p->Ck || !aligned16(p->w)) return 0;
+    if (p->stride < 1 || p->stride > 2 || p->R * p->S > kMaxTaps) return 0;
+    if (p->bias && !aligned16(p->bias)) return 0;
+    if (p->temb && (!aligned16(p->temb) || p->temb_pitch % 4 != 0)) return 0;
+    if (encode_tiled_fn() == nullptr) return 0;
+    return 1;
+}
+
+static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
+    Maps maps;
+    ConvArgs A;
+    memset(&A, 0, sizeof(A));
+    const int st = p->stride;
+    int nph = 1, THmax = p->Ho, TWmax = p->Wo;
+    if (p->gather == 1) {
+        nph = st * st;
+        THmax = (p->Ho + st - 1) / st;
+        TWmax = (p->Wo + st - 1) / st;
+    }
+    const Box b = make_box(p->N, THmax, TWmax, 128);
+    if (p->gather == 0) {
+        A.os = 1;
+        A.phases[0] = Phase{0, p->R * p->S, 0, 0, p->Ho, p->Wo};
+        if (int rc = build_gather0(p->x, p->N, p->Hi, p->Wi, p->Ck, p->R, p->S, st, p->pad, b, A.taps, &maps, A.map_h, A.map_w, "dmu_conv2d/tc"))
+            return rc;
+    } else {
+        // transposed gather: output parity class (oph, opw) uses the taps with (oph + pad - r) divisible by stride
+        A.os = st;
+        int nt = 0;
+        for (int oph = 0; oph < st; ++oph)
+            for (int opw = 0; opw < st; ++opw) {
+                Phase& ph = A.phases[oph * st + opw];
+                ph.tap0 = nt; ph.oph = oph; ph.opw = opw;
+                ph.TH = p->Ho > oph ? (p->Ho - oph + st - 1) / st : 0;
+                ph.TW = p->Wo > opw ? (p->Wo - opw + st - 1) / st : 0;
+                for (int r = 0; r < p->R; ++r)
+                    for (int s = 0; s < p->S; ++s) {
+                        const int eh = oph + p->pad - r, ew = opw + p->pad - s;
+                        if (eh - floordiv(eh, st) * st != 0 || ew - floordiv(ew, st) * st != 0) continue;
+                        DMU_REQUIRE(nt < kMaxTaps, "dmu_conv2d/tc: too many taps");
+                        A.taps[nt++] = Tap{floordiv(eh, st), floordiv(ew, st), 0, (r * p->S + s) * p->Ck};
+                    }
+                ph.ntaps = nt - ph.tap0;
+            }
+        A.map_h[0] = p->Hi; A.map_w[0] = p->Wi;
+        const uint64_t dims[4] = {(uint64_t)p->Ck, (uint64_t)p->Wi, (uint64_t)p->Hi, (uint64_t)p->N};
+        const uint64_t str[4] = {1, (uint64_t)p->x.sw, (uint64_t)p->x.sh, (uint64_t)p->x.sn};
+        const uint32_t box[4] = {64, (uint32_t)b.BW, (uint32_t)b.BH, (uint32_t)b.BN};
+        if (int rc = make_map_bf16(&maps.a[0], p->x.ptr, 4, dims, str, box, "dmu_conv2d/tc")) return rc;
+    }
+    const int NT = (p->Cj % 128 == 0) ? 128 : 64;
+    {
+        const uint64_t dims[2] = {(uint64_t)p->R * p->S * p->Ck, (uint64_t)p->Cj};
+        const uint64_t str[2] = {1, (uint64_t)p->w_sn};
+        const uint32_t box[2] = {64, (uint32_t)NT};
+        if (int rc = make_map_bf16(&maps.b, p->w, 2, dims, str, box, "dmu_conv2d/tc weights")) return rc;
+    }
+    A.N = p->N; A.Ho = p->Ho; A.Wo = p->Wo; A.Ck = p->Ck; A.Cj = p->Cj;
+    A.BN = b.BN; A.BH = b.BH; A.BW = b.BW; A.tiles_h = b.tiles_h; A.tiles_w = b.tiles_w;
+    A.y = reinterpret_cast<__nv_bfloat16*>(p->y.ptr); A.y_sn = p->y.sn; A.y_sh = p->y.sh; A.y_sw = p->y.sw;
+    A.res = reinterpret_cast<const __nv_bfloat16*>(p->res.ptr); A.r_sn = p->res.sn; A.r_sh = p->res.sh; A.r_sw = p->res.sw;
+    A.bias = p->bias; A.temb = p->temb; A.temb_pitch = p->temb_pitch;
+    dim3 grid(b.tiles_n * b.tiles_h * b.tiles_w, p->Cj / NT, nph);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmem);
+        attr_done = true;
+    }
+    if (NT == 64) conv_tc_kernel<64><<<grid, 128, ConvCfg<64>::kSmem, stream>>>(maps, A);
+    else conv_tc_kernel<128><<<grid, 128, ConvCfg<128>::kSmem, stream>>>(maps, A);
+    return check_launch("dmu_conv2d/tc");
+}
+
+// ================================================================================================ wgrad kernel
+struct WgradArgs {
+    Tap taps[kMaxTaps];
+    int map_h[4], map_w[4];
+    int N, Hp, Wp, Ca, Cb, RS;
+    int BN, BH, BW, tiles_h, tiles_w, tiles_total, tiles_per_split;
+    int units;                    // RS * Cb/64 (tap, 64-channel chunk) row blocks; two per CTA
+    float* dw; int64_t dw_sa, dw_sb, dw_st;
+};
+
+template <int NT>
+struct WgradCfg {
+    static constexpr int kStages = NT == 64 ? 6 : 4;
+    static constexpr int kBlk = 64 * 128;         // 64 pixels x 64 bf16 channels
+    static constexpr int kABytes = 2 * kBlk;
+    static constexpr int kBBytes = (NT / 64) * kBlk;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kSmem = kStages * kStageBytes + 1024;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs P) {
+    using Cfg = WgradCfg<NT>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
+    __shared__ uint32_t s_tmem, s_issued;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = P.Cb >> 6;
+    const int u0 = blockIdx.x * 2, u1 = u0 + 1;
+    const bool has1 = u1 < P.units;
+    const Tap t0 = P.taps[u0 / chunks];
+    const Tap t1 = P.taps[(has1 ? u1 : u0) / chunks];
+    const int cb0 = (u0 % chunks) * 64, cb1 = ((has1 ? u1 : u0) % chunks) * 64;
+    const int a0 = blockIdx.y * NT;
+    const int tile_lo = blockIdx.z * P.tiles_per_split;
+    const int tile_hi = min(P.tiles_total, tile_lo + P.tiles_per_split);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&acc_bar, 2);
+        fence_mbar_init();
+        s_issued = 0;
+    }
+    if (warp == 1) tmem_alloc(&s_tmem, NT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    auto live = [&](const Tap& t, int th0, int tw0) {
+        const int h = th0 + t.dh, w = tw0 + t.dw;
+        return h < P.map_h[t.map] && h + P.BH > 0 && w < P.map_w[t.map] && w + P.BW > 0;
+    };
+
+    if (warp == 0 && lane == 0) {
+        const uint32_t blk_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
+        int it = 0;
+        for (int tile = tile_lo; tile < tile_hi; ++tile) {
+            const int tw0 = (tile % P.tiles_w) * P.BW;
+            const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
+            const int n0 = (tile / (P.tiles_w * P.tiles_h)) * P.BN;
+            const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
+            if (!l0 && !l1) continue;
+            const int st = it % kStages;
+            mbar_wait(&empty_bar[st], ((it / kStages) & 1) ^ 1);
+            uint8_t* sa = smem + st * Cfg::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[st], blk_bytes * (2 + NT / 64));
+            // a dead tap still issues its (fully out-of-bounds, zero-filled) load so the block holds zeros, not stale data
+            tma_load_4d(sa, &maps.a[t0.map], &full_bar[st], cb0, tw0 + t0.dw, th0 + t0.dh, n0);
+            tma_load_4d(sa + Cfg::kBlk, &maps.a[t1.map], &full_bar[st], cb1, tw0 + t1.dw, th0 + t1.dh, n0);
+#pragma unroll
+            for (int q = 0; q < NT / 64; ++q)
+                tma_load_4d(sa + Cfg::kABytes + q * Cfg::kBlk, &maps.b, &full_bar[st], a0 + q * 64, tw0, th0, n0);
+            ++it;
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);   // both operands MN-major (channels contiguous, K = pixels)
+        const int kpix = P.BN * P.BH * P.BW;                           // pixels actually in a box (<= 64, multiple of 16 or padded)
+        int it = 0;
+        for (int tile = tile_lo; tile < tile_hi; ++tile) {
+            const int tw0 = (tile % P.tiles_w) * P.BW;
+            const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
+            const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
+            if (!l0 && !l1) continue;
+            const int st = it % kStages;
+            mbar_wait(&full_bar[st], (it / kStages) & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
+            const uint64_t da = smem_desc_sw128(sa, Cfg::kBlk, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, Cfg::kBlk, 1024);
+            for (int k = 0; k * 16 < kpix; ++k)   // K = 16 pixels = 16 rows of 128 B = 2048 B per step
+                umma_bf16(tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) != 0);
+            umma_commit(&empty_bar[st]);
+            ++it;
+        }
+        s_issued = (uint32_t)it;
+        umma_commit(&acc_bar);      // arrival 1: all MMAs retired
+        mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
+    }
+    __syncwarp();
+
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    const bool have_acc = *reinterpret_cast<volatile uint32_t*>(&s_issued) != 0;
+    // thread = accumulator row m = (block, channel b); columns = channels a of P
+    const int blk = threadIdx.x >> 6, bl = threadIdx.x & 63;
+    const bool row_ok = have_acc && (blk == 0 || has1);
+    const int tap = (blk == 0 ? u0 : u1) / chunks;
+    const int b = (blk == 0 ? cb0 : cb1) + bl;
+    float* dwp = P.dw + (int64_t)b * P.dw_sb + (int64_t)tap * P.dw_st;
+#pragma unroll 1
+    for (int c = 0; c < NT; c += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dwp + (int64_t)(a0 + c + i) * P.dw_sa, v[i]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, NT);
+}
+
+static int wgrad_supported(const dmu_wgrad_params* p) {
+    if (!p || !p->p.ptr || !p->q.ptr || !p->dw) return 0;
+    if (!nhwc_bf16_ok(p->p) || !nhwc_bf16_ok(p->q)) return 0;
+    if (p->Ca % 64 != 0 || p->Cb % 64 != 0) return 0;
+    if (p->stride < 1 || p->stride > 2 || p->R * p->S > kMaxTaps) return 0;
+    if (encode_tiled_fn() == nullptr) return 0;
+    return 1;
+}
+
+static int wgrad_launch(const dmu_wgrad_params* p, cudaStream_t stream) {
+    Maps maps;
+    WgradArgs A;
+    memset(&A, 0, sizeof(A));
+    Box b = make_box(p->N, p->Hp, p->Wp, 64);
+    // the UMMA K step is 16 pixels: the box must hold a multiple of 16 pixels (tiny batches of tiny images: pad the image
+    // count of the box, TMA zero-fills the images past N)
+    if (b.BH * b.BW < 16) {
+        const int mult = 16 / (b.BH * b.BW);
+        b.BN = (b.BN + mult - 1) / mult * mult;
+        b.tiles_n = (p->N + b.BN - 1) / b.BN;
+    }
+    if (int rc = build_gather0(p->q, p->N, p->Hq, p->Wq, p->Cb, p->R, p->S, p->stride, p->pad, b, A.taps, &maps, A.map_h, A.map_w, "dmu_conv2d_wgrad/tc"))
+        return rc;
+    {
+        const uint64_t dims[4] = {(uint64_t)p->Ca, (uint64_t)p->Wp, (uint64_t)p->Hp, (uint64_t)p->N};
+        const uint64_t str[4] = {1, (uint64_t)p->p.sw, (uint64_t)p->p.sh, (uint64_t)p->p.sn};
+        const uint32_t box[4] = {64, (uint32_t)b.BW, (uint32_t)b.BH, (uint32_t)b.BN};
+        if (int rc = make_map_bf16(&maps.b, p->p.ptr, 4, dims, str, box, "dmu_conv2d_wgrad/tc P")) return rc;
+    }
+    const int NT = (p->Ca % 128 == 0) ? 128 : 64;
+    A.N = p->N; A.Hp = p->Hp; A.Wp = p->Wp; A.Ca = p->Ca; A.Cb = p->Cb; A.RS = p->R * p->S;
+    A.BN = b.BN; A.BH = b.BH; A.BW = b.BW; A.tiles_h = b.tiles_h; A.tiles_w = b.tiles_w;
+    A.tiles_total = b.tiles_n * b.tiles_h * b.tiles_w;
+    A.units = A.RS * (p->Cb / 64);
+    A.dw = p->dw; A.dw_sa = p->dw_sa; A.dw_sb = p->dw_sb; A.dw_st = p->dw_st;
+    const int mt = (A.units + 1) / 2, ntl = p->Ca / NT;
+    int splits = (2 * sm_count() + mt * ntl - 1) / (mt * ntl);
+    if (splits > A.tiles_total) splits = A.tiles_total;
+    if (splits < 1) splits = 1;
+    A.tiles_per_split = (A.tiles_total + splits - 1) / splits;
+    splits = (A.tiles_total + A.tiles_per_split - 1) / A.tiles_per_split;
+    dim3 grid(mt, ntl, splits);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<64>::kSmem);
+        cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<128>::kSmem);
+        attr_done = true;
+    }
+    if (NT == 64) wgrad_tc_kernel<64><<<grid, 128, WgradCfg<64>::kSmem, stream>>>(maps, A);
+    else wgrad_tc_kernel<128><<<grid, 128, WgradCfg<128>::kSmem, stream>>>(maps, A);
+    if (int rc = check_launch("dmu_conv2d_wgrad/tc")) return rc;
+    if (p->dbias) return dmu_colsum(&p->p, p->N, p->Hp, p->Wp, p->Ca, nullptr, 0, p->dbias, 1.0f, (dmu_stream_t)stream);
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace dmu
 
 using namespace dmu;
 
 extern "C" {
-int dmu_conv2d_tc_supported(const dmu_conv_params*) { return 0; }
-int dmu_conv2d_tc(const dmu_conv_params*, dmu_stream_t) { return fail("dmu_conv2d_tc: not built"); }
-int dmu_wgrad_tc_supported(const dmu_wgrad_params*) { return 0; }
-int dmu_wgrad_tc(const dmu_wgrad_params*, dmu_stream_t) { return fail("dmu_wgrad_tc: not built"); }
+int dmu_conv2d_tc_supported(const dmu_conv_params* p) { return tc::conv_supported(p); }
+int dmu_conv2d_tc(const dmu_conv_params* p, dmu_stream_t stream) { return tc::conv_launch(p, as_stream(stream)); }
+int dmu_wgrad_tc_supported(const dmu_wgrad_params* p) { return tc::wgrad_supported(p); }
+int dmu_wgrad_tc(const dmu_wgrad_params* p, dmu_stream_t stream) { return tc::wgrad_launch(p, as_stream(stream)); }
 }

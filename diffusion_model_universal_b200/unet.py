@@ -12,7 +12,8 @@ Data layout in HBM:
     ``torch.cat`` of the up path never happens — producers write straight into
     channel slices of the consumer's buffer (row pitch != C);
   * parameters: one flat fp32 arena (the nn.Parameters are views into it),
-    conv filters additionally repacked to [O][R][S][I] in the compute dtype;
+    conv filters additionally repacked to [O][R][S][I] (fprop) and [I][R][S][O]
+    (dgrad) in the compute dtype;
   * gradients: flat fp32 arena with the same offsets (``param.grad`` views).
 """
 
@@ -288,13 +289,24 @@ class Engine:
             if p.dim() == 4:
                 self.wc_off[k] = wc_total
                 wc_total += (p.numel() + 7) // 8 * 8
-        self.wcache = torch.zeros(max(wc_total, 8), device=device, dtype=self.tdtype)
+        # two derived copies per filter: [O][R][S][I] for fprop and [I][R][S][O] for dgrad, so that the contraction axis is
+        # contiguous in both directions (what the TMA/UMMA K-major operand needs); second half of the cache = dgrad copies
+        self.wc_half = max(wc_total, 8)
+        self.wcache = torch.zeros(2 * self.wc_half, device=device, dtype=self.tdtype)
         max_numel = 1
         for k, off in self.wc_off.items():
             p = named[k]
-            is_t = k.endswith("upsample.weight")
-            O, I = (p.shape[1], p.shape[0]) if is_t else (p.shape[0], p.shape[1])
-            descs.append(RepackDesc(p.data_ptr(), self.wcache.data_ptr() + off * self.esize, O, I, p.shape[2], p.shape[3], 1 if is_t else 0, self.code))
+            is_t = k.endswith("upsample.weight")    # ConvTranspose2d stores IOHW
+            a, b = p.shape[0], p.shape[1]
+            RS = (p.shape[2], p.shape[3])
+            fwd = self.wcache.data_ptr() + off * self.esize
+            bwd = self.wcache.data_ptr() + (self.wc_half + off) * self.esize
+            if is_t:
+                descs.append(RepackDesc(p.data_ptr(), fwd, b, a, RS[0], RS[1], 1, self.code))   # [O][R][S][I]
+                descs.append(RepackDesc(p.data_ptr(), bwd, a, b, RS[0], RS[1], 0, self.code))   # [I][R][S][O]
+            else:
+                descs.append(RepackDesc(p.data_ptr(), fwd, a, b, RS[0], RS[1], 0, self.code))   # [O][R][S][I]
+                descs.append(RepackDesc(p.data_ptr(), bwd, b, a, RS[0], RS[1], 1, self.code))   # [I][R][S][O]
             max_numel = max(max_numel, p.numel())
         arr = (RepackDesc * len(descs))(*descs)
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -323,8 +335,11 @@ class Engine:
     def gaddr(self, name):
         return self.gflat.data_ptr() + self.offs[name][0] * 4
 
-    def waddr(self, name):  # repacked filter
+    def waddr(self, name):  # repacked filter, fprop layout [O][R][S][I]
         return self.wcache.data_ptr() + self.wc_off[name] * self.esize
+
+    def waddr_t(self, name):  # repacked filter, dgrad layout [I][R][S][O]
+        return self.wcache.data_ptr() + (self.wc_half + self.wc_off[name]) * self.esize
 
     def repack(self, stream):
         ops.LAUNCHES += 1
@@ -527,7 +542,7 @@ class _PlanBuilder:
         dy = y.grad
         if need_dx:
             # dx[n,hi,wi,ci] = sum dy[n,(hi+pad-r)/s,..,co] w[co][r][s][ci]
-            self.conv(self.plan.bwd, dy.t4(), dx.t4(), self.e.waddr(wname), (1, R * R * Ci, Ci), self.code,
+            self.conv(self.plan.bwd, dy.t4(), dx.t4(), self.e.waddr_t(wname), (R * R * Co, 1, Co), self.code,
                       (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad), gather=1)
         self.wgrad(dy.t4(), x.t4(), self.gp(wname), (Ci * R * R, R * R, 1), self.gp(bname),
                    (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad))
@@ -735,7 +750,7 @@ class _PlanBuilder:
                 def up_bwd(y=y, u=u, pfx=pfx, co=co):
                     du = u.grad
                     # dgrad of a transposed conv is a strided conv over du
-                    self.conv(plan.bwd, du.t4(), y.grad.t4(), e.waddr(pfx + "upsample.weight"), (1, 16 * co, co), self.code,
+                    self.conv(plan.bwd, du.t4(), y.grad.t4(), e.waddr_t(pfx + "upsample.weight"), (16 * co, 1, co), self.code,
                               (N, u.H, u.W, co, y.H, y.W, co), (4, 4, 2, 1), gather=0)
                     y.grad_written = True
                     # dW[ci][co][r][s] (IOHW) += x[.., ci] * du[gathered, co]

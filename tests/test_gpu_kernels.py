@@ -37,10 +37,13 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _repack(w, transposed, dtype):
-    """OIHW (or IOHW for ConvTranspose2d) -> [O][R][S][I] via the library's own repack kernel."""
+def _repack(w, transposed, dtype, dgrad=False):
+    """OIHW (or IOHW for ConvTranspose2d) -> [O][R][S][I] via the library's own repack kernel.
+    dgrad=True gives the layout of the input-gradient contraction instead: [I][R][S][O] (rows = original input channels)."""
     ops, _abi = _mods()
     w = w.contiguous()
+    if dgrad:   # the same kernel with the roles of the two channel axes exchanged
+        transposed = not transposed
     O, I = (w.shape[1], w.shape[0]) if transposed else (w.shape[0], w.shape[1])
     dst = torch.empty(O * w.shape[2] * w.shape[3] * I, device=w.device, dtype=dtype)
     d = _abi.RepackDesc(w.data_ptr(), dst.data_ptr(), O, I, w.shape[2], w.shape[3], 1 if transposed else 0, ops.dtype_code(dst))
@@ -67,9 +70,28 @@ CONV_CASES = [
 ]
 
 
+TC_CASES = [c for c in CONV_CASES if c[3] % 64 == 0 and c[4] % 64 == 0] + [
+    (128, 1, 1, 256, 256, 3, 1, 1, "conv"),   # bottleneck at the bench batch: 8 of 9 taps are entirely padding
+    (16, 32, 32, 64, 64, 3, 1, 1, "conv"),    # several pixel tiles per image, several images
+    (9, 8, 8, 128, 256, 3, 1, 1, "conv"),     # batch not a multiple of the images-per-box
+    (8, 4, 4, 128, 128, 4, 2, 1, "convT"),
+    (4, 16, 16, 128, 64, 1, 1, 0, "conv"),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05(case):
+    """The tcgen05/TMA implicit-GEMM kernels (impl=2) against ATen on bf16-rounded operands."""
+    _conv_case(case, torch.bfloat16, 2)
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_fprop_dgrad_wgrad(case, dtype):
+    _conv_case(case, dtype, 1)
+
+
+def _conv_case(case, dtype, impl):
     ops, _abi = _mods()
     from diffusion_model_universal_b200._abi import ConvParams, WgradParams
     N, H, W, Ci, Co, R, stride, pad, kind = case
@@ -94,7 +116,7 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
     code = ops.dtype_code(xh)
     p = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(y_full, 8, Co), ops.t4_nhwc(res_full, 16, Co), wk.data_ptr(), R * R * Ci, 1, Ci,
                    bias.data_ptr(), temb.data_ptr() + 4 * 4, Co + 8, N, H, W, Ci, Ho, Wo, Co, R, R, stride, pad,
-                   0 if kind == "conv" else 1, code, 1, 0)
+                   0 if kind == "conv" else 1, code, impl, 0)
     ops.conv2d_raw(p)
     if kind == "conv":
         ref = F.conv2d(xq, wq, bias, stride=stride, padding=pad)
@@ -110,8 +132,13 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
     dyh = ops.nchw_to_nhwc(dy, dtype)
     dyq = dyh.float().permute(0, 3, 1, 2)
     dx = torch.empty(N, H, W, Ci, device=dev, dtype=dtype)
-    p2 = ConvParams(ops.t4_nhwc(dyh), ops.t4_nhwc(dx), _null(), wk.data_ptr(), 1, R * R * Ci, Ci, None, None, 0,
-                    N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1 if kind == "conv" else 0, code, 1, 0)
+    if impl == 2:   # tensor-core path contracts over a K-contiguous filter: [Ci][R][S][Co]
+        wkt = _repack(w, kind == "convT", dtype, dgrad=True)
+        p2 = ConvParams(ops.t4_nhwc(dyh), ops.t4_nhwc(dx), _null(), wkt.data_ptr(), R * R * Co, 1, Co, None, None, 0,
+                        N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1 if kind == "conv" else 0, code, impl, 0)
+    else:
+        p2 = ConvParams(ops.t4_nhwc(dyh), ops.t4_nhwc(dx), _null(), wk.data_ptr(), 1, R * R * Ci, Ci, None, None, 0,
+                        N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1 if kind == "conv" else 0, code, impl, 0)
     ops.conv2d_raw(p2)
     if kind == "conv":
         dref = torch.nn.grad.conv2d_input((N, Ci, H, W), wq, dyq, stride=stride, padding=pad)
@@ -124,11 +151,11 @@ def test_conv_fprop_dgrad_wgrad(case, dtype):
     db = torch.ones(Co, device=dev)
     if kind == "conv":
         p3 = WgradParams(ops.t4_nhwc(dyh), ops.t4_nhwc(xh), dw.data_ptr(), Ci * R * R, R * R, 1, db.data_ptr(),
-                         N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1)
+                         N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, impl)
         wref = torch.nn.grad.conv2d_weight(xq, w.shape, dyq, stride=stride, padding=pad)
     else:
         p3 = WgradParams(ops.t4_nhwc(xh), ops.t4_nhwc(dyh), dw.data_ptr(), Co * R * R, R * R, 1, None,
-                         N, H, W, Ci, Ho, Wo, Co, R, R, stride, pad, 1)
+                         N, H, W, Ci, Ho, Wo, Co, R, R, stride, pad, impl)
         wref = torch.nn.grad.conv2d_weight(dyq, (Ci, Co, R, R), xq, stride=stride, padding=pad)
     ops.wgrad_raw(p3)
     assert rel_l2(dw - 1, wref) < 5e-5, "wgrad"
