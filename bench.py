@@ -268,9 +268,7 @@ def run_ours(args):
             eps = model.forward(x, t)          # builds/uses the train plan, leaves it busy
         plan = eps.grad_fn.plan
         dout = torch.randn_like(eps)
-        plan.head_dgrad.x.ptr = dout.data_ptr()
-        plan.head_wgrad.p.ptr = dout.data_ptr()
-        plan.stem_wgrad.q.ptr = x.data_ptr()
+        plan.dout.copy_(dout)
         prof = profile_plan(eng, plan, x, t, dout)
         plan.busy = False
         pk = peaks()

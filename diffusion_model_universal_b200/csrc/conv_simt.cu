@@ -242,6 +242,72 @@ __global__ void __launch_bounds__(128) conv_small_n_kernel(dmu_conv_params P) {
     }
 }
 
+
+// Skinny GEMM with split-K for the Linear layers whose M (batch rows) is too small to fill the chip with 128x64 tiles
+// (time-embedding MLP, the 22-way time projection and their input gradients: M = batch, K up to 3328).
+//   y[m, j] (+)= bias[j] + res[m, j] + sum_k x[m, k] * w[j*w_sn + k*w_sk]      fp32 output, pre-zeroed, fp32 atomics
+constexpr int LM = 32, LN = 64, LK = 32;
+__global__ void __launch_bounds__(128) linear_splitk_kernel(dmu_conv_params P, int k_per_split) {
+    __shared__ float As[LK][LM + 1];
+    __shared__ __align__(16) float Bs[LK][LN + 4];
+    const int tid = threadIdx.x;
+    const int M = P.N, K = P.Ck;
+    const int m_base = blockIdx.x * LM, j_base = blockIdx.y * LN;
+    const int k_lo = blockIdx.z * k_per_split, k_hi = min(K, k_lo + k_per_split);
+    const int ty = tid >> 4, tx = tid & 15;   // 8 x 16 threads, 4 rows x 4 cols each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const bool w_kcontig = P.w_sk == 1;
+    for (int k0 = k_lo; k0 < k_hi; k0 += LK) {
+        // A tile: LM rows x LK k (k fastest across threads: x rows are k-contiguous)
+        for (int i = tid; i < LM * LK; i += 128) {
+            const int kk = i % LK, mm = i / LK;
+            const int m = m_base + mm, k = k0 + kk;
+            As[kk][mm] = (m < M && k < k_hi) ? ld_as_float(P.x.ptr, (int64_t)m * P.x.sn + (int64_t)k * P.x.sc, P.x.dtype) : 0.f;
+        }
+        // B tile: LK k x LN j, thread order along whichever axis of w is contiguous
+        for (int i = tid; i < LK * LN; i += 128) {
+            const int kk = w_kcontig ? i % LK : i / LN, jj = w_kcontig ? i / LK : i % LN;
+            const int j = j_base + jj, k = k0 + kk;
+            Bs[kk][jj] = (j < P.Cj && k < k_hi) ? ld_as_float(P.w, (int64_t)j * P.w_sn + (int64_t)k * P.w_sk, P.w_dtype) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < LK; ++kk) {
+            float a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* y = reinterpret_cast<float*>(P.y.ptr);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m_base + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jc = j_base + tx * 4 + j;
+            if (jc >= P.Cj) continue;
+            float v = acc[i][j];
+            if (blockIdx.z == 0) {
+                if (P.bias) v += P.bias[jc];
+                if (P.res.ptr) v += ld_as_float(P.res.ptr, (int64_t)m * P.res.sn + (int64_t)jc * P.res.sc, P.res.dtype);
+            }
+            atomicAdd(&y[(int64_t)m * P.y.sn + jc], v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ wgrad
 // out[a][rs][b] += sum_pixels P[pix, a] * Q[gather(pix, rs), b]; split over pixel ranges (blockIdx.z).
 constexpr int WK = 16;  // pixels per step
@@ -382,6 +448,20 @@ int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream) {
     if (p->impl == 0 && dmu_conv2d_tc_supported(p)) return dmu_conv2d_tc(p, stream);
     const int M = p->N * p->Ho * p->Wo;
     const int K = p->R * p->S * p->Ck;
+    // Linear layer with few rows and a long contraction: split K across CTAs (fp32 rows, zeroed then accumulated)
+    if (p->R == 1 && p->S == 1 && p->stride == 1 && p->pad == 0 && p->Hi == 1 && p->Wi == 1 && p->Ho == 1 && p->Wo == 1 && !p->temb &&
+        p->y.dtype == DMU_F32 && p->y.sc == 1 && p->y.sn == p->Cj && p->y.ptr != p->res.ptr &&
+        ((M + BM - 1) / BM) * ((p->Cj + BN - 1) / BN) < sm_count() / 2 && (int64_t)M * p->Cj * K >= (1 << 18)) {
+        dim3 grid((M + LM - 1) / LM, (p->Cj + LN - 1) / LN, 1);
+        int splits = (2 * sm_count() + grid.x * grid.y - 1) / (grid.x * grid.y);
+        int per = (K + splits - 1) / splits;
+        per = ((per + LK - 1) / LK) * LK;
+        if (per < 2 * LK) per = 2 * LK;
+        grid.z = (K + per - 1) / per;
+        if (cudaMemsetAsync(p->y.ptr, 0, (size_t)M * p->Cj * sizeof(float), as_stream(stream)) != cudaSuccess) return check_launch("dmu_conv2d/linear zero");
+        linear_splitk_kernel<<<grid, 128, 0, as_stream(stream)>>>(*p, per);
+        return check_launch("dmu_conv2d/linear_splitk");
+    }
     if (p->Cj <= 4 && K <= kSmallMaxK) {
         const size_t smem = (size_t)K * 4 * sizeof(float);
         if (smem > 48 * 1024) cudaFuncSetAttribute(conv_small_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -279,7 +279,7 @@ static int conv_supported(const dmu_conv_params* p) {
     if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y)) return 0;
     if (p->res.ptr && !nhwc_bf16_ok(p->res)) return 0;
     if (p->Ck % 64 != 0 || p->Cj % 64 != 0) return 0;
-    if (p->w_sk != 1 || p->w_st != p->Ck || p->w_sn != (int64_t)p->R * p->S * p->Ck || !aligned16(p->w)) return 0;
+    if (p->w_sk != 1 || (p->R * p->S > 1 && p->w_st != p->Ck) || p->w_sn != (int64_t)p->R * p->S * p->Ck || !aligned16(p->w)) return 0;
     if (p->stride < 1 || p->stride > 2 || p->R * p->S > kMaxTaps) return 0;
     if (p->bias && !aligned16(p->bias)) return 0;
     if (p->temb && (!aligned16(p->temb) || p->temb_pitch % 4 != 0)) return 0;

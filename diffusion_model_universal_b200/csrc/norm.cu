@@ -30,31 +30,78 @@ __device__ __forceinline__ int64_t pix_off(const dmu_tensor4& t, int n, int p, i
     return (int64_t)n * t.sn + (int64_t)(p / W) * t.sh + (int64_t)(p % W) * t.sw;
 }
 
+// 16-byte raw vectors: loads are issued kUnroll at a time before any arithmetic so that each thread keeps several
+// independent 128-bit requests in flight (these passes are HBM-bound; one dependent load per iteration is latency-bound).
+template <typename T>
+__device__ __forceinline__ uint4 ld_raw(const T* p) { return *reinterpret_cast<const uint4*>(p); }
+template <typename T>
+__device__ __forceinline__ void unpack(const uint4& r, float* out) {
+    if constexpr (sizeof(T) == 4) {
+        out[0] = __uint_as_float(r.x); out[1] = __uint_as_float(r.y); out[2] = __uint_as_float(r.z); out[3] = __uint_as_float(r.w);
+    } else {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+            out[2 * i] = f.x; out[2 * i + 1] = f.y;
+        }
+    }
+}
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ float silu_f(float u) { return __fdividef(u, 1.f + __expf(-u)); }
+
+
+// Block-wide per-channel sum of per-thread partials WITHOUT shared-memory float atomics (those compile to a CAS spin loop
+// and serialise under same-address contention).  Every thread parks its kVec partials in s_red[lane][channel]
+// (lanes * C == 256 * kVec floats, whatever C is), then thread c adds the `lanes` rows of column c.
+template <int kVec>
+__device__ __forceinline__ void block_channel_sum(const RowMap& m, const float* a, float* s_red, float* s_out, int C) {
+    if (m.active) {
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) s_red[m.lane * C + m.v * kVec + i] = a[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int l = 0; l < m.lanes; ++l) t += s_red[l * C + c];
+        s_out[c] = t;
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------ stats
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(dmu_gn_params P) {
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s_sum[kMaxC], s_sq[kMaxC];
+    __shared__ float s_red[256 * kVec];
     const int n = blockIdx.y, HW = P.H * P.W, C = P.C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_sum[c] = 0.f; s_sq[c] = 0.f; }
-    __syncthreads();
     RowMap m(C, kVec);
     int p0, p1; chunk_range(HW, p0, p1);
+    float a[kVec], q[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { a[i] = 0.f; q[i] = 0.f; }
     if (m.active) {
-        float a[kVec], q[kVec];
+        const T* base = reinterpret_cast<const T*>(P.x.ptr) + m.v * kVec;
+        for (int p = p0 + m.lane; p < p1; p += m.lanes * kUnroll) {
+            uint4 r[kUnroll];
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) { a[i] = 0.f; q[i] = 0.f; }
-        const T* base = reinterpret_cast<const T*>(P.x.ptr);
-        for (int p = p0 + m.lane; p < p1; p += m.lanes) {
-            float v[kVec];
-            load_vec<T>(base + pix_off(P.x, n, p, P.W) + m.v * kVec, v);
+            for (int u = 0; u < kUnroll; ++u) {
+                const int pp = p + u * m.lanes;
+                r[u] = pp < p1 ? ld_raw<T>(base + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-            for (int i = 0; i < kVec; ++i) { a[i] += v[i]; q[i] += v[i] * v[i]; }
+            for (int u = 0; u < kUnroll; ++u) {
+                float v[kVec];
+                unpack<T>(r[u], v);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) { a[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+            }
         }
-#pragma unroll
-        for (int i = 0; i < kVec; ++i) { atomicAdd(&s_sum[m.v * kVec + i], a[i]); atomicAdd(&s_sq[m.v * kVec + i], q[i]); }
     }
-    __syncthreads();
+    block_channel_sum<kVec>(m, a, s_red, s_sum, C);
+    block_channel_sum<kVec>(m, q, s_red, s_sq, C);
     const int cpg = C / P.G;
     for (int g = threadIdx.x; g < P.G; g += blockDim.x) {
         float a = 0.f, q = 0.f;
@@ -92,67 +139,96 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(dmu_gn_params P) {
     RowMap m(P.C, kVec);
     if (!m.active) return;
     int p0, p1; chunk_range(HW, p0, p1);
-    const T* xb = reinterpret_cast<const T*>(P.x.ptr);
-    T* yb = reinterpret_cast<T*>(P.y.ptr);
-    float mu[kVec], sc[kVec], be[kVec];
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr) + m.v * kVec;
+    T* yb = reinterpret_cast<T*>(P.y.ptr) + m.v * kVec;
+    float sc[kVec], sh[kVec];   // u = x*sc + sh
 #pragma unroll
-    for (int i = 0; i < kVec; ++i) { mu[i] = s_mean[m.v * kVec + i]; sc[i] = s_scale[m.v * kVec + i]; be[i] = s_beta[m.v * kVec + i]; }
-    for (int p = p0 + m.lane; p < p1; p += m.lanes) {
-        float v[kVec];
-        load_vec<T>(xb + pix_off(P.x, n, p, P.W) + m.v * kVec, v);
+    for (int i = 0; i < kVec; ++i) {
+        sc[i] = s_scale[m.v * kVec + i];
+        sh[i] = s_beta[m.v * kVec + i] - s_mean[m.v * kVec + i] * sc[i];
+    }
+    for (int p = p0 + m.lane; p < p1; p += m.lanes * kUnroll) {
+        uint4 r[kUnroll];
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) {
-            float u = (v[i] - mu[i]) * sc[i] + be[i];
-            v[i] = P.silu ? u / (1.f + expf(-u)) : u;
+        for (int u = 0; u < kUnroll; ++u) {
+            const int pp = p + u * m.lanes;
+            if (pp < p1) r[u] = ld_raw<T>(xb + pix_off(P.x, n, pp, P.W));
         }
-        store_vec<T>(yb + pix_off(P.y, n, p, P.W) + m.v * kVec, v);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int pp = p + u * m.lanes;
+            if (pp >= p1) break;
+            float v[kVec];
+            unpack<T>(r[u], v);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) {
+                const float t = fmaf(v[i], sc[i], sh[i]);
+                v[i] = P.silu ? silu_f(t) : t;
+            }
+            store_vec<T>(yb + pix_off(P.y, n, pp, P.W), v);
+        }
     }
 }
 
 // du = dy * act'(u)
 __device__ __forceinline__ float act_grad(float u, float dy, int silu) {
     if (!silu) return dy;
-    const float s = 1.f / (1.f + expf(-u));
-    return dy * (s * (1.f + u * (1.f - s)));
+    const float s = __fdividef(1.f, 1.f + __expf(-u));
+    return dy * (s * fmaf(u, 1.f - s, 1.f));
 }
 
 // ------------------------------------------------------------------ bwd reduce
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(dmu_gn_params P) {
     constexpr int kVec = Elem<T>::kVec;
+    constexpr int kU = 2;
     __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
     __shared__ float s_a[kMaxC], s_b[kMaxC];
+    __shared__ float s_red[256 * kVec];
     const int n = blockIdx.y, HW = P.H * P.W, C = P.C;
     stage_affine(P, n, s_mean, s_scale, s_beta, s_rstd);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_a[c] = 0.f; s_b[c] = 0.f; }
     __syncthreads();
     RowMap m(C, kVec);
     int p0, p1; chunk_range(HW, p0, p1);
+    float a[kVec], b[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { a[i] = 0.f; b[i] = 0.f; }
     if (m.active) {
-        float a[kVec], b[kVec], mu[kVec], sc[kVec], be[kVec], rs[kVec];
+        float mu[kVec], sc[kVec], be[kVec];
 #pragma unroll
         for (int i = 0; i < kVec; ++i) {
-            a[i] = 0.f; b[i] = 0.f;
-            mu[i] = s_mean[m.v * kVec + i]; sc[i] = s_scale[m.v * kVec + i]; be[i] = s_beta[m.v * kVec + i]; rs[i] = s_rstd[m.v * kVec + i];
+            mu[i] = s_mean[m.v * kVec + i]; sc[i] = s_scale[m.v * kVec + i]; be[i] = s_beta[m.v * kVec + i];
         }
-        const T* xb = reinterpret_cast<const T*>(P.x.ptr);
-        const T* dyb = reinterpret_cast<const T*>(P.y.ptr);
-        for (int p = p0 + m.lane; p < p1; p += m.lanes) {
-            float xv[kVec], dv[kVec];
-            load_vec<T>(xb + pix_off(P.x, n, p, P.W) + m.v * kVec, xv);
-            load_vec<T>(dyb + pix_off(P.y, n, p, P.W) + m.v * kVec, dv);
+        const T* xb = reinterpret_cast<const T*>(P.x.ptr) + m.v * kVec;
+        const T* dyb = reinterpret_cast<const T*>(P.y.ptr) + m.v * kVec;
+        for (int p = p0 + m.lane; p < p1; p += m.lanes * kU) {
+            uint4 rx[kU], rd[kU];
 #pragma unroll
-            for (int i = 0; i < kVec; ++i) {
-                const float d = xv[i] - mu[i];
-                const float du = act_grad(d * sc[i] + be[i], dv[i], P.silu);
-                a[i] += du;
-                b[i] += du * (d * rs[i]);
+            for (int u = 0; u < kU; ++u) {
+                const int pp = p + u * m.lanes;
+                const bool ok = pp < p1;
+                rx[u] = ok ? ld_raw<T>(xb + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
+                rd[u] = ok ? ld_raw<T>(dyb + pix_off(P.y, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);   // dy = 0 -> no contribution
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                float xv[kVec], dv[kVec];
+                unpack<T>(rx[u], xv);
+                unpack<T>(rd[u], dv);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) {
+                    const float d = xv[i] - mu[i];
+                    const float du = act_grad(fmaf(d, sc[i], be[i]), dv[i], P.silu);
+                    a[i] += du;
+                    b[i] = fmaf(du, d, b[i]);     // sum du*(x-mean); scaled by rstd below
+                }
             }
         }
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) { atomicAdd(&s_a[m.v * kVec + i], a[i]); atomicAdd(&s_b[m.v * kVec + i], b[i]); }
+        for (int i = 0; i < kVec; ++i) b[i] *= s_rstd[m.v * kVec + i];
     }
-    __syncthreads();
+    block_channel_sum<kVec>(m, a, s_red, s_a, C);
+    block_channel_sum<kVec>(m, b, s_red, s_b, C);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         atomicAdd(&P.red[((int64_t)n * C + c) * 2 + 0], s_a[c]);
         atomicAdd(&P.red[((int64_t)n * C + c) * 2 + 1], s_b[c]);
@@ -165,6 +241,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(dmu_gn_params P) {
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dmu_gn_params P) {
     constexpr int kVec = Elem<T>::kVec;
+    constexpr int kU = 2;
     __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
     __shared__ float s_A[kMaxC], s_B[kMaxC];  // per channel: group sums / cnt
     const int n = blockIdx.y, HW = P.H * P.W, C = P.C;
@@ -186,73 +263,99 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dmu_gn_params P) {
     RowMap m(C, kVec);
     if (!m.active) return;
     int p0, p1; chunk_range(HW, p0, p1);
-    float mu[kVec], sc[kVec], be[kVec], rs[kVec], A[kVec], B[kVec];
+    // dx = du*sc - rstd*A - (x-mean)*rstd^2*B  =  du*sc + x*k1 + k0
+    float mu[kVec], sc[kVec], be[kVec], k0[kVec], k1[kVec];
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
         const int c = m.v * kVec + i;
-        mu[i] = s_mean[c]; sc[i] = s_scale[c]; be[i] = s_beta[c]; rs[i] = s_rstd[c]; A[i] = s_A[c]; B[i] = s_B[c];
+        const float rs = s_rstd[c];
+        mu[i] = s_mean[c]; sc[i] = s_scale[c]; be[i] = s_beta[c];
+        k1[i] = -rs * rs * s_B[c];
+        k0[i] = -rs * s_A[c] - mu[i] * k1[i];
     }
-    const T* xb = reinterpret_cast<const T*>(P.x.ptr);
-    const T* dyb = reinterpret_cast<const T*>(P.y.ptr);
-    T* dxb = reinterpret_cast<T*>(P.dx.ptr);
-    const T* a0 = reinterpret_cast<const T*>(P.add0.ptr);
-    const T* a1 = reinterpret_cast<const T*>(P.add1.ptr);
-    for (int p = p0 + m.lane; p < p1; p += m.lanes) {
-        float xv[kVec], dv[kVec], o[kVec];
-        load_vec<T>(xb + pix_off(P.x, n, p, P.W) + m.v * kVec, xv);
-        load_vec<T>(dyb + pix_off(P.y, n, p, P.W) + m.v * kVec, dv);
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr) + m.v * kVec;
+    const T* dyb = reinterpret_cast<const T*>(P.y.ptr) + m.v * kVec;
+    T* dxb = reinterpret_cast<T*>(P.dx.ptr) + m.v * kVec;
+    const T* a0 = P.add0.ptr ? reinterpret_cast<const T*>(P.add0.ptr) + m.v * kVec : nullptr;
+    const T* a1 = P.add1.ptr ? reinterpret_cast<const T*>(P.add1.ptr) + m.v * kVec : nullptr;
+    for (int p = p0 + m.lane; p < p1; p += m.lanes * kU) {
+        uint4 rx[kU], rd[kU], r0[kU], r1[kU];
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) {
-            const float d = xv[i] - mu[i];
-            const float xhat = d * rs[i];
-            const float du = act_grad(d * sc[i] + be[i], dv[i], P.silu);
-            // sc = rstd*gamma
-            o[i] = du * sc[i] - rs[i] * (A[i] + xhat * B[i]);
+        for (int u = 0; u < kU; ++u) {
+            const int pp = p + u * m.lanes;
+            if (pp < p1) {
+                rx[u] = ld_raw<T>(xb + pix_off(P.x, n, pp, P.W));
+                rd[u] = ld_raw<T>(dyb + pix_off(P.y, n, pp, P.W));
+                if (a0) r0[u] = ld_raw<T>(a0 + pix_off(P.add0, n, pp, P.W));
+                if (a1) r1[u] = ld_raw<T>(a1 + pix_off(P.add1, n, pp, P.W));
+            }
         }
-        if (a0) {
-            float t[kVec];
-            load_vec<T>(a0 + pix_off(P.add0, n, p, P.W) + m.v * kVec, t);
 #pragma unroll
-            for (int i = 0; i < kVec; ++i) o[i] += t[i];
-        }
-        if (a1) {
-            float t[kVec];
-            load_vec<T>(a1 + pix_off(P.add1, n, p, P.W) + m.v * kVec, t);
+        for (int u = 0; u < kU; ++u) {
+            const int pp = p + u * m.lanes;
+            if (pp >= p1) break;
+            float xv[kVec], dv[kVec], o[kVec];
+            unpack<T>(rx[u], xv);
+            unpack<T>(rd[u], dv);
 #pragma unroll
-            for (int i = 0; i < kVec; ++i) o[i] += t[i];
+            for (int i = 0; i < kVec; ++i) {
+                const float du = act_grad(fmaf(xv[i] - mu[i], sc[i], be[i]), dv[i], P.silu);
+                o[i] = fmaf(du, sc[i], fmaf(xv[i], k1[i], k0[i]));
+            }
+            if (a0) {
+                float t[kVec];
+                unpack<T>(r0[u], t);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) o[i] += t[i];
+            }
+            if (a1) {
+                float t[kVec];
+                unpack<T>(r1[u], t);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) o[i] += t[i];
+            }
+            store_vec<T>(dxb + pix_off(P.dx, n, pp, P.W), o);
         }
-        store_vec<T>(dxb + pix_off(P.dx, n, p, P.W) + m.v * kVec, o);
     }
 }
 
 // ------------------------------------------------------------------ column sums
+// grid (pixel chunks, N): per-CTA partial sums, then atomics (out_nc / out_c must hold the running value: zero-initialised
+// by the caller when a fresh sum is wanted).
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(dmu_tensor4 X, int H, int W, int C, float* out_nc, int64_t pitch,
                                                      float* out_c, float scale) {
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s[kMaxC];
+    __shared__ float s_red[256 * kVec];
     const int n = blockIdx.y, HW = H * W;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) s[c] = 0.f;
-    __syncthreads();
     RowMap m(C, kVec);
+    int p0, p1; chunk_range(HW, p0, p1);
+    float a[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) a[i] = 0.f;
     if (m.active) {
-        float a[kVec];
+        const T* xb = reinterpret_cast<const T*>(X.ptr) + m.v * kVec;
+        for (int p = p0 + m.lane; p < p1; p += m.lanes * kUnroll) {
+            uint4 r[kUnroll];
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) a[i] = 0.f;
-        const T* xb = reinterpret_cast<const T*>(X.ptr);
-        for (int p = m.lane; p < HW; p += m.lanes) {
-            float v[kVec];
-            load_vec<T>(xb + pix_off(X, n, p, W) + m.v * kVec, v);
+            for (int u = 0; u < kUnroll; ++u) {
+                const int pp = p + u * m.lanes;
+                r[u] = pp < p1 ? ld_raw<T>(xb + pix_off(X, n, pp, W)) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-            for (int i = 0; i < kVec; ++i) a[i] += v[i];
+            for (int u = 0; u < kUnroll; ++u) {
+                float v[kVec];
+                unpack<T>(r[u], v);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) a[i] += v[i];
+            }
         }
-#pragma unroll
-        for (int i = 0; i < kVec; ++i) atomicAdd(&s[m.v * kVec + i], a[i]);
     }
-    __syncthreads();
+    block_channel_sum<kVec>(m, a, s_red, s, C);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float v = s[c] * scale;
-        if (out_nc) out_nc[(int64_t)n * pitch + c] = v;
+        if (out_nc) atomicAdd(&out_nc[(int64_t)n * pitch + c], v);
         if (out_c) atomicAdd(&out_c[c], v);
     }
 }
@@ -393,7 +496,7 @@ static int gn_check(const dmu_gn_params* p, const char* who, bool need_y, bool n
 static dim3 gn_grid(int N, int HW, int C, int vec) {
     const int lanes = 256 / (C / vec);
     int chunks = (HW + lanes * 4 - 1) / (lanes * 4);  // >= 4 pixels per lane
-    const int want = (sm_count() * 4 + N - 1) / N;
+    const int want = (sm_count() * 8 + N - 1) / N;
     if (chunks > want) chunks = want;
     if (chunks < 1) chunks = 1;
     return dim3(chunks, N);
@@ -443,7 +546,13 @@ int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C,
     DMU_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C <= kMaxC, "dmu_colsum: bad dims");
     const int vec = x->dtype == DMU_BF16 ? 8 : 4;
     DMU_REQUIRE(x->sc == 1 && C % vec == 0 && x->sw % vec == 0 && x->sn % vec == 0 && C / vec <= 256, "dmu_colsum: needs NHWC, C multiple of %d", vec);
-    DISPATCH_T(x->dtype, colsum_kernel, dim3(1, N), 256, as_stream(stream), *x, H, W, C, out_nc, pitch, out_c, scale);
+    dmu_tensor4 t = *x;
+    int Nn = N, Hh = H, Ww = W;
+    if (!out_nc && t.sh == (int64_t)W * t.sw && t.sn == (int64_t)H * t.sh) {   // only the total is wanted: one flat pixel range
+        Ww = N * H * W; Hh = 1; Nn = 1;
+        t.sh = t.sn = (int64_t)Ww * t.sw;
+    }
+    DISPATCH_T(t.dtype, colsum_kernel, gn_grid(Nn, Hh * Ww, C, vec), 256, as_stream(stream), t, Hh, Ww, C, out_nc, pitch, out_c, scale);
     return check_launch("dmu_colsum");
 }
 

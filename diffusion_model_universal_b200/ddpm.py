@@ -29,6 +29,7 @@ class DDPM(BaseDiffusion):
         self.model = UNet(in_channels=config.get("in_channels", 3), model_channels=config.get("model_channels", 64),
                           out_channels=config.get("in_channels", 3), precision=config.get("precision", "fp32"))
         self.loss_fn = DiffusionLoss(loss_type=config.get("loss_type", "mse"), loss_config=config.get("loss_config", {}))
+        self.loss_fn.max_t = self.num_timesteps    # t < num_timesteps: lets the 'snr' time weights stay on the device
 
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         return self.model(x, t)

@@ -51,12 +51,39 @@ class DiffusionLoss:
             return (0.0, 0.0, float(self.huber_weight))
         raise ValueError(f"Unsupported single loss type: {self.loss_type}")  # 'hybrid' without use_hybrid, losses.py:113-114
 
+    max_t = None   # upper bound on the timesteps (set by the owning model): enables the host-sync-free 'snr' weights
+
+    def _snr_alphas_cumprod(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """losses.py:150-157: ``cumprod(1 - linspace(1e-4, 2e-2, t_max + 1))[t]``.  The reference reads ``t_max`` back to the
+        host (``timesteps.max().item()``) to size the table; when an upper bound is known the same table is built for the
+        bound with ``t_max`` kept on the device (linspace's own two-sided formula), so the training loop never syncs."""
+        dev = timesteps.device
+        if self.max_t is None:
+            betas = torch.linspace(1e-4, 2e-2, timesteps.max().item() + 1, device=dev)
+            return torch.cumprod(1 - betas, dim=0).index_select(0, timesteps)
+        tmax = timesteps.max()
+        i = torch.arange(int(self.max_t), device=dev)
+        start = torch.tensor(1e-4, device=dev, dtype=torch.float32)
+        end = torch.tensor(2e-2, device=dev, dtype=torch.float32)
+        step = (end - start) / tmax.clamp(min=1).to(torch.float32)
+        steps = tmax + 1
+        lo = start + step * i.to(torch.float32)
+        hi = end - step * (steps - 1 - i).to(torch.float32)
+        betas = torch.where(i < steps // 2, lo, hi)
+        betas = torch.where(steps == 1, start, betas)        # linspace(a, b, 1) == [a]
+        return torch.cumprod(1 - betas, dim=0).index_select(0, timesteps)
+
+    def time_weights(self, timesteps: torch.Tensor) -> Optional[torch.Tensor]:
+        """The [B] weights this loss would apply for ``timesteps`` (None = unweighted)."""
+        if not self.use_time_weighting or timesteps is None:
+            return None
+        return self._get_time_weights(timesteps).float().contiguous()
+
     def _get_time_weights(self, timesteps: torch.Tensor) -> torch.Tensor:
         """losses.py:133-181, returned flat [B]."""
         lo, hi = self.time_weight_params["min_weight"], self.time_weight_params["max_weight"]
         if self.time_weight_type == "snr":
-            betas = torch.linspace(1e-4, 2e-2, timesteps.max().item() + 1, device=timesteps.device)
-            acp = torch.cumprod(1 - betas, dim=0).index_select(0, timesteps)
+            acp = self._snr_alphas_cumprod(timesteps)
             snr = acp / (1 - acp)
             w = (snr / snr.max()).clamp(min=1e-5)
         elif self.time_weight_type == "linear":
@@ -68,9 +95,7 @@ class DiffusionLoss:
         return lo + (hi - lo) * ((w - w.min()) / (w.max() - w.min() + 1e-5))
 
     def __call__(self, pred: torch.Tensor, target: torch.Tensor, timesteps: Optional[torch.Tensor] = None) -> torch.Tensor:
-        w = None
-        if self.use_time_weighting and timesteps is not None:
-            w = self._get_time_weights(timesteps).float().contiguous()
+        w = self.time_weights(timesteps)
         wm, wl, wh = self.coefficients()
         return _LossFn.apply(pred, target, w, wm, wl, wh, float(self.huber_delta))
 

@@ -15,6 +15,8 @@ from typing import Optional
 
 import torch
 
+from . import ops
+from .losses import DiffusionLoss
 from .optim import FusedAdamEMA
 from .parallel import GradAllReducer
 
@@ -37,11 +39,32 @@ class TrainStep:
                 self._stage = torch.empty(images.shape, device=dev, dtype=torch.float32)
             self._stage.copy_(images, non_blocking=True)
             images = self._stage
-        loss = self.model.loss_function(images)
-        loss.backward()
+        m = self.model
+        if isinstance(getattr(m, "loss_fn", None), DiffusionLoss) and hasattr(m, "alphas_cumprod"):
+            loss = self._ddpm_step(images)
+        else:   # generic route through autograd (score / energy variants)
+            loss = m.loss_function(images)
+            loss.backward()
+            for p in m.parameters():      # the arena holds this step's gradients; views must not accumulate into the next
+                p.grad = None
         scale = self.reducer.allreduce()
         self.opt.step(grad_scale=scale)
-        # the arena holds this step's gradients; param.grad views must not accumulate into the next step
-        for p in self.model.parameters():
-            p.grad = None
         return loss.detach()
+
+    def _ddpm_step(self, images: torch.Tensor) -> torch.Tensor:
+        """``DDPM.loss_function`` + ``backward`` (models/ddpm.py:207-235) straight on the engine: same RNG calls in the same
+        order and the same launches, without the autograd graph (314 AccumulateGrad nodes cost more host time than the
+        GPU needs for the whole backward pass).  Gradients land in the engine's flat arena, which the optimizer reads."""
+        m = self.model
+        eng = m.model.engine
+        t = torch.randint(0, m.num_timesteps, (images.shape[0],), device=images.device)
+        noise = torch.randn_like(images)
+        w = m.loss_fn.time_weights(t)          # [B]-sized torch ops, issued before the forward so nothing waits on them later
+        xt = m._add_noise(images, t, noise)
+        eng.prepare(images.device)
+        plan = eng.get_plan(xt.shape, True)
+        eps = eng.run_forward(xt, t, plan)
+        wm, wl, wh = m.loss_fn.coefficients()
+        loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True)
+        eng.run_backward(plan, dpred)
+        return loss

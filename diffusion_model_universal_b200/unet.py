@@ -213,12 +213,13 @@ class Plan:
     def __init__(self):
         self.fwd, self.bwd = [], []
         self.arena = None       # torch uint8 tensor keeping all plan buffers alive
-        self.stem = None        # ConvParams whose x.ptr is patched per call
-        self.temb_in = None     # (op index in fwd) first-op args patched per call
-        self.head = None        # ConvParams whose y.ptr is patched per call
-        self.head_dgrad = None  # ConvParams whose x.ptr (dout) is patched
-        self.head_wgrad = None  # WgradParams whose p.ptr (dout) is patched
-        self.stem_wgrad = None  # WgradParams whose q.ptr (input x) is patched
+        # static I/O buffers: every pointer in the recorded launches is fixed, so a plan can be replayed as a CUDA graph
+        self.x_in = None        # fp32 [N,Cin,H,W] (NCHW) network input, read by the stem conv (and its wgrad)
+        self.t_in = None        # fp32 [N] timesteps (or sigmas)
+        self.out = None         # fp32 [N,Cout,H,W] written by the head conv
+        self.dout = None        # fp32 [N,Cout,H,W] upstream gradient (training plans)
+        self.graphs = {}        # "fwd"/"bwd" -> torch.cuda.CUDAGraph
+        self.runs = {}          # "fwd"/"bwd" -> eager executions so far (the first one is the warm-up before capture)
         self.busy = False       # activations saved for a pending backward
 
 
@@ -237,6 +238,7 @@ class Engine:
         self.plans = {}
         self.frozen = False     # weights known unchanged: skip the repack launch
         self.impl = 0           # conv implementation selector forwarded to the kernels (0 auto)
+        self.use_graphs = True  # replay recorded plans as CUDA graphs (second execution onwards)
         self._lib = None
 
     # ------------------------------------------------------------------ parameters
@@ -283,31 +285,39 @@ class Engine:
         self.flat, self.offs, self.total = flat, offs, total
         self.named = named
         self.gflat = torch.zeros(total, device=device, dtype=torch.float32)
-        # conv filter cache in the compute dtype, [O][R][S][I]
-        self.wc_off, wc_total, descs = {}, 0, []
+        # Derived filter caches in the compute dtype (refreshed by ONE repack launch per step).  Every conv filter twice:
+        # [O][R][S][I] for fprop and [I][R][S][O] for dgrad, so that the contraction axis is contiguous in both directions
+        # (what the TMA/UMMA K-major operand needs).  In bf16 mode the attention projections (q|k|v stacked, final) get
+        # the same treatment so that they run on the tensor-core path too.
+        entries = []   # (key, src tensor, rows, cols, R, S, is ConvTranspose2d)
         for k, p in named.items():
             if p.dim() == 4:
-                self.wc_off[k] = wc_total
-                wc_total += (p.numel() + 7) // 8 * 8
-        # two derived copies per filter: [O][R][S][I] for fprop and [I][R][S][O] for dgrad, so that the contraction axis is
-        # contiguous in both directions (what the TMA/UMMA K-major operand needs); second half of the cache = dgrad copies
-        self.wc_half = max(wc_total, 8)
+                entries.append((k, p, p.shape[0], p.shape[1], p.shape[2], p.shape[3], k.endswith("upsample.weight")))
+        if self.code == BF16:
+            for ap in self.attn_block_prefixes():
+                q = named[ap + "query_projection.weight"]
+                Cc = q.shape[0]
+                entries.append((ap + "qkv", q, 3 * Cc, Cc, 1, 1, False))          # q, k, v weights are adjacent in the arena
+                f = named[ap + "final_projection.weight"]
+                entries.append((ap + "final_projection.weight", f, Cc, Cc, 1, 1, False))
+        self.wc_off, wc_total, descs = {}, 0, []
+        for key, p, a, b, R, S, is_t in entries:
+            self.wc_off[key] = wc_total
+            wc_total += (a * b * R * S + 63) // 64 * 64
+        self.wc_half = max(wc_total, 64)
         self.wcache = torch.zeros(2 * self.wc_half, device=device, dtype=self.tdtype)
         max_numel = 1
-        for k, off in self.wc_off.items():
-            p = named[k]
-            is_t = k.endswith("upsample.weight")    # ConvTranspose2d stores IOHW
-            a, b = p.shape[0], p.shape[1]
-            RS = (p.shape[2], p.shape[3])
+        for key, p, a, b, R, S, is_t in entries:
+            off = self.wc_off[key]
             fwd = self.wcache.data_ptr() + off * self.esize
             bwd = self.wcache.data_ptr() + (self.wc_half + off) * self.esize
-            if is_t:
-                descs.append(RepackDesc(p.data_ptr(), fwd, b, a, RS[0], RS[1], 1, self.code))   # [O][R][S][I]
-                descs.append(RepackDesc(p.data_ptr(), bwd, a, b, RS[0], RS[1], 0, self.code))   # [I][R][S][O]
-            else:
-                descs.append(RepackDesc(p.data_ptr(), fwd, a, b, RS[0], RS[1], 0, self.code))   # [O][R][S][I]
-                descs.append(RepackDesc(p.data_ptr(), bwd, b, a, RS[0], RS[1], 1, self.code))   # [I][R][S][O]
-            max_numel = max(max_numel, p.numel())
+            if is_t:   # IOHW
+                descs.append(RepackDesc(p.data_ptr(), fwd, b, a, R, S, 1, self.code))   # [O][R][S][I]
+                descs.append(RepackDesc(p.data_ptr(), bwd, a, b, R, S, 0, self.code))   # [I][R][S][O]
+            else:      # OIHW (or a Linear's [O][I])
+                descs.append(RepackDesc(p.data_ptr(), fwd, a, b, R, S, 0, self.code))   # [O][R][S][I]
+                descs.append(RepackDesc(p.data_ptr(), bwd, b, a, R, S, 1, self.code))   # [I][R][S][O]
+            max_numel = max(max_numel, a * b * R * S)
         arr = (RepackDesc * len(descs))(*descs)
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         self.repack_table = host.to(device)
@@ -357,9 +367,6 @@ class Engine:
         self.prepare(x.device)
         need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.net.parameters()))
         x = x.contiguous().float()
-        if t.dtype not in (torch.int64, torch.float32):
-            t = t.float() if t.is_floating_point() else t.long()
-        t = t.contiguous()
         if need_grad:
             params = [self.named[k] for k in self.offs]
             return _UNetFn.apply(self, x, t, *params)
@@ -382,24 +389,39 @@ class Engine:
             if rc != 0:
                 _abi.check(rc, fn.__name__)
 
-    def run_forward(self, x, t, plan: Plan) -> torch.Tensor:
-        stream = ops._stream()
-        if not self.frozen:
-            self.repack(stream)
-        out = torch.empty_like(x)
-        plan.stem.x.ptr = x.data_ptr()
-        plan.head.y.ptr = out.data_ptr()
-        fn, args = plan.fwd[plan.temb_in]
-        if self.net.sigma_embed:   # (sigma, log_sigma_out, n, kind)
-            plan.fwd[plan.temb_in] = (fn, (t.data_ptr(),) + tuple(args[1:]))
-        else:                      # (t, t_is_float, emb, batch, dim)
-            plan.fwd[plan.temb_in] = (fn, (t.data_ptr(), 1 if t.dtype == torch.float32 else 0) + tuple(args[2:]))
-        self._run(plan.fwd, stream)
-        return out
+    def _execute(self, plan: Plan, which: str):
+        """Run plan.fwd / plan.bwd: eagerly the first time (warms every lazy one-time initialisation), then captured once
+        into a CUDA graph and replayed — ~250 launches (and their tensor-map encodes) become one host call."""
+        oplist = plan.fwd if which == "fwd" else plan.bwd
+        g = plan.graphs.get(which)
+        if g is not None:
+            g.replay()
+            ops.LAUNCHES += len(oplist)
+            return
+        n = plan.runs.get(which, 0)
+        plan.runs[which] = n + 1
+        graphable = self.use_graphs and self.device.type == "cuda" and n >= 1 and not torch.cuda.is_current_stream_capturing()
+        if not graphable:
+            self._run(oplist, ops._stream())
+            return
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run(oplist, ops._stream())     # recorded on the capture stream, not executed
+        ops.LAUNCHES -= len(oplist)
+        plan.graphs[which] = g
+        g.replay()
+        ops.LAUNCHES += len(oplist)
 
-    def run_backward(self, plan: Plan, x, dout):
+    def run_forward(self, x, t, plan: Plan) -> torch.Tensor:
+        if not self.frozen:
+            self.repack(ops._stream())
+        plan.x_in.copy_(x)
+        plan.t_in.copy_(t)       # int64 timesteps are cast to fp32 here exactly like embeddings.py:35 promotes them
+        self._execute(plan, "fwd")
+        return plan.out.clone()
+
+    def run_backward(self, plan: Plan, dout):
         """Fills the gradient arena; returns it (flat fp32, same offsets as the parameter arena)."""
-        stream = ops._stream()
         g = self.gflat
         # param.grad tensors handed out by an earlier backward are views of this arena.  If any is still installed
         # (gradient accumulation, zero_grad(set_to_none=False)) detach it first so autograd's `grad += new` stays correct.
@@ -407,12 +429,8 @@ class Engine:
         for p in self.named.values():
             if p.grad is not None and lo <= p.grad.data_ptr() < hi:
                 p.grad = p.grad.clone()
-        dout = dout.contiguous().float()
-        plan.head_dgrad.x.ptr = dout.data_ptr()
-        plan.head_wgrad.p.ptr = dout.data_ptr()
-        plan.stem_wgrad.q.ptr = x.data_ptr()
-        _abi.check(self._lib.dmu_zero(g.data_ptr(), g.numel() * 4, stream), "zero grads")
-        self._run(plan.bwd, stream)
+        plan.dout.copy_(dout)
+        self._execute(plan, "bwd")
         return g
 
     # ------------------------------------------------------------------ plan construction
@@ -425,6 +443,12 @@ class Engine:
         arena = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
         base = rnd(arena.data_ptr())
         real = _PlanBuilder(self, N, H, W, train, base=(base, base + n_main, base + n_main + n_stats))
+        net = self.net
+        real.plan.x_in = torch.zeros(N, net.in_channels, H, W, device=self.device, dtype=torch.float32)
+        real.plan.t_in = torch.zeros(N, device=self.device, dtype=torch.float32)
+        real.plan.out = torch.zeros(N, net.out_channels, H, W, device=self.device, dtype=torch.float32)
+        if train:
+            real.plan.dout = torch.zeros(N, net.out_channels, H, W, device=self.device, dtype=torch.float32)
         plan = real.build()
         plan.arena = arena
         plan.nbytes = nbytes
@@ -438,15 +462,13 @@ class _UNetFn(torch.autograd.Function):
         plan.busy = True
         out = eng.run_forward(x, t, plan)
         ctx.eng, ctx.plan = eng, plan
-        ctx.save_for_backward(x)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         eng, plan = ctx.eng, ctx.plan
-        (x,) = ctx.saved_tensors
         try:
-            g = eng.run_backward(plan, x, dout)
+            g = eng.run_backward(plan, dout)
         finally:
             plan.busy = False
         grads = []
@@ -550,8 +572,12 @@ class _PlanBuilder:
     def linear(self, lst, x4: Tensor4, y4: Tensor4, M, I, O, w_addr, b_addr, res4=None, w_code=F32):
         self.conv(lst, x4, y4, w_addr, (I, 1, 0), w_code, (M, 1, 1, I, 1, 1, O), (1, 1, 1, 0), bias=b_addr, res=res4)
 
-    def linear_bwd(self, x4, dy4, dx4, M, I, O, wname_addr, gw_addr, gb_addr, res4=None, need_dx=True):
-        if need_dx:
+    def linear_bwd(self, x4, dy4, dx4, M, I, O, wname_addr, gw_addr, gb_addr, res4=None, need_dx=True, w_t=None):
+        """w_t: address of the [I][O] copy in the compute dtype (contraction axis contiguous: tensor-core path);
+        None = contract the fp32 [O][I] parameter through its strides."""
+        if need_dx and w_t is not None:
+            self.conv(self.plan.bwd, dy4, dx4, w_t, (O, 1, 0), self.code, (M, 1, 1, O, 1, 1, I), (1, 1, 1, 0), res=res4)
+        elif need_dx:
             self.conv(self.plan.bwd, dy4, dx4, wname_addr, (1, I, 0), F32, (M, 1, 1, O, 1, 1, I), (1, 1, 1, 0), res=res4)
         self.wgrad(dy4, x4, gw_addr, (I, 1, 0), gb_addr, (M, 1, 1, O, 1, 1, I), (1, 1, 1, 0))
 
@@ -605,17 +631,20 @@ class _PlanBuilder:
         Cc, S = x.C, x.H * x.W
         M = self.N * S
         qkv = self.act(x.H, x.W, 3 * Cc)
-        wq, bq = e.paddr(pfx + "query_projection.weight"), e.paddr(pfx + "query_projection.bias")
-        self.linear(self.plan.fwd, _rows_t4(x.addr, x.pitch, self.code), _rows_t4(qkv.addr, 3 * Cc, self.code), M, Cc, 3 * Cc, wq, bq)
+        bq = e.paddr(pfx + "query_projection.bias")
+        tc = self.code == BF16      # projections through the filter cache (tensor-core path) in bf16 mode, fp32 arena otherwise
+        wq, wq_t, wcode = (e.waddr(pfx + "qkv"), e.waddr_t(pfx + "qkv"), BF16) if tc else (e.paddr(pfx + "query_projection.weight"), None, F32)
+        self.linear(self.plan.fwd, _rows_t4(x.addr, x.pitch, self.code), _rows_t4(qkv.addr, 3 * Cc, self.code), M, Cc, 3 * Cc, wq, bq, w_code=wcode)
         o = self.act(x.H, x.W, Cc)
         lse = self.f32(self.N * heads * S)
         ap = AttnParams(qkv.addr, 3 * Cc, o.addr, Cc, None, 0, None, 0, lse, self.N, S, Cc, heads, self.code, 0)
         self.plan.keep.append(ap)
         self.plan.fwd.append((self.lib.dmu_attn_fwd, (C.byref(ap),)))
         z = self.act(x.H, x.W, Cc)
-        wf, bf = e.paddr(pfx + "final_projection.weight"), e.paddr(pfx + "final_projection.bias")
+        bf = e.paddr(pfx + "final_projection.bias")
+        wf, wf_t = (e.waddr(pfx + "final_projection.weight"), e.waddr_t(pfx + "final_projection.weight")) if tc else (e.paddr(pfx + "final_projection.weight"), None)
         self.linear(self.plan.fwd, _rows_t4(o.addr, Cc, self.code), _rows_t4(z.addr, Cc, self.code), M, Cc, Cc, wf, bf,
-                    res4=_rows_t4(x.addr, x.pitch, self.code))
+                    res4=_rows_t4(x.addr, x.pitch, self.code), w_code=wcode)
         G = gn_groups(Cc)
         sums = self.stats.take(self.N * G * 2 * 4, 16)
         gp_ = GnParams(z.t4(), y.t4(), _null_t4(), _null_t4(), _null_t4(), sums, e.paddr(pfx + "norm.weight"), e.paddr(pfx + "norm.bias"),
@@ -632,14 +661,14 @@ class _PlanBuilder:
             dz4 = _rows_t4(z.grad.addr, Cc, self.code)
             # final projection: do = dz Wf ; dWf += dz^T o
             self.linear_bwd(_rows_t4(o.addr, Cc, self.code), dz4, _rows_t4(o.grad.addr, Cc, self.code), M, Cc, Cc, wf,
-                            self.gp(pfx + "final_projection.weight"), self.gp(pfx + "final_projection.bias"))
+                            self.gp(pfx + "final_projection.weight"), self.gp(pfx + "final_projection.bias"), w_t=wf_t)
             bp = AttnParams(qkv.addr, 3 * Cc, o.addr, Cc, o.grad.addr, Cc, qkv.grad.addr, 3 * Cc, lse, self.N, S, Cc, heads, self.code, 0)
             self.plan.keep.append(bp)
             self.plan.bwd.append((self.lib.dmu_attn_bwd, (C.byref(bp),)))
             # qkv projection: dx = dqkv Wqkv + dz ; dWqkv += dqkv^T x
             self.linear_bwd(_rows_t4(x.addr, x.pitch, self.code), _rows_t4(qkv.grad.addr, 3 * Cc, self.code),
                             _rows_t4(x.grad.addr, x.grad.pitch, self.code), M, Cc, 3 * Cc, wq,
-                            self.gp(pfx + "query_projection.weight"), self.gp(pfx + "query_projection.bias"), res4=dz4)
+                            self.gp(pfx + "query_projection.weight"), self.gp(pfx + "query_projection.bias"), res4=dz4, w_t=wq_t)
             x.grad_written = True
         self.tape.append(bwd)
 
@@ -672,10 +701,10 @@ class _PlanBuilder:
         self.tp_total = off
 
         # -------- time embedding
-        plan.temb_in = len(plan.fwd)
+        t_ptr = plan.t_in.data_ptr() if plan.t_in is not None else 0   # dry (sizing) pass has no buffers yet
         if not net.sigma_embed:
             emb = self.f32(N * Cm)
-            plan.fwd.append((lib.dmu_sinusoidal_embedding, (None, 0, emb, N, Cm)))   # t pointer patched per call
+            plan.fwd.append((lib.dmu_sinusoidal_embedding, (t_ptr, 1, emb, N, Cm)))
             h1 = self.f32(N * T4)
             te = "time_embedding.positional_encoding."
             self.linear(plan.fwd, _rows_t4(emb, Cm), _rows_t4(h1, T4), N, Cm, T4, e.paddr(te + "1.weight"), e.paddr(te + "1.bias"))
@@ -686,7 +715,7 @@ class _PlanBuilder:
         else:
             # score_based.py:57-61,82-83: Linear(1,C) -> SiLU -> Linear(C,4C) on log(sigma)
             ls = self.f32(N)
-            plan.fwd.append((lib.dmu_act_fwd, (None, ls, N, 2)))                      # sigma pointer patched per call
+            plan.fwd.append((lib.dmu_act_fwd, (t_ptr, ls, N, 2)))
             h1 = self.f32(N * Cm)
             self.linear(plan.fwd, _rows_t4(ls, 1), _rows_t4(h1, Cm), N, 1, Cm, e.paddr("time_embed.0.weight"), e.paddr("time_embed.0.bias"))
             g1 = self.f32(N * Cm)
@@ -697,11 +726,15 @@ class _PlanBuilder:
         first = e.res_block_prefixes()[0]
         self.linear(plan.fwd, _rows_t4(temb, T4), _rows_t4(self.tproj, self.tp_total), N, T4, self.tp_total,
                     e.paddr(first + "time_mlp.weight"), e.paddr(first + "time_mlp.bias"))
-        self.dtproj = self.f32(N * self.tp_total) if self.train else 0
+        # per-image channel sums of dh (time-projection gradient): accumulated with atomics -> lives in the zeroed region
+        self.dtproj = self.red.take(N * self.tp_total * 4, 16) if self.train else 0
 
         # -------- stem (NCHW fp32 -> NHWC)
         h0 = self.act(H, W, Cm)
-        plan.stem = self.conv(plan.fwd, _nchw_t4(None, net.in_channels, H, W), h0.t4(), e.waddr("initial_conv.weight"),
+        x_ptr = plan.x_in.data_ptr() if plan.x_in is not None else 0
+        out_ptr = plan.out.data_ptr() if plan.out is not None else 0
+        dout_ptr = plan.dout.data_ptr() if plan.dout is not None else 0
+        self.conv(plan.fwd, _nchw_t4(x_ptr, net.in_channels, H, W), h0.t4(), e.waddr("initial_conv.weight"),
                               (9 * net.in_channels, 1, net.in_channels), self.code, (N, H, W, net.in_channels, H, W, Cm), (3, 3, 1, 1),
                               bias=e.paddr("initial_conv.bias"))
 
@@ -763,29 +796,28 @@ class _PlanBuilder:
             x = u
         # -------- head: GroupNorm -> SiLU -> conv3x3 -> NCHW fp32
         a, rec = self.gn(x, 32, "output_conv.0.weight", "output_conv.0.bias", True)
-        plan.head = self.conv(plan.fwd, a.t4(), _nchw_t4(None, net.out_channels, H, W), e.waddr("output_conv.2.weight"), (9 * Cm, 1, Cm), self.code,
+        self.conv(plan.fwd, a.t4(), _nchw_t4(out_ptr, net.out_channels, H, W), e.waddr("output_conv.2.weight"), (9 * Cm, 1, Cm), self.code,
                               (N, H, W, Cm, H, W, net.out_channels), (3, 3, 1, 1), bias=e.paddr("output_conv.2.bias"))
         # one launch zeroes every GroupNorm statistics accumulator of the forward
         plan.fwd.insert(0, (lib.dmu_zero, (self.stats.base, max(self.stats.off, 4))))
-        plan.temb_in += 1
 
         if not self.train:
             return plan
 
         # ======================= backward =======================
         Co = net.out_channels
-        dout4 = _nchw_t4(None, Co, H, W)
+        dout4 = _nchw_t4(dout_ptr, Co, H, W)
         # head conv: da = dgrad(dout), dW, db
-        plan.head_dgrad = self.conv(plan.bwd, dout4, a.grad.t4(), e.waddr("output_conv.2.weight"), (1, 9 * Cm, Cm), self.code,
-                                    (N, H, W, Co, H, W, Cm), (3, 3, 1, 1), gather=1)
-        plan.head_wgrad = self.wgrad(_nchw_t4(None, Co, H, W), a.t4(), self.gp("output_conv.2.weight"), (Cm * 9, 9, 1), self.gp("output_conv.2.bias"),
-                                     (N, H, W, Co, H, W, Cm), (3, 3, 1, 1))
+        self.conv(plan.bwd, dout4, a.grad.t4(), e.waddr("output_conv.2.weight"), (1, 9 * Cm, Cm), self.code,
+                  (N, H, W, Co, H, W, Cm), (3, 3, 1, 1), gather=1)
+        self.wgrad(_nchw_t4(dout_ptr, Co, H, W), a.t4(), self.gp("output_conv.2.weight"), (Cm * 9, 9, 1), self.gp("output_conv.2.bias"),
+                   (N, H, W, Co, H, W, Cm), (3, 3, 1, 1))
         self.gn_bwd(rec, x.grad)
         x.grad_written = True
         for fn in reversed(self.tape):
             fn()
         # stem: wgrad only (the network input needs no gradient on this path)
-        plan.stem_wgrad = self.wgrad(h0.grad.t4(), _nchw_t4(None, net.in_channels, H, W), self.gp("initial_conv.weight"),
+        self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), self.gp("initial_conv.weight"),
                                      (net.in_channels * 9, 9, 1), self.gp("initial_conv.bias"), (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
         # time projections (one GEMM for all 22 blocks), then the embedding MLP
         dtemb = self.f32(N * T4)
@@ -810,4 +842,6 @@ class _PlanBuilder:
                             self.gp("time_embed.0.weight"), self.gp("time_embed.0.bias"), need_dx=False)
         # one launch zeroes every GroupNorm backward accumulator
         plan.bwd.insert(0, (lib.dmu_zero, (self.red.base, max(self.red.off, 4))))
+        # ... and one zeroes the gradient arena the wgrad kernels accumulate into
+        plan.bwd.insert(0, (lib.dmu_zero, (e.gflat.data_ptr(), e.gflat.numel() * 4)))
         return plan

@@ -183,7 +183,8 @@ int dmu_gn_bwd_reduce(const dmu_gn_params* p, dmu_stream_t stream);
 int dmu_gn_bwd_apply(const dmu_gn_params* p, dmu_stream_t stream);
 
 /* Per-image and total channel sums of an NHWC tensor (bias / time_mlp grads):
- *   out_nc[n*pitch + c] = sum_p x[n,p,c] (optional);  out_c[c] += sum_{n,p} x[n,p,c] (optional)
+ *   out_nc[n*pitch + c] += sum_p x[n,p,c] (optional);  out_c[c] += sum_{n,p} x[n,p,c] (optional)
+ * Both outputs are accumulated with atomics (several CTAs per image): zero them first for a fresh sum.
  * scale multiplies both (1/HW gives the spatial mean of energy_based.py:83). */
 int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C,
                float* out_nc, int64_t out_nc_pitch, float* out_c, float scale, dmu_stream_t stream);

@@ -201,7 +201,7 @@ class FakeLib:
         self._count()
         x = _view4(_obj(ref), N, H, W, Cc).float().sum(dim=(1, 2)) * scale
         if _addr(out_nc):
-            _flat(_addr(out_nc), (N - 1) * pitch + Cc).as_strided((N, Cc), (pitch, 1)).copy_(x)
+            _flat(_addr(out_nc), (N - 1) * pitch + Cc).as_strided((N, Cc), (pitch, 1)).add_(x)
         if _addr(out_c):
             _flat(_addr(out_c), Cc).add_(x.sum(0))
         return 0

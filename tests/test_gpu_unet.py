@@ -266,3 +266,41 @@ def test_full_size_properties_bf16():
         z2 = net32(x[5:7].contiguous(), t[5:7].contiguous())
     assert rel_l2(z[5:7], z2) < 1e-5      # rows of a batch are independent
     assert rel_l2(z[:8], ref) < EPS_TOL["fp32"]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+def test_graph_replay_matches_eager_and_trainstep_matches_autograd(precision, tol):
+    """(1) The CUDA-graph replay of a recorded plan computes what the eager launches compute.  (2) TrainStep's autograd-free
+    DDPM step leaves the same gradients in the arena as loss_function(x).backward() with the same RNG state.
+    fp32 mode is reproducible to accumulation order (atomics); bf16 mode re-rounds every activation to 8 bits, so two runs
+    of the SAME launches already differ by ~1e-2 rel-L2 after 60 layers (scripts/determinism_check.py) - hence the loose bound."""
+    import diffusion_model_universal_b200 as D
+    from diffusion_model_universal_b200.trainer import TrainStep
+    f = load_golden("ddpm_train.pt")
+    dev = torch.device("cuda:0")
+    m = _load(D.DDPM(_cfg(f["C"], precision)), W.unet_param_spec(f["C"], 3, "model."), f["wseed"]).to(dev)
+    x0, t = f["x0"].to(dev), f["t"].to(dev)
+    eng = m.model.engine
+    with torch.no_grad():
+        eng.use_graphs = False
+        e0 = m.forward(x0, t)
+        eng.use_graphs = True
+        e1 = m.forward(x0, t)      # second execution of the plan: captured + replayed
+        e2 = m.forward(x0, t)      # pure replay
+    plan = eng.get_plan(x0.shape, False)
+    assert "fwd" in plan.graphs
+    assert rel_l2(e1, e0) < tol and rel_l2(e2, e0) < tol
+    grads = []
+    for it in range(3):            # iteration 0 eager, 1 capture, 2 replay
+        torch.manual_seed(11)
+        m.zero_grad(set_to_none=True)
+        loss = m.loss_function(x0)
+        loss.backward()
+        grads.append((loss.item(), eng.gflat.clone()))
+    assert rel_l2(grads[1][1], grads[0][1]) < 5 * tol and rel_l2(grads[2][1], grads[0][1]) < 5 * tol
+    m.zero_grad(set_to_none=True)
+    ts = TrainStep(m, lr=0.0, ema_decay=None)          # lr 0: the arena keeps the weights, only the gradients are compared
+    torch.manual_seed(11)
+    l2 = ts.step(x0)
+    assert abs(l2.item() - grads[0][0]) < 5 * tol * abs(grads[0][0])
+    assert rel_l2(eng.gflat, grads[0][1]) < 5 * tol

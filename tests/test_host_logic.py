@@ -155,3 +155,21 @@ def test_ddim_and_ddpm_loops(monkeypatch):
         assert rel_l2(u, v) < 1e-3
     torch.manual_seed(f["rng_seed"])
     assert rel_l2(m.generate_samples(2, torch.device("cpu")), f["final"]) < 1e-3
+
+
+def test_snr_time_weights_without_host_sync_match_the_reference_formula():
+    """losses.py:150-157 sizes its beta table with timesteps.max().item(); the device-resident variant must give the same
+    weights (same linspace formula, t_max kept as a tensor) for every t_max, including the degenerate ones."""
+    from diffusion_model_universal_b200.losses import DiffusionLoss
+    from oracle import losses as OL
+    g = torch.Generator().manual_seed(3)
+    cases = [torch.randint(0, 1000, (128,), generator=g), torch.randint(0, 10, (16,), generator=g), torch.zeros(4, dtype=torch.long),
+             torch.tensor([1, 0, 1]), torch.tensor([999]), torch.tensor([5, 5, 5, 5]), torch.arange(0, 1000, 37)]
+    for t in cases:
+        a = DiffusionLoss("mse", dict(SHIPPED_LOSS))
+        b = DiffusionLoss("mse", dict(SHIPPED_LOSS))
+        b.max_t = 1000
+        wa, wb = a.time_weights(t), b.time_weights(t)
+        assert torch.allclose(wa, wb, rtol=2e-6, atol=1e-7), (t, wa, wb)
+        ref = OL.time_weights(t, "snr", 0.1, 1.0).reshape(-1)
+        assert torch.allclose(wb, ref, rtol=2e-6, atol=1e-7)
