@@ -431,6 +431,11 @@ extern "C" int dmu_conv2d_tc(const dmu_conv_params* p, dmu_stream_t stream);
 extern "C" int dmu_conv2d_tc_supported(const dmu_conv_params* p);
 extern "C" int dmu_wgrad_tc(const dmu_wgrad_params* p, dmu_stream_t stream);
 extern "C" int dmu_wgrad_tc_supported(const dmu_wgrad_params* p);
+// implemented in conv_edge.cu
+extern "C" int dmu_conv2d_edge(const dmu_conv_params* p, dmu_stream_t stream);
+extern "C" int dmu_conv2d_edge_supported(const dmu_conv_params* p);
+extern "C" int dmu_wgrad_edge(const dmu_wgrad_params* p, dmu_stream_t stream);
+extern "C" int dmu_wgrad_edge_supported(const dmu_wgrad_params* p);
 
 extern "C" {
 
@@ -446,6 +451,11 @@ int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream) {
         return dmu_conv2d_tc(p, stream);
     }
     if (p->impl == 0 && dmu_conv2d_tc_supported(p)) return dmu_conv2d_tc(p, stream);
+    if (p->impl == 3) {
+        DMU_REQUIRE(dmu_conv2d_edge_supported(p), "dmu_conv2d: impl=edge requested for an unsupported shape");
+        return dmu_conv2d_edge(p, stream);
+    }
+    if (p->impl == 0 && dmu_conv2d_edge_supported(p)) return dmu_conv2d_edge(p, stream);
     const int M = p->N * p->Ho * p->Wo;
     const int K = p->R * p->S * p->Ck;
     // Linear layer with few rows and a long contraction: split K across CTAs (fp32 rows, zeroed then accumulated)
@@ -487,6 +497,11 @@ int dmu_conv2d_wgrad(const dmu_wgrad_params* p, dmu_stream_t stream) {
         return dmu_wgrad_tc(p, stream);
     }
     if (p->impl == 0 && dmu_wgrad_tc_supported(p)) return dmu_wgrad_tc(p, stream);
+    if (p->impl == 3) {
+        DMU_REQUIRE(dmu_wgrad_edge_supported(p), "dmu_conv2d_wgrad: impl=edge requested for an unsupported shape");
+        return dmu_wgrad_edge(p, stream);
+    }
+    if (p->impl == 0 && dmu_wgrad_edge_supported(p)) return dmu_wgrad_edge(p, stream);
     const int Mtot = p->N * p->Hp * p->Wp;
     const int ncols = p->R * p->S * p->Cb;
     const bool small_a = p->Ca <= 16;

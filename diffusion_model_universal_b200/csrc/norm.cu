@@ -405,6 +405,16 @@ __global__ void repack_kernel(const dmu_repack_desc* __restrict__ descs) {
     const dmu_repack_desc d = descs[blockIdx.y];
     const int64_t RS = (int64_t)d.R * d.S;
     const int64_t total = (int64_t)d.O * d.I * RS;
+    if (d.kind == 3) {
+        // gradient staging [O][R][S][I] (what the wgrad kernels accumulate, coalesced) -> stored layout [O][I][R][S]
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t rs = i % RS;
+            const int64_t ci = (i / RS) % d.I;
+            const int64_t o = i / (RS * d.I);
+            st_from_float(d.dst, i, d.dst_dtype, d.src[(o * RS + rs) * d.I + ci]);
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         // i enumerates the destination [O][R][S][I]
         const int64_t ci = i % d.I;

@@ -306,6 +306,18 @@ class Engine:
             wc_total += (a * b * R * S + 63) // 64 * 64
         self.wc_half = max(wc_total, 64)
         self.wcache = torch.zeros(2 * self.wc_half, device=device, dtype=self.tdtype)
+        # Filter-gradient staging, fp32, [first dim][R][S][second dim] per filter (same offsets as the cache): the wgrad
+        # kernels' atomics are contiguous across a warp in this layout; one unpack launch per backward writes the
+        # stored layout ([first][second][R][S]) into the gradient arena.
+        self.gstage = torch.zeros(self.wc_half, device=device, dtype=torch.float32)
+        undescs = []
+        for key, p, a, b, R, S, is_t in entries:
+            if p.dim() == 4:
+                undescs.append(RepackDesc(self.gstage.data_ptr() + self.wc_off[key] * 4, self.gflat.data_ptr() + offs[key][0] * 4,
+                                          a, b, R, S, 3, F32))
+        uarr = (RepackDesc * len(undescs))(*undescs)
+        self.unpack_table = torch.frombuffer(bytearray(bytes(uarr)), dtype=torch.uint8).to(device)
+        self.unpack_n = len(undescs)
         max_numel = 1
         for key, p, a, b, R, S, is_t in entries:
             off = self.wc_off[key]
@@ -347,6 +359,9 @@ class Engine:
 
     def waddr(self, name):  # repacked filter, fprop layout [O][R][S][I]
         return self.wcache.data_ptr() + self.wc_off[name] * self.esize
+
+    def gsaddr(self, name):  # fp32 gradient staging of a filter, [first dim][R][S][second dim]
+        return self.gstage.data_ptr() + self.wc_off[name] * 4
 
     def waddr_t(self, name):  # repacked filter, dgrad layout [I][R][S][O]
         return self.wcache.data_ptr() + (self.wc_half + self.wc_off[name]) * self.esize
@@ -566,7 +581,7 @@ class _PlanBuilder:
             # dx[n,hi,wi,ci] = sum dy[n,(hi+pad-r)/s,..,co] w[co][r][s][ci]
             self.conv(self.plan.bwd, dy.t4(), dx.t4(), self.e.waddr_t(wname), (R * R * Co, 1, Co), self.code,
                       (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad), gather=1)
-        self.wgrad(dy.t4(), x.t4(), self.gp(wname), (Ci * R * R, R * R, 1), self.gp(bname),
+        self.wgrad(dy.t4(), x.t4(), self.e.gsaddr(wname), (R * R * Ci, 1, Ci), self.gp(bname),
                    (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad))
 
     def linear(self, lst, x4: Tensor4, y4: Tensor4, M, I, O, w_addr, b_addr, res4=None, w_code=F32):
@@ -787,7 +802,7 @@ class _PlanBuilder:
                               (N, u.H, u.W, co, y.H, y.W, co), (4, 4, 2, 1), gather=0)
                     y.grad_written = True
                     # dW[ci][co][r][s] (IOHW) += x[.., ci] * du[gathered, co]
-                    self.wgrad(y.t4(), du.t4(), self.gp(pfx + "upsample.weight"), (co * 16, 16, 1), None,
+                    self.wgrad(y.t4(), du.t4(), e.gsaddr(pfx + "upsample.weight"), (16 * co, 1, co), None,
                                (N, y.H, y.W, co, u.H, u.W, co), (4, 4, 2, 1))
                     t4 = du.t4()
                     plan.keep.append(t4)
@@ -810,15 +825,15 @@ class _PlanBuilder:
         # head conv: da = dgrad(dout), dW, db
         self.conv(plan.bwd, dout4, a.grad.t4(), e.waddr("output_conv.2.weight"), (1, 9 * Cm, Cm), self.code,
                   (N, H, W, Co, H, W, Cm), (3, 3, 1, 1), gather=1)
-        self.wgrad(_nchw_t4(dout_ptr, Co, H, W), a.t4(), self.gp("output_conv.2.weight"), (Cm * 9, 9, 1), self.gp("output_conv.2.bias"),
+        self.wgrad(_nchw_t4(dout_ptr, Co, H, W), a.t4(), e.gsaddr("output_conv.2.weight"), (9 * Cm, 1, Cm), self.gp("output_conv.2.bias"),
                    (N, H, W, Co, H, W, Cm), (3, 3, 1, 1))
         self.gn_bwd(rec, x.grad)
         x.grad_written = True
         for fn in reversed(self.tape):
             fn()
         # stem: wgrad only (the network input needs no gradient on this path)
-        self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), self.gp("initial_conv.weight"),
-                                     (net.in_channels * 9, 9, 1), self.gp("initial_conv.bias"), (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
+        self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), e.gsaddr("initial_conv.weight"),
+                   (9 * net.in_channels, 1, net.in_channels), self.gp("initial_conv.bias"), (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
         # time projections (one GEMM for all 22 blocks), then the embedding MLP
         dtemb = self.f32(N * T4)
         self.linear_bwd(_rows_t4(temb, T4), _rows_t4(self.dtproj, self.tp_total), _rows_t4(dtemb, T4), N, T4, self.tp_total,
@@ -844,4 +859,7 @@ class _PlanBuilder:
         plan.bwd.insert(0, (lib.dmu_zero, (self.red.base, max(self.red.off, 4))))
         # ... and one zeroes the gradient arena the wgrad kernels accumulate into
         plan.bwd.insert(0, (lib.dmu_zero, (e.gflat.data_ptr(), e.gflat.numel() * 4)))
+        plan.bwd.insert(0, (lib.dmu_zero, (e.gstage.data_ptr(), e.gstage.numel() * 4)))
+        # filter gradients: staging layout -> the parameters' own layout inside the gradient arena
+        plan.bwd.append((lib.dmu_repack_weights, (e.unpack_table.data_ptr(), e.unpack_n, e.repack_max)))
         return plan

@@ -115,7 +115,8 @@ int dmu_diffusion_loss(const float* pred, const float* target, const float* w,
  *   gather 1 (transposed):  hi = (ho + pad - r) / stride   when divisible
  *
  * With the weight strides this one contraction covers fprop and dgrad of
- * both layer kinds.  impl: 0 = auto, 1 = SIMT fp32-FMA kernel, 2 = tcgen05.
+ * both layer kinds.  impl: 0 = auto, 1 = generic SIMT fp32-FMA kernel, 2 = tcgen05 (bf16, channels % 64 == 0),
+ * 3 = the direct kernels for the 3-channel boundary layers (at most 4 channels on one side, stride 1).
  */
 typedef struct {
     dmu_tensor4 x;       /* gathered input, channels K = Ck */
@@ -217,7 +218,9 @@ int dmu_act_bwd(const float* x, const float* dy, float* dx, int64_t n, int32_t k
 /* Layout / dtype repack of parameters into kernel-friendly caches (derived,
  * never the stored format; SURVEY.md §8b "Ownership").  One launch for a
  * whole table.  kind 0: OIHW -> [O][R][S][I];  kind 1: IOHW (ConvTranspose2d)
- * -> [O][R][S][I];  kind 2: plain copy/cast ([O][I] Linear, vectors). */
+ * -> [O][R][S][I];  kind 2: plain copy/cast ([O][I] Linear, vectors);  kind 3: the inverse of kind 0,
+ * [O][R][S][I] -> [O][I][R][S] (filter gradients are accumulated in the tap-major staging layout, where the wgrad
+ * kernels' atomics coalesce, and unpacked once per backward into the parameter's own layout). */
 typedef struct {
     const float* src;
     void* dst;

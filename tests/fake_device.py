@@ -83,6 +83,8 @@ class FakeLib:
                 v = src.view(d.O, d.I, d.R, d.S).permute(0, 2, 3, 1)
             elif d.kind == 1:
                 v = src.view(d.I, d.O, d.R, d.S).permute(1, 2, 3, 0)
+            elif d.kind == 3:   # staging [O][R][S][I] -> stored [O][I][R][S]
+                v = src.view(d.O, d.R, d.S, d.I).permute(0, 3, 1, 2)
             else:
                 v = src
             _flat(d.dst, numel, d.dst_dtype).copy_(v.reshape(-1))

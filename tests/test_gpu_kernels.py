@@ -163,8 +163,9 @@ def _conv_case(case, dtype, impl):
         assert rel_l2(db - 1, dyq.sum(dim=(0, 2, 3))) < 5e-5, "dbias"
 
 
+@pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_stem_and_head_layouts(dtype):
+def test_stem_and_head_layouts(dtype, impl):
     """3-channel NCHW fp32 boundary tensors: stem fprop/wgrad, head fprop (small-N kernel)/dgrad/wgrad."""
     ops, _abi = _mods()
     from diffusion_model_universal_b200._abi import ConvParams, WgradParams
@@ -178,14 +179,15 @@ def test_stem_and_head_layouts(dtype):
     code = ops.dtype_code(wk)
     y = torch.empty(N, H, W, Cm, device=dev, dtype=dtype)
     ops.conv2d_raw(ConvParams(ops.t4_nchw(x), ops.t4_nhwc(y), _null(), wk.data_ptr(), 27, 1, 3, b.data_ptr(), None, 0,
-                              N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 0, code, 1, 0))
+                              N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 0, code, impl, 0))
     wq = w.to(dtype).float()
     assert rel_l2(y.float().permute(0, 3, 1, 2), F.conv2d(x, wq, b, padding=1)) < TOL[dtype]
     dy = torch.randn(N, Cm, H, W, generator=g).to(dev)
     dyh = ops.nchw_to_nhwc(dy, dtype)
     dw, db = torch.zeros_like(w), torch.zeros_like(b)
-    ops.wgrad_raw(WgradParams(ops.t4_nhwc(dyh), ops.t4_nchw(x), dw.data_ptr(), 27, 9, 1, db.data_ptr(), N, H, W, Cm, H, W, 3, 3, 3, 1, 1, 1))
+    ops.wgrad_raw(WgradParams(ops.t4_nhwc(dyh), ops.t4_nchw(x), dw.data_ptr(), 27, 9, 1, db.data_ptr(), N, H, W, Cm, H, W, 3, 3, 3, 1, 1, impl))
     assert rel_l2(dw, torch.nn.grad.conv2d_weight(x, w.shape, dyh.float().permute(0, 3, 1, 2), padding=1)) < 5e-5
+    assert rel_l2(db, dyh.float().sum(dim=(0, 1, 2))) < 5e-5
     # head: Cm -> 3, NHWC in, NCHW fp32 out
     a = torch.randn(N, Cm, H, W, generator=g).to(dev)
     ah = ops.nchw_to_nhwc(a, dtype)
@@ -194,16 +196,16 @@ def test_stem_and_head_layouts(dtype):
     whk = _repack(wh, False, dtype)
     out = torch.empty(N, 3, H, W, device=dev)
     ops.conv2d_raw(ConvParams(ops.t4_nhwc(ah), ops.t4_nchw(out), _null(), whk.data_ptr(), 9 * Cm, 1, Cm, bh.data_ptr(), None, 0,
-                              N, H, W, Cm, H, W, 3, 3, 3, 1, 1, 0, code, 1, 0))
+                              N, H, W, Cm, H, W, 3, 3, 3, 1, 1, 0, code, impl, 0))
     aq, whq = ah.float().permute(0, 3, 1, 2), wh.to(dtype).float()
     assert rel_l2(out, F.conv2d(aq, whq, bh, padding=1)) < TOL[dtype]
     dout = torch.randn(N, 3, H, W, generator=g).to(dev)
     da = torch.empty(N, H, W, Cm, device=dev, dtype=dtype)
     ops.conv2d_raw(ConvParams(ops.t4_nchw(dout), ops.t4_nhwc(da), _null(), whk.data_ptr(), 1, 9 * Cm, Cm, None, None, 0,
-                              N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 1, code, 1, 0))
+                              N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 1, code, impl, 0))
     assert rel_l2(da.float().permute(0, 3, 1, 2), torch.nn.grad.conv2d_input(a.shape, whq, dout, padding=1)) < TOL[dtype]
     dwh, dbh = torch.zeros_like(wh), torch.zeros_like(bh)
-    ops.wgrad_raw(WgradParams(ops.t4_nchw(dout), ops.t4_nhwc(ah), dwh.data_ptr(), Cm * 9, 9, 1, dbh.data_ptr(), N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 1))
+    ops.wgrad_raw(WgradParams(ops.t4_nchw(dout), ops.t4_nhwc(ah), dwh.data_ptr(), Cm * 9, 9, 1, dbh.data_ptr(), N, H, W, 3, H, W, Cm, 3, 3, 1, 1, impl))
     assert rel_l2(dwh, torch.nn.grad.conv2d_weight(aq, wh.shape, dout, padding=1)) < 5e-5
     assert rel_l2(dbh, dout.sum(dim=(0, 2, 3))) < 5e-5
 
