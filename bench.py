@@ -180,6 +180,7 @@ def profile_plan(eng, plan, x, t, dout):
     stream = ops._stream()
     out = {}
     for lst in (plan.fwd, plan.bwd):
+        lst = [(op[0], op[1]) for op in lst if op[0] is not None]
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(lst) + 1)]
         evs[0].record()
         for i, (fn, a) in enumerate(lst):

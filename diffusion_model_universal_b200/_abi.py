@@ -29,6 +29,7 @@ class ConvParams(C.Structure):
         ("Ho", c_i32), ("Wo", c_i32), ("Cj", c_i32),
         ("R", c_i32), ("S", c_i32), ("stride", c_i32), ("pad", c_i32),
         ("gather", c_i32), ("w_dtype", c_i32), ("impl", c_i32), ("_pad", c_i32),
+        ("workspace", c_vp), ("workspace_bytes", c_i64),
     ]
 
 
@@ -86,6 +87,7 @@ _SIGS = {
     "dmu_loss_workspace_floats": (c_i64, [c_i64]),
     "dmu_diffusion_loss": (c_i32, [c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "dmu_conv2d": (c_i32, [P(ConvParams), c_vp]),
+    "dmu_conv2d_workspace_bytes": (c_i64, []),
     "dmu_conv2d_wgrad": (c_i32, [P(WgradParams), c_vp]),
     "dmu_gn_stats": (c_i32, [P(GnParams), c_vp]),
     "dmu_gn_apply": (c_i32, [P(GnParams), c_vp]),

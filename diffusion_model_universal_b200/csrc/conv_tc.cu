@@ -132,7 +132,20 @@ struct ConvArgs {
     const __nv_bfloat16* res; int64_t r_sn, r_sh, r_sw;
     const float* bias;
     const float* temb; int64_t temb_pitch;
+    // split-K: gridDim.z = phases * splits, the `splits` CTAs of one output tile form a thread-block cluster; partial tiles
+    // go to `ws` (fp32 [slot][split][128][NT], plain stores), and after a cluster barrier every CTA folds and finishes
+    // 128/splits rows of the tile.  No atomics (REDG tops out near 0.2 G floats/us chip-wide) and no counters.
+    int splits;
+    float* ws;
 };
+
+constexpr int kMaxSplitCtas = 160;      // CTAs of a split launch: about one wave
+constexpr int64_t kSplitWsBytes = (int64_t)kMaxSplitCtas * 128 * 128 * 4;
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 template <int NT>
 struct ConvCfg {
@@ -152,7 +165,8 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
     __shared__ uint32_t s_tmem, s_issued;
 
-    const Phase ph = P.phases[blockIdx.z];
+    const int split = (int)blockIdx.z % P.splits;
+    const Phase ph = P.phases[blockIdx.z / P.splits];
     const int tile = blockIdx.x;
     const int tw0 = (tile % P.tiles_w) * P.BW;
     const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
@@ -179,6 +193,11 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
         return h < P.map_h[t.map] && h + P.BH > 0 && w < P.map_w[t.map] && w + P.BW > 0;
     };
 
+    // this CTA's share of the (tap, 64-channel chunk) k-blocks
+    const int kb_total = ph.ntaps * chunks;
+    const int kb_per = (kb_total + P.splits - 1) / P.splits;
+    const int kb_lo = split * kb_per, kb_hi = min(kb_total, kb_lo + kb_per);
+
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------ TMA producer
         const uint32_t a_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
@@ -186,13 +205,16 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
         for (int ti = 0; ti < ph.ntaps; ++ti) {
             const Tap t = P.taps[ph.tap0 + ti];
             if (!tap_live(t)) continue;
-            for (int c = 0; c < chunks; ++c, ++it) {
+            for (int c = 0; c < chunks; ++c) {
+                const int kb = ti * chunks + c;
+                if (kb < kb_lo || kb >= kb_hi) continue;
                 const int st = it % kStages;
                 mbar_wait(&empty_bar[st], ((it / kStages) & 1) ^ 1);
                 uint8_t* sa = smem + st * Cfg::kStageBytes;
                 mbar_arrive_expect_tx(&full_bar[st], a_bytes + Cfg::kBBytes);
                 tma_load_4d(sa, &maps.a[t.map], &full_bar[st], c * 64, tw0 + t.dw, th0 + t.dh, n0);
                 tma_load_2d(sa + Cfg::kABytes, &maps.b, &full_bar[st], t.wk + c * 64, j0);
+                ++it;
             }
         }
     } else if (warp == 1 && lane == 0) {
@@ -202,7 +224,9 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
         for (int ti = 0; ti < ph.ntaps; ++ti) {
             const Tap t = P.taps[ph.tap0 + ti];
             if (!tap_live(t)) continue;
-            for (int c = 0; c < chunks; ++c, ++it) {
+            for (int c = 0; c < chunks; ++c) {
+                const int kb = ti * chunks + c;
+                if (kb < kb_lo || kb >= kb_hi) continue;
                 const int st = it % kStages;
                 mbar_wait(&full_bar[st], (it / kStages) & 1);
                 tc_fence_after();
@@ -212,6 +236,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
                 for (int k = 0; k < 4; ++k)   // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
                     umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
                 umma_commit(&empty_bar[st]);
+                ++it;
             }
         }
         s_issued = (uint32_t)it;
@@ -229,6 +254,64 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     const int n = n0 + nl, th = th0 + hl, tw = tw0 + wl;
     const int ho = th * P.os + ph.oph, wo = tw * P.os + ph.opw;
     const bool valid = nl < P.BN && n < P.N && th < ph.TH && tw < ph.TW && ho < P.Ho && wo < P.Wo;
+    if (P.splits > 1) {
+        // ---- split-K: park the partial tile, cluster barrier, then fold + finish this CTA's share of the rows
+        const int slot = ((int)(blockIdx.z / P.splits) * (int)gridDim.y + (int)blockIdx.y) * (int)gridDim.x + tile;
+        float* tile_ws = P.ws + (size_t)slot * P.splits * 128 * NT;
+        float* mine = tile_ws + ((size_t)split * 128 + row) * NT;
+#pragma unroll 1
+        for (int c = 0; c < NT; c += 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 o = have_acc ? make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                __stcg(reinterpret_cast<float4*>(mine + c + i), o);
+            }
+        }
+        __threadfence();
+        cluster_sync_all();
+        constexpr int kGroups = NT / 8;               // 8-column groups per row
+        constexpr int kRowsPar = 128 / kGroups;       // rows handled at once by the 128 threads
+        const int rows_mine = 128 / P.splits;
+        const int cg = threadIdx.x % kGroups, rsub = threadIdx.x / kGroups;
+        for (int r0 = 0; r0 < rows_mine; r0 += kRowsPar) {
+            const int rr = split * rows_mine + r0 + rsub;
+            if (r0 + rsub >= rows_mine) break;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int sp = 0; sp < P.splits; ++sp) {
+                const float* src = tile_ws + ((size_t)sp * 128 + rr) * NT + cg * 8;
+                const float4 a4 = __ldcg(reinterpret_cast<const float4*>(src)), b4 = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                v[0] += a4.x; v[1] += a4.y; v[2] += a4.z; v[3] += a4.w; v[4] += b4.x; v[5] += b4.y; v[6] += b4.z; v[7] += b4.w;
+            }
+            const int wl2 = rr % P.BW, hl2 = (rr / P.BW) % P.BH, nl2 = rr / (P.BW * P.BH);
+            const int n2 = n0 + nl2, th2 = th0 + hl2, tw2 = tw0 + wl2;
+            const int ho2 = th2 * P.os + ph.oph, wo2 = tw2 * P.os + ph.opw;
+            if (!(nl2 < P.BN && n2 < P.N && th2 < ph.TH && tw2 < ph.TW && ho2 < P.Ho && wo2 < P.Wo)) continue;
+            const int jc = j0 + cg * 8;
+            if (P.bias) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(P.bias + jc)), b4 = __ldg(reinterpret_cast<const float4*>(P.bias + jc + 4));
+                v[0] += a4.x; v[1] += a4.y; v[2] += a4.z; v[3] += a4.w; v[4] += b4.x; v[5] += b4.y; v[6] += b4.z; v[7] += b4.w;
+            }
+            if (P.temb) {
+                const float* tp2 = P.temb + (int64_t)n2 * P.temb_pitch + jc;
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(tp2)), b4 = __ldg(reinterpret_cast<const float4*>(tp2 + 4));
+                v[0] += a4.x; v[1] += a4.y; v[2] += a4.z; v[3] += a4.w; v[4] += b4.x; v[5] += b4.y; v[6] += b4.z; v[7] += b4.w;
+            }
+            if (P.res) {
+                float r8[8];
+                load_vec<__nv_bfloat16>(P.res + (int64_t)n2 * P.r_sn + (int64_t)ho2 * P.r_sh + (int64_t)wo2 * P.r_sw + jc, r8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += r8[k];
+            }
+            store_vec<__nv_bfloat16>(P.y + (int64_t)n2 * P.y_sn + (int64_t)ho2 * P.y_sh + (int64_t)wo2 * P.y_sw + jc, v);
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem, NT);
+        return;
+    }
     __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0;
     const __nv_bfloat16* rp = P.res ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
     const float* tp = P.temb ? P.temb + (int64_t)n * P.temb_pitch + j0 : nullptr;
@@ -341,15 +424,52 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     A.y = reinterpret_cast<__nv_bfloat16*>(p->y.ptr); A.y_sn = p->y.sn; A.y_sh = p->y.sh; A.y_sw = p->y.sw;
     A.res = reinterpret_cast<const __nv_bfloat16*>(p->res.ptr); A.r_sn = p->res.sn; A.r_sh = p->res.sh; A.r_sw = p->res.sw;
     A.bias = p->bias; A.temb = p->temb; A.temb_pitch = p->temb_pitch;
-    dim3 grid(b.tiles_n * b.tiles_h * b.tiles_w, p->Cj / NT, nph);
+    // split-K for layers with few output tiles and a long contraction (the <= 4x4 stages: K up to 4608, 1-16 tiles):
+    // the splits of one tile are a thread-block cluster along z (co-scheduled by hardware, so the in-kernel barrier is safe)
+    const int slots = b.tiles_n * b.tiles_h * b.tiles_w * (p->Cj / NT) * nph;
+    // k-blocks that actually run in the first tile of each phase (taps whose whole box is padding are skipped in-kernel);
+    // measured on B200: a launch has a ~9 us floor, so splitting pays only from ~40 live k-blocks per CTA upwards
+    int kb_min = 1 << 30;
+    for (int i = 0; i < nph; ++i) {
+        int live = 0;
+        for (int t = 0; t < A.phases[i].ntaps; ++t) {
+            const Tap& tp = A.taps[A.phases[i].tap0 + t];
+            if (tp.dh < A.map_h[tp.map] && tp.dh + b.BH > 0 && tp.dw < A.map_w[tp.map] && tp.dw + b.BW > 0) ++live;
+        }
+        const int kb = live * (p->Ck / 64);
+        if (kb < kb_min) kb_min = kb;
+    }
+    A.splits = 1;
+    if (p->workspace && p->workspace_bytes >= kSplitWsBytes && slots * 2 <= sm_count() && kb_min >= 40) {
+        int sp = 8;                                               // portable cluster limit
+        while (sp > 1 && (slots * sp > kMaxSplitCtas || slots * sp > sm_count() + sm_count() / 4 || kb_min / sp < 12)) sp >>= 1;
+        if (sp >= 2) {
+            A.splits = sp;
+            A.ws = reinterpret_cast<float*>(p->workspace);
+        }
+    }
+    dim3 grid(b.tiles_n * b.tiles_h * b.tiles_w, p->Cj / NT, nph * A.splits);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmem);
         cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmem);
         attr_done = true;
     }
-    if (NT == 64) conv_tc_kernel<64><<<grid, 128, ConvCfg<64>::kSmem, stream>>>(maps, A);
-    else conv_tc_kernel<128><<<grid, 128, ConvCfg<128>::kSmem, stream>>>(maps, A);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = NT == 64 ? ConvCfg<64>::kSmem : ConvCfg<128>::kSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)A.splits;
+    cfg.attrs = attr;
+    cfg.numAttrs = A.splits > 1 ? 1 : 0;
+    cudaError_t e = NT == 64 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<64>, maps, A) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<128>, maps, A);
+    if (e != cudaSuccess) return fail("dmu_conv2d/tc: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/tc");
 }
 
@@ -541,6 +661,7 @@ static int wgrad_launch(const dmu_wgrad_params* p, cudaStream_t stream) {
 using namespace dmu;
 
 extern "C" {
+int64_t dmu_conv2d_workspace_bytes(void) { return tc::kSplitWsBytes; }
 int dmu_conv2d_tc_supported(const dmu_conv_params* p) { return tc::conv_supported(p); }
 int dmu_conv2d_tc(const dmu_conv_params* p, dmu_stream_t stream) { return tc::conv_launch(p, as_stream(stream)); }
 int dmu_wgrad_tc_supported(const dmu_wgrad_params* p) { return tc::wgrad_supported(p); }

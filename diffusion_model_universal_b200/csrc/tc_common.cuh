@@ -97,6 +97,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16-byte fire-and-forget reduction (atomicAdd(float4*) compiles to ATOMG, which returns the old value and serialises
+// on its latency; this is REDG.F32x4)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, 128-byte swizzle (the layout a TMA box with a 128-byte inner extent lands in):
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4

@@ -218,8 +218,10 @@ class Plan:
         self.t_in = None        # fp32 [N] timesteps (or sigmas)
         self.out = None         # fp32 [N,Cout,H,W] written by the head conv
         self.dout = None        # fp32 [N,Cout,H,W] upstream gradient (training plans)
+        self.ws = None          # split-K scratch of the tensor-core convs (zero between launches)
         self.graphs = {}        # "fwd"/"bwd" -> torch.cuda.CUDAGraph
         self.runs = {}          # "fwd"/"bwd" -> eager executions so far (the first one is the warm-up before capture)
+        self.nlaunch = {}       # "fwd"/"bwd" -> kernels per replay
         self.busy = False       # activations saved for a pending backward
 
 
@@ -398,11 +400,40 @@ class Engine:
         return p
 
     def _run(self, oplist, stream):
-        ops.LAUNCHES += len(oplist)
-        for fn, args in oplist:
-            rc = fn(*args, stream)
+        """Eager execution: one stream, list order (side-lane tags and join markers are ignored)."""
+        for op in oplist:
+            if op[0] is None:
+                continue
+            ops.LAUNCHES += 1
+            rc = op[0](*op[1], stream)
             if rc != 0:
-                _abi.check(rc, fn.__name__)
+                _abi.check(rc, op[0].__name__)
+
+    def _run_forked(self, oplist, side):
+        """Capture-time execution: ops tagged with lane 1 (weight gradients, bias/time-projection column sums: they only
+        read finished tensors and accumulate into their own outputs) go to a second stream so that the graph has two
+        parallel branches; an op on the side lane depends on everything issued on the main lane before it, a join marker
+        makes the main lane wait for the side lane.  The many latency-bound launches of the <= 8x8 stages then overlap."""
+        main = torch.cuda.current_stream()
+        main_ptr, side_ptr = C.c_void_p(main.cuda_stream), C.c_void_p(side.cuda_stream)
+        forked = False
+        for op in oplist:
+            if op[0] is None:                  # join marker
+                if forked:
+                    main.wait_stream(side)
+                    forked = False
+                continue
+            ops.LAUNCHES += 1
+            if len(op) == 3:
+                side.wait_stream(main)
+                rc = op[0](*op[1], side_ptr)
+                forked = True
+            else:
+                rc = op[0](*op[1], main_ptr)
+            if rc != 0:
+                _abi.check(rc, op[0].__name__)
+        if forked:
+            main.wait_stream(side)
 
     def _execute(self, plan: Plan, which: str):
         """Run plan.fwd / plan.bwd: eagerly the first time (warms every lazy one-time initialisation), then captured once
@@ -411,7 +442,7 @@ class Engine:
         g = plan.graphs.get(which)
         if g is not None:
             g.replay()
-            ops.LAUNCHES += len(oplist)
+            ops.LAUNCHES += plan.nlaunch[which]
             return
         n = plan.runs.get(which, 0)
         plan.runs[which] = n + 1
@@ -420,12 +451,15 @@ class Engine:
             self._run(oplist, ops._stream())
             return
         g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        n0 = ops.LAUNCHES
         with torch.cuda.graph(g):
-            self._run(oplist, ops._stream())     # recorded on the capture stream, not executed
-        ops.LAUNCHES -= len(oplist)
+            self._run_forked(oplist, side)       # recorded on the capture stream (+ one forked lane), not executed
+        plan.nlaunch[which] = ops.LAUNCHES - n0
+        ops.LAUNCHES = n0
         plan.graphs[which] = g
         g.replay()
-        ops.LAUNCHES += len(oplist)
+        ops.LAUNCHES += plan.nlaunch[which]
 
     def run_forward(self, x, t, plan: Plan) -> torch.Tensor:
         if not self.frozen:
@@ -462,6 +496,8 @@ class Engine:
         real.plan.x_in = torch.zeros(N, net.in_channels, H, W, device=self.device, dtype=torch.float32)
         real.plan.t_in = torch.zeros(N, device=self.device, dtype=torch.float32)
         real.plan.out = torch.zeros(N, net.out_channels, H, W, device=self.device, dtype=torch.float32)
+        if self.code == BF16:
+            real.plan.ws = torch.zeros(int(self._lib.dmu_conv2d_workspace_bytes()), device=self.device, dtype=torch.uint8)
         if train:
             real.plan.dout = torch.zeros(N, net.out_channels, H, W, device=self.device, dtype=torch.float32)
         plan = real.build()
@@ -505,6 +541,7 @@ class _PlanBuilder:
         self.lib = eng._lib
         self.code, self.esize = eng.code, eng.esize
         self.tape = []   # backward emitters, run in reverse
+        self.side_lane = True   # weight-gradient / column-sum launches of the backward go to the graph's second branch
 
     # ---- allocation helpers
     def act(self, H, W, Cc, want_grad=True) -> Buf:
@@ -531,7 +568,8 @@ class _PlanBuilder:
         N, Hi, Wi, Ck, Ho, Wo, Cj = dims
         R, S, stride, pad = geom
         p = ConvParams(x, y, res if res is not None else _null_t4(), w, w_strides[0], w_strides[1], w_strides[2], bias, temb, temb_pitch,
-                       N, Hi, Wi, Ck, Ho, Wo, Cj, R, S, stride, pad, gather, w_code, self.e.impl, 0)
+                       N, Hi, Wi, Ck, Ho, Wo, Cj, R, S, stride, pad, gather, w_code, self.e.impl, 0,
+                       self.plan.ws.data_ptr() if self.plan.ws is not None else None, self.plan.ws.numel() if self.plan.ws is not None else 0)
         lst.append((self.lib.dmu_conv2d, (C.byref(p),)))
         self.plan.keep.append(p)
         return p
@@ -540,7 +578,7 @@ class _PlanBuilder:
         N, Hp, Wp, Ca, Hq, Wq, Cb = dims
         R, S, stride, pad = geom
         p = WgradParams(p4, q4, dw, dw_strides[0], dw_strides[1], dw_strides[2], dbias, N, Hp, Wp, Ca, Hq, Wq, Cb, R, S, stride, pad, self.e.impl)
-        self.plan.bwd.append((self.lib.dmu_conv2d_wgrad, (C.byref(p),)))
+        self.plan.bwd.append((self.lib.dmu_conv2d_wgrad, (C.byref(p),), 1) if self.side_lane else (self.lib.dmu_conv2d_wgrad, (C.byref(p),)))
         self.plan.keep.append(p)
         return p
 
@@ -624,7 +662,7 @@ class _PlanBuilder:
             # time projection: per-image channel sums of dh
             t4 = h.grad.t4()
             self.plan.keep.append(t4)
-            self.plan.bwd.append((self.lib.dmu_colsum, (C.byref(t4), self.N, h.H, h.W, Co, self.dtproj + self.tp_off[pfx] * 4, self.tp_total, None, 1.0)))
+            self.plan.bwd.append((self.lib.dmu_colsum, (C.byref(t4), self.N, h.H, h.W, Co, self.dtproj + self.tp_off[pfx] * 4, self.tp_total, None, 1.0), 1))
             # conv1
             self.conv_layer_bwd(a1, h, pfx + "conv1.weight", pfx + "conv1.bias", 3, 1, 1, a1.grad)
             # shortcut
@@ -806,7 +844,7 @@ class _PlanBuilder:
                                (N, y.H, y.W, co, u.H, u.W, co), (4, 4, 2, 1))
                     t4 = du.t4()
                     plan.keep.append(t4)
-                    plan.bwd.append((lib.dmu_colsum, (C.byref(t4), N, u.H, u.W, co, None, 0, self.gp(pfx + "upsample.bias"), 1.0)))
+                    plan.bwd.append((lib.dmu_colsum, (C.byref(t4), N, u.H, u.W, co, None, 0, self.gp(pfx + "upsample.bias"), 1.0), 1))
                 self.tape.append(up_bwd)
             x = u
         # -------- head: GroupNorm -> SiLU -> conv3x3 -> NCHW fp32
@@ -834,7 +872,10 @@ class _PlanBuilder:
         # stem: wgrad only (the network input needs no gradient on this path)
         self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), e.gsaddr("initial_conv.weight"),
                    (9 * net.in_channels, 1, net.in_channels), self.gp("initial_conv.bias"), (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
-        # time projections (one GEMM for all 22 blocks), then the embedding MLP
+        # time projections (one GEMM for all 22 blocks), then the embedding MLP: they consume the per-image column sums the
+        # side lane produced, so the lanes join here
+        plan.bwd.append((None, ()))
+        self.side_lane = False
         dtemb = self.f32(N * T4)
         self.linear_bwd(_rows_t4(temb, T4), _rows_t4(self.dtproj, self.tp_total), _rows_t4(dtemb, T4), N, T4, self.tp_total,
                         e.paddr(first + "time_mlp.weight"), self.gp(first + "time_mlp.weight"), self.gp(first + "time_mlp.bias"))

@@ -134,8 +134,16 @@ typedef struct {
     int32_t w_dtype;
     int32_t impl;
     int32_t _pad;
+    /* Optional split-K scratch for the tensor-core path (layers with few output pixels and a long contraction are
+     * split along K over the CTAs of a thread-block cluster, which park their partial tiles here before folding
+     * them).  Caller-owned, contents undefined before and after, at least dmu_conv2d_workspace_bytes(); it must not
+     * be shared by launches that may run concurrently.  NULL/0 = never split. */
+    void* workspace;
+    int64_t workspace_bytes;
 } dmu_conv_params;
 int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream);
+/* bytes of split-K scratch that let dmu_conv2d split every eligible layer (a constant upper bound) */
+int64_t dmu_conv2d_workspace_bytes(void);
 
 /* Weight gradient of the same contraction (autograd of the call sites above):
  *   dw[a*dw_sa + b*dw_sb + (r*S+s)*dw_st] += sum_{n,po,qo} p[n,po,qo,a] * q[n, po*stride-pad+r, qo*stride-pad+s, b]

@@ -61,6 +61,9 @@ class FakeLib:
     def dmu_loss_workspace_floats(self, n):
         return 1
 
+    def dmu_conv2d_workspace_bytes(self):
+        return 64
+
     # ---------------------------------------------------------------- memory
     def dmu_zero(self, ptr, nbytes, stream):
         self._count()

@@ -85,13 +85,33 @@ def test_conv_tcgen05(case):
     _conv_case(case, torch.bfloat16, 2)
 
 
+SPLITK_CASES = [
+    (128, 1, 1, 512, 256, 3, 1, 1, "conv"),
+    (128, 2, 2, 384, 128, 3, 1, 1, "conv"),
+    (32, 4, 4, 256, 128, 3, 1, 1, "conv"),
+    (64, 2, 2, 256, 256, 4, 2, 1, "conv"),
+    (64, 2, 2, 256, 256, 4, 2, 1, "convT"),
+    (5, 4, 4, 128, 128, 3, 1, 1, "conv"),
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES)
+def test_conv_tcgen05_split_k(case):
+    """Same kernels with the split-K scratch supplied: few output tiles, long contraction -> a cluster of CTAs per tile.
+    The scratch starts as garbage (NaN bit patterns) and is reused by a second launch: its prior contents must not matter."""
+    ops, _abi = _mods()
+    ws = torch.full((int(_abi.lib().dmu_conv2d_workspace_bytes()),), 0xFF, device="cuda:0", dtype=torch.uint8)
+    _conv_case(case, torch.bfloat16, 2, ws)
+    _conv_case(case, torch.bfloat16, 2, ws)
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_fprop_dgrad_wgrad(case, dtype):
     _conv_case(case, dtype, 1)
 
 
-def _conv_case(case, dtype, impl):
+def _conv_case(case, dtype, impl, ws=None):
     ops, _abi = _mods()
     from diffusion_model_universal_b200._abi import ConvParams, WgradParams
     N, H, W, Ci, Co, R, stride, pad, kind = case
@@ -116,7 +136,7 @@ def _conv_case(case, dtype, impl):
     code = ops.dtype_code(xh)
     p = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(y_full, 8, Co), ops.t4_nhwc(res_full, 16, Co), wk.data_ptr(), R * R * Ci, 1, Ci,
                    bias.data_ptr(), temb.data_ptr() + 4 * 4, Co + 8, N, H, W, Ci, Ho, Wo, Co, R, R, stride, pad,
-                   0 if kind == "conv" else 1, code, impl, 0)
+                   0 if kind == "conv" else 1, code, impl, 0, ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0)
     ops.conv2d_raw(p)
     if kind == "conv":
         ref = F.conv2d(xq, wq, bias, stride=stride, padding=pad)
@@ -135,7 +155,8 @@ def _conv_case(case, dtype, impl):
     if impl == 2:   # tensor-core path contracts over a K-contiguous filter: [Ci][R][S][Co]
         wkt = _repack(w, kind == "convT", dtype, dgrad=True)
         p2 = ConvParams(ops.t4_nhwc(dyh), ops.t4_nhwc(dx), _null(), wkt.data_ptr(), R * R * Co, 1, Co, None, None, 0,
-                        N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1 if kind == "conv" else 0, code, impl, 0)
+                        N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1 if kind == "conv" else 0, code, impl, 0,
+                        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0)
     else:
         p2 = ConvParams(ops.t4_nhwc(dyh), ops.t4_nhwc(dx), _null(), wk.data_ptr(), 1, R * R * Ci, Ci, None, None, 0,
                         N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1 if kind == "conv" else 0, code, impl, 0)
