@@ -63,6 +63,10 @@ class AttnParams(C.Structure):
     ]
 
 
+class GnPgDesc(C.Structure):
+    _fields_ = [("red", c_vp), ("dgamma", c_vp), ("dbeta", c_vp), ("C", c_i32), ("_pad", c_i32)]
+
+
 class RepackDesc(C.Structure):
     _fields_ = [("src", c_vp), ("dst", c_vp), ("O", c_i32), ("I", c_i32), ("R", c_i32), ("S", c_i32), ("kind", c_i32), ("dst_dtype", c_i32)]
 
@@ -89,6 +93,9 @@ _SIGS = {
     "dmu_conv2d": (c_i32, [P(ConvParams), c_vp]),
     "dmu_conv2d_workspace_bytes": (c_i64, []),
     "dmu_conv2d_wgrad": (c_i32, [P(WgradParams), c_vp]),
+    "dmu_gn_forward": (c_i32, [P(GnParams), c_vp]),
+    "dmu_gn_backward": (c_i32, [P(GnParams), c_vp]),
+    "dmu_gn_param_grads": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp]),
     "dmu_gn_stats": (c_i32, [P(GnParams), c_vp]),
     "dmu_gn_apply": (c_i32, [P(GnParams), c_vp]),
     "dmu_gn_bwd_reduce": (c_i32, [P(GnParams), c_vp]),

@@ -2,6 +2,8 @@
 // embedding, parameter repack and the fused Adam+EMA update.
 // All HBM-bound: 128-bit accesses on NHWC rows, warp-shuffle / smem reductions,
 // fp32 statistics.  Call sites: see include/dmu_b200.h.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace dmu {
@@ -319,6 +321,273 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dmu_gn_params P) {
     }
 }
 
+// ------------------------------------------------------------------ single-pass GroupNorm (cluster per image)
+// One thread-block cluster (1, 2, 4 or 8 CTAs) owns one image; every thread keeps its share of the image in registers
+// (at most kHold 16-byte vectors per tensor), the per-channel partial sums of the CTAs meet through distributed shared
+// memory, and the result is written from the registers: forward = 1 read + 1 write of the activation instead of
+// stats (1 read) + apply (1 read + 1 write); backward = 1 read of (x, dy) instead of 2.  Also halves the launch count of
+// the many latency-bound <= 16x16 tensors.
+constexpr int kHold = 8;
+
+__device__ __forceinline__ void cluster_sync_() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(local), r;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(r) : "memory");
+    return v;
+}
+// totals over the cluster of two per-channel arrays (in place); every CTA ends up with the full sums
+__device__ __forceinline__ void cluster_channel_total(float* s_a, float* s_b, float* s_ta, float* s_tb, int C, int cs) {
+    if (cs == 1) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { s_ta[c] = s_a[c]; s_tb[c] = s_b[c]; }
+        __syncthreads();
+        return;
+    }
+    cluster_sync_();                     // partials of every CTA are in place
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int r = 0; r < cs; ++r) { a += ld_dsmem(s_a + c, r); b += ld_dsmem(s_b + c, r); }
+        s_ta[c] = a; s_tb[c] = b;
+    }
+    cluster_sync_();                     // nobody leaves (or overwrites its partials) while peers still read them
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_fwd_fused_kernel(dmu_gn_params P) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s_a[kMaxC], s_b[kMaxC], s_ta[kMaxC], s_tb[kMaxC];
+    __shared__ float s_red[256 * kVec];
+    const int n = blockIdx.y, HW = P.H * P.W, C = P.C, cs = gridDim.x;
+    RowMap m(C, kVec);
+    int p0, p1; chunk_range(HW, p0, p1);
+    uint4 r[kHold];
+    float a[kVec], q[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { a[i] = 0.f; q[i] = 0.f; }
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr) + m.v * kVec;
+#pragma unroll
+    for (int u = 0; u < kHold; ++u) {
+        const int pp = p0 + m.lane + u * m.lanes;
+        r[u] = (m.active && pp < p1) ? ld_raw<T>(xb + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < kHold; ++u) {
+        float v[kVec];
+        unpack<T>(r[u], v);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { a[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+    }
+    block_channel_sum<kVec>(m, a, s_red, s_a, C);
+    block_channel_sum<kVec>(m, q, s_red, s_b, C);
+    cluster_channel_total(s_a, s_b, s_ta, s_tb, C, cs);
+    // group statistics -> per-channel scale/shift (reuse s_a / s_b), raw sums saved for the backward
+    const int cpg = C / P.G;
+    const float cnt = (float)cpg * (float)HW;
+    for (int g = threadIdx.x; g < P.G; g += blockDim.x) {
+        float su = 0.f, sq = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { su += s_ta[c]; sq += s_tb[c]; }
+        if (blockIdx.x == 0) {
+            P.sums[((int64_t)n * P.G + g) * 2 + 0] = su;
+            P.sums[((int64_t)n * P.G + g) * 2 + 1] = sq;
+        }
+        const float mean = su / cnt;
+        const float rstd = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + P.eps);
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float sc = rstd * P.gamma[c];
+            s_a[c] = sc;
+            s_b[c] = P.beta[c] - mean * sc;
+        }
+    }
+    __syncthreads();
+    if (!m.active) return;
+    float sc[kVec], sh[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { sc[i] = s_a[m.v * kVec + i]; sh[i] = s_b[m.v * kVec + i]; }
+    T* yb = reinterpret_cast<T*>(P.y.ptr) + m.v * kVec;
+#pragma unroll
+    for (int u = 0; u < kHold; ++u) {
+        const int pp = p0 + m.lane + u * m.lanes;
+        if (pp < p1) {
+            float v[kVec];
+            unpack<T>(r[u], v);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) {
+                const float t = fmaf(v[i], sc[i], sh[i]);
+                v[i] = P.silu ? silu_f(t) : t;
+            }
+            store_vec<T>(yb + pix_off(P.y, n, pp, P.W), v);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_fused_kernel(dmu_gn_params P) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
+    __shared__ float s_a[kMaxC], s_b[kMaxC], s_ta[kMaxC], s_tb[kMaxC];
+    __shared__ float s_red[256 * kVec];
+    const int n = blockIdx.y, HW = P.H * P.W, C = P.C, cs = gridDim.x;
+    stage_affine(P, n, s_mean, s_scale, s_beta, s_rstd);
+    __syncthreads();
+    RowMap m(C, kVec);
+    int p0, p1; chunk_range(HW, p0, p1);
+    uint4 rx[kHold], rd[kHold];
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr) + m.v * kVec;
+    const T* dyb = reinterpret_cast<const T*>(P.y.ptr) + m.v * kVec;
+#pragma unroll
+    for (int u = 0; u < kHold; ++u) {
+        const int pp = p0 + m.lane + u * m.lanes;
+        const bool ok = m.active && pp < p1;
+        rx[u] = ok ? ld_raw<T>(xb + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
+        rd[u] = ok ? ld_raw<T>(dyb + pix_off(P.y, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float mu[kVec], sc[kVec], be[kVec];
+    const int cbase = m.active ? m.v * kVec : 0;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { mu[i] = s_mean[cbase + i]; sc[i] = s_scale[cbase + i]; be[i] = s_beta[cbase + i]; }
+    {
+        float a[kVec], b[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { a[i] = 0.f; b[i] = 0.f; }
+#pragma unroll
+        for (int u = 0; u < kHold; ++u) {
+            float xv[kVec], dv[kVec];
+            unpack<T>(rx[u], xv);
+            unpack<T>(rd[u], dv);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) {
+                const float d = xv[i] - mu[i];
+                const float du = act_grad(fmaf(d, sc[i], be[i]), dv[i], P.silu);    // dy == 0 for the padding slots
+                a[i] += du;
+                b[i] = fmaf(du, d, b[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) b[i] *= s_rstd[cbase + i];
+        block_channel_sum<kVec>(m, a, s_red, s_a, C);
+        block_channel_sum<kVec>(m, b, s_red, s_b, C);
+    }
+    cluster_channel_total(s_a, s_b, s_ta, s_tb, C, cs);
+    const int cpg = C / P.G;
+    const float inv_cnt = 1.f / ((float)cpg * (float)HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (blockIdx.x == 0) {
+            if (P.red) {      // per-image sums, folded over the batch by dmu_gn_param_grads (or by the caller)
+                P.red[((int64_t)n * C + c) * 2 + 0] = s_ta[c];
+                P.red[((int64_t)n * C + c) * 2 + 1] = s_tb[c];
+            }
+            if (P.dbeta) atomicAdd(&P.dbeta[c], s_ta[c]);
+            if (P.dgamma) atomicAdd(&P.dgamma[c], s_tb[c]);
+        }
+        const int g0 = (c / cpg) * cpg;
+        float A = 0.f, B = 0.f;
+        for (int k = g0; k < g0 + cpg; ++k) {
+            const float gam = P.gamma[k];
+            A += gam * s_ta[k];
+            B += gam * s_tb[k];
+        }
+        s_a[c] = A * inv_cnt;
+        s_b[c] = B * inv_cnt;
+    }
+    __syncthreads();
+    if (!m.active) return;
+    float k0[kVec], k1[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+        const float rs = s_rstd[cbase + i];
+        k1[i] = -rs * rs * s_b[cbase + i];
+        k0[i] = -rs * s_a[cbase + i] - mu[i] * k1[i];
+    }
+    T* dxb = reinterpret_cast<T*>(P.dx.ptr) + m.v * kVec;
+    const T* a0 = P.add0.ptr ? reinterpret_cast<const T*>(P.add0.ptr) + m.v * kVec : nullptr;
+    const T* a1 = P.add1.ptr ? reinterpret_cast<const T*>(P.add1.ptr) + m.v * kVec : nullptr;
+#pragma unroll
+    for (int u = 0; u < kHold; ++u) {
+        const int pp = p0 + m.lane + u * m.lanes;
+        if (pp < p1) {
+            float xv[kVec], dv[kVec], o[kVec];
+            unpack<T>(rx[u], xv);
+            unpack<T>(rd[u], dv);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) {
+                const float du = act_grad(fmaf(xv[i] - mu[i], sc[i], be[i]), dv[i], P.silu);
+                o[i] = fmaf(du, sc[i], fmaf(xv[i], k1[i], k0[i]));
+            }
+            if (a0) {
+                float t[kVec];
+                unpack<T>(ld_raw<T>(a0 + pix_off(P.add0, n, pp, P.W)), t);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) o[i] += t[i];
+            }
+            if (a1) {
+                float t[kVec];
+                unpack<T>(ld_raw<T>(a1 + pix_off(P.add1, n, pp, P.W)), t);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) o[i] += t[i];
+            }
+            store_vec<T>(dxb + pix_off(P.dx, n, pp, P.W), o);
+        }
+    }
+}
+
+// dgamma[c] += sum_n red[n,c,1], dbeta[c] += sum_n red[n,c,0] for a whole table of GroupNorm layers in one launch:
+// the batch reduction of the affine-parameter gradients, kept out of the per-layer kernels (where it was a same-address
+// atomic from every CTA of every image).
+struct GnPgDesc { const float* red; float* dgamma; float* dbeta; int32_t C; int32_t _pad; };
+__global__ void __launch_bounds__(256) gn_param_grads_kernel(const GnPgDesc* __restrict__ table, int N) {
+    const GnPgDesc d = table[blockIdx.y];
+    // thread = (channel, quantity); 256 threads cover 128 channels x 2
+    const int e0 = blockIdx.x * 256 + threadIdx.x;
+    if (e0 >= d.C * 2) return;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    int n = 0;
+    for (; n + 3 < N; n += 4) {
+        t0 += d.red[(int64_t)(n + 0) * d.C * 2 + e0];
+        t1 += d.red[(int64_t)(n + 1) * d.C * 2 + e0];
+        t2 += d.red[(int64_t)(n + 2) * d.C * 2 + e0];
+        t3 += d.red[(int64_t)(n + 3) * d.C * 2 + e0];
+    }
+    for (; n < N; ++n) t0 += d.red[(int64_t)n * d.C * 2 + e0];
+    const float t = (t0 + t1) + (t2 + t3);
+    const int c = e0 >> 1;
+    if (e0 & 1) d.dgamma[c] += t;
+    else d.dbeta[c] += t;
+}
+
+// cluster size for the single-pass kernels: smallest of {1,2,4,8} whose per-CTA pixel slab fits kHold vectors per thread
+static int gn_fused_cluster(int HW, int C, int vec) {
+    const int lanes = 256 / (C / vec);
+    if (lanes < 1) return 0;
+    for (int cs = 1; cs <= 8; cs <<= 1) {
+        const int per = (HW + cs - 1) / cs;
+        if (per <= lanes * kHold) return cs <= HW ? cs : 0;
+    }
+    return 0;
+}
+
+template <typename K>
+static int launch_cluster(K kernel, int cs, int N, cudaStream_t stream, const dmu_gn_params& p) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cs, N);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cs > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e != cudaSuccess) return fail("GroupNorm cluster launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 // ------------------------------------------------------------------ column sums
 // grid (pixel chunks, N): per-CTA partial sums, then atomics (out_nc / out_c must hold the running value: zero-initialised
 // by the caller when a fresh sum is wanted).
@@ -550,6 +819,37 @@ int dmu_gn_bwd_apply(const dmu_gn_params* p, dmu_stream_t stream) {
     return check_launch("dmu_gn_bwd_apply");
 }
 
+int dmu_gn_forward(const dmu_gn_params* p, dmu_stream_t stream) {
+    if (int e = gn_check(p, "dmu_gn_forward", true, false)) return e;
+    const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
+    const int cs = gn_fused_cluster(p->H * p->W, p->C, vec);
+    if (cs == 0) {
+        if (int e = dmu_gn_stats(p, stream)) return e;
+        return dmu_gn_apply(p, stream);
+    }
+    if (p->x.dtype == DMU_BF16) return launch_cluster(gn_fwd_fused_kernel<__nv_bfloat16>, cs, p->N, as_stream(stream), *p);
+    return launch_cluster(gn_fwd_fused_kernel<float>, cs, p->N, as_stream(stream), *p);
+}
+int dmu_gn_param_grads(const void* table_device, int32_t n_desc, int32_t max_c, int32_t N, dmu_stream_t stream) {
+    DMU_REQUIRE(table_device && n_desc > 0 && max_c > 0 && N > 0, "dmu_gn_param_grads: bad arguments");
+    gn_param_grads_kernel<<<dim3((max_c * 2 + 255) / 256, n_desc), 256, 0, as_stream(stream)>>>(reinterpret_cast<const GnPgDesc*>(table_device), N);
+    return check_launch("dmu_gn_param_grads");
+}
+
+int dmu_gn_backward(const dmu_gn_params* p, dmu_stream_t stream) {
+    if (int e = gn_check(p, "dmu_gn_backward", true, true)) return e;
+    const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
+    // measured on B200: holding (x, dy) in registers costs the single-pass backward its occupancy (225 registers), so it
+    // only pays for images one CTA can hold, where it saves a launch; larger images take the two-pass kernels
+    const int cs = gn_fused_cluster(p->H * p->W, p->C, vec) == 1 ? 1 : 0;
+    if (cs == 0) {
+        if (int e = dmu_gn_bwd_reduce(p, stream)) return e;
+        return dmu_gn_bwd_apply(p, stream);
+    }
+    if (p->x.dtype == DMU_BF16) return launch_cluster(gn_bwd_fused_kernel<__nv_bfloat16>, cs, p->N, as_stream(stream), *p);
+    return launch_cluster(gn_bwd_fused_kernel<float>, cs, p->N, as_stream(stream), *p);
+}
+
 int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out_nc, int64_t pitch, float* out_c,
                float scale, dmu_stream_t stream) {
     DMU_REQUIRE(x && x->ptr, "dmu_colsum: null input");
@@ -562,7 +862,12 @@ int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C,
         Ww = N * H * W; Hh = 1; Nn = 1;
         t.sh = t.sn = (int64_t)Ww * t.sw;
     }
-    DISPATCH_T(t.dtype, colsum_kernel, gn_grid(Nn, Hh * Ww, C, vec), 256, as_stream(stream), t, Hh, Ww, C, out_nc, pitch, out_c, scale);
+    dim3 grid = gn_grid(Nn, Hh * Ww, C, vec);
+    if (out_c) {   // every CTA ends in C atomics on the same C addresses: keep the CTA count near one per SM
+        const int cap = (sm_count() + Nn - 1) / Nn;
+        if ((int)grid.x > cap) grid.x = cap;
+    }
+    DISPATCH_T(t.dtype, colsum_kernel, grid, 256, as_stream(stream), t, Hh, Ww, C, out_nc, pitch, out_c, scale);
     return check_launch("dmu_colsum");
 }
 

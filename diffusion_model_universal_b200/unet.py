@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _abi, ops
-from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, RepackDesc
+from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, RepackDesc, GnPgDesc
 
 
 def gn_groups(channels: int, num_groups: int = 32) -> int:
@@ -541,6 +541,7 @@ class _PlanBuilder:
         self.lib = eng._lib
         self.code, self.esize = eng.code, eng.esize
         self.tape = []   # backward emitters, run in reverse
+        self.gn_pg = []         # (red, dgamma, dbeta, C) of every GroupNorm backward: folded by one launch at the end
         self.side_lane = True   # weight-gradient / column-sum launches of the backward go to the graph's second branch
 
     # ---- allocation helpers
@@ -589,20 +590,20 @@ class _PlanBuilder:
         p = GnParams(x.t4(), y.t4(), _null_t4(), _null_t4(), _null_t4(), sums, self.e.paddr(gamma_name), self.e.paddr(beta_name),
                      None, None, None, self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, 0)
         self.plan.keep.append(p)
-        self.plan.fwd.append((self.lib.dmu_gn_stats, (C.byref(p),)))
-        self.plan.fwd.append((self.lib.dmu_gn_apply, (C.byref(p),)))
+        self.plan.fwd.append((self.lib.dmu_gn_forward, (C.byref(p),)))
         return y, (x, y, sums, G, gamma_name, beta_name, silu)
 
     def gn_bwd(self, rec, dx: Buf, add0: Buf = None, add1: Buf = None):
         """Backward of gn(): reads rec.y.grad, writes dx (+ addends)."""
         x, y, sums, G, gname, bname, silu = rec
         red = self.red.take(self.N * x.C * 2 * 4, 16)
+        # dgamma/dbeta are left out here: one dmu_gn_param_grads launch folds every layer's per-image sums at the end
         p = GnParams(x.t4(), y.grad.t4(), dx.t4(), add0.t4() if add0 is not None else _null_t4(), add1.t4() if add1 is not None else _null_t4(),
-                     sums, self.e.paddr(gname), self.e.paddr(bname), red, self.gp(gname), self.gp(bname),
+                     sums, self.e.paddr(gname), self.e.paddr(bname), red, None, None,
                      self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, 0)
+        self.gn_pg.append(GnPgDesc(red, self.gp(gname), self.gp(bname), x.C, 0))
         self.plan.keep.append(p)
-        self.plan.bwd.append((self.lib.dmu_gn_bwd_reduce, (C.byref(p),)))
-        self.plan.bwd.append((self.lib.dmu_gn_bwd_apply, (C.byref(p),)))
+        self.plan.bwd.append((self.lib.dmu_gn_backward, (C.byref(p),)))
 
     # ---- conv layer helpers (filters repacked [O][R][S][I])
     def conv_layer(self, x: Buf, y: Buf, wname, bname, R, stride, pad, temb=None, temb_pitch=0, res: Buf = None):
@@ -703,8 +704,7 @@ class _PlanBuilder:
         gp_ = GnParams(z.t4(), y.t4(), _null_t4(), _null_t4(), _null_t4(), sums, e.paddr(pfx + "norm.weight"), e.paddr(pfx + "norm.bias"),
                        None, None, None, self.N, x.H, x.W, Cc, G, 0, 1e-5, 0)
         self.plan.keep.append(gp_)
-        self.plan.fwd.append((self.lib.dmu_gn_stats, (C.byref(gp_),)))
-        self.plan.fwd.append((self.lib.dmu_gn_apply, (C.byref(gp_),)))
+        self.plan.fwd.append((self.lib.dmu_gn_forward, (C.byref(gp_),)))
         rec = (z, y, sums, G, pfx + "norm.weight", pfx + "norm.bias", False)
         if not self.train:
             return
@@ -901,6 +901,10 @@ class _PlanBuilder:
         # ... and one zeroes the gradient arena the wgrad kernels accumulate into
         plan.bwd.insert(0, (lib.dmu_zero, (e.gflat.data_ptr(), e.gflat.numel() * 4)))
         plan.bwd.insert(0, (lib.dmu_zero, (e.gstage.data_ptr(), e.gstage.numel() * 4)))
+        if self.gn_pg:
+            arr = (GnPgDesc * len(self.gn_pg))(*self.gn_pg)
+            plan.gn_pg_table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(e.device)
+            plan.bwd.append((lib.dmu_gn_param_grads, (plan.gn_pg_table.data_ptr(), len(self.gn_pg), max(d.C for d in self.gn_pg), N)))
         # filter gradients: staging layout -> the parameters' own layout inside the gradient arena
         plan.bwd.append((lib.dmu_repack_weights, (e.unpack_table.data_ptr(), e.unpack_n, e.repack_max)))
         return plan

@@ -186,6 +186,17 @@ typedef struct {
     float eps;
     int32_t _pad;
 } dmu_gn_params;
+/* One-call forms: forward = stats + apply (sums must NOT be pre-zeroed: they are overwritten when the single-pass
+ * cluster kernel runs and accumulated by the two-pass fallback, so zero them as for dmu_gn_stats), backward =
+ * bwd_reduce + bwd_apply.  An image that fits the registers of at most 8 CTAs (a thread-block cluster, partial sums
+ * exchanged through distributed shared memory) is read once; larger ones fall back to the two-pass kernels below. */
+int dmu_gn_forward(const dmu_gn_params* p, dmu_stream_t stream);
+int dmu_gn_backward(const dmu_gn_params* p, dmu_stream_t stream);
+/* Batch reduction of the affine-parameter gradients for a table of layers in one launch:
+ *   dgamma[c] += sum_n red[n,c,1];  dbeta[c] += sum_n red[n,c,0]
+ * (run once after the backward of all layers, with dgamma/dbeta left NULL in their dmu_gn_params).  The table lives in
+ * device memory: n_desc entries of { const float* red; float* dgamma; float* dbeta; int32_t C; int32_t pad; }. */
+int dmu_gn_param_grads(const void* table_device, int32_t n_desc, int32_t max_c, int32_t N, dmu_stream_t stream);
 int dmu_gn_stats(const dmu_gn_params* p, dmu_stream_t stream);
 int dmu_gn_apply(const dmu_gn_params* p, dmu_stream_t stream);
 int dmu_gn_bwd_reduce(const dmu_gn_params* p, dmu_stream_t stream);

@@ -202,6 +202,22 @@ class FakeLib:
         _view4(p.dx, p.N, p.H, p.W, p.C).copy_(dx)
         return 0
 
+    def dmu_gn_param_grads(self, table, n, max_c, N, stream):
+        from diffusion_model_universal_b200._abi import GnPgDesc
+        self._count()
+        arr = (GnPgDesc * n).from_address(_addr(table))
+        for d in arr:
+            red = _flat(d.red, N * d.C * 2, F32).view(N, d.C, 2).sum(0)
+            _flat(d.dbeta, d.C, F32).add_(red[:, 0])
+            _flat(d.dgamma, d.C, F32).add_(red[:, 1])
+        return 0
+
+    def dmu_gn_forward(self, ref, stream):
+        return self.dmu_gn_stats(ref, stream) or self.dmu_gn_apply(ref, stream)
+
+    def dmu_gn_backward(self, ref, stream):
+        return self.dmu_gn_bwd_reduce(ref, stream) or self.dmu_gn_bwd_apply(ref, stream)
+
     def dmu_colsum(self, ref, N, H, W, Cc, out_nc, pitch, out_c, scale, stream):
         self._count()
         x = _view4(_obj(ref), N, H, W, Cc).float().sum(dim=(1, 2)) * scale

@@ -84,13 +84,15 @@ def test_bucket_ranges_cover_the_arena_tail_first():
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_step_equals_single_process_mean(tmp_path):
+def test_two_rank_step_equals_single_process_mean(tmp_path, monkeypatch):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
     assert torch.equal(r0["g"], r1["g"]) and torch.equal(r0["p"], r1["p"]) and torch.equal(r0["ema"], r1["ema"])
     # single-process emulation: mean of the two shard gradients == gradient of the mean loss over the full batch
-    _setup_fake()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_device
+    fake_device.install(monkeypatch)
     g = torch.Generator().manual_seed(100)
     x = torch.randn(4, 3, 32, 32, generator=g)
     t = torch.randint(0, 1000, (4,), generator=g)

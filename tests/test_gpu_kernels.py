@@ -255,12 +255,26 @@ def test_linear_via_conv(M, I, O):
 @pytest.mark.parametrize("C_,G", [(64, 32), (128, 32), (192, 32), (256, 32), (384, 32), (512, 32), (32, 32), (16, 8)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("silu", [1, 0])
-def test_groupnorm_fwd_bwd(C_, G, dtype, silu):
+@pytest.mark.parametrize("one_call", [False, True])
+def test_groupnorm_fwd_bwd(C_, G, dtype, silu, one_call):
+    N, H, W = (3, 8, 8) if C_ > 128 else (2, 16, 16)
+    _groupnorm_case(N, H, W, C_, G, dtype, silu, one_call)
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 32, 64), (2, 32, 32, 128), (5, 1, 1, 256), (4, 2, 2, 384), (3, 4, 4, 128), (2, 64, 64, 64), (2, 12, 20, 48)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_groupnorm_single_pass_cluster_sizes(shape, dtype):
+    """dmu_gn_forward / dmu_gn_backward over the image sizes of the UNet: 1-, 2-, 4- and 8-CTA clusters per image, and the
+    two-pass fallback (64x64x64 does not fit eight CTAs' registers)."""
+    N, H, W, C_ = shape
+    _groupnorm_case(N, H, W, C_, 16 if C_ % 32 else 32, dtype, 1, True)
+
+
+def _groupnorm_case(N, H, W, C_, G, dtype, silu, one_call):
     ops, _abi = _mods()
     from diffusion_model_universal_b200._abi import GnParams
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(C_ + silu)
-    N, H, W = (3, 8, 8) if C_ > 128 else (2, 16, 16)
     x = (torch.randn(N, C_, H, W, generator=g) * 2 + 0.5).to(dev)
     gamma, beta = (1 + 0.2 * torch.randn(C_, generator=g)).to(dev), (0.1 * torch.randn(C_, generator=g)).to(dev)
     xh = ops.nchw_to_nhwc(x, dtype)
@@ -270,8 +284,11 @@ def test_groupnorm_fwd_bwd(C_, G, dtype, silu):
     lib = _abi.lib()
     p = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(yh), _null(), _null(), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                  None, None, None, N, H, W, C_, G, silu, 1e-5, 0)
-    _abi.check(lib.dmu_gn_stats(C.byref(p), _stream()))
-    _abi.check(lib.dmu_gn_apply(C.byref(p), _stream()))
+    if one_call:
+        _abi.check(lib.dmu_gn_forward(C.byref(p), _stream()))
+    else:
+        _abi.check(lib.dmu_gn_stats(C.byref(p), _stream()))
+        _abi.check(lib.dmu_gn_apply(C.byref(p), _stream()))
     gq, bq = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     ref = F.group_norm(xq, G, gq, bq, eps=1e-5)
     ref = F.silu(ref) if silu else ref
@@ -284,8 +301,11 @@ def test_groupnorm_fwd_bwd(C_, G, dtype, silu):
     dgam, dbet = torch.zeros(C_, device=dev), torch.zeros(C_, device=dev)
     p2 = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(dyh), ops.t4_nhwc(dxh), ops.t4_nhwc(add), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                   red.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), N, H, W, C_, G, silu, 1e-5, 0)
-    _abi.check(lib.dmu_gn_bwd_reduce(C.byref(p2), _stream()))
-    _abi.check(lib.dmu_gn_bwd_apply(C.byref(p2), _stream()))
+    if one_call:
+        _abi.check(lib.dmu_gn_backward(C.byref(p2), _stream()))
+    else:
+        _abi.check(lib.dmu_gn_bwd_reduce(C.byref(p2), _stream()))
+        _abi.check(lib.dmu_gn_bwd_apply(C.byref(p2), _stream()))
     ref.backward(dyh.float().permute(0, 3, 1, 2))
     tol = 3e-5 if dtype == torch.float32 else 8e-3
     assert rel_l2(dxh.float().permute(0, 3, 1, 2), xq.grad + add.float().permute(0, 3, 1, 2)) < tol
