@@ -6,6 +6,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <utility>
 
 #include "../../include/dmu_b200.h"
 
@@ -92,5 +95,42 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 inline bool is_nhwc(const dmu_tensor4& t) { return t.sc == 1; }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A recorded plan is a chain of hundreds of short dependent kernels; with the launch attribute below the next kernel's CTAs
+// are scheduled (and run their prologue) while the previous kernel drains, and block in pdl_wait() until that kernel's
+// memory is visible.  Contract: EVERY kernel launched through launch_pdl() executes pdl_wait() in every CTA before it
+// touches global memory produced by an earlier launch (a kernel that skipped it could complete before its predecessor
+// and release ITS successor too early).  Both intrinsics are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // DMU_PDL=0 in the environment turns the attribute off
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, dim3 cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster.x;
+        attr[n].val.clusterDim.y = cluster.y;
+        attr[n].val.clusterDim.z = cluster.z;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 }  // namespace dmu

@@ -137,6 +137,7 @@ struct ConvArgs {
     // 128/splits rows of the tile.  No atomics (REDG tops out near 0.2 G floats/us chip-wide) and no counters.
     int splits;
     float* ws;
+    long long* dbg;   // development aid (dmu_debug_set_buffer): per-CTA clock64 stamps of the pipeline phases
 };
 
 constexpr int kMaxSplitCtas = 160;      // CTAs of a split launch: about one wave
@@ -147,18 +148,21 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int NT>
+// DEEP = 0: 2 CTAs per SM with a short ring (grids of several waves: the co-resident CTA hides the pipeline bubbles);
+// DEEP = 1: 1 CTA per SM with as many stages as shared memory holds.  One TMA round trip is ~1 us, so a CTA moves at most
+// (stages x stage bytes) per us: layers whose whole grid is under one wave (the <= 8x8 stages) are bound by exactly that.
+template <int NT, int DEEP>
 struct ConvCfg {
-    static constexpr int kStages = NT == 64 ? 4 : 3;
+    static constexpr int kStages = DEEP ? (NT == 64 ? 8 : 6) : (NT == 64 ? 4 : 3);
     static constexpr int kABytes = 128 * 128;     // 128 pixels x 64 bf16
     static constexpr int kBBytes = NT * 128;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kSmem = kStages * kStageBytes + 1024;   // + alignment slack
 };
 
-template <int NT>
+template <int NT, int DEEP>
 __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
-    using Cfg = ConvCfg<NT>;
+    using Cfg = ConvCfg<NT, DEEP>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -171,22 +175,31 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     const int tw0 = (tile % P.tiles_w) * P.BW;
     const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
     const int n0 = (tile / (P.tiles_w * P.tiles_h)) * P.BN;
-    if (th0 >= ph.TH || tw0 >= ph.TW) return;   // phase smaller than the grid's tile space (whole CTA leaves)
+    if (th0 >= ph.TH || tw0 >= ph.TW) {          // phase smaller than the grid's tile space (whole CTA leaves)
+        pdl_wait();
+        return;
+    }
     const int j0 = blockIdx.y * NT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = P.Ck >> 6;
 
+    pdl_trigger();
+    long long* dbg = P.dbg ? P.dbg + 8 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&acc_bar, 2);
         fence_mbar_init();
         s_issued = 0;
+        tma_prefetch_desc(&maps.b);
     }
     if (warp == 1) tmem_alloc(&s_tmem, NT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
     auto tap_live = [&](const Tap& t) {   // does the shifted box intersect its sub-lattice at all?
         const int h = th0 + t.dh, w = tw0 + t.dw;
@@ -230,6 +243,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
                 const int st = it % kStages;
                 mbar_wait(&full_bar[st], (it / kStages) & 1);
                 tc_fence_after();
+                if (dbg && it == 0) dbg[2] = clock64();      // first stage landed
                 const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
                 const uint64_t da = smem_desc_sw128(sa, 16, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, 16, 1024);
 #pragma unroll
@@ -240,6 +254,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
             }
         }
         s_issued = (uint32_t)it;
+        if (dbg) { dbg[3] = clock64(); dbg[6] = it; }   // last MMA issued
         umma_commit(&acc_bar);      // arrival 1: all MMAs retired
         mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
     }
@@ -248,6 +263,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     // ---------------------------------------------------- epilogue: all 4 warps, thread = one output pixel (TMEM lane)
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
+    if (dbg && threadIdx.x == 0) dbg[4] = clock64();   // accumulator complete
     const bool have_acc = *reinterpret_cast<volatile uint32_t*>(&s_issued) != 0;
     const int row = threadIdx.x;
     const int wl = row % P.BW, hl = (row / P.BW) % P.BH, nl = row / (P.BW * P.BH);
@@ -352,10 +368,13 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
             for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp + c + i, v + i);
         }
     }
+    if (dbg && threadIdx.x == 0) dbg[5] = clock64();   // epilogue stores issued
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, NT);
 }
+
+static long long* g_debug_buffer = nullptr;
 
 static int conv_supported(const dmu_conv_params* p) {
     if (!p || !p->x.ptr || !p->y.ptr || !p->w) return 0;
@@ -424,6 +443,7 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     A.y = reinterpret_cast<__nv_bfloat16*>(p->y.ptr); A.y_sn = p->y.sn; A.y_sh = p->y.sh; A.y_sw = p->y.sw;
     A.res = reinterpret_cast<const __nv_bfloat16*>(p->res.ptr); A.r_sn = p->res.sn; A.r_sh = p->res.sh; A.r_sw = p->res.sw;
     A.bias = p->bias; A.temb = p->temb; A.temb_pitch = p->temb_pitch;
+    A.dbg = g_debug_buffer;
     // split-K for layers with few output tiles and a long contraction (the <= 4x4 stages: K up to 4608, 1-16 tiles):
     // the splits of one tile are a thread-block cluster along z (co-scheduled by hardware, so the in-kernel barrier is safe)
     const int slots = b.tiles_n * b.tiles_h * b.tiles_w * (p->Cj / NT) * nph;
@@ -451,24 +471,19 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     dim3 grid(b.tiles_n * b.tiles_h * b.tiles_w, p->Cj / NT, nph * A.splits);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64>::kSmem);
-        cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 0>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 0>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 1>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 1>::kSmem);
         attr_done = true;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(128);
-    cfg.dynamicSmemBytes = NT == 64 ? ConvCfg<64>::kSmem : ConvCfg<128>::kSmem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = (unsigned)A.splits;
-    cfg.attrs = attr;
-    cfg.numAttrs = A.splits > 1 ? 1 : 0;
-    cudaError_t e = NT == 64 ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<64>, maps, A) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<128>, maps, A);
+    const dim3 cluster(1, 1, (unsigned)A.splits);
+    const bool deep = (int)(grid.x * grid.y * grid.z) <= sm_count();
+    cudaError_t e;
+    if (NT == 64) e = deep ? launch_pdl(conv_tc_kernel<64, 1>, grid, dim3(128), ConvCfg<64, 1>::kSmem, stream, cluster, maps, A)
+                           : launch_pdl(conv_tc_kernel<64, 0>, grid, dim3(128), ConvCfg<64, 0>::kSmem, stream, cluster, maps, A);
+    else e = deep ? launch_pdl(conv_tc_kernel<128, 1>, grid, dim3(128), ConvCfg<128, 1>::kSmem, stream, cluster, maps, A)
+                  : launch_pdl(conv_tc_kernel<128, 0>, grid, dim3(128), ConvCfg<128, 0>::kSmem, stream, cluster, maps, A);
     if (e != cudaSuccess) return fail("dmu_conv2d/tc: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/tc");
 }
@@ -485,7 +500,7 @@ struct WgradArgs {
 
 template <int NT>
 struct WgradCfg {
-    static constexpr int kStages = NT == 64 ? 6 : 4;
+    static constexpr int kStages = NT == 64 ? 8 : 6;   // 1 CTA per SM: 8 x 24 KB / 6 x 32 KB in flight
     static constexpr int kBlk = 64 * 128;         // 64 pixels x 64 bf16 channels
     static constexpr int kABytes = 2 * kBlk;
     static constexpr int kBBytes = (NT / 64) * kBlk;
@@ -513,17 +528,20 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ M
     const int tile_lo = blockIdx.z * P.tiles_per_split;
     const int tile_hi = min(P.tiles_total, tile_lo + P.tiles_per_split);
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&acc_bar, 2);
         fence_mbar_init();
         s_issued = 0;
+        tma_prefetch_desc(&maps.b);
     }
     if (warp == 1) tmem_alloc(&s_tmem, NT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    pdl_wait();
 
     auto live = [&](const Tap& t, int th0, int tw0) {
         const int h = th0 + t.dh, w = tw0 + t.dw;
@@ -648,8 +666,9 @@ static int wgrad_launch(const dmu_wgrad_params* p, cudaStream_t stream) {
         cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<128>::kSmem);
         attr_done = true;
     }
-    if (NT == 64) wgrad_tc_kernel<64><<<grid, 128, WgradCfg<64>::kSmem, stream>>>(maps, A);
-    else wgrad_tc_kernel<128><<<grid, 128, WgradCfg<128>::kSmem, stream>>>(maps, A);
+    cudaError_t e = NT == 64 ? launch_pdl(wgrad_tc_kernel<64>, grid, dim3(128), WgradCfg<64>::kSmem, stream, dim3(1, 1, 1), maps, A)
+                             : launch_pdl(wgrad_tc_kernel<128>, grid, dim3(128), WgradCfg<128>::kSmem, stream, dim3(1, 1, 1), maps, A);
+    if (e != cudaSuccess) return fail("dmu_conv2d_wgrad/tc: launch failed: %s", cudaGetErrorString(e));
     if (int rc = check_launch("dmu_conv2d_wgrad/tc")) return rc;
     if (p->dbias) return dmu_colsum(&p->p, p->N, p->Hp, p->Wp, p->Ca, nullptr, 0, p->dbias, 1.0f, (dmu_stream_t)stream);
     return 0;
@@ -662,6 +681,8 @@ using namespace dmu;
 
 extern "C" {
 int64_t dmu_conv2d_workspace_bytes(void) { return tc::kSplitWsBytes; }
+// development aid, not part of include/dmu_b200.h: int64 device buffer (8 per CTA) receiving clock64 stamps of conv_tc_kernel
+void dmu_debug_set_buffer(void* p) { tc::g_debug_buffer = reinterpret_cast<long long*>(p); }
 int dmu_conv2d_tc_supported(const dmu_conv_params* p) { return tc::conv_supported(p); }
 int dmu_conv2d_tc(const dmu_conv_params* p, dmu_stream_t stream) { return tc::conv_launch(p, as_stream(stream)); }
 int dmu_wgrad_tc_supported(const dmu_wgrad_params* p) { return tc::wgrad_supported(p); }

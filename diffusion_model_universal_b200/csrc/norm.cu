@@ -75,6 +75,8 @@ __device__ __forceinline__ void block_channel_sum(const RowMap& m, const float* 
 // ------------------------------------------------------------------ stats
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(dmu_gn_params P) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s_sum[kMaxC], s_sq[kMaxC];
     __shared__ float s_red[256 * kVec];
@@ -133,6 +135,8 @@ __device__ __forceinline__ void stage_affine(const dmu_gn_params& P, int n, floa
 // ------------------------------------------------------------------ apply
 template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(dmu_gn_params P) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC];
     const int n = blockIdx.y, HW = P.H * P.W;
@@ -182,6 +186,8 @@ __device__ __forceinline__ float act_grad(float u, float dy, int silu) {
 // ------------------------------------------------------------------ bwd reduce
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(dmu_gn_params P) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kVec = Elem<T>::kVec;
     constexpr int kU = 2;
     __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
@@ -242,6 +248,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(dmu_gn_params P) {
 // ------------------------------------------------------------------ bwd apply
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dmu_gn_params P) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kVec = Elem<T>::kVec;
     constexpr int kU = 2;
     __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
@@ -358,6 +366,8 @@ __device__ __forceinline__ void cluster_channel_total(float* s_a, float* s_b, fl
 
 template <typename T>
 __global__ void __launch_bounds__(256) gn_fwd_fused_kernel(dmu_gn_params P) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s_a[kMaxC], s_b[kMaxC], s_ta[kMaxC], s_tb[kMaxC];
     __shared__ float s_red[256 * kVec];
@@ -426,6 +436,8 @@ __global__ void __launch_bounds__(256) gn_fwd_fused_kernel(dmu_gn_params P) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(dmu_gn_params P) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
     __shared__ float s_a[kMaxC], s_b[kMaxC], s_ta[kMaxC], s_tb[kMaxC];
@@ -571,19 +583,7 @@ static int gn_fused_cluster(int HW, int C, int vec) {
 
 template <typename K>
 static int launch_cluster(K kernel, int cs, int N, cudaStream_t stream, const dmu_gn_params& p) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(cs, N);
-    cfg.blockDim = dim3(256);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = cs > 1 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    cudaError_t e = launch_pdl(kernel, dim3(cs, N), dim3(256), 0, stream, dim3(cs, 1, 1), p);
     if (e != cudaSuccess) return fail("GroupNorm cluster launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -594,6 +594,8 @@ static int launch_cluster(K kernel, int cs, int N, cudaStream_t stream, const dm
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(dmu_tensor4 X, int H, int W, int C, float* out_nc, int64_t pitch,
                                                      float* out_c, float scale) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s[kMaxC];
     __shared__ float s_red[256 * kVec];
@@ -785,10 +787,11 @@ static dim3 gn_grid(int N, int HW, int C, int vec) {
 
 using namespace dmu;
 
-#define DISPATCH_T(dtype, KERNEL, grid, block, stream, ...)                                     \
-    do {                                                                                        \
-        if ((dtype) == DMU_BF16) KERNEL<__nv_bfloat16><<<grid, block, 0, stream>>>(__VA_ARGS__); \
-        else KERNEL<float><<<grid, block, 0, stream>>>(__VA_ARGS__);                             \
+// every kernel dispatched through this macro starts with pdl_trigger(); pdl_wait();
+#define DISPATCH_T(dtype, KERNEL, grid, block, stream, ...)                                                               \
+    do {                                                                                                                  \
+        if ((dtype) == DMU_BF16) launch_pdl(KERNEL<__nv_bfloat16>, grid, dim3(block), 0, stream, dim3(1, 1, 1), __VA_ARGS__); \
+        else launch_pdl(KERNEL<float>, grid, dim3(block), 0, stream, dim3(1, 1, 1), __VA_ARGS__);                            \
     } while (0)
 
 extern "C" {

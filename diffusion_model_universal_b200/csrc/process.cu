@@ -15,6 +15,14 @@ int fail(const char* fmt, ...) {
     va_end(ap);
     return 1;
 }
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DMU_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 int sm_count() {
     static int n = 0;
     if (n == 0) {
