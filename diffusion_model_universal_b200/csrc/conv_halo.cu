@@ -1,0 +1,322 @@
+// 3x3 stride-1 convolution (fprop and dgrad) as a persistent tcgen05 kernel that reads every input pixel ONCE per CTA.
+//
+// Why: conv_tc.cu issues one TMA box per (tap, 64-channel chunk), i.e. it pulls the activation tile nine times through the
+// SM's L2 port, plus the weights once per tile.  Measured on B200 (scripts/conv_timeline.py): an SM ingests ~60 B/clk from
+// L2 whatever the grid, so that kernel is bound by bytes-per-SM (216 KB per 128-pixel tile of a 64->64 layer), not by the
+// tensor pipe (23 % at best).  Here:
+//   * the output tile is 128 consecutive positions of the zero-padded flat space [N][H+2][W+2]; in that space every tap is
+//     a pure shift, so ONE shared-memory halo tile (NR padded rows x (W+2) pixels x 64 channels, loaded by NR single-row TMA
+//     boxes whose out-of-bounds pixels are the zero padding) serves all nine taps: tap (r,s) is the same tile read through
+//     a UMMA descriptor whose start address is advanced by (r*(W+2)+s) rows.  Row-granular start offsets inside the
+//     128-byte swizzle pattern are legal: both TMA writes and UMMA reads swizzle on absolute shared-memory address bits
+//     (scripts/probes/umma_rowoffset.cu, tma_unaligned_dst.cu, verified on hardware).
+//   * the kernel is persistent (one CTA per SM, static round-robin over tiles); when the whole filter bank of the CTA's
+//     output-channel tile fits (9 x Ck x NT bf16 <= ~144 KB) it is loaded once and stays resident, otherwise it streams
+//     through its own mbarrier ring.
+//   * warp roles: 4 epilogue warps, 1 TMA warp, 1 MMA warp; two TMEM accumulators so the epilogue of tile i overlaps the
+//     MMAs of tile i+1.
+// Positions of the padded space that are padding themselves are computed and dropped (efficiency H*W/((H+2)(W+2)): 89 %
+// at 32x32, 79 % at 16x16, 64 % at 8x8); below 8x8 the per-tap kernel (with split-K) is used instead.
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace dmu {
+namespace tc {
+
+extern long long* g_debug_buffer;   // conv_tc.cu (dmu_debug_set_buffer)
+
+struct HaloMaps { CUtensorMap a, b; };
+
+struct HaloArgs {
+    int N, H, W, Ck, Cj;
+    int PW, PH, NR, tiles, chunks, flip, resident;
+    int a_stage_bytes, a_stages, w_stages;
+    __nv_bfloat16* y; int64_t y_sn, y_sh, y_sw;
+    const __nv_bfloat16* res; int64_t r_sn, r_sh, r_sw;
+    const float* bias;
+    const float* temb; int64_t temb_pitch;
+    long long* dbg;     // development aid: CTA 0 stamps clock64 per tile (8 slots per tile)
+};
+
+constexpr int kMaxAStages = 4, kMaxWStages = 8;
+
+__device__ __forceinline__ int floordiv_dev(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+template <int NT>
+__global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloArgs P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t a_full[kMaxAStages], a_empty[kMaxAStages], w_full[kMaxWStages], w_empty[kMaxWStages];
+    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_bias[NT];
+
+    constexpr int kWTile = NT * 128;                       // one (tap, chunk) weight block: NT rows x 64 bf16
+    uint8_t* smem_a = smem;
+    uint8_t* smem_w = smem + (size_t)P.a_stages * P.a_stage_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j0 = blockIdx.y * NT;
+    const int kblocks = 9 * P.chunks;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_mbar_init();
+        tma_prefetch_desc(&maps.a);
+        tma_prefetch_desc(&maps.b);
+    }
+    if (warp == 5) tmem_alloc(&s_tmem, 2 * NT);
+    for (int i = threadIdx.x; i < NT; i += blockDim.x) s_bias[i] = P.bias ? P.bias[j0 + i] : 0.f;   // parameters: not produced by the previous launch
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    pdl_wait();
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            if (P.resident) {
+                mbar_arrive_expect_tx(&w_full[0], (uint32_t)(kblocks * kWTile));
+                for (int c = 0; c < P.chunks; ++c)
+                    for (int t = 0; t < 9; ++t)
+                        tma_load_2d(smem_w + (size_t)(c * 9 + t) * kWTile, &maps.b, &w_full[0], t * P.Ck + c * 64, j0);
+            }
+            int ia = 0, iw = 0;
+            const uint32_t a_bytes = (uint32_t)(P.NR * P.PW) * 128u;
+            for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+                const int L0 = floordiv_dev(tile * 128 - P.PW - 1, P.PW);
+                for (int c = 0; c < P.chunks; ++c) {
+                    const int sa = ia % P.a_stages;
+                    mbar_wait(&a_empty[sa], ((ia / P.a_stages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+                    uint8_t* dst = smem_a + (size_t)sa * P.a_stage_bytes;
+                    for (int i = 0; i < P.NR; ++i) {
+                        const int L = L0 + i;
+                        const int n = floordiv_dev(L, P.PH);
+                        const int hp = L - n * P.PH;
+                        tma_load_4d(dst + (size_t)i * P.PW * 128, &maps.a, &a_full[sa], c * 64, -1, hp - 1, n);
+                    }
+                    ++ia;
+                    if (!P.resident) {
+                        for (int t = 0; t < 9; ++t) {
+                            const int sw = iw % P.w_stages;
+                            mbar_wait(&w_empty[sw], ((iw / P.w_stages) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&w_full[sw], (uint32_t)kWTile);
+                            tma_load_2d(smem_w + (size_t)sw * kWTile, &maps.b, &w_full[sw], t * P.Ck + c * 64, j0);
+                            ++iw;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
+            if (P.resident) mbar_wait(&w_full[0], 0);
+            int ia = 0, iw = 0, it = 0;
+            for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                long long* dbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) ? P.dbg + 8 * it : nullptr;
+                if (dbg) dbg[0] = clock64();
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                if (dbg) dbg[1] = clock64();
+                const uint32_t d_tmem = tmem + (uint32_t)(buf * NT);
+                const int Q0 = tile * 128;
+                const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
+                const int base_off = Q0 - P.PW - 1 - L0 * P.PW;       // smem row of padded position (Q0 - PW - 1)
+                for (int c = 0; c < P.chunks; ++c) {
+                    const int sa = ia % P.a_stages;
+                    mbar_wait(&a_full[sa], (ia / P.a_stages) & 1);
+                    tc_fence_after();
+                    if (dbg && c == 0) dbg[2] = clock64();
+                    const uint32_t a_base = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes);
+                    for (int t = 0; t < 9; ++t) {
+                        const int r = t / 3, s = t % 3;
+                        const int dr = P.flip ? 2 - r : r, ds = P.flip ? 2 - s : s;
+                        uint32_t w_addr;
+                        int sw = 0;
+                        if (P.resident) {
+                            w_addr = smem_u32(smem_w + (size_t)(c * 9 + t) * kWTile);
+                        } else {
+                            sw = iw % P.w_stages;
+                            mbar_wait(&w_full[sw], (iw / P.w_stages) & 1);
+                            tc_fence_after();
+                            w_addr = smem_u32(smem_w + (size_t)sw * kWTile);
+                        }
+                        const uint64_t da = smem_desc_sw128(a_base + (uint32_t)(base_off + dr * P.PW + ds) * 128u, 16, 1024);
+                        const uint64_t db = smem_desc_sw128(w_addr, 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
+                        if (!P.resident) { umma_commit(&w_empty[sw]); ++iw; }
+                    }
+                    umma_commit(&a_empty[sa]);
+                    ++ia;
+                }
+                umma_commit(&acc_full[buf]);
+                if (dbg) dbg[3] = clock64();
+            }
+        }
+    } else {
+        // ---------------------------------------------------- epilogue warps 0..3: thread = one output position (TMEM lane)
+        const int row = threadIdx.x;          // 0..127
+        const int plane = P.PH * P.PW;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const int Q = tile * 128 + row;
+            const int n = Q / plane, rem = Q - n * plane;
+            const int hp = rem / P.PW, wp = rem - hp * P.PW;
+            const bool valid = n < P.N && hp >= 1 && hp <= P.H && wp >= 1 && wp <= P.W;
+            const int ho = hp - 1, wo = wp - 1;
+            __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0;
+            const __nv_bfloat16* rp = (P.res && valid) ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
+            const float* tp = (P.temb && valid) ? P.temb + (int64_t)n * P.temb_pitch + j0 : nullptr;
+            // prefetch the first 64 channels of the residual (the loads fly while the MMAs of this tile run)
+            uint4 rpre[8];
+            if (rp) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rpre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+            }
+            long long* dbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && threadIdx.x == 0) ? P.dbg + 8 * it : nullptr;
+            if (dbg) dbg[4] = clock64();
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            if (dbg) dbg[5] = clock64();
+#pragma unroll
+            for (int c = 0; c < NT; c += 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * NT + c), v);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
+                    if (tp) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(tp + c + i));
+                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                        }
+                    }
+                    if (rp) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            float r8[8];
+                            if (c < 64) {
+                                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rpre[(c + i) >> 3]);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); r8[2 * k] = f.x; r8[2 * k + 1] = f.y; }
+                            } else {
+                                load_vec<__nv_bfloat16>(rp + c + i, r8);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[i + k] += r8[k];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp + c + i, v + i);
+                }
+            }
+            if (dbg) dbg[6] = clock64();
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);      // 128 arrivals release the accumulator to the MMA warp
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem, 2 * NT);
+}
+
+int halo_supported(const dmu_conv_params* p, int force) {
+    if (p->R != 3 || p->S != 3 || p->stride != 1 || p->pad != 1) return 0;
+    if (p->Hi != p->Ho || p->Wi != p->Wo) return 0;
+    if (p->Hi < 8 || p->Wi < 8 || p->Wi + 2 > 256) return 0;     // below 8x8 most of the padded space is padding
+    if ((int64_t)p->N * (p->Hi + 2) * (p->Wi + 2) >= (1ll << 31)) return 0;
+    // Measured on B200 (scripts/conv_timeline.py, DMU_HALO=0/1): SS-mode UMMA at M=128 fetches its operands from shared
+    // memory at ~64 B/clk, which bounds BOTH kernels (96 clk per 128x64x16 MMA, 3x the tensor floor), so fetching the
+    // activations once only wins where the per-tap kernel's extra TMA traffic and per-CTA prologue dominate: one 64-channel
+    // chunk with the whole filter bank resident and at least four tiles per CTA (27.5 vs 31.6 us at 128x32x32x64->64,
+    // 166 vs 215 us at 256x64x64); smaller or multi-chunk layers are faster per-tap.
+    if (force) return 1;
+    if (p->Ck != 64 || p->Cj > 128) return 0;
+    const int64_t tiles = ((int64_t)p->N * (p->Hi + 2) * (p->Wi + 2) + 127) / 128;
+    if (tiles < 4 * (int64_t)sm_count()) return 0;
+    return 1;
+}
+
+static int pick_smem(const dmu_conv_params* p, int NT, HaloArgs& A) {
+    const int budget = 214 * 1024;
+    const int kblocks = 9 * A.chunks, wtile = NT * 128;
+    A.resident = (kblocks * wtile + 2 * A.a_stage_bytes <= budget) ? 1 : 0;
+    int wbytes;
+    if (A.resident) {
+        wbytes = kblocks * wtile;
+        A.w_stages = 1;
+    } else {
+        A.w_stages = kMaxWStages;
+        while (A.w_stages > 3 && A.w_stages * wtile + 2 * A.a_stage_bytes > budget) --A.w_stages;
+        wbytes = A.w_stages * wtile;
+    }
+    A.a_stages = (budget - wbytes) / A.a_stage_bytes;
+    if (A.a_stages > kMaxAStages) A.a_stages = kMaxAStages;
+    if (A.a_stages < 2) return -1;
+    return A.a_stages * A.a_stage_bytes + wbytes + 1024;
+}
+
+int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
+    HaloMaps maps;
+    HaloArgs A;
+    memset(&A, 0, sizeof(A));
+    A.N = p->N; A.H = p->Hi; A.W = p->Wi; A.Ck = p->Ck; A.Cj = p->Cj;
+    A.PW = A.W + 2; A.PH = A.H + 2;
+    A.NR = 3 + (129 + A.PW - 1) / A.PW;
+    A.tiles = (int)(((int64_t)A.N * A.PH * A.PW + 127) / 128);
+    A.chunks = A.Ck / 64;
+    A.flip = p->gather;
+    A.a_stage_bytes = ((A.NR * A.PW * 128) + 1023) / 1024 * 1024;
+    const int NT = (p->Cj % 128 == 0) ? 128 : 64;
+    const int smem = pick_smem(p, NT, A);
+    DMU_REQUIRE(smem > 0 && smem <= 224 * 1024, "dmu_conv2d/halo: tile does not fit shared memory");
+    {
+        const uint64_t dims[4] = {(uint64_t)p->Ck, (uint64_t)p->Wi, (uint64_t)p->Hi, (uint64_t)p->N};
+        const uint64_t str[4] = {1, (uint64_t)p->x.sw, (uint64_t)p->x.sh, (uint64_t)p->x.sn};
+        const uint32_t box[4] = {64, (uint32_t)A.PW, 1, 1};
+        if (int rc = make_map_bf16(&maps.a, p->x.ptr, 4, dims, str, box, "dmu_conv2d/halo")) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)9 * p->Ck, (uint64_t)p->Cj};
+        const uint64_t str[2] = {1, (uint64_t)p->w_sn};
+        const uint32_t box[2] = {64, (uint32_t)NT};
+        if (int rc = make_map_bf16(&maps.b, p->w, 2, dims, str, box, "dmu_conv2d/halo weights")) return rc;
+    }
+    A.y = reinterpret_cast<__nv_bfloat16*>(p->y.ptr); A.y_sn = p->y.sn; A.y_sh = p->y.sh; A.y_sw = p->y.sw;
+    A.res = reinterpret_cast<const __nv_bfloat16*>(p->res.ptr); A.r_sn = p->res.sn; A.r_sh = p->res.sh; A.r_sw = p->res.sw;
+    A.bias = p->bias; A.temb = p->temb; A.temb_pitch = p->temb_pitch;
+    A.dbg = g_debug_buffer;
+    const int ntiles_n = p->Cj / NT;
+    int gx = sm_count() / ntiles_n;
+    if (gx < 1) gx = 1;
+    if (gx > A.tiles) gx = A.tiles;
+    // even out the tail: every CTA gets the same number of tiles (+-1)
+    const int rounds = (A.tiles + gx - 1) / gx;
+    gx = (A.tiles + rounds - 1) / rounds;
+    dim3 grid(gx, ntiles_n);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv3x3_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(conv3x3_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        attr_done = true;
+    }
+    cudaError_t e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64>, grid, dim3(192), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
+                             : launch_pdl(conv3x3_halo_kernel<128>, grid, dim3(192), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
+    if (e != cudaSuccess) return fail("dmu_conv2d/halo: launch failed: %s", cudaGetErrorString(e));
+    return check_launch("dmu_conv2d/halo");
+}
+
+}  // namespace tc
+}  // namespace dmu

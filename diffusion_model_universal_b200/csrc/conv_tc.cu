@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     if (warp == 1) tmem_dealloc(tmem, NT);
 }
 
-static long long* g_debug_buffer = nullptr;
+long long* g_debug_buffer = nullptr;
 
 static int conv_supported(const dmu_conv_params* p) {
     if (!p || !p->x.ptr || !p->y.ptr || !p->w) return 0;
@@ -389,7 +389,27 @@ static int conv_supported(const dmu_conv_params* p) {
     return 1;
 }
 
+// conv_halo.cu
+int halo_supported(const dmu_conv_params* p, int force);
+int halo_launch(const dmu_conv_params* p, cudaStream_t stream);
+
+static bool halo_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DMU_HALO");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
+    // 3x3 stride-1 layers of 8x8 pixels and up: the persistent halo kernel (each input pixel fetched once per CTA);
+    // impl 4 forces the per-tap kernel below
+    if (p->impl == 5) {
+        DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3, stride 1, pad 1, >= 8x8)");
+        return halo_launch(p, stream);
+    }
+    if (p->impl != 4 && halo_enabled() && halo_supported(p, 0)) return halo_launch(p, stream);
     Maps maps;
     ConvArgs A;
     memset(&A, 0, sizeof(A));

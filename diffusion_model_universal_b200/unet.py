@@ -19,6 +19,7 @@ Data layout in HBM:
 
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -241,6 +242,10 @@ class Engine:
         self.frozen = False     # weights known unchanged: skip the repack launch
         self.impl = 0           # conv implementation selector forwarded to the kernels (0 auto)
         self.use_graphs = True  # replay recorded plans as CUDA graphs (second execution onwards)
+        # Independent sub-plans per batch, run as parallel graph branches.  Measured on B200 (scripts/phase_times.py): 1.43 /
+        # 1.48 / 1.48 ms forward at 1 / 2 / 4 lanes for 128x32x32 - a chain of latency-bound kernels is as long for half the
+        # batch, so lanes over the batch buy nothing; the default stays 1 (the machinery also carries the dgrad | wgrad lanes).
+        self.micro_batches = int(os.environ.get("DMU_MICROBATCHES", "1"))
         self._lib = None
 
     # ------------------------------------------------------------------ parameters
@@ -409,31 +414,62 @@ class Engine:
             if rc != 0:
                 _abi.check(rc, op[0].__name__)
 
-    def _run_forked(self, oplist, side):
-        """Capture-time execution: ops tagged with lane 1 (weight gradients, bias/time-projection column sums: they only
-        read finished tensors and accumulate into their own outputs) go to a second stream so that the graph has two
-        parallel branches; an op on the side lane depends on everything issued on the main lane before it, a join marker
-        makes the main lane wait for the side lane.  The many latency-bound launches of the <= 8x8 stages then overlap."""
+    def _run_forked(self, oplist):
+        """Capture-time execution over lanes.  Lane 0 is the capturing stream; lane 2k is the main chain of micro-batch k,
+        lane 2k+1 its side chain (weight gradients, bias / time-projection column sums: they only read finished tensors and
+        accumulate into their own outputs).  Markers: (None, (), -2) = fork point (main lanes start after everything issued
+        on lane 0 so far), (None, (), 2k) = side lane 2k+1 joins main lane 2k, (None, (), -1) = every lane joins lane 0.
+        An op on a side lane depends on everything issued on its main lane before it."""
         main = torch.cuda.current_stream()
-        main_ptr, side_ptr = C.c_void_p(main.cuda_stream), C.c_void_p(side.cuda_stream)
-        forked = False
+        streams, ptrs, started, dirty = {0: main}, {}, {0}, set()
+        fork = None
+
+        def lane_stream(lane):
+            if lane not in streams:
+                streams[lane] = torch.cuda.Stream(device=self.device)
+            if lane not in started:
+                started.add(lane)
+                if lane % 2 == 0:
+                    if fork is not None:
+                        streams[lane].wait_event(fork)
+                    else:
+                        streams[lane].wait_stream(main)
+            if lane not in ptrs:
+                ptrs[lane] = C.c_void_p(streams[lane].cuda_stream)
+            return streams[lane]
+
         for op in oplist:
-            if op[0] is None:                  # join marker
-                if forked:
-                    main.wait_stream(side)
-                    forked = False
+            lane = op[2] if len(op) > 2 else 0
+            if op[0] is None:
+                if lane == -2:
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                elif lane == -1:
+                    for l in sorted(dirty, reverse=True):      # sides into their mains first, then mains into lane 0
+                        tgt = l - 1 if l % 2 == 1 else 0
+                        if l != 0:
+                            lane_stream(tgt).wait_stream(streams[l])
+                            if tgt != 0:
+                                dirty.add(tgt)
+                    dirty.clear()
+                else:
+                    if lane + 1 in dirty:
+                        lane_stream(lane).wait_stream(streams[lane + 1])
+                        dirty.discard(lane + 1)
+                        dirty.add(lane)
                 continue
+            st = lane_stream(lane)
+            if lane % 2 == 1:
+                st.wait_stream(lane_stream(lane - 1))
             ops.LAUNCHES += 1
-            if len(op) == 3:
-                side.wait_stream(main)
-                rc = op[0](*op[1], side_ptr)
-                forked = True
-            else:
-                rc = op[0](*op[1], main_ptr)
+            rc = op[0](*op[1], ptrs[lane])
             if rc != 0:
                 _abi.check(rc, op[0].__name__)
-        if forked:
-            main.wait_stream(side)
+            if lane != 0:
+                dirty.add(lane)
+        for l in sorted(dirty, reverse=True):
+            if l != 0:
+                main.wait_stream(streams[l])
 
     def _execute(self, plan: Plan, which: str):
         """Run plan.fwd / plan.bwd: eagerly the first time (warms every lazy one-time initialisation), then captured once
@@ -451,10 +487,9 @@ class Engine:
             self._run(oplist, ops._stream())
             return
         g = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(device=self.device)
         n0 = ops.LAUNCHES
         with torch.cuda.graph(g):
-            self._run_forked(oplist, side)       # recorded on the capture stream (+ one forked lane), not executed
+            self._run_forked(oplist)             # recorded on the capture stream (+ forked lanes), not executed
         plan.nlaunch[which] = ops.LAUNCHES - n0
         ops.LAUNCHES = n0
         plan.graphs[which] = g
@@ -484,25 +519,75 @@ class Engine:
 
     # ------------------------------------------------------------------ plan construction
     def _build(self, N, H, W, train) -> Plan:
-        dry = _PlanBuilder(self, N, H, W, train, base=(0, 0, 0))
+        """A plan is K independent sub-plans over N/K images each ("micro-batch lanes").  Per-image arithmetic is untouched
+        (GroupNorm and attention are per image, weight gradients accumulate atomically), but in the captured graph the K
+        chains run side by side: the launches of the <= 8x8 stages are latency-bound and leave most SMs idle, so two of
+        them overlap almost for free."""
+        K = self.micro_batches if (self.device.type == "cuda" and N % max(self.micro_batches, 1) == 0 and
+                                   N // max(self.micro_batches, 1) >= 8) else 1
+        Ns = N // K
+        net = self.net
+        plan = Plan()
+        plan.keep = []
+        plan.x_in = torch.zeros(N, net.in_channels, H, W, device=self.device, dtype=torch.float32)
+        plan.t_in = torch.zeros(N, device=self.device, dtype=torch.float32)
+        plan.out = torch.zeros(N, net.out_channels, H, W, device=self.device, dtype=torch.float32)
+        if train:
+            plan.dout = torch.zeros(N, net.out_channels, H, W, device=self.device, dtype=torch.float32)
+        dry = _PlanBuilder(self, Ns, H, W, train, base=(0, 0, 0))
         dry.build()
         rnd = lambda v: (v + 255) // 256 * 256
         n_main, n_stats, n_red = rnd(dry.bump.off), rnd(dry.stats.off + 4), rnd(dry.red.off + 4)
-        nbytes = n_main + n_stats + n_red + 256
+        per = n_main + n_stats + n_red
+        nbytes = K * per + 256
         arena = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
         base = rnd(arena.data_ptr())
-        real = _PlanBuilder(self, N, H, W, train, base=(base, base + n_main, base + n_main + n_stats))
-        net = self.net
-        real.plan.x_in = torch.zeros(N, net.in_channels, H, W, device=self.device, dtype=torch.float32)
-        real.plan.t_in = torch.zeros(N, device=self.device, dtype=torch.float32)
-        real.plan.out = torch.zeros(N, net.out_channels, H, W, device=self.device, dtype=torch.float32)
-        if self.code == BF16:
-            real.plan.ws = torch.zeros(int(self._lib.dmu_conv2d_workspace_bytes()), device=self.device, dtype=torch.uint8)
+        subs, gn_pg = [], []
+        for k in range(K):
+            b0 = base + k * per
+            sub = _PlanBuilder(self, Ns, H, W, train, base=(b0, b0 + n_main, b0 + n_main + n_stats))
+            sp = sub.plan
+            sp.x_in, sp.t_in, sp.out = plan.x_in[k * Ns:(k + 1) * Ns], plan.t_in[k * Ns:(k + 1) * Ns], plan.out[k * Ns:(k + 1) * Ns]
+            if train:
+                sp.dout = plan.dout[k * Ns:(k + 1) * Ns]
+            if self.code == BF16:   # split-K scratch: one per lane (the lanes run concurrently)
+                sp.ws = torch.zeros(int(self._lib.dmu_conv2d_workspace_bytes()), device=self.device, dtype=torch.uint8)
+            sub.build()
+            subs.append(sub)
+            plan.keep.append(sp)
+            gn_pg += sub.gn_pg
+
+        def retag(ops_, k):
+            out = []
+            for op in ops_:
+                if op[0] is None:
+                    out.append((None, (), 2 * k))                        # join this sub-plan's side lane into its main lane
+                else:
+                    out.append((op[0], op[1], 2 * k + (1 if len(op) == 3 else 0)))
+            return out
+
+        lib = self._lib
+        plan.fwd = [(None, (), -2)]                                      # fork point
+        for k, sub in enumerate(subs):
+            plan.fwd += retag(sub.plan.fwd, k)
+        plan.fwd.append((None, (), -1))                                  # join all lanes
         if train:
-            real.plan.dout = torch.zeros(N, net.out_channels, H, W, device=self.device, dtype=torch.float32)
-        plan = real.build()
+            # one zeroing of the gradient arena / staging for all lanes, then the lanes, then the batch-folded tails
+            plan.bwd = [(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4), 0),
+                        (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4), 0),
+                        (None, (), -2)]
+            for k, sub in enumerate(subs):
+                plan.bwd += retag(sub.plan.bwd, k)
+            plan.bwd.append((None, (), -1))
+            if gn_pg:
+                arr = (GnPgDesc * len(gn_pg))(*gn_pg)
+                plan.gn_pg_table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+                plan.bwd.append((lib.dmu_gn_param_grads, (plan.gn_pg_table.data_ptr(), len(gn_pg), max(d.C for d in gn_pg), Ns), 0))
+            # filter gradients: staging layout -> the parameters' own layout inside the gradient arena
+            plan.bwd.append((lib.dmu_repack_weights, (self.unpack_table.data_ptr(), self.unpack_n, self.repack_max), 0))
         plan.arena = arena
         plan.nbytes = nbytes
+        plan.lanes = K
         return plan
 
 
@@ -898,13 +983,7 @@ class _PlanBuilder:
                             self.gp("time_embed.0.weight"), self.gp("time_embed.0.bias"), need_dx=False)
         # one launch zeroes every GroupNorm backward accumulator
         plan.bwd.insert(0, (lib.dmu_zero, (self.red.base, max(self.red.off, 4))))
-        # ... and one zeroes the gradient arena the wgrad kernels accumulate into
-        plan.bwd.insert(0, (lib.dmu_zero, (e.gflat.data_ptr(), e.gflat.numel() * 4)))
-        plan.bwd.insert(0, (lib.dmu_zero, (e.gstage.data_ptr(), e.gstage.numel() * 4)))
-        if self.gn_pg:
-            arr = (GnPgDesc * len(self.gn_pg))(*self.gn_pg)
-            plan.gn_pg_table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(e.device)
-            plan.bwd.append((lib.dmu_gn_param_grads, (plan.gn_pg_table.data_ptr(), len(self.gn_pg), max(d.C for d in self.gn_pg), N)))
-        # filter gradients: staging layout -> the parameters' own layout inside the gradient arena
-        plan.bwd.append((lib.dmu_repack_weights, (e.unpack_table.data_ptr(), e.unpack_n, e.repack_max)))
+        plan.bwd.append((None, ()))      # side lane joins
+        # (zeroing of the gradient arena / staging, the GroupNorm parameter-gradient fold and the staging unpack are
+        #  emitted once for all micro-batch lanes by Engine._build)
         return plan

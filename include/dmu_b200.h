@@ -116,7 +116,9 @@ int dmu_diffusion_loss(const float* pred, const float* target, const float* w,
  *
  * With the weight strides this one contraction covers fprop and dgrad of
  * both layer kinds.  impl: 0 = auto, 1 = generic SIMT fp32-FMA kernel, 2 = tcgen05 (bf16, channels % 64 == 0),
- * 3 = the direct kernels for the 3-channel boundary layers (at most 4 channels on one side, stride 1).
+ * 3 = the direct kernels for the 3-channel boundary layers (at most 4 channels on one side, stride 1),
+ * 4 = tcgen05 per-tap kernel only, 5 = tcgen05 persistent halo kernel only (3x3 stride 1 pad 1, >= 8x8); impl 2 picks
+ * between the two by measured shape heuristics.
  */
 typedef struct {
     dmu_tensor4 x;       /* gathered input, channels K = Ck */

@@ -79,10 +79,31 @@ TC_CASES = [c for c in CONV_CASES if c[3] % 64 == 0 and c[4] % 64 == 0] + [
 ]
 
 
+HALO_CASES = [
+    (2, 32, 32, 64, 64, 3, 1, 1, "conv"),       # resident weights, 4-stage halo ring
+    (128, 32, 32, 64, 64, 3, 1, 1, "conv"),     # the bench layer: 7 tiles per CTA
+    (3, 16, 16, 64, 128, 3, 1, 1, "conv"),      # NT = 128, resident
+    (5, 16, 16, 128, 64, 3, 1, 1, "conv"),      # two 64-channel chunks, resident
+    (4, 8, 8, 128, 128, 3, 1, 1, "conv"),       # streamed weights
+    (3, 8, 8, 192, 64, 3, 1, 1, "conv"),        # three chunks, streamed
+    (7, 8, 8, 64, 64, 3, 1, 1, "conv"),         # tiles straddle images
+    (2, 64, 64, 64, 64, 3, 1, 1, "conv"),       # 64x64 (DDIM config)
+    (1, 8, 16, 128, 128, 3, 1, 1, "conv"),      # non-square
+]
+
+
+@pytest.mark.parametrize("impl", [2, 4])
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv_tcgen05(case):
-    """The tcgen05/TMA implicit-GEMM kernels (impl=2) against ATen on bf16-rounded operands."""
-    _conv_case(case, torch.bfloat16, 2)
+def test_conv_tcgen05(case, impl):
+    """The tcgen05/TMA implicit-GEMM kernels against ATen on bf16-rounded operands: impl 2 = auto (persistent halo kernel
+    for 3x3 stride-1 layers of 8x8 and up, per-tap kernel otherwise), impl 4 = per-tap kernel only."""
+    _conv_case(case, torch.bfloat16, impl)
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_tcgen05_halo(case):
+    """impl 5 = the persistent halo kernel, forced (impl 2 only picks it for large single-chunk layers)."""
+    _conv_case(case, torch.bfloat16, 5)
 
 
 SPLITK_CASES = [
@@ -152,7 +173,7 @@ def _conv_case(case, dtype, impl, ws=None):
     dyh = ops.nchw_to_nhwc(dy, dtype)
     dyq = dyh.float().permute(0, 3, 1, 2)
     dx = torch.empty(N, H, W, Ci, device=dev, dtype=dtype)
-    if impl == 2:   # tensor-core path contracts over a K-contiguous filter: [Ci][R][S][Co]
+    if impl in (2, 4, 5):   # tensor-core path contracts over a K-contiguous filter: [Ci][R][S][Co]
         wkt = _repack(w, kind == "convT", dtype, dgrad=True)
         p2 = ConvParams(ops.t4_nhwc(dyh), ops.t4_nhwc(dx), _null(), wkt.data_ptr(), R * R * Co, 1, Co, None, None, 0,
                         N, Ho, Wo, Co, H, W, Ci, R, R, stride, pad, 1 if kind == "conv" else 0, code, impl, 0,
