@@ -173,15 +173,18 @@ def conv_flops(p):
     return 2.0 * p.N * p.Hp * p.Wp * p.Ca * p.Cb * p.R * p.S
 
 
-def profile_plan(eng, plan, x, t, dout):
-    """Replay the recorded launch plan once with a CUDA event after every launch (no host syncs in between) and
-    return {entry point: (launches, ms, flops)}.  Same stream as the timed region."""
+def profile_plan(eng, plan):
+    """Replay the recorded launches of one training step eagerly with a CUDA event after every launch and return
+    {entry point: (launches, ms, flops)}.  The stream is first held busy (torch.cuda._sleep) so that the host runs ahead and
+    the kernels execute back to back: the event deltas are then device durations, not host launch gaps."""
     from diffusion_model_universal_b200 import ops
     stream = ops._stream()
     out = {}
+    big = None      # the single largest conv launch (most FLOPs)
     for lst in (plan.fwd, plan.bwd):
         lst = [(op[0], op[1]) for op in lst if op[0] is not None]
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(lst) + 1)]
+        torch.cuda._sleep(int(60e6))          # ~30 ms of spinning: enough for the host to enqueue everything below
         evs[0].record()
         for i, (fn, a) in enumerate(lst):
             fn(*a, stream)
@@ -192,9 +195,33 @@ def profile_plan(eng, plan, x, t, dout):
             fl = 0.0
             if fn.__name__ in ("dmu_conv2d", "dmu_conv2d_wgrad"):
                 fl = conv_flops(a[0]._obj)
+                if fn.__name__ == "dmu_conv2d" and (big is None or fl > big[0] or (fl == big[0] and ms < big[1])):
+                    big = (fl, ms)
             n, m, f = out.get(fn.__name__, (0, 0.0, 0.0))
             out[fn.__name__] = (n + 1, m + ms, f + fl)
-    return out
+    return out, big
+
+
+def ddim_sample_rate(dev, batch=256, size=64):
+    """BASELINE configs[2]: DDIM 50-step deterministic sampling at 64x64, batch 256 per GPU (no communication)."""
+    import diffusion_model_universal_b200 as D
+    m = D.DDIM(model_config(size, "bf16"))
+    reseed_zero_init(m, 7)
+    m.to(dev)
+    with torch.no_grad():
+        m.generate_samples(batch, dev)          # builds the plan, captures the graph
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x = m.generate_samples(batch, dev)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ok = bool(torch.isfinite(x).all())
+    del m
+    torch.cuda.empty_cache()
+    return {"img_per_s": batch / (ms * 1e-3), "ms_per_batch": ms, "batch": batch, "image": [3, size, size], "steps": 50, "eta": 0.0,
+            "unet_evals_per_s": 50 * batch / (ms * 1e-3), "model_tflops": 50 * batch * FLOP_FWD[size] / (ms * 1e-3) / 1e12, "finite": ok}
 
 
 def run_ours(args):
@@ -261,32 +288,36 @@ def run_ours(args):
     # ---- roofline of the dominant kernel family (implicit-GEMM conv), live CUDA events over one replayed step
     roof = None
     cpu = None
+    extra = {}
     if rank == 0:
         eng = model.model.engine
-        x = devb[0]
-        t = torch.randint(0, 1000, (B,), device=dev)
-        with torch.enable_grad():
-            eps = model.forward(x, t)          # builds/uses the train plan, leaves it busy
-        plan = eps.grad_fn.plan
-        dout = torch.randn_like(eps)
-        plan.dout.copy_(dout)
-        prof = profile_plan(eng, plan, x, t, dout)
-        plan.busy = False
+        plan = eng.get_plan(devb[0].shape, True)
+        prof, big = profile_plan(eng, plan)
         pk = peaks()
         conv_ms = sum(prof[k][1] for k in ("dmu_conv2d", "dmu_conv2d_wgrad") if k in prof)
         conv_fl = sum(prof[k][2] for k in ("dmu_conv2d", "dmu_conv2d_wgrad") if k in prof)
         conv_n = sum(prof[k][0] for k in ("dmu_conv2d", "dmu_conv2d_wgrad") if k in prof)
         total_ms = sum(v[1] for v in prof.values())
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "dmu_conv2d + dmu_conv2d_wgrad (implicit-GEMM conv fprop/dgrad/wgrad)",
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)
+        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv family (conv_tc_kernel / conv3x3_halo_kernel / wgrad_tc_kernel behind dmu_conv2d + dmu_conv2d_wgrad; all launches of one step, incl. the latency-bound <= 8x8 layers)",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
                 "peak_source": pk["src"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
-                "traffic": None, "launches_per_step": conv_n, "flops_per_step": conv_fl,
+                "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_note": traffic["note"] if traffic else None,
+                "launches_per_step": conv_n, "flops_per_step": conv_fl,
                 "avg_launch_us": conv_ms * 1e3 / max(conv_n, 1), "share_of_step": conv_ms / total_ms if total_ms else None,
+                "largest_launch": {"what": "64->64 3x3 at 32x32 x batch (fprop/dgrad)", "flops": big[0], "us": big[1] * 1e3,
+                                   "tflops": big[0] / (big[1] * 1e-3) / 1e12, "frac": big[0] / (big[1] * 1e-3) / 1e12 / pk["tf_sustained"]} if big else None,
                 "by_entry_point_ms": {k: round(v[1], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
         if world == 1 and not args.no_cpu:
             v, cores, sample = cpu_train_sample(budget_s=args.cpu_budget)
             cpu = {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample, "host_cpus": os.cpu_count()}
+        if world == 1 and not args.no_ddim:
+            extra["ddim50_64x64"] = ddim_sample_rate(dev)
 
     if rank == 0:
         gb = B * world
@@ -304,7 +335,7 @@ def run_ours(args):
                     "api": "TrainStep.step(pinned host batch) -> loss.item()"},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "flops_per_image": FLOP_FWD_BWD[R], "model_tflops": value * FLOP_FWD_BWD[R] / 1e12,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
+            "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(), "extra": extra,
             "last_loss": losses[-1] if losses else None,
         }
         print(json.dumps(line), flush=True)
@@ -322,6 +353,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (BASELINE configs[1]: 128)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ddim", action="store_true", help="skip the DDIM-50 64x64 sampling rate reported under extra")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

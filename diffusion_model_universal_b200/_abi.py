@@ -101,6 +101,8 @@ _SIGS = {
     "dmu_gn_bwd_reduce": (c_i32, [P(GnParams), c_vp]),
     "dmu_gn_bwd_apply": (c_i32, [P(GnParams), c_vp]),
     "dmu_colsum": (c_i32, [P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_f32, c_vp]),
+    "dmu_silu_pool_fwd": (c_i32, [P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp]),
+    "dmu_silu_pool_bwd": (c_i32, [P(Tensor4), P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp]),
     "dmu_attn_fwd": (c_i32, [P(AttnParams), c_vp]),
     "dmu_attn_bwd": (c_i32, [P(AttnParams), c_vp]),
     "dmu_sinusoidal_embedding": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_i32, c_vp]),

@@ -631,6 +631,59 @@ __global__ void __launch_bounds__(256) colsum_kernel(dmu_tensor4 X, int H, int W
     }
 }
 
+// ------------------------------------------------------------------ SiLU + global average pool (EnergyNet head)
+// models/energy_based.py:79-83:  pooled[n,c] = mean_p silu(x[n,p,c]);   backward: dx[n,p,c] = silu'(x) * g[n,c] * scale
+template <typename T>
+__global__ void __launch_bounds__(256) silu_pool_fwd_kernel(dmu_tensor4 X, int H, int W, int C, float* out, int64_t pitch, float scale) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s[kMaxC];
+    __shared__ float s_red[256 * kVec];
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.y, HW = H * W;
+    RowMap m(C, kVec);
+    int p0, p1; chunk_range(HW, p0, p1);
+    float a[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) a[i] = 0.f;
+    if (m.active) {
+        const T* xb = reinterpret_cast<const T*>(X.ptr) + m.v * kVec;
+        for (int p = p0 + m.lane; p < p1; p += m.lanes) {
+            float v[kVec];
+            unpack<T>(ld_raw<T>(xb + pix_off(X, n, p, W)), v);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) a[i] += v[i] / (1.f + expf(-v[i]));
+        }
+    }
+    block_channel_sum<kVec>(m, a, s_red, s, C);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&out[(int64_t)n * pitch + c], s[c] * scale);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) silu_pool_bwd_kernel(dmu_tensor4 X, dmu_tensor4 DX, int H, int W, int C, const float* g, int64_t pitch, float scale) {
+    constexpr int kVec = Elem<T>::kVec;
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.y, HW = H * W;
+    RowMap m(C, kVec);
+    if (!m.active) return;
+    int p0, p1; chunk_range(HW, p0, p1);
+    float gv[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) gv[i] = g[(int64_t)n * pitch + m.v * kVec + i] * scale;
+    const T* xb = reinterpret_cast<const T*>(X.ptr) + m.v * kVec;
+    T* db = reinterpret_cast<T*>(DX.ptr) + m.v * kVec;
+    for (int p = p0 + m.lane; p < p1; p += m.lanes) {
+        float v[kVec];
+        unpack<T>(ld_raw<T>(xb + pix_off(X, n, p, W)), v);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const float sg = 1.f / (1.f + expf(-v[i]));
+            v[i] = gv[i] * (sg * (1.f + v[i] * (1.f - sg)));
+        }
+        store_vec<T>(db + pix_off(DX, n, p, W), v);
+    }
+}
+
 // ------------------------------------------------------------------ activations (fp32 rows)
 __device__ __forceinline__ float act_f(float x, int kind) {
     if (kind == 0) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
@@ -872,6 +925,26 @@ int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C,
     }
     DISPATCH_T(t.dtype, colsum_kernel, grid, 256, as_stream(stream), t, Hh, Ww, C, out_nc, pitch, out_c, scale);
     return check_launch("dmu_colsum");
+}
+
+int dmu_silu_pool_fwd(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out, int64_t pitch, float scale, dmu_stream_t stream) {
+    DMU_REQUIRE(x && x->ptr && out && N > 0 && H > 0 && W > 0 && C > 0 && C <= kMaxC, "dmu_silu_pool_fwd: bad arguments");
+    const int vec = x->dtype == DMU_BF16 ? 8 : 4;
+    DMU_REQUIRE(x->sc == 1 && C % vec == 0 && x->sw % vec == 0 && x->sn % vec == 0 && C / vec <= 256, "dmu_silu_pool_fwd: needs NHWC, C multiple of %d", vec);
+    dim3 grid = gn_grid(N, H * W, C, vec);
+    const int cap = (2 * sm_count() + N - 1) / N;
+    if ((int)grid.x > cap) grid.x = cap;
+    DISPATCH_T(x->dtype, silu_pool_fwd_kernel, grid, 256, as_stream(stream), *x, H, W, C, out, pitch, scale);
+    return check_launch("dmu_silu_pool_fwd");
+}
+int dmu_silu_pool_bwd(const dmu_tensor4* x, const dmu_tensor4* dx, int32_t N, int32_t H, int32_t W, int32_t C, const float* g, int64_t pitch, float scale,
+                      dmu_stream_t stream) {
+    DMU_REQUIRE(x && x->ptr && dx && dx->ptr && g && N > 0 && H > 0 && W > 0 && C > 0 && C <= kMaxC, "dmu_silu_pool_bwd: bad arguments");
+    const int vec = x->dtype == DMU_BF16 ? 8 : 4;
+    DMU_REQUIRE(x->sc == 1 && dx->sc == 1 && dx->dtype == x->dtype && C % vec == 0 && x->sw % vec == 0 && x->sn % vec == 0 && dx->sw % vec == 0 &&
+                    dx->sn % vec == 0 && C / vec <= 256, "dmu_silu_pool_bwd: needs NHWC tensors of one dtype, C multiple of %d", vec);
+    DISPATCH_T(x->dtype, silu_pool_bwd_kernel, gn_grid(N, H * W, C, vec), 256, as_stream(stream), *x, *dx, H, W, C, g, pitch, scale);
+    return check_launch("dmu_silu_pool_bwd");
 }
 
 int dmu_act_fwd(const float* x, float* y, int64_t n, int32_t kind, dmu_stream_t stream) {

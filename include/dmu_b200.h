@@ -211,6 +211,13 @@ int dmu_gn_bwd_apply(const dmu_gn_params* p, dmu_stream_t stream);
 int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C,
                float* out_nc, int64_t out_nc_pitch, float* out_c, float scale, dmu_stream_t stream);
 
+/* EnergyNet head, models/energy_based.py:79-83: out[n*pitch + c] += scale * sum_p silu(x[n,p,c])  (scale = 1/(H*W) gives the
+ * mean; out is accumulated: zero it first) and its input gradient dx[n,p,c] = silu'(x[n,p,c]) * g[n*pitch + c] * scale. */
+int dmu_silu_pool_fwd(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out, int64_t pitch, float scale,
+                      dmu_stream_t stream);
+int dmu_silu_pool_bwd(const dmu_tensor4* x, const dmu_tensor4* dx, int32_t N, int32_t H, int32_t W, int32_t C, const float* g,
+                      int64_t pitch, float scale, dmu_stream_t stream);
+
 /* Multi-head self-attention core, attention.py:49-61.  qkv: [N, S, 3C] rows
  * (pitch), heads*d = C; o: [N, S, C].  lse: [N, heads, S] fp32 (saved for bwd).
  * bwd writes dqkv given do. */

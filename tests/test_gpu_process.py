@@ -150,3 +150,50 @@ def test_cpu_tensor_is_rejected():
     x = torch.randn(2, 3, 4, 4)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.q_sample(x, torch.zeros(2, dtype=torch.long), x, torch.ones(10))
+
+
+@pytest.mark.parametrize("tag,precision,tol", [("c16", "fp32", 2e-4), ("c64", "fp32", 2e-4), ("c64", "bf16", 3e-2)])
+def test_energy_model_against_live_reference_draws(tag, precision, tol):
+    """EnergyNet on the CUDA library: energies, Langevin chain, input gradient, loss value (with the gradient penalty) and
+    the contrastive-divergence parameter gradients, driven with the reference's recorded random draws."""
+    import diffusion_model_universal_b200 as D
+    from oracle import weights as OW
+    r = load_golden("energy_draws.pt")[tag]
+    dev = torch.device("cuda:0")
+    cfg = dict(r["cfg"], precision=precision)
+    m = D.EnergyBasedDiffusion(cfg)
+    sd = m.state_dict()
+    sd.update(OW.make_state_dict(OW.energynet_param_spec(r["C"], 3, "model."), r["wseed"]))
+    m.load_state_dict(sd)
+    m.to(dev)
+    x, t, noise, alpha = r["x"].to(dev), r["t"].to(dev), r["noise"].to(dev), r["alpha"].to(dev)
+    lang = [z.to(dev) for z in r["lang"]]
+    with torch.no_grad():
+        assert rel_l2(m.forward(x), r["energy"]) < tol
+        xf = m._langevin_sampling(m._add_noise(x, t, noise), t, _noises=lang)
+        assert rel_l2(xf, r["x_fake"]) < tol
+        xh = alpha * x + (1 - alpha) * r["x_fake"].to(dev)
+        _, g = m.model.energy_and_input_grad(xh)
+        assert rel_l2(g, r["grad_x_hat"]) < 10 * tol
+    loss = m._loss_from_draws(x, t, noise, lang, alpha)
+    assert abs(loss.item() - float(r["loss_gp"])) < 10 * tol * max(abs(float(r["loss_gp"])), 1e-2)
+    with pytest.raises(NotImplementedError):
+        loss.backward()                                   # the penalty's second-order gradient is not built: fail loudly
+    m.zero_grad()
+    m.regularization_weight = 0.0
+    loss = m._loss_from_draws(x, t, noise, lang, alpha)
+    assert abs(loss.item() - float(r["loss_cd"])) < 10 * tol * max(abs(float(r["loss_cd"])), 1e-2)
+    loss.backward()
+    scale = max(r["grads_cd_norm"].values())
+    for k, p in m.named_parameters():
+        gn = r["grads_cd_norm"][k]
+        assert p.grad is not None, k
+        if gn > 1e-5 * scale:
+            assert abs(p.grad.norm().item() - gn) < 20 * tol * gn + 1e-4 * scale, (k, p.grad.norm().item(), gn)
+        if k in r["grads_cd"] and gn > 1e-3 * scale:
+            assert rel_l2(p.grad, r["grads_cd"][k]) < 20 * tol, k
+    with torch.no_grad():
+        s = m.__class__(dict(cfg, num_timesteps=3, langevin_steps=2)).to(dev)
+        s.model.load_state_dict(m.model.state_dict())
+        out = s.generate_samples(2, dev)
+        assert out.shape == (2, 3, r["R"], r["R"]) and torch.isfinite(out).all()
