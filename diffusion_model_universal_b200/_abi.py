@@ -54,6 +54,14 @@ class GnParams(C.Structure):
     ]
 
 
+class GnBwd2Params(C.Structure):
+    _fields_ = [
+        ("x", Tensor4), ("dy", Tensor4), ("c", Tensor4), ("gx", Tensor4), ("gdy", Tensor4),
+        ("sums", c_vp), ("gamma", c_vp), ("beta", c_vp), ("dgamma", c_vp), ("dbeta", c_vp),
+        ("N", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32), ("G", c_i32), ("silu", c_i32), ("eps", c_f32), ("_pad", c_i32),
+    ]
+
+
 class AttnParams(C.Structure):
     _fields_ = [
         ("qkv", c_vp), ("qkv_pitch", c_i64), ("o", c_vp), ("o_pitch", c_i64),
@@ -73,7 +81,7 @@ class RepackDesc(C.Structure):
 
 STRUCTS = {
     "dmu_tensor4": Tensor4, "dmu_conv_params": ConvParams, "dmu_wgrad_params": WgradParams,
-    "dmu_gn_params": GnParams, "dmu_attn_params": AttnParams, "dmu_repack_desc": RepackDesc,
+    "dmu_gn_params": GnParams, "dmu_attn_params": AttnParams, "dmu_repack_desc": RepackDesc, "dmu_gn_bwd2_params": GnBwd2Params,
 }
 
 P = C.POINTER
@@ -103,6 +111,8 @@ _SIGS = {
     "dmu_colsum": (c_i32, [P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_f32, c_vp]),
     "dmu_silu_pool_fwd": (c_i32, [P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp]),
     "dmu_silu_pool_bwd": (c_i32, [P(Tensor4), P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp]),
+    "dmu_gn_bwd_bwd": (c_i32, [P(GnBwd2Params), c_vp]),
+    "dmu_silu_pool_bwd_bwd": (c_i32, [P(Tensor4), P(Tensor4), P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp]),
     "dmu_attn_fwd": (c_i32, [P(AttnParams), c_vp]),
     "dmu_attn_bwd": (c_i32, [P(AttnParams), c_vp]),
     "dmu_sinusoidal_embedding": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_i32, c_vp]),

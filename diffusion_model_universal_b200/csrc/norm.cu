@@ -684,6 +684,210 @@ __global__ void __launch_bounds__(256) silu_pool_bwd_kernel(dmu_tensor4 X, dmu_t
     }
 }
 
+// ------------------------------------------------------------------ second-order pieces (EnergyBasedLoss gradient penalty)
+// utils/losses.py:277-285 differentiates grad_x E with create_graph=True, i.e. it back-propagates through the BACKWARD of the
+// energy network.  Convolutions are linear (their double backward is the existing fprop / dgrad / wgrad kernels); the two
+// nonlinear backward ops need their own derivative:
+//
+// (1) B(x, gamma, beta, dy) = backward of y = silu(GroupNorm(x)):   with xh = (x-mu) r, u = gamma xh + beta, du = dy phi'(u),
+//     t = gamma du, M1 = mean_g t, M2 = mean_g (t xh):    dx = r (t - M1 - xh M2)            (means over one image's group)
+//     Given a cotangent c of dx, S = sum c dx = r sum_i t_i w_i with w = c - mean_g c - xh mean_g(c xh).  Then
+//        dS/d(dy) = r w gamma phi'(u)
+//        e := dS/du = r w gamma dy phi''(u)             (phi'(u) inside t)
+//        q := dS/dxh = e gamma - r (c M2 + t mean_g(c xh))
+//        dS/dx  = r (q - mean_g q - xh mean_g(q xh) - r xh mean_g(t w))     (last term: the explicit factor r of dx)
+//        dS/dgamma_c = sum (r w du + e xh),   dS/dbeta_c = sum e
+// (2) P(h, g) = backward of pooled[n,c] = s sum_p silu(h):  dh = phi'(h) g[n,c] s;  given a cotangent c of dh:
+//        dS/dh = c phi''(h) g s,   dS/dg[n,c] = s sum_p c phi'(h)
+__device__ __forceinline__ void silu_d12(float u, int silu, float& d1, float& d2) {
+    if (!silu) { d1 = 1.f; d2 = 0.f; return; }
+    const float sg = 1.f / (1.f + expf(-u));
+    d1 = sg * (1.f + u * (1.f - sg));
+    d2 = sg * (1.f - sg) * (2.f + u * (1.f - 2.f * sg));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_bwd_kernel(dmu_gn_bwd2_params P) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
+    __shared__ float s_q[5][kMaxC];          // per-channel sums, then per-channel copies of their group totals
+    __shared__ float s_red[256 * kVec];
+    const int n = blockIdx.x, HW = P.H * P.W, C = P.C, cpg = C / P.G;
+    {   // statistics of image n (same convention as stage_affine)
+        const float cnt = (float)cpg * (float)HW;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g = c / cpg;
+            const float su = P.sums[((int64_t)n * P.G + g) * 2 + 0], sq = P.sums[((int64_t)n * P.G + g) * 2 + 1];
+            const float mean = su / cnt;
+            const float rstd = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + P.eps);
+            s_mean[c] = mean; s_rstd[c] = rstd; s_scale[c] = P.gamma[c]; s_beta[c] = P.beta[c];
+        }
+    }
+    __syncthreads();
+    RowMap m(C, kVec);
+    const int cb = m.active ? m.v * kVec : 0;
+    float mu[kVec], rs[kVec], ga[kVec], be[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { mu[i] = s_mean[cb + i]; rs[i] = s_rstd[cb + i]; ga[i] = s_scale[cb + i]; be[i] = s_beta[cb + i]; }
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr) + cb;
+    const T* dyb = reinterpret_cast<const T*>(P.dy.ptr) + cb;
+    const T* ccb = reinterpret_cast<const T*>(P.c.ptr) + cb;
+    const float inv_m = 1.f / ((float)cpg * (float)HW);
+
+    auto group_totals = [&](int nq) {   // s_q[k][c] <- sum over the channels of c's group of s_q[k][.]
+        __syncthreads();
+        float tot[5];
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g0 = (c / cpg) * cpg;
+            for (int k = 0; k < nq; ++k) {
+                float t = 0.f;
+                for (int j = g0; j < g0 + cpg; ++j) t += s_q[k][j];
+                tot[k] = t;
+            }
+            // all reads of this group's channels by this thread are done; other threads of the group read the same values,
+            // so write back only after a barrier
+            for (int k = 0; k < nq; ++k) s_red[k * C + c] = tot[k];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x)
+            for (int k = 0; k < nq; ++k) s_q[k][c] = s_red[k * C + c];
+        __syncthreads();
+    };
+
+    // ---- pass 1: A = sum c, Bc = sum c xh, T1 = sum t, T2 = sum t xh
+    {
+        float a0[kVec], a1[kVec], a2[kVec], a3[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { a0[i] = a1[i] = a2[i] = a3[i] = 0.f; }
+        if (m.active) {
+            for (int p = m.lane; p < HW; p += m.lanes) {
+                float xv[kVec], dv[kVec], cv[kVec];
+                unpack<T>(ld_raw<T>(xb + pix_off(P.x, n, p, P.W)), xv);
+                unpack<T>(ld_raw<T>(dyb + pix_off(P.dy, n, p, P.W)), dv);
+                unpack<T>(ld_raw<T>(ccb + pix_off(P.c, n, p, P.W)), cv);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) {
+                    const float xh = (xv[i] - mu[i]) * rs[i];
+                    float d1, d2;
+                    silu_d12(fmaf(ga[i], xh, be[i]), P.silu, d1, d2);
+                    const float t = ga[i] * dv[i] * d1;
+                    a0[i] += cv[i]; a1[i] = fmaf(cv[i], xh, a1[i]); a2[i] += t; a3[i] = fmaf(t, xh, a3[i]);
+                }
+            }
+        }
+        block_channel_sum<kVec>(m, a0, s_red, s_q[0], C);
+        block_channel_sum<kVec>(m, a1, s_red, s_q[1], C);
+        block_channel_sum<kVec>(m, a2, s_red, s_q[2], C);
+        block_channel_sum<kVec>(m, a3, s_red, s_q[3], C);
+    }
+    group_totals(4);
+    float Am[kVec], Bm[kVec], M1[kVec], M2[kVec];      // group means
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { Am[i] = s_q[0][cb + i] * inv_m; Bm[i] = s_q[1][cb + i] * inv_m; M1[i] = s_q[2][cb + i] * inv_m; M2[i] = s_q[3][cb + i] * inv_m; }
+    __syncthreads();
+
+    // ---- pass 2: Q1 = sum q, Q2 = sum q xh, K = sum t w, dgamma, dbeta
+    {
+        float a0[kVec], a1[kVec], a2[kVec], a3[kVec], a4[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { a0[i] = a1[i] = a2[i] = a3[i] = a4[i] = 0.f; }
+        if (m.active) {
+            for (int p = m.lane; p < HW; p += m.lanes) {
+                float xv[kVec], dv[kVec], cv[kVec];
+                unpack<T>(ld_raw<T>(xb + pix_off(P.x, n, p, P.W)), xv);
+                unpack<T>(ld_raw<T>(dyb + pix_off(P.dy, n, p, P.W)), dv);
+                unpack<T>(ld_raw<T>(ccb + pix_off(P.c, n, p, P.W)), cv);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) {
+                    const float xh = (xv[i] - mu[i]) * rs[i];
+                    float d1, d2;
+                    silu_d12(fmaf(ga[i], xh, be[i]), P.silu, d1, d2);
+                    const float du = dv[i] * d1, t = ga[i] * du;
+                    const float w = cv[i] - Am[i] - xh * Bm[i];
+                    const float e = rs[i] * w * ga[i] * dv[i] * d2;
+                    const float q = e * ga[i] - rs[i] * (cv[i] * M2[i] + t * Bm[i]);
+                    a0[i] += q; a1[i] = fmaf(q, xh, a1[i]); a2[i] = fmaf(t, w, a2[i]);
+                    a3[i] += rs[i] * w * du + e * xh;      // dgamma
+                    a4[i] += e;                            // dbeta
+                }
+            }
+        }
+        block_channel_sum<kVec>(m, a0, s_red, s_q[0], C);
+        block_channel_sum<kVec>(m, a1, s_red, s_q[1], C);
+        block_channel_sum<kVec>(m, a2, s_red, s_q[2], C);
+        block_channel_sum<kVec>(m, a3, s_red, s_q[3], C);
+        block_channel_sum<kVec>(m, a4, s_red, s_q[4], C);
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (P.dgamma) atomicAdd(&P.dgamma[c], s_q[3][c]);
+        if (P.dbeta) atomicAdd(&P.dbeta[c], s_q[4][c]);
+    }
+    group_totals(3);
+    float Q1[kVec], Q2[kVec], Km[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { Q1[i] = s_q[0][cb + i] * inv_m; Q2[i] = s_q[1][cb + i] * inv_m; Km[i] = s_q[2][cb + i] * inv_m; }
+
+    // ---- pass 3: outputs
+    if (!m.active) return;
+    T* gxb = reinterpret_cast<T*>(P.gx.ptr) + cb;
+    T* gdb = P.gdy.ptr ? reinterpret_cast<T*>(P.gdy.ptr) + cb : nullptr;
+    for (int p = m.lane; p < HW; p += m.lanes) {
+        float xv[kVec], dv[kVec], cv[kVec], ox[kVec], od[kVec];
+        unpack<T>(ld_raw<T>(xb + pix_off(P.x, n, p, P.W)), xv);
+        unpack<T>(ld_raw<T>(dyb + pix_off(P.dy, n, p, P.W)), dv);
+        unpack<T>(ld_raw<T>(ccb + pix_off(P.c, n, p, P.W)), cv);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const float xh = (xv[i] - mu[i]) * rs[i];
+            float d1, d2;
+            silu_d12(fmaf(ga[i], xh, be[i]), P.silu, d1, d2);
+            const float t = ga[i] * dv[i] * d1;
+            const float w = cv[i] - Am[i] - xh * Bm[i];
+            const float e = rs[i] * w * ga[i] * dv[i] * d2;
+            const float q = e * ga[i] - rs[i] * (cv[i] * M2[i] + t * Bm[i]);
+            ox[i] = rs[i] * (q - Q1[i] - xh * Q2[i] - rs[i] * xh * Km[i]);
+            od[i] = rs[i] * w * ga[i] * d1;
+        }
+        store_vec<T>(gxb + pix_off(P.gx, n, p, P.W), ox);
+        if (gdb) store_vec<T>(gdb + pix_off(P.gdy, n, p, P.W), od);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) silu_pool_bwd_bwd_kernel(dmu_tensor4 X, dmu_tensor4 Cc, dmu_tensor4 GX, int H, int W, int C, const float* g, int64_t pitch,
+                                                                float* gg, int64_t gg_pitch, float scale) {
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s[kMaxC];
+    __shared__ float s_red[256 * kVec];
+    const int n = blockIdx.y, HW = H * W;
+    RowMap m(C, kVec);
+    int p0, p1; chunk_range(HW, p0, p1);
+    float a[kVec], gv[kVec];
+    const int cb = m.active ? m.v * kVec : 0;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { a[i] = 0.f; gv[i] = g[(int64_t)n * pitch + cb + i] * scale; }
+    if (m.active) {
+        const T* xb = reinterpret_cast<const T*>(X.ptr) + cb;
+        const T* cc = reinterpret_cast<const T*>(Cc.ptr) + cb;
+        T* ob = reinterpret_cast<T*>(GX.ptr) + cb;
+        for (int p = p0 + m.lane; p < p1; p += m.lanes) {
+            float v[kVec], cv[kVec];
+            unpack<T>(ld_raw<T>(xb + pix_off(X, n, p, W)), v);
+            unpack<T>(ld_raw<T>(cc + pix_off(Cc, n, p, W)), cv);
+#pragma unroll
+            for (int i = 0; i < kVec; ++i) {
+                float d1, d2;
+                silu_d12(v[i], 1, d1, d2);
+                a[i] = fmaf(cv[i], d1, a[i]);
+                v[i] = cv[i] * d2 * gv[i];
+            }
+            store_vec<T>(ob + pix_off(GX, n, p, W), v);
+        }
+    }
+    block_channel_sum<kVec>(m, a, s_red, s, C);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&gg[(int64_t)n * gg_pitch + c], s[c] * scale);
+}
+
 // ------------------------------------------------------------------ activations (fp32 rows)
 __device__ __forceinline__ float act_f(float x, int kind) {
     if (kind == 0) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
@@ -945,6 +1149,35 @@ int dmu_silu_pool_bwd(const dmu_tensor4* x, const dmu_tensor4* dx, int32_t N, in
                     dx->sn % vec == 0 && C / vec <= 256, "dmu_silu_pool_bwd: needs NHWC tensors of one dtype, C multiple of %d", vec);
     DISPATCH_T(x->dtype, silu_pool_bwd_kernel, gn_grid(N, H * W, C, vec), 256, as_stream(stream), *x, *dx, H, W, C, g, pitch, scale);
     return check_launch("dmu_silu_pool_bwd");
+}
+
+int dmu_gn_bwd_bwd(const dmu_gn_bwd2_params* p, dmu_stream_t stream) {
+    DMU_REQUIRE(p && p->x.ptr && p->dy.ptr && p->c.ptr && p->gx.ptr && p->sums && p->gamma && p->beta, "dmu_gn_bwd_bwd: null pointer");
+    DMU_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->G > 0 && p->C % p->G == 0 && p->C <= kMaxC, "dmu_gn_bwd_bwd: bad dims");
+    const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
+    const dmu_tensor4* ts[5] = {&p->x, &p->dy, &p->c, &p->gx, &p->gdy};
+    for (int i = 0; i < 5; ++i) {
+        if (!ts[i]->ptr) continue;
+        DMU_REQUIRE(ts[i]->sc == 1 && ts[i]->dtype == p->x.dtype && ts[i]->sw % vec == 0 && ts[i]->sh % vec == 0 && ts[i]->sn % vec == 0,
+                    "dmu_gn_bwd_bwd: tensors must be NHWC of one dtype with pitches multiple of %d", vec);
+    }
+    DMU_REQUIRE(p->C % vec == 0 && p->C / vec <= 256 && 5 * p->C <= 256 * vec, "dmu_gn_bwd_bwd: unsupported channel count %d", p->C);
+    if (p->x.dtype == DMU_BF16) gn_bwd_bwd_kernel<__nv_bfloat16><<<p->N, 256, 0, as_stream(stream)>>>(*p);
+    else gn_bwd_bwd_kernel<float><<<p->N, 256, 0, as_stream(stream)>>>(*p);
+    return check_launch("dmu_gn_bwd_bwd");
+}
+int dmu_silu_pool_bwd_bwd(const dmu_tensor4* x, const dmu_tensor4* c, const dmu_tensor4* gx, int32_t N, int32_t H, int32_t W, int32_t C, const float* g,
+                          int64_t pitch, float* gg, int64_t gg_pitch, float scale, dmu_stream_t stream) {
+    DMU_REQUIRE(x && x->ptr && c && c->ptr && gx && gx->ptr && g && gg && N > 0 && H > 0 && W > 0 && C > 0 && C <= kMaxC, "dmu_silu_pool_bwd_bwd: bad arguments");
+    const int vec = x->dtype == DMU_BF16 ? 8 : 4;
+    DMU_REQUIRE(x->sc == 1 && c->sc == 1 && gx->sc == 1 && c->dtype == x->dtype && gx->dtype == x->dtype && C % vec == 0 && C / vec <= 256,
+                "dmu_silu_pool_bwd_bwd: needs NHWC tensors of one dtype, C multiple of %d", vec);
+    dim3 grid = gn_grid(N, H * W, C, vec);
+    const int cap = (2 * sm_count() + N - 1) / N;
+    if ((int)grid.x > cap) grid.x = cap;
+    if (x->dtype == DMU_BF16) silu_pool_bwd_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(*x, *c, *gx, H, W, C, g, pitch, gg, gg_pitch, scale);
+    else silu_pool_bwd_bwd_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(*x, *c, *gx, H, W, C, g, pitch, gg, gg_pitch, scale);
+    return check_launch("dmu_silu_pool_bwd_bwd");
 }
 
 int dmu_act_fwd(const float* x, float* y, int64_t n, int32_t kind, dmu_stream_t stream) {

@@ -9,10 +9,9 @@ EnergyNet (energy_based.py:51-85) is NOT a UNet: conv3x3(in->C) -> GN(8) -> SiLU
 conv3x3(2C->4C) -> SiLU -> global mean -> Linear(4C, 1).  Forward and the first-order backward (input gradient for the
 Langevin dynamics, parameter gradients of the contrastive-divergence terms) run on the same kernels as the UNet.
 
-NOT built in this round: the parameter gradient of the gradient-penalty term of ``EnergyBasedLoss``
-(utils/losses.py:277-285, ``create_graph=True``), which needs second-order backward kernels (SiLU'' and the GroupNorm
-double backward).  The loss VALUE includes the penalty exactly; ``backward()`` of a loss with ``regularization_weight > 0``
-raises unless the config opts into ``gradient_penalty_grad: "skip"`` (penalty treated as a constant for the gradient).
+The gradient penalty of ``EnergyBasedLoss`` (utils/losses.py:277-285, ``create_graph=True``) is differentiated exactly:
+the double backward through the network runs on the conv kernels (a convolution's second-order terms are convolutions)
+plus ``dmu_gn_bwd_bwd`` and ``dmu_silu_pool_bwd_bwd`` (include/dmu_b200.h).
 """
 
 import ctypes as C
@@ -23,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import _abi, ops
-from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, RepackDesc
+from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, GnBwd2Params, RepackDesc
 from .base_model import BaseDiffusion
 from .losses import DiffusionLoss
 
@@ -61,127 +60,227 @@ class EnergyNet(nn.Module):
     def _run(self, x: torch.Tensor, dE: Optional[torch.Tensor], want_dx: bool, want_dw: bool):
         """Forward (and, when dE is given, backward) of the energy network.
         Returns (E [B], dx [B,C,H,W] or None, {param name: grad} or None)."""
-        lib = _abi.lib()
-        st = ops._stream()
-        dev = x.device
-        code = BF16 if self.precision == "bf16" else F32
-        tdt = torch.bfloat16 if code == BF16 else torch.float32
-        N, Ci, H, W = x.shape
-        Cm = self.model_channels
-        chans = [Ci, Cm, 2 * Cm, 4 * Cm]
-        keep = []
-
-        def chk(rc, what):
-            ops._launched()
-            _abi.check(rc, what)
-
-        # ---- filters in the compute dtype: [O][R][S][I] for fprop, [I][R][S][O] for dgrad
-        convs = [self.conv1, self.conv2, self.conv3]
-        wf, wb, descs = [], [], []
-        for i, cv in enumerate(convs):
-            O, I = chans[i + 1], chans[i]
-            f = torch.empty(O * 9 * I, device=dev, dtype=tdt)
-            b = torch.empty(O * 9 * I, device=dev, dtype=tdt)
-            wsrc = cv.weight.detach().contiguous()
-            keep.append(wsrc)
-            descs.append(RepackDesc(wsrc.data_ptr(), f.data_ptr(), O, I, 3, 3, 0, code))
-            descs.append(RepackDesc(wsrc.data_ptr(), b.data_ptr(), I, O, 3, 3, 1, code))
-            wf.append(f)
-            wb.append(b)
-        arr = (RepackDesc * len(descs))(*descs)
-        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-        chk(lib.dmu_repack_weights(table.data_ptr(), len(descs), max(c.weight.numel() for c in convs), st), "repack_weights")
-
-        def conv(xt4, yt4, w, Ck, Cj, bias, gather, w_strides):
-            p = ConvParams(xt4, yt4, _null(), w.data_ptr(), w_strides[0], w_strides[1], w_strides[2], bias, None, 0,
-                           N, H, W, Ck, H, W, Cj, 3, 3, 1, 1, gather, code, 0, 0, None, 0)
-            chk(lib.dmu_conv2d(C.byref(p), st), "conv2d")
-
-        def gn(xh, yh, sums, norm, silu=1):
-            p = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(yh), _null(), _null(), _null(), sums.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(),
-                         None, None, None, N, H, W, xh.shape[3], 8, silu, 1e-5, 0)
-            chk(lib.dmu_gn_forward(C.byref(p), st), "gn_forward")
-
-        # ---- forward
-        h1 = torch.empty(N, H, W, chans[1], device=dev, dtype=tdt)
-        conv(ops.t4_nchw(x), ops.t4_nhwc(h1), wf[0], Ci, chans[1], self.conv1.bias.data_ptr(), 0, (9 * Ci, 1, Ci))
-        s1 = torch.zeros(N, 8, 2, device=dev)
-        a1 = torch.empty_like(h1)
-        gn(h1, a1, s1, self.norm1)
-        h2 = torch.empty(N, H, W, chans[2], device=dev, dtype=tdt)
-        conv(ops.t4_nhwc(a1), ops.t4_nhwc(h2), wf[1], chans[1], chans[2], self.conv2.bias.data_ptr(), 0, (9 * chans[1], 1, chans[1]))
-        s2 = torch.zeros(N, 8, 2, device=dev)
-        a2 = torch.empty_like(h2)
-        gn(h2, a2, s2, self.norm2)
-        h3 = torch.empty(N, H, W, chans[3], device=dev, dtype=tdt)
-        conv(ops.t4_nhwc(a2), ops.t4_nhwc(h3), wf[2], chans[2], chans[3], self.conv3.bias.data_ptr(), 0, (9 * chans[2], 1, chans[2]))
-        pooled = torch.zeros(N, chans[3], device=dev)
-        t3 = ops.t4_nhwc(h3)
-        chk(lib.dmu_silu_pool_fwd(C.byref(t3), N, H, W, chans[3], pooled.data_ptr(), chans[3], 1.0 / (H * W), st), "silu_pool_fwd")
-        E = torch.empty(N, 1, device=dev)
-        pl = ConvParams(ops.t4_rows(pooled), ops.t4_rows(E), _null(), self.dense.weight.data_ptr(), chans[3], 1, 0, self.dense.bias.data_ptr(), None, 0,
-                        N, 1, 1, chans[3], 1, 1, 1, 1, 1, 1, 0, 0, F32, 0, 0, None, 0)
-        chk(lib.dmu_conv2d(C.byref(pl), st), "dense")
+        k = _Launcher(self, x)
+        E = k.forward()
         if dE is None:
-            return E.view(N), None, None
-
-        # ---- backward: dE [N] -> dx (and parameter gradients)
-        grads = {}
-        dE2 = dE.reshape(N, 1).contiguous().float()
-        dpooled = torch.empty(N, chans[3], device=dev)
-        pd = ConvParams(ops.t4_rows(dE2), ops.t4_rows(dpooled), _null(), self.dense.weight.data_ptr(), 1, chans[3], 0, None, None, 0,
-                        N, 1, 1, 1, 1, 1, chans[3], 1, 1, 1, 0, 0, F32, 0, 0, None, 0)
-        chk(lib.dmu_conv2d(C.byref(pd), st), "dense dgrad")
-
-        def wgrad(p4, q4, Ca, Cb, name, cv, rows=False):
-            dw = torch.zeros_like(cv.weight)
-            db = torch.zeros_like(cv.bias)
-            if rows:
-                p = WgradParams(p4, q4, dw.data_ptr(), Cb, 1, 0, db.data_ptr(), N, 1, 1, Ca, 1, 1, Cb, 1, 1, 1, 0, 0)
-            else:
-                p = WgradParams(p4, q4, dw.data_ptr(), Cb * 9, 9, 1, db.data_ptr(), N, H, W, Ca, H, W, Cb, 3, 3, 1, 1, 0)
-            chk(lib.dmu_conv2d_wgrad(C.byref(p), st), "wgrad " + name)
-            grads[name + ".weight"], grads[name + ".bias"] = dw, db
-
-        def gn_bwd(xh, dyh, dxh, sums, norm, name):
-            red = torch.zeros(N, xh.shape[3], 2, device=dev)
-            dg, db = (torch.zeros_like(norm.weight), torch.zeros_like(norm.bias)) if want_dw else (None, None)
-            p = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(dyh), ops.t4_nhwc(dxh), _null(), _null(), sums.data_ptr(), norm.weight.data_ptr(), norm.bias.data_ptr(),
-                         red.data_ptr(), dg.data_ptr() if want_dw else None, db.data_ptr() if want_dw else None, N, H, W, xh.shape[3], 8, 1, 1e-5, 0)
-            chk(lib.dmu_gn_backward(C.byref(p), st), "gn_backward")
-            if want_dw:
-                grads[name + ".weight"], grads[name + ".bias"] = dg, db
-
-        if want_dw:
-            wgrad(ops.t4_rows(dE2), ops.t4_rows(pooled), 1, chans[3], "dense", self.dense, rows=True)
-        dh3 = torch.empty_like(h3)
-        t3d = ops.t4_nhwc(dh3)
-        chk(lib.dmu_silu_pool_bwd(C.byref(t3), C.byref(t3d), N, H, W, chans[3], dpooled.data_ptr(), chans[3], 1.0 / (H * W), st), "silu_pool_bwd")
-        da2 = torch.empty_like(a2)
-        conv(ops.t4_nhwc(dh3), ops.t4_nhwc(da2), wb[2], chans[3], chans[2], None, 1, (9 * chans[3], 1, chans[3]))
-        if want_dw:
-            wgrad(ops.t4_nhwc(dh3), ops.t4_nhwc(a2), chans[3], chans[2], "conv3", self.conv3)
-        dh2 = torch.empty_like(h2)
-        gn_bwd(h2, da2, dh2, s2, self.norm2, "norm2")
-        da1 = torch.empty_like(a1)
-        conv(ops.t4_nhwc(dh2), ops.t4_nhwc(da1), wb[1], chans[2], chans[1], None, 1, (9 * chans[2], 1, chans[2]))
-        if want_dw:
-            wgrad(ops.t4_nhwc(dh2), ops.t4_nhwc(a1), chans[2], chans[1], "conv2", self.conv2)
-        dh1 = torch.empty_like(h1)
-        gn_bwd(h1, da1, dh1, s1, self.norm1, "norm1")
-        dx = None
-        if want_dx:
-            dx = torch.empty_like(x)
-            conv(ops.t4_nhwc(dh1), ops.t4_nchw(dx), wb[0], chans[1], Ci, None, 1, (9 * chans[1], 1, chans[1]))
-        if want_dw:
-            wgrad(ops.t4_nhwc(dh1), ops.t4_nchw(x), chans[1], Ci, "conv1", self.conv1)
-        return E.view(N), dx, grads if want_dw else None
+            return E, None, None
+        dx = k.backward(dE, want_dx, want_dw)
+        return E, dx, (k.grads if want_dw else None)
 
     def energy_and_input_grad(self, x: torch.Tensor):
         """(E(x) [B], d sum(E) / dx) in one forward+backward pass: what a Langevin step needs (energy_based.py:266-268)."""
         ones = torch.ones(x.shape[0], device=x.device)
         E, dx, _ = self._run(x.contiguous().float(), ones, True, False)
         return E, dx
+
+    def gradient_penalty(self, x_hat: torch.Tensor, want_param_grads: bool):
+        """utils/losses.py:275-285: penalty = mean_{n,h,w} (||grad_x E(x_hat)||_2 over channels - 1)^2, and (optionally) its
+        gradient with respect to every parameter - the double backward through the energy network.  Convolutions are linear,
+        so their second-order terms are the ordinary fprop / dgrad / wgrad kernels applied to cotangents; the GroupNorm+SiLU
+        backward and the SiLU+pool backward have dedicated derivative kernels (dmu_gn_bwd_bwd, dmu_silu_pool_bwd_bwd)."""
+        k = _Launcher(self, x_hat.contiguous().float())
+        k.forward()
+        g = k.backward(torch.ones(x_hat.shape[0], device=x_hat.device), True, False, keep=True)
+        nrm = g.norm(2, dim=1, keepdim=True)                       # [B,1,H,W]: host-side reduction of a 3-channel tensor
+        penalty = ((nrm - 1) ** 2).mean()
+        if not want_param_grads:
+            return penalty, None
+        v = (2.0 / nrm.numel()) * (nrm - 1) * g / nrm                # d penalty / d g
+        k.second_order(v.contiguous())
+        return penalty, k.grads
+
+
+class _Launcher:
+    """One evaluation of EnergyNet on the C ABI (eager launches; the network is 3 convolutions)."""
+
+    def __init__(self, net: EnergyNet, x: torch.Tensor):
+        self.net, self.x = net, x
+        self.lib = _abi.lib()
+        self.st = ops._stream()
+        self.dev = x.device
+        self.code = BF16 if net.precision == "bf16" else F32
+        self.tdt = torch.bfloat16 if self.code == BF16 else torch.float32
+        self.N, self.Ci, self.H, self.W = x.shape
+        Cm = net.model_channels
+        self.ch = [self.Ci, Cm, 2 * Cm, 4 * Cm]
+        self.convs = [net.conv1, net.conv2, net.conv3]
+        self.norms = [net.norm1, net.norm2]
+        self.grads = {n: torch.zeros_like(p) for n, p in net.named_parameters()}
+        self.keep = []
+        # filters in the compute dtype: [O][R][S][I] for fprop, [I][R][S][O] for dgrad
+        self.wf, self.wb, descs = [], [], []
+        for i, cv in enumerate(self.convs):
+            O, I = self.ch[i + 1], self.ch[i]
+            f = torch.empty(O * 9 * I, device=self.dev, dtype=self.tdt)
+            b = torch.empty(O * 9 * I, device=self.dev, dtype=self.tdt)
+            wsrc = cv.weight.detach().contiguous()
+            self.keep.append(wsrc)
+            descs.append(RepackDesc(wsrc.data_ptr(), f.data_ptr(), O, I, 3, 3, 0, self.code))
+            descs.append(RepackDesc(wsrc.data_ptr(), b.data_ptr(), I, O, 3, 3, 1, self.code))
+            self.wf.append(f)
+            self.wb.append(b)
+        arr = (RepackDesc * len(descs))(*descs)
+        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.dev)
+        self.keep.append(table)
+        self._chk(self.lib.dmu_repack_weights(table.data_ptr(), len(descs), max(c.weight.numel() for c in self.convs), self.st), "repack_weights")
+
+    def _chk(self, rc, what):
+        ops._launched()
+        _abi.check(rc, what)
+
+    def _act(self, c):
+        return torch.empty(self.N, self.H, self.W, c, device=self.dev, dtype=self.tdt)
+
+    # ---- primitives
+    def conv(self, i, xt4, yt4, bias=True):
+        """layer i fprop: channels ch[i] -> ch[i+1]"""
+        Ck, Cj = self.ch[i], self.ch[i + 1]
+        p = ConvParams(xt4, yt4, _null(), self.wf[i].data_ptr(), 9 * Ck, 1, Ck, self.convs[i].bias.data_ptr() if bias else None, None, 0,
+                       self.N, self.H, self.W, Ck, self.H, self.W, Cj, 3, 3, 1, 1, 0, self.code, 0, 0, None, 0)
+        self._chk(self.lib.dmu_conv2d(C.byref(p), self.st), "conv2d")
+
+    def conv_t(self, i, dyt4, dxt4):
+        """layer i dgrad: channels ch[i+1] -> ch[i]"""
+        Ck, Cj = self.ch[i + 1], self.ch[i]
+        p = ConvParams(dyt4, dxt4, _null(), self.wb[i].data_ptr(), 9 * Ck, 1, Ck, None, None, 0,
+                       self.N, self.H, self.W, Ck, self.H, self.W, Cj, 3, 3, 1, 1, 1, self.code, 0, 0, None, 0)
+        self._chk(self.lib.dmu_conv2d(C.byref(p), self.st), "conv2d dgrad")
+
+    def wgrad(self, i, p4, q4, bias: bool):
+        """layer i: dW[o][i][r][s] += sum P[.., o] Q[shifted, i]  (+ dbias += sum P)"""
+        name = "conv%d" % (i + 1)
+        Ca, Cb = self.ch[i + 1], self.ch[i]
+        p = WgradParams(p4, q4, self.grads[name + ".weight"].data_ptr(), Cb * 9, 9, 1, self.grads[name + ".bias"].data_ptr() if bias else None,
+                        self.N, self.H, self.W, Ca, self.H, self.W, Cb, 3, 3, 1, 1, 0)
+        self._chk(self.lib.dmu_conv2d_wgrad(C.byref(p), self.st), "wgrad " + name)
+
+    def gn_fwd(self, j, xh, yh):
+        sums = torch.zeros(self.N, 8, 2, device=self.dev)
+        nm = self.norms[j]
+        p = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(yh), _null(), _null(), _null(), sums.data_ptr(), nm.weight.data_ptr(), nm.bias.data_ptr(),
+                     None, None, None, self.N, self.H, self.W, xh.shape[3], 8, 1, 1e-5, 0)
+        self._chk(self.lib.dmu_gn_forward(C.byref(p), self.st), "gn_forward")
+        return sums
+
+    def gn_bwd(self, j, xh, dyh, dxh, sums, want_dw, add0=None):
+        nm = self.norms[j]
+        name = "norm%d" % (j + 1)
+        red = torch.zeros(self.N, xh.shape[3], 2, device=self.dev)
+        p = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(dyh), ops.t4_nhwc(dxh), ops.t4_nhwc(add0) if add0 is not None else _null(), _null(), sums.data_ptr(),
+                     nm.weight.data_ptr(), nm.bias.data_ptr(), red.data_ptr(),
+                     self.grads[name + ".weight"].data_ptr() if want_dw else None, self.grads[name + ".bias"].data_ptr() if want_dw else None,
+                     self.N, self.H, self.W, xh.shape[3], 8, 1, 1e-5, 0)
+        self._chk(self.lib.dmu_gn_backward(C.byref(p), self.st), "gn_backward")
+
+    def gn_bwd2(self, j, xh, dyh, ch, gx, gdy, sums):
+        nm = self.norms[j]
+        name = "norm%d" % (j + 1)
+        p = GnBwd2Params(ops.t4_nhwc(xh), ops.t4_nhwc(dyh), ops.t4_nhwc(ch), ops.t4_nhwc(gx), ops.t4_nhwc(gdy), sums.data_ptr(), nm.weight.data_ptr(),
+                         nm.bias.data_ptr(), self.grads[name + ".weight"].data_ptr(), self.grads[name + ".bias"].data_ptr(),
+                         self.N, self.H, self.W, xh.shape[3], 8, 1, 1e-5, 0)
+        self._chk(self.lib.dmu_gn_bwd_bwd(C.byref(p), self.st), "gn_bwd_bwd")
+
+    # ---- passes
+    def forward(self) -> torch.Tensor:
+        N, H, W, ch, net = self.N, self.H, self.W, self.ch, self.net
+        self.h1 = self._act(ch[1])
+        self.conv(0, ops.t4_nchw(self.x), ops.t4_nhwc(self.h1))
+        self.a1 = torch.empty_like(self.h1)
+        self.s1 = self.gn_fwd(0, self.h1, self.a1)
+        self.h2 = self._act(ch[2])
+        self.conv(1, ops.t4_nhwc(self.a1), ops.t4_nhwc(self.h2))
+        self.a2 = torch.empty_like(self.h2)
+        self.s2 = self.gn_fwd(1, self.h2, self.a2)
+        self.h3 = self._act(ch[3])
+        self.conv(2, ops.t4_nhwc(self.a2), ops.t4_nhwc(self.h3))
+        self.pooled = torch.zeros(N, ch[3], device=self.dev)
+        t3 = ops.t4_nhwc(self.h3)
+        self._chk(self.lib.dmu_silu_pool_fwd(C.byref(t3), N, H, W, ch[3], self.pooled.data_ptr(), ch[3], 1.0 / (H * W), self.st), "silu_pool_fwd")
+        E = torch.empty(N, 1, device=self.dev)
+        pl = ConvParams(ops.t4_rows(self.pooled), ops.t4_rows(E), _null(), net.dense.weight.data_ptr(), ch[3], 1, 0, net.dense.bias.data_ptr(), None, 0,
+                        N, 1, 1, ch[3], 1, 1, 1, 1, 1, 1, 0, 0, F32, 0, 0, None, 0)
+        self._chk(self.lib.dmu_conv2d(C.byref(pl), self.st), "dense")
+        return E.view(N)
+
+    def _dense_wgrad(self, dE2, q):
+        """ddense.weight[0, c] += sum_n dE[n] q[n, c];  ddense.bias += sum dE (only when q is the pooled activations)"""
+        ch = self.ch
+        p = WgradParams(ops.t4_rows(dE2), ops.t4_rows(q), self.grads["dense.weight"].data_ptr(), ch[3], 1, 0,
+                        self.grads["dense.bias"].data_ptr() if q is self.pooled else None, self.N, 1, 1, 1, 1, 1, ch[3], 1, 1, 1, 0, 0)
+        self._chk(self.lib.dmu_conv2d_wgrad(C.byref(p), self.st), "wgrad dense")
+
+    def backward(self, dE, want_dx, want_dw, keep=False):
+        """First-order backward from dE [N]; returns dx (fp32 NCHW) if wanted.  keep=True retains the intermediate gradients
+        the second-order pass differentiates."""
+        N, H, W, ch, net = self.N, self.H, self.W, self.ch, self.net
+        dE2 = dE.reshape(N, 1).contiguous().float()
+        dpooled = torch.empty(N, ch[3], device=self.dev)
+        pd = ConvParams(ops.t4_rows(dE2), ops.t4_rows(dpooled), _null(), net.dense.weight.data_ptr(), 1, ch[3], 0, None, None, 0,
+                        N, 1, 1, 1, 1, 1, ch[3], 1, 1, 1, 0, 0, F32, 0, 0, None, 0)
+        self._chk(self.lib.dmu_conv2d(C.byref(pd), self.st), "dense dgrad")
+        if want_dw:
+            self._dense_wgrad(dE2, self.pooled)
+        dh3 = torch.empty_like(self.h3)
+        t3, t3d = ops.t4_nhwc(self.h3), ops.t4_nhwc(dh3)
+        self._chk(self.lib.dmu_silu_pool_bwd(C.byref(t3), C.byref(t3d), N, H, W, ch[3], dpooled.data_ptr(), ch[3], 1.0 / (H * W), self.st), "silu_pool_bwd")
+        da2 = torch.empty_like(self.a2)
+        self.conv_t(2, ops.t4_nhwc(dh3), ops.t4_nhwc(da2))
+        if want_dw:
+            self.wgrad(2, ops.t4_nhwc(dh3), ops.t4_nhwc(self.a2), True)
+        dh2 = torch.empty_like(self.h2)
+        self.gn_bwd(1, self.h2, da2, dh2, self.s2, want_dw)
+        da1 = torch.empty_like(self.a1)
+        self.conv_t(1, ops.t4_nhwc(dh2), ops.t4_nhwc(da1))
+        if want_dw:
+            self.wgrad(1, ops.t4_nhwc(dh2), ops.t4_nhwc(self.a1), True)
+        dh1 = torch.empty_like(self.h1)
+        self.gn_bwd(0, self.h1, da1, dh1, self.s1, want_dw)
+        dx = None
+        if want_dx:
+            dx = torch.empty_like(self.x)
+            self.conv_t(0, ops.t4_nhwc(dh1), ops.t4_nchw(dx))
+        if want_dw:
+            self.wgrad(0, ops.t4_nhwc(dh1), ops.t4_nchw(self.x), True)
+        if keep:
+            self.dE2, self.dpooled, self.dh3, self.da2, self.dh2, self.da1, self.dh1 = dE2, dpooled, dh3, da2, dh2, da1, dh1
+        return dx
+
+    def second_order(self, v: torch.Tensor):
+        """Accumulate into self.grads the parameter gradient of <v, grad_x E(x)> (v fp32 [N,Cin,H,W], treated as constant):
+        back-propagation through the first-order backward pass kept by backward(keep=True), then through the forward pass."""
+        N, H, W, ch = self.N, self.H, self.W, self.ch
+        # --- through the backward pass, in reverse: g = ConvT1(dh1) <- dh1 = B1(h1, da1) <- da1 = ConvT2(dh2) <- ...
+        c_dh1 = self._act(ch[1])
+        self.conv(0, ops.t4_nchw(v), ops.t4_nhwc(c_dh1), bias=False)                       # d<v,g>/d dh1 = Conv1(v)
+        self.wgrad(0, ops.t4_nhwc(self.dh1), ops.t4_nchw(v), False)                          # dW1 += dh1 (x) v
+        c_h1, c_da1 = torch.empty_like(self.h1), torch.empty_like(self.a1)
+        self.gn_bwd2(0, self.h1, self.da1, c_dh1, c_h1, c_da1, self.s1)
+        c_dh2 = self._act(ch[2])
+        self.conv(1, ops.t4_nhwc(c_da1), ops.t4_nhwc(c_dh2), bias=False)
+        self.wgrad(1, ops.t4_nhwc(self.dh2), ops.t4_nhwc(c_da1), False)
+        c_h2, c_da2 = torch.empty_like(self.h2), torch.empty_like(self.a2)
+        self.gn_bwd2(1, self.h2, self.da2, c_dh2, c_h2, c_da2, self.s2)
+        c_dh3 = self._act(ch[3])
+        self.conv(2, ops.t4_nhwc(c_da2), ops.t4_nhwc(c_dh3), bias=False)
+        self.wgrad(2, ops.t4_nhwc(self.dh3), ops.t4_nhwc(c_da2), False)
+        c_h3 = torch.empty_like(self.h3)
+        c_dpooled = torch.zeros(N, ch[3], device=self.dev)
+        t3, tc, tg = ops.t4_nhwc(self.h3), ops.t4_nhwc(c_dh3), ops.t4_nhwc(c_h3)
+        self._chk(self.lib.dmu_silu_pool_bwd_bwd(C.byref(t3), C.byref(tc), C.byref(tg), N, H, W, ch[3], self.dpooled.data_ptr(), ch[3],
+                                                 c_dpooled.data_ptr(), ch[3], 1.0 / (H * W), self.st), "silu_pool_bwd_bwd")
+        self._dense_wgrad(self.dE2, c_dpooled)                                               # dpooled = dE * w_dense
+        # --- through the forward pass with the cotangents of h3, h2, h1 collected above
+        self.wgrad(2, ops.t4_nhwc(c_h3), ops.t4_nhwc(self.a2), True)
+        c_a2 = torch.empty_like(self.a2)
+        self.conv_t(2, ops.t4_nhwc(c_h3), ops.t4_nhwc(c_a2))
+        t_h2 = torch.empty_like(self.h2)
+        self.gn_bwd(1, self.h2, c_a2, t_h2, self.s2, True, add0=c_h2)
+        self.wgrad(1, ops.t4_nhwc(t_h2), ops.t4_nhwc(self.a1), True)
+        c_a1 = torch.empty_like(self.a1)
+        self.conv_t(1, ops.t4_nhwc(t_h2), ops.t4_nhwc(c_a1))
+        t_h1 = torch.empty_like(self.h1)
+        self.gn_bwd(0, self.h1, c_a1, t_h1, self.s1, True, add0=c_h1)
+        self.wgrad(0, ops.t4_nhwc(t_h1), ops.t4_nchw(self.x), True)
 
 
 class _EnergyFn(torch.autograd.Function):
@@ -206,22 +305,22 @@ class _EnergyFn(torch.autograd.Function):
 
 
 class _PenaltyFn(torch.autograd.Function):
-    """Value of the gradient penalty as a function of the network output it is attached to; its parameter gradient is the
-    second-order term this round does not implement."""
+    """Gradient penalty as a node of the autograd graph: the forward computes the value and (if anything requires grad) its
+    parameter gradients with the second-order launches of EnergyNet.gradient_penalty; the backward hands them out."""
 
     @staticmethod
-    def forward(ctx, anchor, value, skip):
-        ctx.skip = skip
-        return value.clone()
+    def forward(ctx, net: EnergyNet, x_hat, *params):
+        need = any(p.requires_grad for p in params)
+        value, grads = net.gradient_penalty(x_hat, need)
+        ctx.names = [n for n, _ in net.named_parameters()]
+        ctx.grads = grads
+        return value
 
     @staticmethod
     def backward(ctx, g):
-        if not ctx.skip:
-            raise NotImplementedError(
-                "EnergyBasedLoss gradient penalty (utils/losses.py:277-285): its parameter gradient needs second-order backward "
-                "kernels that are not built yet.  Set regularization_weight to 0, or opt into treating the penalty as a constant "
-                "for the gradient with model_config['gradient_penalty_grad'] = 'skip'.")
-        return torch.zeros_like(g), None, None
+        if ctx.grads is None:
+            return (None, None) + (None,) * len(ctx.names)
+        return (None, None) + tuple(ctx.grads[n] * g for n in ctx.names)
 
 
 class EnergyBasedDiffusion(BaseDiffusion):
@@ -272,11 +371,8 @@ class EnergyBasedDiffusion(BaseDiffusion):
         # interpolation x_hat = alpha x + (1 - alpha) x_fake: one fused launch (per-sample a, c coefficients)
         a = alpha.reshape(x.shape[0]).contiguous()
         x_hat = ops.scale_add(x, x_fake, a, 1.0 - a)
-        with torch.no_grad():
-            _, g = self.model.energy_and_input_grad(x_hat)
-            penalty = ((g.norm(2, dim=1) - 1) ** 2).mean()         # [B,3,H,W]-sized reduction of the input gradient
-        skip = self.config.get("gradient_penalty_grad", "error") == "skip" or lam == 0.0
-        return cd + lam * _PenaltyFn.apply(cd, penalty, skip)
+        params = [p for _, p in self.model.named_parameters()]
+        return cd + lam * _PenaltyFn.apply(self.model, x_hat, *params)
 
     # ------------------------------------------------------------------ sampling
     def _langevin_sampling(self, x: torch.Tensor, t: torch.Tensor, _noises: Optional[List[torch.Tensor]] = None) -> torch.Tensor:

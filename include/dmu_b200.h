@@ -218,6 +218,28 @@ int dmu_silu_pool_fwd(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int
 int dmu_silu_pool_bwd(const dmu_tensor4* x, const dmu_tensor4* dx, int32_t N, int32_t H, int32_t W, int32_t C, const float* g,
                       int64_t pitch, float scale, dmu_stream_t stream);
 
+/* Second-order pieces of the EnergyBasedLoss gradient penalty (utils/losses.py:277-285, create_graph=True): the derivative
+ * of the BACKWARD of y = act(GroupNorm(x)) and of the SiLU+pool head.  With dx = B(x, gamma, beta, dy) the first backward
+ * and c a cotangent of dx:  gx = d<c,dx>/dx,  gdy = d<c,dx>/d(dy) (optional),  dgamma/dbeta += d<c,dx>/d(gamma/beta).
+ * One CTA per image (three passes): sized for EnergyNet, not tuned. */
+typedef struct {
+    dmu_tensor4 x, dy, c, gx, gdy;   /* NHWC, one dtype; gdy.ptr may be NULL */
+    const float* sums;               /* [N, G, 2] raw sums saved by the forward */
+    const float* gamma;
+    const float* beta;
+    float* dgamma;                   /* [C] accumulated, or NULL */
+    float* dbeta;
+    int32_t N, H, W, C, G;
+    int32_t silu;
+    float eps;
+    int32_t _pad;
+} dmu_gn_bwd2_params;
+int dmu_gn_bwd_bwd(const dmu_gn_bwd2_params* p, dmu_stream_t stream);
+/* dh = silu'(h) g[n,c] scale is the first backward of dmu_silu_pool_fwd; c = cotangent of dh:
+ *   gx[n,p,ch] = c silu''(h) g[n,ch] scale;   gg[n*gg_pitch + ch] += scale * sum_p c silu'(h) */
+int dmu_silu_pool_bwd_bwd(const dmu_tensor4* x, const dmu_tensor4* c, const dmu_tensor4* gx, int32_t N, int32_t H, int32_t W, int32_t C,
+                          const float* g, int64_t pitch, float* gg, int64_t gg_pitch, float scale, dmu_stream_t stream);
+
 /* Multi-head self-attention core, attention.py:49-61.  qkv: [N, S, 3C] rows
  * (pitch), heads*d = C; o: [N, S, C].  lse: [N, heads, S] fp32 (saved for bwd).
  * bwd writes dqkv given do. */

@@ -413,3 +413,47 @@ def test_adam_ema_matches_torch():
         _abi.check(_abi.lib().dmu_adam_ema(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n,
                                            2e-4, 0.9, 0.999, 1e-8, 0.0, step, 0.999, 1.0, _stream()))
     assert rel_l2(p, p_ref) < 1e-6 and rel_l2(ema, ema_ref) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 8, 64, 8), (2, 16, 16, 128, 8), (2, 4, 4, 16, 8), (2, 8, 8, 64, 32)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("silu", [1, 0])
+def test_groupnorm_silu_double_backward(shape, dtype, silu):
+    """dmu_gn_bwd_bwd (derivative of the GroupNorm+SiLU backward) against torch's double backward."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import GnParams, GnBwd2Params
+    N, H, W, C_, G = shape
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C_ + silu)
+    x = (torch.randn(N, C_, H, W, generator=g) * 1.5 + 0.3).to(dev)
+    dy = torch.randn(N, C_, H, W, generator=g).to(dev)
+    cc = torch.randn(N, C_, H, W, generator=g).to(dev)
+    gamma, beta = (1 + 0.2 * torch.randn(C_, generator=g)).to(dev), (0.1 * torch.randn(C_, generator=g)).to(dev)
+    xh, dyh, ch = ops.nchw_to_nhwc(x, dtype), ops.nchw_to_nhwc(dy, dtype), ops.nchw_to_nhwc(cc, dtype)
+    lib = _abi.lib()
+    sums = torch.zeros(N, G, 2, device=dev)
+    yh = torch.empty_like(xh)
+    p = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(yh), _null(), _null(), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                 None, None, None, N, H, W, C_, G, silu, 1e-5, 0)
+    _abi.check(lib.dmu_gn_forward(C.byref(p), _stream()))
+    gx, gdy = torch.empty_like(xh), torch.empty_like(xh)
+    dgam, dbet = torch.zeros(C_, device=dev), torch.zeros(C_, device=dev)
+    p2 = GnBwd2Params(ops.t4_nhwc(xh), ops.t4_nhwc(dyh), ops.t4_nhwc(ch), ops.t4_nhwc(gx), ops.t4_nhwc(gdy), sums.data_ptr(), gamma.data_ptr(),
+                      beta.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), N, H, W, C_, G, silu, 1e-5, 0)
+    _abi.check(lib.dmu_gn_bwd_bwd(C.byref(p2), _stream()))
+    xq = xh.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    dq = dyh.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    cq = ch.float().permute(0, 3, 1, 2)
+    gq, bq = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.group_norm(xq, G, gq, bq, eps=1e-5)
+    y = F.silu(y) if silu else y
+    (dx,) = torch.autograd.grad(y, xq, dq, create_graph=True)
+    rx, rd, rg, rb = torch.autograd.grad((cq * dx).sum(), [xq, dq, gq, bq], allow_unused=True)
+    tol = 1e-4 if dtype == torch.float32 else 1.5e-2
+    assert rel_l2(gx.float().permute(0, 3, 1, 2), rx) < tol
+    assert rel_l2(gdy.float().permute(0, 3, 1, 2), rd) < tol
+    assert rel_l2(dgam, rg) < 1e-3
+    if silu:
+        assert rel_l2(dbet, rb) < 1e-3
+    else:
+        assert dbet.abs().max() < 1e-3 * max(1.0, float(dgam.abs().max()))

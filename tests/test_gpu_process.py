@@ -177,8 +177,15 @@ def test_energy_model_against_live_reference_draws(tag, precision, tol):
         assert rel_l2(g, r["grad_x_hat"]) < 10 * tol
     loss = m._loss_from_draws(x, t, noise, lang, alpha)
     assert abs(loss.item() - float(r["loss_gp"])) < 10 * tol * max(abs(float(r["loss_gp"])), 1e-2)
-    with pytest.raises(NotImplementedError):
-        loss.backward()                                   # the penalty's second-order gradient is not built: fail loudly
+    loss.backward()                                       # CD terms + 0.01 x gradient penalty (double backward)
+    scale = max(r["grads_gp_norm"].values())
+    for k, p in m.named_parameters():
+        gn = r["grads_gp_norm"][k]
+        assert p.grad is not None, k
+        if gn > 1e-5 * scale:
+            assert abs(p.grad.norm().item() - gn) < 20 * tol * gn + 1e-4 * scale, (k, p.grad.norm().item(), gn)
+        if k in r["grads_gp"] and gn > 1e-3 * scale:
+            assert rel_l2(p.grad, r["grads_gp"][k]) < 20 * tol, k
     m.zero_grad()
     m.regularization_weight = 0.0
     loss = m._loss_from_draws(x, t, noise, lang, alpha)
