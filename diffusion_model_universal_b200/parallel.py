@@ -37,14 +37,15 @@ class GradAllReducer:
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
-    def launch(self):
-        """Issue all buckets asynchronously; returns the work handles."""
+    def launch(self, lo: int = 0, hi: int = None):
+        """Issue the buckets of gflat[lo:hi] asynchronously (tail first); returns the work handles."""
         if self.world == 1:
             return []
         g = self.unet.engine.gflat
+        hi = g.numel() if hi is None else hi
         works = []
-        for lo, hi in bucket_ranges(g.numel(), self.bucket_elems):
-            works.append(dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for a, b in bucket_ranges(hi - lo, self.bucket_elems):
+            works.append(dist.all_reduce(g[lo + a:lo + b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         return works
 
     def finish(self, works) -> float:

@@ -28,6 +28,7 @@ class TrainStep:
         self.opt = FusedAdamEMA(model.model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay)
         self.reducer = GradAllReducer(model.model, bucket_mb=bucket_mb, group=group)
         self._stage = None
+        self._works = None
 
     def step(self, images: torch.Tensor) -> torch.Tensor:
         """images: fp32 [B,C,H,W] on the device, or a (pinned) host tensor which is
@@ -47,7 +48,10 @@ class TrainStep:
             loss.backward()
             for p in m.parameters():      # the arena holds this step's gradients; views must not accumulate into the next
                 p.grad = None
-        scale = self.reducer.allreduce()
+        if self._works is None:
+            self._works = self.reducer.launch()
+        scale = self.reducer.finish(self._works)
+        self._works = None
         self.opt.step(grad_scale=scale)
         return loss.detach()
 
@@ -66,5 +70,12 @@ class TrainStep:
         eps = eng.run_forward(xt, t, plan)
         wm, wl, wh = m.loss_fn.coefficients()
         loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True)
-        eng.run_backward(plan, dpred)
+        if self.reducer.world > 1:
+            # all-reduce the head / up-path half of the gradient arena while the second half of the backward runs
+            works = []
+            eng.run_backward(plan, dpred, between=lambda: works.extend(self.reducer.launch(eng.tail_lo, eng.gflat.numel())))
+            works.extend(self.reducer.launch(0, eng.tail_lo))
+            self._works = works
+        else:
+            eng.run_backward(plan, dpred)
         return loss

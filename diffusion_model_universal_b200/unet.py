@@ -213,6 +213,7 @@ class Plan:
 
     def __init__(self):
         self.fwd, self.bwd = [], []
+        self.bwd_a, self.bwd_b = [], []   # the two halves of bwd (head + up path | rest), for overlapping the DP all-reduce
         self.arena = None       # torch uint8 tensor keeping all plan buffers alive
         # static I/O buffers: every pointer in the recorded launches is fixed, so a plan can be replayed as a CUDA graph
         self.x_in = None        # fp32 [N,Cin,H,W] (NCHW) network input, read by the stem conv (and its wgrad)
@@ -322,9 +323,17 @@ class Engine:
             if p.dim() == 4:
                 undescs.append(RepackDesc(self.gstage.data_ptr() + self.wc_off[key] * 4, self.gflat.data_ptr() + offs[key][0] * 4,
                                           a, b, R, S, 3, F32))
-        uarr = (RepackDesc * len(undescs))(*undescs)
-        self.unpack_table = torch.frombuffer(bytearray(bytes(uarr)), dtype=torch.uint8).to(device)
-        self.unpack_n = len(undescs)
+        # two unpack tables: filters of the head + up path (their gradients are complete after the first half of the
+        # backward) and the rest; in the gradient arena the first group is the tail [self.tail_lo, total)
+        tail_keys = [k for (k, p, a, b, R, S, is_t) in entries if p.dim() == 4 and (k.startswith("up_blocks.") or k.startswith("output_conv."))]
+        und_a = [d for d, (k, p, *_r) in zip(undescs, [e_ for e_ in entries if e_[1].dim() == 4]) if k in tail_keys]
+        und_b = [d for d, (k, p, *_r) in zip(undescs, [e_ for e_ in entries if e_[1].dim() == 4]) if k not in tail_keys]
+        self.unpack_tables = []
+        for und in (und_a, und_b):
+            uarr = (RepackDesc * max(len(und), 1))(*und)
+            self.unpack_tables.append((torch.frombuffer(bytearray(bytes(uarr)), dtype=torch.uint8).to(device), len(und)))
+        rest_lo = offs["initial_conv.weight"][0]
+        self.tail_lo = min(offs[k][0] for k in order if offs[k][0] >= rest_lo and (k.startswith("up_blocks.") or k.startswith("output_conv.")))
         max_numel = 1
         for key, p, a, b, R, S, is_t in entries:
             off = self.wc_off[key]
@@ -474,7 +483,7 @@ class Engine:
     def _execute(self, plan: Plan, which: str):
         """Run plan.fwd / plan.bwd: eagerly the first time (warms every lazy one-time initialisation), then captured once
         into a CUDA graph and replayed — ~250 launches (and their tensor-map encodes) become one host call."""
-        oplist = plan.fwd if which == "fwd" else plan.bwd
+        oplist = {"fwd": plan.fwd, "bwd": plan.bwd, "bwd_a": plan.bwd_a, "bwd_b": plan.bwd_b}[which]
         g = plan.graphs.get(which)
         if g is not None:
             g.replay()
@@ -504,7 +513,7 @@ class Engine:
         self._execute(plan, "fwd")
         return plan.out.clone()
 
-    def run_backward(self, plan: Plan, dout):
+    def run_backward(self, plan: Plan, dout, between=None):
         """Fills the gradient arena; returns it (flat fp32, same offsets as the parameter arena)."""
         g = self.gflat
         # param.grad tensors handed out by an earlier backward are views of this arena.  If any is still installed
@@ -514,7 +523,12 @@ class Engine:
             if p.grad is not None and lo <= p.grad.data_ptr() < hi:
                 p.grad = p.grad.clone()
         plan.dout.copy_(dout)
-        self._execute(plan, "bwd")
+        if between is None:
+            self._execute(plan, "bwd")
+        else:
+            self._execute(plan, "bwd_a")
+            between()            # the tail [tail_lo, total) of the gradient arena is final: e.g. start its all-reduce
+            self._execute(plan, "bwd_b")
         return g
 
     # ------------------------------------------------------------------ plan construction
@@ -573,18 +587,33 @@ class Engine:
         plan.fwd.append((None, (), -1))                                  # join all lanes
         if train:
             # one zeroing of the gradient arena / staging for all lanes, then the lanes, then the batch-folded tails
-            plan.bwd = [(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4), 0),
-                        (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4), 0),
-                        (None, (), -2)]
+            # Two halves.  A = head + up path: afterwards the tail [tail_lo, total) of the gradient arena is final, so a
+            # data-parallel step can all-reduce it while B (bottleneck, down path, stem, time embedding) still runs.
+            halves = ([], [])
             for k, sub in enumerate(subs):
-                plan.bwd += retag(sub.plan.bwd, k)
-            plan.bwd.append((None, (), -1))
-            if gn_pg:
-                arr = (GnPgDesc * len(gn_pg))(*gn_pg)
-                plan.gn_pg_table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
-                plan.bwd.append((lib.dmu_gn_param_grads, (plan.gn_pg_table.data_ptr(), len(gn_pg), max(d.C for d in gn_pg), Ns), 0))
-            # filter gradients: staging layout -> the parameters' own layout inside the gradient arena
-            plan.bwd.append((lib.dmu_repack_weights, (self.unpack_table.data_ptr(), self.unpack_n, self.repack_max), 0))
+                ops_k = retag(sub.plan.bwd, k)
+                cut = next(i for i, op in enumerate(ops_k) if op[0] == "split")
+                halves[0].extend(ops_k[:cut])
+                halves[1].extend(ops_k[cut + 1:])
+            pg = ([d for sub in subs for d in sub.gn_pg[:sub.gn_pg_split]], [d for sub in subs for d in sub.gn_pg[sub.gn_pg_split:]])
+            plan.gn_pg_tables = []
+            plan.bwd_a = [(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4), 0),
+                          (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4), 0)]
+            plan.bwd_b = []
+            for h, lst in enumerate((plan.bwd_a, plan.bwd_b)):
+                lst.append((None, (), -2))
+                lst.extend(halves[h])
+                lst.append((None, (), -1))
+                if pg[h]:
+                    arr = (GnPgDesc * len(pg[h]))(*pg[h])
+                    tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+                    plan.gn_pg_tables.append(tab)
+                    lst.append((lib.dmu_gn_param_grads, (tab.data_ptr(), len(pg[h]), max(d.C for d in pg[h]), Ns), 0))
+                # filter gradients: staging layout -> the parameters' own layout inside the gradient arena
+                tab, n_un = self.unpack_tables[h]
+                if n_un:
+                    lst.append((lib.dmu_repack_weights, (tab.data_ptr(), n_un, self.repack_max), 0))
+            plan.bwd = plan.bwd_a + plan.bwd_b
         plan.arena = arena
         plan.nbytes = nbytes
         plan.lanes = K
@@ -627,6 +656,7 @@ class _PlanBuilder:
         self.code, self.esize = eng.code, eng.esize
         self.tape = []   # backward emitters, run in reverse
         self.gn_pg = []         # (red, dgamma, dbeta, C) of every GroupNorm backward: folded by one launch at the end
+        self.gn_pg_split = 0    # how many of them belong to the head / up path (first half of the backward)
         self.side_lane = True   # weight-gradient / column-sum launches of the backward go to the graph's second branch
 
     # ---- allocation helpers
@@ -907,6 +937,7 @@ class _PlanBuilder:
         b2 = cat[0].slice(0, 4 * Cm)
         self.res_block("bottleneck.2.", b1, b2, self.tproj + self.tp_off["bottleneck.2."] * 4, self.tp_total)
         # -------- up path
+        up_tape_start = len(self.tape)
         for k, (attn, ci, co) in enumerate(uplan):
             pfx = f"up_blocks.{k}."
             y = self.stage(pfx, attn, cat[k], co)
@@ -952,8 +983,13 @@ class _PlanBuilder:
                    (N, H, W, Co, H, W, Cm), (3, 3, 1, 1))
         self.gn_bwd(rec, x.grad)
         x.grad_written = True
-        for fn in reversed(self.tape):
-            fn()
+        for i in range(len(self.tape) - 1, -1, -1):
+            if i == up_tape_start - 1:
+                # everything emitted so far is the backward of the head and of the up path: their parameter gradients are
+                # final here (except the time projections), which is where a data-parallel step can start its all-reduce
+                plan.bwd.append(("split", ()))
+                self.gn_pg_split = len(self.gn_pg)
+            self.tape[i]()
         # stem: wgrad only (the network input needs no gradient on this path)
         self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), e.gsaddr("initial_conv.weight"),
                    (9 * net.in_channels, 1, net.in_channels), self.gp("initial_conv.bias"), (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))

@@ -36,7 +36,7 @@ def _model(C=32):
     return m
 
 
-def _shard_grads(m, x, t, noise):
+def _shard_grads(m, x, t, noise, between=None):
     """gradient arena of mean-MSE on one shard, through the engine (no RNG: t and noise injected)"""
     from diffusion_model_universal_b200 import ops
     eng = m.model.engine
@@ -44,7 +44,7 @@ def _shard_grads(m, x, t, noise):
     plan = eng.get_plan(x.shape, True)
     eps = eng.run_forward(m._add_noise(x, t, noise), t, plan)
     loss, dpred = ops.diffusion_loss(eps, noise, None, 1.0, 0.0, 0.0, 1.0, True)
-    eng.run_backward(plan, dpred)
+    eng.run_backward(plan, dpred, between=between)
     return loss, eng.gflat
 
 
@@ -61,9 +61,19 @@ def _worker(rank, world, port, out_dir):
     noise = torch.randn(4, 3, 32, 32, generator=g)
     lo, hi = rank * 2, rank * 2 + 2
     m = _model()
-    loss, gflat = _shard_grads(m, x[lo:hi], t[lo:hi], noise[lo:hi])
     red = GradAllReducer(m.model, bucket_mb=1.0)      # several buckets
-    scale = red.allreduce()
+    eng = m.model.engine
+    works, snap = [], {}
+
+    def between():
+        # the head / up-path half of the arena must be final here: start reducing it while the second half still runs
+        snap["tail"] = eng.gflat[eng.tail_lo:].clone()
+        works.extend(red.launch(eng.tail_lo, eng.gflat.numel()))
+
+    loss, gflat = _shard_grads(m, x[lo:hi], t[lo:hi], noise[lo:hi], between=between)
+    works.extend(red.launch(0, eng.tail_lo))
+    scale = red.finish(works)
+    assert 0 < eng.tail_lo < gflat.numel() and float(snap["tail"].abs().sum()) > 0
     opt = FusedAdamEMA(m.model, lr=1e-3, ema_decay=0.99)
     opt.step(grad_scale=scale)
     torch.save({"g": gflat.clone() * scale, "p": m.model.engine.flat.clone(), "ema": opt.ema.clone(), "loss": loss.clone()},
