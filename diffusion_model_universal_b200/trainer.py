@@ -71,10 +71,9 @@ class TrainStep:
         wm, wl, wh = m.loss_fn.coefficients()
         loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True)
         if self.reducer.world > 1:
-            # all-reduce the head / up-path half of the gradient arena while the second half of the backward runs
+            # all-reduce each third of the gradient arena as soon as its part of the backward has finished
             works = []
-            eng.run_backward(plan, dpred, between=lambda: works.extend(self.reducer.launch(eng.tail_lo, eng.gflat.numel())))
-            works.extend(self.reducer.launch(0, eng.tail_lo))
+            eng.run_backward(plan, dpred, between=lambda lo, hi: works.extend(self.reducer.launch(lo, hi)))
             self._works = works
         else:
             eng.run_backward(plan, dpred)

@@ -213,7 +213,8 @@ class Plan:
 
     def __init__(self):
         self.fwd, self.bwd = [], []
-        self.bwd_a, self.bwd_b = [], []   # the two halves of bwd (head + up path | rest), for overlapping the DP all-reduce
+        self.bwd_parts = []     # bwd cut in three (head + up | bottleneck + down 4,3 | rest), for overlapping the DP all-reduce
+        self.ranges = []        # gradient-arena range that is final after each part
         self.arena = None       # torch uint8 tensor keeping all plan buffers alive
         # static I/O buffers: every pointer in the recorded launches is fixed, so a plan can be replayed as a CUDA graph
         self.x_in = None        # fp32 [N,Cin,H,W] (NCHW) network input, read by the stem conv (and its wgrad)
@@ -323,17 +324,24 @@ class Engine:
             if p.dim() == 4:
                 undescs.append(RepackDesc(self.gstage.data_ptr() + self.wc_off[key] * 4, self.gflat.data_ptr() + offs[key][0] * 4,
                                           a, b, R, S, 3, F32))
-        # two unpack tables: filters of the head + up path (their gradients are complete after the first half of the
-        # backward) and the rest; in the gradient arena the first group is the tail [self.tail_lo, total)
-        tail_keys = [k for (k, p, a, b, R, S, is_t) in entries if p.dim() == 4 and (k.startswith("up_blocks.") or k.startswith("output_conv."))]
-        und_a = [d for d, (k, p, *_r) in zip(undescs, [e_ for e_ in entries if e_[1].dim() == 4]) if k in tail_keys]
-        und_b = [d for d, (k, p, *_r) in zip(undescs, [e_ for e_ in entries if e_[1].dim() == 4]) if k not in tail_keys]
+        # The backward is cut in three parts (head + up path | bottleneck + down 4, 3 | down 2..0 + stem + time embedding);
+        # the filters whose gradients are complete after each part get their own unpack table, and in the gradient arena
+        # (registration order) they are the ranges [cuts[0], total), [cuts[1], cuts[0]) and [0, cuts[1]).
+        def part_of(k):
+            if k.startswith("up_blocks.") or k.startswith("output_conv."):
+                return 0
+            if k.startswith("bottleneck.") or k.startswith("down_blocks.3.") or k.startswith("down_blocks.4."):
+                return 1
+            return 2
+        conv_entries = [e_ for e_ in entries if e_[1].dim() == 4]
         self.unpack_tables = []
-        for und in (und_a, und_b):
+        for part in range(3):
+            und = [d for d, e_ in zip(undescs, conv_entries) if part_of(e_[0]) == part]
             uarr = (RepackDesc * max(len(und), 1))(*und)
             self.unpack_tables.append((torch.frombuffer(bytearray(bytes(uarr)), dtype=torch.uint8).to(device), len(und)))
         rest_lo = offs["initial_conv.weight"][0]
-        self.tail_lo = min(offs[k][0] for k in order if offs[k][0] >= rest_lo and (k.startswith("up_blocks.") or k.startswith("output_conv.")))
+        self.cuts = [min(offs[k][0] for k in order if offs[k][0] >= rest_lo and part_of(k) == part) for part in (0, 1)]
+        self.tail_lo = self.cuts[0]
         max_numel = 1
         for key, p, a, b, R, S, is_t in entries:
             off = self.wc_off[key]
@@ -483,7 +491,7 @@ class Engine:
     def _execute(self, plan: Plan, which: str):
         """Run plan.fwd / plan.bwd: eagerly the first time (warms every lazy one-time initialisation), then captured once
         into a CUDA graph and replayed — ~250 launches (and their tensor-map encodes) become one host call."""
-        oplist = {"fwd": plan.fwd, "bwd": plan.bwd, "bwd_a": plan.bwd_a, "bwd_b": plan.bwd_b}[which]
+        oplist = plan.fwd if which == "fwd" else plan.bwd if which == "bwd" else plan.bwd_parts[int(which[3:])]
         g = plan.graphs.get(which)
         if g is not None:
             g.replay()
@@ -514,7 +522,8 @@ class Engine:
         return plan.out.clone()
 
     def run_backward(self, plan: Plan, dout, between=None):
-        """Fills the gradient arena; returns it (flat fp32, same offsets as the parameter arena)."""
+        """Fills the gradient arena; returns it (flat fp32, same offsets as the parameter arena).  ``between(lo, hi)`` is
+        called after each of the three parts of the backward with the arena range that just became final."""
         g = self.gflat
         # param.grad tensors handed out by an earlier backward are views of this arena.  If any is still installed
         # (gradient accumulation, zero_grad(set_to_none=False)) detach it first so autograd's `grad += new` stays correct.
@@ -526,9 +535,9 @@ class Engine:
         if between is None:
             self._execute(plan, "bwd")
         else:
-            self._execute(plan, "bwd_a")
-            between()            # the tail [tail_lo, total) of the gradient arena is final: e.g. start its all-reduce
-            self._execute(plan, "bwd_b")
+            for i in range(len(plan.bwd_parts)):
+                self._execute(plan, "bwd%d" % i)
+                between(*plan.ranges[i])      # gflat[lo:hi] is final: e.g. start its all-reduce while the next part runs
         return g
 
     # ------------------------------------------------------------------ plan construction
@@ -587,22 +596,25 @@ class Engine:
         plan.fwd.append((None, (), -1))                                  # join all lanes
         if train:
             # one zeroing of the gradient arena / staging for all lanes, then the lanes, then the batch-folded tails
-            # Two halves.  A = head + up path: afterwards the tail [tail_lo, total) of the gradient arena is final, so a
-            # data-parallel step can all-reduce it while B (bottleneck, down path, stem, time embedding) still runs.
-            halves = ([], [])
+            # Three parts (see Engine._flatten): after part i the arena range ranges[i] is final, so a data-parallel step can
+            # all-reduce it while the next part still runs.
+            parts = ([], [], [])
+            pg = ([], [], [])
             for k, sub in enumerate(subs):
                 ops_k = retag(sub.plan.bwd, k)
-                cut = next(i for i, op in enumerate(ops_k) if op[0] == "split")
-                halves[0].extend(ops_k[:cut])
-                halves[1].extend(ops_k[cut + 1:])
-            pg = ([d for sub in subs for d in sub.gn_pg[:sub.gn_pg_split]], [d for sub in subs for d in sub.gn_pg[sub.gn_pg_split:]])
+                cuts = [i for i, op in enumerate(ops_k) if op[0] == "split"]
+                assert len(cuts) == 2
+                parts[0].extend(ops_k[:cuts[0]])
+                parts[1].extend(ops_k[cuts[0] + 1:cuts[1]])
+                parts[2].extend(ops_k[cuts[1] + 1:])
+                g0, g1 = sub.gn_pg_split
+                pg[0].extend(sub.gn_pg[:g0]); pg[1].extend(sub.gn_pg[g0:g1]); pg[2].extend(sub.gn_pg[g1:])
             plan.gn_pg_tables = []
-            plan.bwd_a = [(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4), 0),
-                          (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4), 0)]
-            plan.bwd_b = []
-            for h, lst in enumerate((plan.bwd_a, plan.bwd_b)):
+            plan.bwd_parts = [[(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4), 0),
+                               (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4), 0)], [], []]
+            for h, lst in enumerate(plan.bwd_parts):
                 lst.append((None, (), -2))
-                lst.extend(halves[h])
+                lst.extend(parts[h])
                 lst.append((None, (), -1))
                 if pg[h]:
                     arr = (GnPgDesc * len(pg[h]))(*pg[h])
@@ -613,7 +625,9 @@ class Engine:
                 tab, n_un = self.unpack_tables[h]
                 if n_un:
                     lst.append((lib.dmu_repack_weights, (tab.data_ptr(), n_un, self.repack_max), 0))
-            plan.bwd = plan.bwd_a + plan.bwd_b
+            total = self.gflat.numel()
+            plan.ranges = [(self.cuts[0], total), (self.cuts[1], self.cuts[0]), (0, self.cuts[1])]
+            plan.bwd = plan.bwd_parts[0] + plan.bwd_parts[1] + plan.bwd_parts[2]
         plan.arena = arena
         plan.nbytes = nbytes
         plan.lanes = K
@@ -656,7 +670,7 @@ class _PlanBuilder:
         self.code, self.esize = eng.code, eng.esize
         self.tape = []   # backward emitters, run in reverse
         self.gn_pg = []         # (red, dgamma, dbeta, C) of every GroupNorm backward: folded by one launch at the end
-        self.gn_pg_split = 0    # how many of them belong to the head / up path (first half of the backward)
+        self.gn_pg_split = []   # len(gn_pg) at each split marker of the backward
         self.side_lane = True   # weight-gradient / column-sum launches of the backward go to the graph's second branch
 
     # ---- allocation helpers
@@ -915,8 +929,11 @@ class _PlanBuilder:
         # -------- down path
         x = h0
         skips = []
+        down3_tape_start = 0
         for i, (attn, ci, co) in enumerate(dplan):
             pfx = f"down_blocks.{i}."
+            if i == 3:
+                down3_tape_start = len(self.tape)
             y = self.stage(pfx, attn, x, co)
             kcat = 4 - i
             hpart = uplan[kcat][1] - co
@@ -983,12 +1000,14 @@ class _PlanBuilder:
                    (N, H, W, Co, H, W, Cm), (3, 3, 1, 1))
         self.gn_bwd(rec, x.grad)
         x.grad_written = True
+        self.gn_pg_split = []
         for i in range(len(self.tape) - 1, -1, -1):
-            if i == up_tape_start - 1:
-                # everything emitted so far is the backward of the head and of the up path: their parameter gradients are
-                # final here (except the time projections), which is where a data-parallel step can start its all-reduce
+            if i == up_tape_start - 1 or i == down3_tape_start - 1:
+                # Everything emitted so far is the backward of (head + up path) or of (... + bottleneck + down 4, 3): the
+                # parameter gradients of those layers are final here (except their time projections and q/k/v, which live at
+                # the head of the arena), which is where a data-parallel step can start all-reducing them.
                 plan.bwd.append(("split", ()))
-                self.gn_pg_split = len(self.gn_pg)
+                self.gn_pg_split.append(len(self.gn_pg))
             self.tape[i]()
         # stem: wgrad only (the network input needs no gradient on this path)
         self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), e.gsaddr("initial_conv.weight"),

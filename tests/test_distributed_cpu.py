@@ -65,15 +65,15 @@ def _worker(rank, world, port, out_dir):
     eng = m.model.engine
     works, snap = [], {}
 
-    def between():
-        # the head / up-path half of the arena must be final here: start reducing it while the second half still runs
-        snap["tail"] = eng.gflat[eng.tail_lo:].clone()
-        works.extend(red.launch(eng.tail_lo, eng.gflat.numel()))
+    def between(a, b):
+        # gflat[a:b] must be final here: start reducing it while the next part of the backward still runs
+        snap[(a, b)] = float(eng.gflat[a:b].abs().sum())
+        works.extend(red.launch(a, b))
 
     loss, gflat = _shard_grads(m, x[lo:hi], t[lo:hi], noise[lo:hi], between=between)
-    works.extend(red.launch(0, eng.tail_lo))
     scale = red.finish(works)
-    assert 0 < eng.tail_lo < gflat.numel() and float(snap["tail"].abs().sum()) > 0
+    assert len(snap) == 3 and all(v > 0 for v in snap.values())
+    assert sorted(snap)[0][0] == 0 and sum(b - a for a, b in snap) == gflat.numel()
     opt = FusedAdamEMA(m.model, lr=1e-3, ema_decay=0.99)
     opt.step(grad_scale=scale)
     torch.save({"g": gflat.clone() * scale, "p": m.model.engine.flat.clone(), "ema": opt.ema.clone(), "loss": loss.clone()},
