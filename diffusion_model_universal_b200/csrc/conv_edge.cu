@@ -85,6 +85,85 @@ __global__ void __launch_bounds__(256) narrow_in_kernel(dmu_conv_params P) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ narrow in -> wide out, v2
+// 3x3 / pad 1 / stride 1 only (stem fprop, head dgrad).  CTA = one band of rows of one image: the few-channel input band
+// (+halo) and the filter bank are staged in shared memory as fp32, thread = 4 consecutive output pixels x 8 output channels
+// (a 6-wide input window per (filter row, channel) serves 3 taps x 4 pixels; weights are 2 LDS.128 per tap), so the inner loop
+// is ~30 instructions per output instead of a latency-bound global gather.  bf16 or fp32 NHWC output, + bias.
+constexpr int kBandV2 = 4;
+template <typename TY>
+__global__ void __launch_bounds__(256) narrow_in_v2_kernel(dmu_conv_params P) {
+    extern __shared__ float smem_f[];
+    const int K = 9 * P.Ck;
+    const int PW = P.Wi + 2;
+    float* s_w = smem_f;                          // [K][Cj]
+    float* s_x = smem_f + (size_t)K * P.Cj;       // [kBandV2 + 2][Ck][PW]
+    for (int i = threadIdx.x; i < K * P.Cj; i += blockDim.x) {
+        const int j = i % P.Cj, k = i / P.Cj;
+        const int tap = k / P.Ck, kc = k % P.Ck;
+        s_w[i] = ld_as_float(P.w, (int64_t)j * P.w_sn + (int64_t)kc * P.w_sk + (int64_t)tap * P.w_st, P.w_dtype);
+    }
+    const int groups = P.Cj >> 3;
+    const int g = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = blockDim.x / groups;
+    const int QW = (P.Wo + 3) >> 2;
+    const int bands_per_img = (P.Ho + kBandV2 - 1) / kBandV2;
+    const int nbands = P.N * bands_per_img;
+    float bj[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bj[i] = P.bias ? P.bias[g * 8 + i] : 0.f;
+    for (int band = blockIdx.x; band < nbands; band += gridDim.x) {
+        const int n = band / bands_per_img, h0 = (band % bands_per_img) * kBandV2;
+        const int rows = min(kBandV2, P.Ho - h0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < (kBandV2 + 2) * P.Ck * PW; i += blockDim.x) {
+            const int pw = i % PW, kc = (i / PW) % P.Ck, rr = i / (PW * P.Ck);
+            const int hh = h0 + rr - 1, ww = pw - 1;
+            float v = 0.f;
+            if (hh >= 0 && hh < P.Hi && ww >= 0 && ww < P.Wi)
+                v = ld_as_float(P.x.ptr, (int64_t)n * P.x.sn + (int64_t)hh * P.x.sh + (int64_t)ww * P.x.sw + (int64_t)kc * P.x.sc, P.x.dtype);
+            s_x[i] = v;
+        }
+        __syncthreads();
+        if (pl >= lanes) continue;
+        for (int q = pl; q < rows * QW; q += lanes) {
+            const int hl = q / QW, w0 = (q % QW) * 4;
+            float acc[4][8];
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[p][i] = bj[i];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int dr = P.gather ? 2 - r : r;
+                for (int kc = 0; kc < P.Ck; ++kc) {
+                    const float* xr = s_x + ((size_t)(hl + dr) * P.Ck + kc) * PW + w0;
+                    float xw[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) xw[i] = (w0 + i < PW) ? xr[i] : 0.f;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const int ds = P.gather ? 2 - t : t;
+                        const float* wr = s_w + (size_t)((r * 3 + t) * P.Ck + kc) * P.Cj + g * 8;
+                        const float4 wa = *reinterpret_cast<const float4*>(wr), wb = *reinterpret_cast<const float4*>(wr + 4);
+                        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                        for (int p = 0; p < 4; ++p)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(xw[p + ds], wv[i], acc[p][i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                if (w0 + p >= P.Wo) break;
+                TY* yp = reinterpret_cast<TY*>(P.y.ptr) + (int64_t)n * P.y.sn + (int64_t)(h0 + hl) * P.y.sh + (int64_t)(w0 + p) * P.y.sw + g * 8;
+                store_vec<TY>(yp, acc[p]);
+                if constexpr (sizeof(TY) == 4) store_vec<TY>(yp + 4, acc[p] + 4);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ wide in -> narrow out
 // 8 threads per output pixel, each owning 8 of every 64 input channels (one 16-byte load per tap and 64-channel chunk, all
 // independent), then a 3-step shuffle reduction; weights fp32 [j][tap][k] in smem.
@@ -310,6 +389,21 @@ int dmu_conv2d_edge_supported(const dmu_conv_params* p) {
 int dmu_conv2d_edge(const dmu_conv_params* p, dmu_stream_t stream) {
     const size_t smem = (size_t)p->R * p->S * p->Ck * p->Cj * sizeof(float);
     const int64_t M = (int64_t)p->N * p->Ho * p->Wo;
+    if (p->Ck <= edge::kMaxNarrow && p->R == 3 && p->S == 3 && p->pad == 1 && !p->temb && !p->res.ptr && p->Cj <= 256 && p->Hi == p->Ho && p->Wi == p->Wo) {
+        const size_t smem2 = ((size_t)9 * p->Ck * p->Cj + (size_t)(edge::kBandV2 + 2) * p->Ck * (p->Wi + 2)) * sizeof(float);
+        if (smem2 <= 160 * 1024) {
+            const int nbands = p->N * ((p->Ho + edge::kBandV2 - 1) / edge::kBandV2);
+            int grid = nbands < 4 * sm_count() ? nbands : 4 * sm_count();
+            if (p->y.dtype == DMU_BF16) {
+                if (smem2 > 48 * 1024) cudaFuncSetAttribute(edge::narrow_in_v2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                edge::narrow_in_v2_kernel<__nv_bfloat16><<<grid, 256, smem2, as_stream(stream)>>>(*p);
+            } else {
+                if (smem2 > 48 * 1024) cudaFuncSetAttribute(edge::narrow_in_v2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                edge::narrow_in_v2_kernel<float><<<grid, 256, smem2, as_stream(stream)>>>(*p);
+            }
+            return check_launch("dmu_conv2d/narrow_in_v2");
+        }
+    }
     if (p->Ck <= edge::kMaxNarrow) {
         const int64_t items = (int64_t)p->N * p->Ho * ((p->Wo + 1) / 2) * (p->Cj / 8);
         int grid = (int)((items + 255) / 256);

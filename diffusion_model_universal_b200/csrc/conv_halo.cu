@@ -36,6 +36,9 @@ struct HaloArgs {
     const __nv_bfloat16* res; int64_t r_sn, r_sh, r_sw;
     const float* bias;
     const float* temb; int64_t temb_pitch;
+    // narrow output (the C->3 head conv): Cj <= 4 channels written as fp32 through arbitrary strides (NCHW at the API
+    // boundary); the weight box still has NT rows, the rows past Cj are TMA out-of-bounds zeros
+    float* yn; int64_t n_sn, n_sh, n_sw, n_sc; int narrow;
     long long* dbg;     // development aid: CTA 0 stamps clock64 per tile (8 slots per tile)
 };
 
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_const
         tma_prefetch_desc(&maps.b);
     }
     if (warp == 5) tmem_alloc(&s_tmem, 2 * NT);
-    for (int i = threadIdx.x; i < NT; i += blockDim.x) s_bias[i] = P.bias ? P.bias[j0 + i] : 0.f;   // parameters: not produced by the previous launch
+    for (int i = threadIdx.x; i < NT; i += blockDim.x)       // parameters: not produced by the previous launch
+        s_bias[i] = (P.bias && j0 + i < P.Cj) ? P.bias[j0 + i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -188,6 +192,20 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_const
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
             tc_fence_after();
             if (dbg) dbg[5] = clock64();
+            if (P.narrow) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * NT), v);
+                tmem_ld_wait();
+                if (valid) {
+                    float* op = P.yn + (int64_t)n * P.n_sn + (int64_t)ho * P.n_sh + (int64_t)wo * P.n_sw;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < P.narrow) op[(int64_t)j * P.n_sc] = v[j] + s_bias[j];
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[buf]);
+                continue;
+            }
 #pragma unroll
             for (int c = 0; c < NT; c += 32) {
                 float v[32];
@@ -243,7 +261,7 @@ int halo_supported(const dmu_conv_params* p, int force) {
     // chunk with the whole filter bank resident and at least four tiles per CTA (27.5 vs 31.6 us at 128x32x32x64->64,
     // 166 vs 215 us at 256x64x64); smaller or multi-chunk layers are faster per-tap.
     if (force) return 1;
-    if (p->Ck != 64 || p->Cj > 128) return 0;
+    if (p->Ck != 64 || (p->Cj > 128)) return 0;
     const int64_t tiles = ((int64_t)p->N * (p->Hi + 2) * (p->Wi + 2) + 127) / 128;
     if (tiles < 4 * (int64_t)sm_count()) return 0;
     return 1;
@@ -279,7 +297,8 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
     A.chunks = A.Ck / 64;
     A.flip = p->gather;
     A.a_stage_bytes = ((A.NR * A.PW * 128) + 1023) / 1024 * 1024;
-    const int NT = (p->Cj % 128 == 0) ? 128 : 64;
+    const bool narrow = p->Cj <= 4;
+    const int NT = narrow ? 64 : (p->Cj % 128 == 0) ? 128 : 64;
     const int smem = pick_smem(p, NT, A);
     DMU_REQUIRE(smem > 0 && smem <= 224 * 1024, "dmu_conv2d/halo: tile does not fit shared memory");
     {
@@ -294,11 +313,15 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
         const uint32_t box[2] = {64, (uint32_t)NT};
         if (int rc = make_map_bf16(&maps.b, p->w, 2, dims, str, box, "dmu_conv2d/halo weights")) return rc;
     }
+    if (narrow) {
+        A.narrow = p->Cj;
+        A.yn = reinterpret_cast<float*>(p->y.ptr); A.n_sn = p->y.sn; A.n_sh = p->y.sh; A.n_sw = p->y.sw; A.n_sc = p->y.sc;
+    }
     A.y = reinterpret_cast<__nv_bfloat16*>(p->y.ptr); A.y_sn = p->y.sn; A.y_sh = p->y.sh; A.y_sw = p->y.sw;
     A.res = reinterpret_cast<const __nv_bfloat16*>(p->res.ptr); A.r_sn = p->res.sn; A.r_sh = p->res.sh; A.r_sw = p->res.sw;
     A.bias = p->bias; A.temb = p->temb; A.temb_pitch = p->temb_pitch;
     A.dbg = g_debug_buffer;
-    const int ntiles_n = p->Cj / NT;
+    const int ntiles_n = narrow ? 1 : p->Cj / NT;
     int gx = sm_count() / ntiles_n;
     if (gx < 1) gx = 1;
     if (gx > A.tiles) gx = A.tiles;

@@ -376,19 +376,6 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
 
 long long* g_debug_buffer = nullptr;
 
-static int conv_supported(const dmu_conv_params* p) {
-    if (!p || !p->x.ptr || !p->y.ptr || !p->w) return 0;
-    if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y)) return 0;
-    if (p->res.ptr && !nhwc_bf16_ok(p->res)) return 0;
-    if (p->Ck % 64 != 0 || p->Cj % 64 != 0) return 0;
-    if (p->w_sk != 1 || (p->R * p->S > 1 && p->w_st != p->Ck) || p->w_sn != (int64_t)p->R * p->S * p->Ck || !aligned16(p->w)) return 0;
-    if (p->stride < 1 || p->stride > 2 || p->R * p->S > kMaxTaps) return 0;
-    if (p->bias && !aligned16(p->bias)) return 0;
-    if (p->temb && (!aligned16(p->temb) || p->temb_pitch % 4 != 0)) return 0;
-    if (encode_tiled_fn() == nullptr) return 0;
-    return 1;
-}
-
 // conv_halo.cu
 int halo_supported(const dmu_conv_params* p, int force);
 int halo_launch(const dmu_conv_params* p, cudaStream_t stream);
@@ -402,6 +389,30 @@ static bool halo_enabled() {
     return v == 1;
 }
 
+// C -> (<= 4) channel 3x3 head conv written as fp32 through arbitrary strides: runs on the halo kernel (the weight box rows
+// past Cj are TMA zeros), reading the wide input once instead of the SIMT kernel's latency-bound gather
+static int narrow_head_supported(const dmu_conv_params* p) {
+    if (!p || !p->x.ptr || !p->y.ptr || !p->w || p->Cj > 4 || p->Cj < 1) return 0;
+    if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || p->y.dtype != DMU_F32 || p->res.ptr || p->temb || p->gather != 0) return 0;
+    if (p->Ck != 64 || p->w_sk != 1 || p->w_st != p->Ck || p->w_sn != (int64_t)9 * p->Ck || !aligned16(p->w)) return 0;
+    if (encode_tiled_fn() == nullptr || !halo_enabled()) return 0;
+    return halo_supported(p, 0);
+}
+
+static int conv_supported(const dmu_conv_params* p) {
+    if (!p || !p->x.ptr || !p->y.ptr || !p->w) return 0;
+    if (narrow_head_supported(p)) return 1;
+    if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y)) return 0;
+    if (p->res.ptr && !nhwc_bf16_ok(p->res)) return 0;
+    if (p->Ck % 64 != 0 || p->Cj % 64 != 0) return 0;
+    if (p->w_sk != 1 || (p->R * p->S > 1 && p->w_st != p->Ck) || p->w_sn != (int64_t)p->R * p->S * p->Ck || !aligned16(p->w)) return 0;
+    if (p->stride < 1 || p->stride > 2 || p->R * p->S > kMaxTaps) return 0;
+    if (p->bias && !aligned16(p->bias)) return 0;
+    if (p->temb && (!aligned16(p->temb) || p->temb_pitch % 4 != 0)) return 0;
+    if (encode_tiled_fn() == nullptr) return 0;
+    return 1;
+}
+
 static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     // 3x3 stride-1 layers of 8x8 pixels and up: the persistent halo kernel (each input pixel fetched once per CTA);
     // impl 4 forces the per-tap kernel below
@@ -409,6 +420,7 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3, stride 1, pad 1, >= 8x8)");
         return halo_launch(p, stream);
     }
+    if (narrow_head_supported(p)) return halo_launch(p, stream);
     if (p->impl != 4 && halo_enabled() && halo_supported(p, 0)) return halo_launch(p, stream);
     Maps maps;
     ConvArgs A;

@@ -457,3 +457,26 @@ def test_groupnorm_silu_double_backward(shape, dtype, silu):
         assert rel_l2(dbet, rb) < 1e-3
     else:
         assert dbet.abs().max() < 1e-3 * max(1.0, float(dgam.abs().max()))
+
+
+def test_head_conv_on_halo_kernel():
+    """C -> 3 head conv at bench size: impl 0 routes it to the persistent halo kernel (weight-box rows past Cj are TMA
+    zeros, fp32 NCHW epilogue); compare with ATen and with the direct SIMT kernel (impl 3)."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    N, H, W, Cm = 80, 32, 32, 64
+    a = torch.randn(N, Cm, H, W, generator=g).to(dev)
+    ah = ops.nchw_to_nhwc(a, torch.bfloat16)
+    wh = (torch.randn(3, Cm, 3, 3, generator=g) / 24).to(dev)
+    bh = torch.randn(3, generator=g).to(dev)
+    whk = _repack(wh, False, torch.bfloat16)
+    outs = []
+    for impl in (0, 3):
+        out = torch.zeros(N, 3, H, W, device=dev)
+        ops.conv2d_raw(ConvParams(ops.t4_nhwc(ah), ops.t4_nchw(out), _null(), whk.data_ptr(), 9 * Cm, 1, Cm, bh.data_ptr(), None, 0,
+                                  N, H, W, Cm, H, W, 3, 3, 3, 1, 1, 0, 1, impl, 0))
+        outs.append(out)
+    ref = F.conv2d(ah.float().permute(0, 3, 1, 2), wh.to(torch.bfloat16).float(), bh, padding=1)
+    assert rel_l2(outs[0], ref) < 1e-5 and rel_l2(outs[1], ref) < 1e-5
