@@ -80,91 +80,105 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_const
     const uint32_t tmem = s_tmem;
     pdl_wait();
 
+    // TMA and MMA roles run as whole converged warps; the asynchronous instructions sit under elect_one() (tc_common.cuh)
     if (warp == 4) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            if (P.resident) {
-                mbar_arrive_expect_tx(&w_full[0], (uint32_t)(kblocks * kWTile));
-                for (int c = 0; c < P.chunks; ++c)
-                    for (int t = 0; t < 9; ++t)
-                        tma_load_2d(smem_w + (size_t)(c * 9 + t) * kWTile, &maps.b, &w_full[0], t * P.Ck + c * 64, j0);
-            }
-            int ia = 0, iw = 0;
-            const uint32_t a_bytes = (uint32_t)(P.NR * P.PW) * 128u;
-            for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
-                const int L0 = floordiv_dev(tile * 128 - P.PW - 1, P.PW);
-                for (int c = 0; c < P.chunks; ++c) {
-                    const int sa = ia % P.a_stages;
-                    mbar_wait(&a_empty[sa], ((ia / P.a_stages) & 1) ^ 1);
+        // ------------------------------------------------ TMA producer
+        if (P.resident && elect_one()) {
+            mbar_arrive_expect_tx(&w_full[0], (uint32_t)(kblocks * kWTile));
+            for (int c = 0; c < P.chunks; ++c)
+                for (int t = 0; t < 9; ++t)
+                    tma_load_2d(smem_w + (size_t)(c * 9 + t) * kWTile, &maps.b, &w_full[0], t * P.Ck + c * 64, j0);
+        }
+        __syncwarp();
+        int sa = 0, pa = 1, sw = 0, pw = 1;
+        const uint32_t a_bytes = (uint32_t)(P.NR * P.PW) * 128u;
+        for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+            const int L0 = floordiv_dev(tile * 128 - P.PW - 1, P.PW);
+            for (int c = 0; c < P.chunks; ++c) {
+                mbar_wait(&a_empty[sa], pa);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&a_full[sa], a_bytes);
                     uint8_t* dst = smem_a + (size_t)sa * P.a_stage_bytes;
+                    int n = floordiv_dev(L0, P.PH), hp = L0 - n * P.PH;
                     for (int i = 0; i < P.NR; ++i) {
-                        const int L = L0 + i;
-                        const int n = floordiv_dev(L, P.PH);
-                        const int hp = L - n * P.PH;
                         tma_load_4d(dst + (size_t)i * P.PW * 128, &maps.a, &a_full[sa], c * 64, -1, hp - 1, n);
+                        if (++hp == P.PH) { hp = 0; ++n; }
                     }
-                    ++ia;
-                    if (!P.resident) {
-                        for (int t = 0; t < 9; ++t) {
-                            const int sw = iw % P.w_stages;
-                            mbar_wait(&w_empty[sw], ((iw / P.w_stages) & 1) ^ 1);
+                }
+                __syncwarp();
+                if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
+                if (!P.resident) {
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(&w_empty[sw], pw);
+                        if (elect_one()) {
                             mbar_arrive_expect_tx(&w_full[sw], (uint32_t)kWTile);
                             tma_load_2d(smem_w + (size_t)sw * kWTile, &maps.b, &w_full[sw], t * P.Ck + c * 64, j0);
-                            ++iw;
                         }
+                        __syncwarp();
+                        if (++sw == P.w_stages) { sw = 0; pw ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
-            if (P.resident) mbar_wait(&w_full[0], 0);
-            int ia = 0, iw = 0, it = 0;
-            for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                long long* dbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) ? P.dbg + 8 * it : nullptr;
-                if (dbg) dbg[0] = clock64();
-                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        // ------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
+        if (P.resident) mbar_wait(&w_full[0], 0);
+        int sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
+        for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            long long* dbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && lane == 0) ? P.dbg + 8 * it : nullptr;
+            if (dbg) dbg[0] = clock64();
+            mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+            tc_fence_after();
+            if (dbg) dbg[1] = clock64();
+            const uint32_t d_tmem = tmem + (uint32_t)(buf * NT);
+            const int Q0 = tile * 128;
+            const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
+            const int base_off = Q0 - P.PW - 1 - L0 * P.PW;       // smem row of padded position (Q0 - PW - 1)
+            for (int c = 0; c < P.chunks; ++c) {
+                mbar_wait(&a_full[sa], pa);
                 tc_fence_after();
-                if (dbg) dbg[1] = clock64();
-                const uint32_t d_tmem = tmem + (uint32_t)(buf * NT);
-                const int Q0 = tile * 128;
-                const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
-                const int base_off = Q0 - P.PW - 1 - L0 * P.PW;       // smem row of padded position (Q0 - PW - 1)
-                for (int c = 0; c < P.chunks; ++c) {
-                    const int sa = ia % P.a_stages;
-                    mbar_wait(&a_full[sa], (ia / P.a_stages) & 1);
-                    tc_fence_after();
-                    if (dbg && c == 0) dbg[2] = clock64();
-                    const uint32_t a_base = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes);
+                if (dbg && c == 0) dbg[2] = clock64();
+                const uint32_t a_base = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes) + (uint32_t)base_off * 128u;
+                if (P.resident) {
+                    const uint32_t w_base = smem_u32(smem_w + (size_t)(c * 9) * kWTile);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const int r = t / 3, s = t % 3;
+                            const int dr = P.flip ? 2 - r : r, ds = P.flip ? 2 - s : s;
+                            const uint64_t da = smem_desc_sw128(a_base + (uint32_t)(dr * P.PW + ds) * 128u, 16, 1024);
+                            const uint64_t db = smem_desc_sw128(w_base + (uint32_t)(t * kWTile), 16, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
+                        }
+                        umma_commit(&a_empty[sa]);
+                    }
+                    __syncwarp();
+                } else {
                     for (int t = 0; t < 9; ++t) {
                         const int r = t / 3, s = t % 3;
                         const int dr = P.flip ? 2 - r : r, ds = P.flip ? 2 - s : s;
-                        uint32_t w_addr;
-                        int sw = 0;
-                        if (P.resident) {
-                            w_addr = smem_u32(smem_w + (size_t)(c * 9 + t) * kWTile);
-                        } else {
-                            sw = iw % P.w_stages;
-                            mbar_wait(&w_full[sw], (iw / P.w_stages) & 1);
-                            tc_fence_after();
-                            w_addr = smem_u32(smem_w + (size_t)sw * kWTile);
-                        }
-                        const uint64_t da = smem_desc_sw128(a_base + (uint32_t)(base_off + dr * P.PW + ds) * 128u, 16, 1024);
-                        const uint64_t db = smem_desc_sw128(w_addr, 16, 1024);
+                        mbar_wait(&w_full[sw], pw);
+                        tc_fence_after();
+                        const uint64_t da = smem_desc_sw128(a_base + (uint32_t)(dr * P.PW + ds) * 128u, 16, 1024);
+                        const uint64_t db = smem_desc_sw128(smem_u32(smem_w + (size_t)sw * kWTile), 16, 1024);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
-                        if (!P.resident) { umma_commit(&w_empty[sw]); ++iw; }
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (c | t | k) != 0);
+                            umma_commit(&w_empty[sw]);
+                            if (t == 8) umma_commit(&a_empty[sa]);
+                        }
+                        __syncwarp();
+                        if (++sw == P.w_stages) { sw = 0; pw ^= 1; }
                     }
-                    umma_commit(&a_empty[sa]);
-                    ++ia;
                 }
-                umma_commit(&acc_full[buf]);
-                if (dbg) dbg[3] = clock64();
+                if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
             }
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            __syncwarp();
+            if (dbg) dbg[3] = clock64();
         }
     } else {
         // ---------------------------------------------------- epilogue warps 0..3: thread = one output position (TMEM lane)

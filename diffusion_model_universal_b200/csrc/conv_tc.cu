@@ -138,8 +138,10 @@ struct ConvArgs {
     int splits;
     float* ws;
     long long* dbg;   // development aid (dmu_debug_set_buffer): per-CTA clock64 stamps of the pipeline phases
+    int prefetch;     // epilogue operands fetched while the pipeline runs (DMU_EPI_PREFETCH=0 turns it off: A/B aid)
 };
 
+constexpr int kBtImgs = 8;
 constexpr int kMaxSplitCtas = 160;      // CTAs of a split launch: about one wave
 constexpr int64_t kSplitWsBytes = (int64_t)kMaxSplitCtas * 128 * 128 * 4;
 
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
     __shared__ uint32_t s_tmem, s_issued;
+    __shared__ __align__(16) float s_bt[kBtImgs * NT];     // bias + temb[n] of the (<= kBtImgs) images this tile touches
 
     const int split = (int)blockIdx.z % P.splits;
     const Phase ph = P.phases[blockIdx.z / P.splits];
@@ -201,6 +204,30 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
+    // Epilogue operands are fetched NOW, while the pipeline below runs: this thread's residual row goes to registers and
+    // (bias + temb[n]) of the tile's images to shared memory, so that after the last MMA only TMEM loads, adds and the
+    // stores remain (they used to be four dependent rounds of L2 loads, ~2 us of a ~8 us sub-wave launch).
+    const int row = threadIdx.x;
+    const int wl = row % P.BW, hl = (row / P.BW) % P.BH, nl = row / (P.BW * P.BH);
+    const int n = n0 + nl, th = th0 + hl, tw = tw0 + wl;
+    const int ho = th * P.os + ph.oph, wo = tw * P.os + ph.opw;
+    const bool valid = nl < P.BN && n < P.N && th < ph.TH && tw < ph.TW && ho < P.Ho && wo < P.Wo;
+    const bool stage_bt = P.prefetch && P.splits == 1 && P.BN <= kBtImgs && (P.bias || P.temb);
+    const __nv_bfloat16* rp = (P.res && valid && P.splits == 1) ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
+    uint4 rpre[NT / 8];
+    if (rp && P.prefetch) {
+#pragma unroll
+        for (int i = 0; i < NT / 8; ++i) rpre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+    }
+    if (stage_bt && warp >= 2) {
+        for (int i = threadIdx.x - 64; i < P.BN * NT; i += 64) {
+            const int img = i / NT, c = i % NT;
+            float v = P.bias ? __ldg(P.bias + j0 + c) : 0.f;
+            if (P.temb && n0 + img < P.N) v += __ldg(P.temb + (int64_t)(n0 + img) * P.temb_pitch + j0 + c);
+            s_bt[i] = v;
+        }
+    }
+
     auto tap_live = [&](const Tap& t) {   // does the shifted box intersect its sub-lattice at all?
         const int h = th0 + t.dh, w = tw0 + t.dw;
         return h < P.map_h[t.map] && h + P.BH > 0 && w < P.map_w[t.map] && w + P.BW > 0;
@@ -211,65 +238,70 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     const int kb_per = (kb_total + P.splits - 1) / P.splits;
     const int kb_lo = split * kb_per, kb_hi = min(kb_total, kb_lo + kb_per);
 
-    if (warp == 0 && lane == 0) {
+    // Both roles run as whole, converged warps; the asynchronous instructions sit under elect_one() (see tc_common.cuh).
+    if (warp == 0) {
         // ------------------------------------------------ TMA producer
         const uint32_t a_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
-        int it = 0;
+        int it = 0, st = 0, par = 1;
         for (int ti = 0; ti < ph.ntaps; ++ti) {
             const Tap t = P.taps[ph.tap0 + ti];
             if (!tap_live(t)) continue;
             for (int c = 0; c < chunks; ++c) {
                 const int kb = ti * chunks + c;
                 if (kb < kb_lo || kb >= kb_hi) continue;
-                const int st = it % kStages;
-                mbar_wait(&empty_bar[st], ((it / kStages) & 1) ^ 1);
-                uint8_t* sa = smem + st * Cfg::kStageBytes;
-                mbar_arrive_expect_tx(&full_bar[st], a_bytes + Cfg::kBBytes);
-                tma_load_4d(sa, &maps.a[t.map], &full_bar[st], c * 64, tw0 + t.dw, th0 + t.dh, n0);
-                tma_load_2d(sa + Cfg::kABytes, &maps.b, &full_bar[st], t.wk + c * 64, j0);
+                mbar_wait(&empty_bar[st], par);
+                if (elect_one()) {
+                    uint8_t* sa = smem + st * Cfg::kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[st], a_bytes + Cfg::kBBytes);
+                    tma_load_4d(sa, &maps.a[t.map], &full_bar[st], c * 64, tw0 + t.dw, th0 + t.dh, n0);
+                    tma_load_2d(sa + Cfg::kABytes, &maps.b, &full_bar[st], t.wk + c * 64, j0);
+                }
+                __syncwarp();
                 ++it;
+                if (++st == kStages) { st = 0; par ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
-        int it = 0;
+        int it = 0, st = 0, par = 0;
         for (int ti = 0; ti < ph.ntaps; ++ti) {
             const Tap t = P.taps[ph.tap0 + ti];
             if (!tap_live(t)) continue;
             for (int c = 0; c < chunks; ++c) {
                 const int kb = ti * chunks + c;
                 if (kb < kb_lo || kb >= kb_hi) continue;
-                const int st = it % kStages;
-                mbar_wait(&full_bar[st], (it / kStages) & 1);
+                mbar_wait(&full_bar[st], par);
                 tc_fence_after();
-                if (dbg && it == 0) dbg[2] = clock64();      // first stage landed
+                if (dbg && it == 0 && lane == 0) dbg[2] = clock64();      // first stage landed
                 const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
                 const uint64_t da = smem_desc_sw128(sa, 16, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, 16, 1024);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)   // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
-                    umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
-                umma_commit(&empty_bar[st]);
+                    for (int k = 0; k < 4; ++k)   // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
+                        umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                    umma_commit(&empty_bar[st]);
+                }
+                __syncwarp();
                 ++it;
+                if (++st == kStages) { st = 0; par ^= 1; }
             }
         }
-        s_issued = (uint32_t)it;
-        if (dbg) { dbg[3] = clock64(); dbg[6] = it; }   // last MMA issued
-        umma_commit(&acc_bar);      // arrival 1: all MMAs retired
-        mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
+        if (dbg && lane == 0) { dbg[3] = clock64(); dbg[6] = it; }   // last MMA issued
+        if (elect_one()) {
+            s_issued = (uint32_t)it;
+            umma_commit(&acc_bar);      // arrival 1: all MMAs retired
+            mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
+        }
     }
     __syncwarp();
 
     // ---------------------------------------------------- epilogue: all 4 warps, thread = one output pixel (TMEM lane)
+    if (stage_bt) __syncthreads();     // s_bt written by warps 2-3 while the pipeline ran
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 0) dbg[4] = clock64();   // accumulator complete
     const bool have_acc = *reinterpret_cast<volatile uint32_t*>(&s_issued) != 0;
-    const int row = threadIdx.x;
-    const int wl = row % P.BW, hl = (row / P.BW) % P.BH, nl = row / (P.BW * P.BH);
-    const int n = n0 + nl, th = th0 + hl, tw = tw0 + wl;
-    const int ho = th * P.os + ph.oph, wo = tw * P.os + ph.opw;
-    const bool valid = nl < P.BN && n < P.N && th < ph.TH && tw < ph.TW && ho < P.Ho && wo < P.Wo;
     if (P.splits > 1) {
         // ---- split-K: park the partial tile, cluster barrier, then fold + finish this CTA's share of the rows
         const int slot = ((int)(blockIdx.z / P.splits) * (int)gridDim.y + (int)blockIdx.y) * (int)gridDim.x + tile;
@@ -329,9 +361,8 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
         return;
     }
     __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0;
-    const __nv_bfloat16* rp = P.res ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
     const float* tp = P.temb ? P.temb + (int64_t)n * P.temb_pitch + j0 : nullptr;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < NT; c += 32) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
@@ -341,27 +372,38 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
-            if (P.bias) {
+            if (stage_bt) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c + i));
+                    const float4 b = *reinterpret_cast<const float4*>(&s_bt[nl * NT + c + i]);
                     v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                }
+            } else {
+                if (P.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c + i));
+                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    }
+                }
+                if (tp) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(tp + c + i));
+                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    }
                 }
             }
-            if (tp) {
+            if (rp && !P.prefetch) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(tp + c + i));
-                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                }
+                for (int i = 0; i < 32; i += 8) rpre[(c + i) >> 3] = *reinterpret_cast<const uint4*>(rp + c + i);
             }
             if (rp) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
-                    float r[8];
-                    load_vec<__nv_bfloat16>(rp + c + i, r);
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rpre[(c + i) >> 3]);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) v[i + k] += r[k];
+                    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[i + 2 * k] += f.x; v[i + 2 * k + 1] += f.y; }
                 }
             }
 #pragma unroll
@@ -476,6 +518,11 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     A.res = reinterpret_cast<const __nv_bfloat16*>(p->res.ptr); A.r_sn = p->res.sn; A.r_sh = p->res.sh; A.r_sw = p->res.sw;
     A.bias = p->bias; A.temb = p->temb; A.temb_pitch = p->temb_pitch;
     A.dbg = g_debug_buffer;
+    {
+        static int pf = -1;
+        if (pf < 0) { const char* e = getenv("DMU_EPI_PREFETCH"); pf = (e && e[0] == '0') ? 0 : 1; }
+        A.prefetch = pf;
+    }
     // split-K for layers with few output tiles and a long contraction (the <= 4x4 stages: K up to 4608, 1-16 tiles):
     // the splits of one tile are a thread-block cluster along z (co-scheduled by hardware, so the in-kernel barrier is safe)
     const int slots = b.tiles_n * b.tiles_h * b.tiles_w * (p->Cj / NT) * nph;
@@ -580,49 +627,57 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ M
         return h < P.map_h[t.map] && h + P.BH > 0 && w < P.map_w[t.map] && w + P.BW > 0;
     };
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         const uint32_t blk_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
-        int it = 0;
+        int st = 0, par = 1;
         for (int tile = tile_lo; tile < tile_hi; ++tile) {
             const int tw0 = (tile % P.tiles_w) * P.BW;
             const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
             const int n0 = (tile / (P.tiles_w * P.tiles_h)) * P.BN;
             const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
             if (!l0 && !l1) continue;
-            const int st = it % kStages;
-            mbar_wait(&empty_bar[st], ((it / kStages) & 1) ^ 1);
-            uint8_t* sa = smem + st * Cfg::kStageBytes;
-            mbar_arrive_expect_tx(&full_bar[st], blk_bytes * (2 + NT / 64));
-            // a dead tap still issues its (fully out-of-bounds, zero-filled) load so the block holds zeros, not stale data
-            tma_load_4d(sa, &maps.a[t0.map], &full_bar[st], cb0, tw0 + t0.dw, th0 + t0.dh, n0);
-            tma_load_4d(sa + Cfg::kBlk, &maps.a[t1.map], &full_bar[st], cb1, tw0 + t1.dw, th0 + t1.dh, n0);
+            mbar_wait(&empty_bar[st], par);
+            if (elect_one()) {
+                uint8_t* sa = smem + st * Cfg::kStageBytes;
+                mbar_arrive_expect_tx(&full_bar[st], blk_bytes * (2 + NT / 64));
+                // a dead tap still issues its (fully out-of-bounds, zero-filled) load so the block holds zeros, not stale data
+                tma_load_4d(sa, &maps.a[t0.map], &full_bar[st], cb0, tw0 + t0.dw, th0 + t0.dh, n0);
+                tma_load_4d(sa + Cfg::kBlk, &maps.a[t1.map], &full_bar[st], cb1, tw0 + t1.dw, th0 + t1.dh, n0);
 #pragma unroll
-            for (int q = 0; q < NT / 64; ++q)
-                tma_load_4d(sa + Cfg::kABytes + q * Cfg::kBlk, &maps.b, &full_bar[st], a0 + q * 64, tw0, th0, n0);
-            ++it;
+                for (int q = 0; q < NT / 64; ++q)
+                    tma_load_4d(sa + Cfg::kABytes + q * Cfg::kBlk, &maps.b, &full_bar[st], a0 + q * 64, tw0, th0, n0);
+            }
+            __syncwarp();
+            if (++st == kStages) { st = 0; par ^= 1; }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);   // both operands MN-major (channels contiguous, K = pixels)
-        const int kpix = P.BN * P.BH * P.BW;                           // pixels actually in a box (<= 64, multiple of 16 or padded)
-        int it = 0;
+        const int ksteps = (P.BN * P.BH * P.BW + 15) >> 4;             // K = 16 pixels per MMA; a box holds <= 64 pixels
+        int it = 0, st = 0, par = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile) {
             const int tw0 = (tile % P.tiles_w) * P.BW;
             const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
             const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
             if (!l0 && !l1) continue;
-            const int st = it % kStages;
-            mbar_wait(&full_bar[st], (it / kStages) & 1);
+            mbar_wait(&full_bar[st], par);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
             const uint64_t da = smem_desc_sw128(sa, Cfg::kBlk, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, Cfg::kBlk, 1024);
-            for (int k = 0; k * 16 < kpix; ++k)   // K = 16 pixels = 16 rows of 128 B = 2048 B per step
-                umma_bf16(tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) != 0);
-            umma_commit(&empty_bar[st]);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // K = 16 pixels = 16 rows of 128 B = 2048 B per step
+                    if (k < ksteps) umma_bf16(tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) != 0);
+                umma_commit(&empty_bar[st]);
+            }
+            __syncwarp();
             ++it;
+            if (++st == kStages) { st = 0; par ^= 1; }
         }
-        s_issued = (uint32_t)it;
-        umma_commit(&acc_bar);      // arrival 1: all MMAs retired
-        mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
+        if (elect_one()) {
+            s_issued = (uint32_t)it;
+            umma_commit(&acc_bar);      // arrival 1: all MMAs retired
+            mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
+        }
     }
     __syncwarp();
 

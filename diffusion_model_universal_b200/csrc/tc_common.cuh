@@ -38,6 +38,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of a CONVERGED warp.  tcgen05.mma / TMA issue must sit under this predicate, not under `lane == 0`: with a plain
+// lane test ptxas cannot prove single-thread execution and wraps every UTCHMMA in an ELECT/BRA.U.ANY waterfall loop with
+// R2UR moves, which costs ~135 clk per MMA (scripts/probes/umma_rate.cu: 135 clk vs 48 / 64 / 128 clk for N = 64 / 128 / 256
+// when issued under elect.sync, i.e. 24 % vs 67-100 % of the tensor peak).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA loads (tile mode, signed coordinates, OOB -> 0)
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
