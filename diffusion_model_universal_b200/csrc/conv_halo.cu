@@ -264,23 +264,6 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_const
     if (warp == 5) tmem_dealloc(tmem, 2 * NT);
 }
 
-int halo_supported(const dmu_conv_params* p, int force) {
-    if (p->R != 3 || p->S != 3 || p->stride != 1 || p->pad != 1) return 0;
-    if (p->Hi != p->Ho || p->Wi != p->Wo) return 0;
-    if (p->Hi < 8 || p->Wi < 8 || p->Wi + 2 > 256) return 0;     // below 8x8 most of the padded space is padding
-    if ((int64_t)p->N * (p->Hi + 2) * (p->Wi + 2) >= (1ll << 31)) return 0;
-    // Measured on B200 (scripts/conv_timeline.py, DMU_HALO=0/1): SS-mode UMMA at M=128 fetches its operands from shared
-    // memory at ~64 B/clk, which bounds BOTH kernels (96 clk per 128x64x16 MMA, 3x the tensor floor), so fetching the
-    // activations once only wins where the per-tap kernel's extra TMA traffic and per-CTA prologue dominate: one 64-channel
-    // chunk with the whole filter bank resident and at least four tiles per CTA (27.5 vs 31.6 us at 128x32x32x64->64,
-    // 166 vs 215 us at 256x64x64); smaller or multi-chunk layers are faster per-tap.
-    if (force) return 1;
-    if (p->Ck != 64 || (p->Cj > 128)) return 0;
-    const int64_t tiles = ((int64_t)p->N * (p->Hi + 2) * (p->Wi + 2) + 127) / 128;
-    if (tiles < 4 * (int64_t)sm_count()) return 0;
-    return 1;
-}
-
 static int pick_smem(const dmu_conv_params* p, int NT, HaloArgs& A) {
     const int budget = 214 * 1024;
     const int kblocks = 9 * A.chunks, wtile = NT * 128;
@@ -300,9 +283,8 @@ static int pick_smem(const dmu_conv_params* p, int NT, HaloArgs& A) {
     return A.a_stages * A.a_stage_bytes + wbytes + 1024;
 }
 
-int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
-    HaloMaps maps;
-    HaloArgs A;
+// geometry shared by halo_supported() and halo_launch(); returns the dynamic shared memory size (or -1)
+static int halo_geometry(const dmu_conv_params* p, HaloArgs& A, int& NT) {
     memset(&A, 0, sizeof(A));
     A.N = p->N; A.H = p->Hi; A.W = p->Wi; A.Ck = p->Ck; A.Cj = p->Cj;
     A.PW = A.W + 2; A.PH = A.H + 2;
@@ -311,9 +293,34 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
     A.chunks = A.Ck / 64;
     A.flip = p->gather;
     A.a_stage_bytes = ((A.NR * A.PW * 128) + 1023) / 1024 * 1024;
+    NT = p->Cj <= 4 ? 64 : (p->Cj % 128 == 0) ? 128 : 64;
+    return pick_smem(p, NT, A);
+}
+
+int halo_supported(const dmu_conv_params* p, int force) {
+    if (p->R != 3 || p->S != 3 || p->stride != 1 || p->pad != 1) return 0;
+    if (p->Hi != p->Ho || p->Wi != p->Wo) return 0;
+    if (p->Hi < 8 || p->Wi < 8 || p->Wi + 2 > 256) return 0;     // below 8x8 most of the padded space is padding
+    if ((int64_t)p->N * (p->Hi + 2) * (p->Wi + 2) >= (1ll << 31)) return 0;
+    if (force) return 1;
+    // Measured on B200 (scripts/halo_vs_tap.py): with the filter bank of the CTA's output-channel tile RESIDENT in shared
+    // memory the halo kernel reads every activation once and wins wherever each CTA gets a few tiles (64->64 @128x32x32:
+    // 16.2 vs 28.2 us, 128->64: 26.4 vs 38.4 us, 64->128 @128x8x8: 6.3 vs 8.4 us); when the filters have to stream through
+    // their ring once per tile the per-tap kernel, whose CTAs share them through L2, is faster (192->64 @128x16x16: 27 vs 14 us).
+    HaloArgs A;
+    int NT;
+    if (halo_geometry(p, A, NT) <= 0 || !A.resident) return 0;
+    if (p->Cj > 128) return 0;
+    if (A.tiles < 4 * (int64_t)sm_count()) return 0;      // fewer tiles per CTA: the resident-filter prologue is not amortised
+    return 1;
+}
+
+int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
+    HaloMaps maps;
+    HaloArgs A;
+    int NT;
+    const int smem = halo_geometry(p, A, NT);
     const bool narrow = p->Cj <= 4;
-    const int NT = narrow ? 64 : (p->Cj % 128 == 0) ? 128 : 64;
-    const int smem = pick_smem(p, NT, A);
     DMU_REQUIRE(smem > 0 && smem <= 224 * 1024, "dmu_conv2d/halo: tile does not fit shared memory");
     {
         const uint64_t dims[4] = {(uint64_t)p->Ck, (uint64_t)p->Wi, (uint64_t)p->Hi, (uint64_t)p->N};

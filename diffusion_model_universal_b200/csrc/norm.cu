@@ -29,7 +29,10 @@ __device__ __forceinline__ void chunk_range(int HW, int& p0, int& p1) {
     p1 = min(HW, p0 + per);
 }
 
+// Every activation of the plans is pixel-contiguous (row pitch = W x pixel pitch, channel slices of the concat buffers
+// included): skip the divide / modulo, which made these kernels instruction-bound (~100 integer instructions per access).
 __device__ __forceinline__ int64_t pix_off(const dmu_tensor4& t, int n, int p, int W) {
+    if (t.sh == (int64_t)W * t.sw) return (int64_t)n * t.sn + (int64_t)p * t.sw;
     return (int64_t)n * t.sn + (int64_t)(p / W) * t.sh + (int64_t)(p % W) * t.sw;
 }
 
@@ -1073,7 +1076,7 @@ __global__ void sinusoidal_kernel(const void* t, int t_is_float, float* emb, int
 // stages a tile in shared memory with coalesced (128-byte) reads and writes it out in destination order, again in
 // contiguous runs: HBM traffic = one read + one write of the filter.  (The first version gathered element-wise with a
 // stride of RS floats: 8x read amplification, 143 us for the 16 M parameters of the UNet against ~25 us of traffic.)
-constexpr int kRepackTile = 32 * (16 * 16 + 1);       // floats: 32 rows of (16 columns x RS <= 16) + 1 pad
+constexpr int kRepackTile = 16 * 16 * 36;             // floats: kind 1 holds (16 o x RS <= 16) rows of 32 + 4 input channels
 
 __device__ __forceinline__ void repack_generic(const dmu_repack_desc& d) {
     const int64_t RS = (int64_t)d.R * d.S;
@@ -1095,50 +1098,122 @@ __device__ __forceinline__ void repack_generic(const dmu_repack_desc& d) {
     }
 }
 
+// 8 consecutive destination elements (16-byte aligned) from 8 floats
+__device__ __forceinline__ void repack_store8(void* dst, int64_t idx, int dtype, const float* v) {
+    if (dtype == DMU_BF16) {
+        store_vec<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(dst) + idx, v);
+    } else {
+        float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + idx);
+        q[0] = make_float4(v[0], v[1], v[2], v[3]);
+        q[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// Shared-memory tile layout [rs][IB + 4] (kinds 0, 3) / [16 o x RS][32 + 4] (kind 1): the +4 pitch keeps the transposing
+// side at <= 2-way bank conflicts and the row-wise side 16-byte aligned.  Global accesses are 16 bytes per thread with
+// four independent requests in flight.
 template <int RS>
-__device__ __forceinline__ void repack_tiled(const dmu_repack_desc& d, float* tile) {
-    constexpr int P = RS | 1;                            // odd pitch: conflict-free transposed shared-memory access
+__device__ __forceinline__ void repack_tiled(const dmu_repack_desc& d, float* __restrict__ tile) {
     if (d.kind == 0 || d.kind == 3) {
         // per output channel o: [I][RS] <-> [RS][I]; work item = (o, block of IB input channels)
         const int IB = d.I % 256 == 0 ? 256 : d.I < 256 ? d.I : d.I % 128 == 0 ? 128 : d.I % 64 == 0 ? 64 : 32;
+        const int IBP = IB + 4;
         const int nib = d.I / IB;
-        const int run = IB * RS;
+        const int run4 = IB * RS / 4;
         for (int item = blockIdx.x; item < d.O * nib; item += gridDim.x) {
             const int o = item / nib, i0 = (item % nib) * IB;
             __syncthreads();
             if (d.kind == 0) {
-                const float* src = d.src + ((int64_t)o * d.I + i0) * RS;              // contiguous [IB][RS]
-                for (int j = threadIdx.x; j < run; j += 256) tile[(j / RS) * P + j % RS] = src[j];
+                const float4* src = reinterpret_cast<const float4*>(d.src + ((int64_t)o * d.I + i0) * RS);   // contiguous [IB][RS]
+                for (int j0 = threadIdx.x; j0 < run4; j0 += 4 * 256) {
+                    float4 r[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (j0 + u * 256 < run4) r[u] = __ldg(src + j0 + u * 256);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (j0 + u * 256 >= run4) break;
+                        const int j = (j0 + u * 256) * 4;
+                        const float e[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) tile[((j + q) % RS) * IBP + (j + q) / RS] = e[q];
+                    }
+                }
                 __syncthreads();
-#pragma unroll 1
-                for (int rs = 0; rs < RS; ++rs)
-                    for (int ci = threadIdx.x; ci < IB; ci += 256)
-                        st_from_float(d.dst, ((int64_t)o * RS + rs) * d.I + i0 + ci, d.dst_dtype, tile[ci * P + rs]);
+                const int c8n = IB / 8;
+                for (int idx = threadIdx.x; idx < RS * c8n; idx += 256) {
+                    const int rs = idx / c8n, c8 = idx % c8n;
+                    const float4 lo = *reinterpret_cast<const float4*>(&tile[rs * IBP + c8 * 8]);
+                    const float4 hi = *reinterpret_cast<const float4*>(&tile[rs * IBP + c8 * 8 + 4]);
+                    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    repack_store8(d.dst, ((int64_t)o * RS + rs) * d.I + i0 + c8 * 8, d.dst_dtype, v);
+                }
             } else {
-#pragma unroll 1
-                for (int rs = 0; rs < RS; ++rs)
-                    for (int ci = threadIdx.x; ci < IB; ci += 256) tile[ci * P + rs] = d.src[((int64_t)o * RS + rs) * d.I + i0 + ci];
+                const int c4n = IB / 4;
+                for (int i0_ = threadIdx.x; i0_ < RS * c4n; i0_ += 4 * 256) {
+                    float4 r[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = i0_ + u * 256;
+                        if (idx < RS * c4n) r[u] = __ldg(reinterpret_cast<const float4*>(d.src + ((int64_t)o * RS + idx / c4n) * d.I + i0) + idx % c4n);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = i0_ + u * 256;
+                        if (idx >= RS * c4n) break;
+                        *reinterpret_cast<float4*>(&tile[(idx / c4n) * IBP + (idx % c4n) * 4]) = r[u];
+                    }
+                }
                 __syncthreads();
                 const int64_t dst0 = ((int64_t)o * d.I + i0) * RS;
-                for (int j = threadIdx.x; j < run; j += 256) st_from_float(d.dst, dst0 + j, d.dst_dtype, tile[(j / RS) * P + j % RS]);
+                for (int j4 = threadIdx.x; j4 < run4; j4 += 256) {
+                    const int j = j4 * 4;
+                    float e[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) e[q] = tile[((j + q) % RS) * IBP + (j + q) / RS];
+                    if (d.dst_dtype == DMU_F32) {
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.dst) + dst0 + j) = make_float4(e[0], e[1], e[2], e[3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) st_from_float(d.dst, dst0 + j + q, d.dst_dtype, e[q]);
+                    }
+                }
             }
         }
         return;
     }
     // kind 1: src [I][O][RS] -> dst [O][RS][I]; work item = 32 input channels x 16 output channels
     const int nbo = d.O / 16, nbi = d.I / 32;
-    constexpr int run = 16 * RS, pitch = run + 1;
+    constexpr int run = 16 * RS, run4 = run / 4, pitch = 36;
     for (int item = blockIdx.x; item < nbo * nbi; item += gridDim.x) {
         const int o0 = (item % nbo) * 16, i0 = (item / nbo) * 32;
         __syncthreads();
-        for (int j = threadIdx.x; j < 32 * run; j += 256) {                             // rows = ci, contiguous run of 16 o x RS
-            const int ci = j / run, k = j % run;
-            tile[ci * pitch + k] = d.src[((int64_t)(i0 + ci) * d.O + o0) * RS + k];
+        // lane -> (8 input channels, 4 consecutive float4 of the run): 64-byte runs per row, <= 2-way bank conflicts
+        for (int b0 = threadIdx.x; b0 < 32 * run4; b0 += 4 * 256) {
+            float4 r[4];
+            int ci_[4], k_[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = b0 + u * 256;                       // idx = ((k4 / 4) * 32 + ci) * 4 + k4 % 4
+                const int k4 = (idx / 128) * 4 + idx % 4, ci = (idx / 4) % 32;
+                ci_[u] = ci; k_[u] = k4 * 4;
+                if (idx < 32 * run4) r[u] = __ldg(reinterpret_cast<const float4*>(d.src + ((int64_t)(i0 + ci) * d.O + o0) * RS) + k4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (b0 + u * 256 >= 32 * run4) break;
+                const float e[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tile[(k_[u] + q) * pitch + ci_[u]] = e[q];
+            }
         }
         __syncthreads();
-        for (int j = threadIdx.x; j < 32 * run; j += 256) {                             // j = (o_l * RS + rs) * 32 + ci
-            const int ci = j % 32, k = j / 32;
-            st_from_float(d.dst, ((int64_t)o0 * RS + k) * d.I + i0 + ci, d.dst_dtype, tile[ci * pitch + k]);
+        for (int idx = threadIdx.x; idx < run * 4; idx += 256) {                        // row k, 8 consecutive ci
+            const int k = idx / 4, c8 = idx % 4;
+            const float4 lo = *reinterpret_cast<const float4*>(&tile[k * pitch + c8 * 8]);
+            const float4 hi = *reinterpret_cast<const float4*>(&tile[k * pitch + c8 * 8 + 4]);
+            const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            repack_store8(d.dst, ((int64_t)o0 * RS + k) * d.I + i0 + c8 * 8, d.dst_dtype, v);
         }
     }
 }
@@ -1147,7 +1222,7 @@ __global__ void __launch_bounds__(256) repack_kernel(const dmu_repack_desc* __re
     __shared__ float tile[kRepackTile];
     const dmu_repack_desc d = descs[blockIdx.y];
     const int RS = d.R * d.S;
-    const bool tiled = d.kind != 2 && d.I % 32 == 0 && d.O % 16 == 0;
+    const bool tiled = d.kind != 2 && d.I % 32 == 0 && d.O % 16 == 0 && ((reinterpret_cast<uintptr_t>(d.src) | reinterpret_cast<uintptr_t>(d.dst)) & 15) == 0;
     if (tiled && RS == 9) repack_tiled<9>(d, tile);
     else if (tiled && RS == 16) repack_tiled<16>(d, tile);
     else if (tiled && RS == 1 && d.kind == 1) repack_tiled<1>(d, tile);      // [I][O] -> [O][I] transpose of a Linear weight
@@ -1280,7 +1355,11 @@ int dmu_gn_bwd_apply(const dmu_gn_params* p, dmu_stream_t stream) {
 int dmu_gn_forward(const dmu_gn_params* p, dmu_stream_t stream) {
     if (int e = gn_check(p, "dmu_gn_forward", true, false)) return e;
     const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
-    const int cs = gn_fused_cluster(p->H * p->W, p->C, vec);
+    // measured on B200 (scripts/gn_time.py): the single-pass cluster kernel holds its slab in registers (2 CTAs per SM) and
+    // wins while the tensor is small enough that launch count matters; from ~12 MB upwards the two streaming passes
+    // (the second one served from L2 when the tensor fits) are faster (33.6 MB: 26.5 vs 36.9 us, 67 MB: 47 vs 98 us)
+    const int64_t bytes = (int64_t)p->N * p->H * p->W * p->C * (p->x.dtype == DMU_BF16 ? 2 : 4);
+    const int cs = bytes <= (12ll << 20) ? gn_fused_cluster(p->H * p->W, p->C, vec) : 0;
     if (cs == 0) {
         if (int e = dmu_gn_stats(p, stream)) return e;
         return dmu_gn_apply(p, stream);
@@ -1299,7 +1378,15 @@ int dmu_gn_backward(const dmu_gn_params* p, dmu_stream_t stream) {
     const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
     // measured on B200: holding (x, dy) in registers costs the single-pass backward its occupancy (225 registers), so it
     // only pays for images one CTA can hold, where it saves a launch; larger images take the two-pass kernels
-    const int cs = gn_fused_cluster(p->H * p->W, p->C, vec) == 1 ? 1 : 0;
+    const int64_t bytes = (int64_t)p->N * p->H * p->W * p->C * (p->x.dtype == DMU_BF16 ? 2 : 4);
+    const int64_t img_bytes = bytes / p->N;
+    // measured (scripts/gn_time.py): register-held single pass up to ~3 MB (launch-bound sizes), shared-memory single pass for
+    // images of >= 128 KB, the two-pass pair in between (4.2 MB: 11.0 vs 14.3 us, 8.4 MB: 20.5 vs 24.7 us)
+    const int cs = (bytes <= (3ll << 20) && gn_fused_cluster(p->H * p->W, p->C, vec) == 1) ? 1 : 0;
+    if (cs == 0 && img_bytes < (128 << 10)) {
+        if (int e = dmu_gn_bwd_reduce(p, stream)) return e;
+        return dmu_gn_bwd_apply(p, stream);
+    }
     if (cs == 0) {
         // larger images: the (x, dy) slab of each CTA of a cluster lives in shared memory (single pass)
         const int HW = p->H * p->W, V = p->C / vec;
