@@ -79,9 +79,15 @@ class RepackDesc(C.Structure):
     _fields_ = [("src", c_vp), ("dst", c_vp), ("O", c_i32), ("I", c_i32), ("R", c_i32), ("S", c_i32), ("kind", c_i32), ("dst_dtype", c_i32)]
 
 
+class ColsumDesc(C.Structure):
+    _fields_ = [("x", Tensor4), ("out_nc", c_vp), ("pitch", c_i64), ("out_c", c_vp), ("N", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32),
+                ("chunks", c_i32), ("scale", c_f32), ("cta0", c_i32), ("_pad", c_i32)]
+
+
 STRUCTS = {
     "dmu_tensor4": Tensor4, "dmu_conv_params": ConvParams, "dmu_wgrad_params": WgradParams,
     "dmu_gn_params": GnParams, "dmu_attn_params": AttnParams, "dmu_repack_desc": RepackDesc, "dmu_gn_bwd2_params": GnBwd2Params,
+    "dmu_colsum_desc": ColsumDesc,
 }
 
 P = C.POINTER
@@ -109,6 +115,7 @@ _SIGS = {
     "dmu_gn_bwd_reduce": (c_i32, [P(GnParams), c_vp]),
     "dmu_gn_bwd_apply": (c_i32, [P(GnParams), c_vp]),
     "dmu_colsum": (c_i32, [P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_f32, c_vp]),
+    "dmu_colsum_multi": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp]),
     "dmu_silu_pool_fwd": (c_i32, [P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp]),
     "dmu_silu_pool_bwd": (c_i32, [P(Tensor4), P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp, c_i64, c_f32, c_vp]),
     "dmu_gn_bwd_bwd": (c_i32, [P(GnBwd2Params), c_vp]),

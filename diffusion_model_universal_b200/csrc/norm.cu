@@ -774,6 +774,57 @@ __global__ void __launch_bounds__(256) colsum_kernel(dmu_tensor4 X, int H, int W
     }
 }
 
+// One launch for a whole table of column sums (the bias gradients and time-projection sums of one part of the backward:
+// ~20 latency-bound launches become one).  1-D grid: descriptor i owns CTAs [cta0_i, cta0_i + N_i * chunks_i).
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_multi_kernel(const dmu_colsum_desc* __restrict__ table, int n_desc) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ int s_idx;
+    for (int i = threadIdx.x; i < n_desc; i += blockDim.x) {
+        const int c0 = table[i].cta0, cnt = table[i].N * table[i].chunks;
+        if ((int)blockIdx.x >= c0 && (int)blockIdx.x < c0 + cnt) s_idx = i;
+    }
+    __syncthreads();
+    const dmu_colsum_desc d = table[s_idx];
+    const int local = (int)blockIdx.x - d.cta0;
+    const int n = local / d.chunks, chunk = local % d.chunks;
+    constexpr int kVec = Elem<T>::kVec;
+    __shared__ float s[kMaxC];
+    __shared__ float s_red[256 * kVec];
+    const int HW = d.H * d.W, C = d.C;
+    RowMap m(C, kVec);
+    const int per = (HW + d.chunks - 1) / d.chunks;
+    const int p0 = chunk * per, p1 = min(HW, p0 + per);
+    float a[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) a[i] = 0.f;
+    if (m.active) {
+        const T* xb = reinterpret_cast<const T*>(d.x.ptr) + m.v * kVec;
+        for (int p = p0 + m.lane; p < p1; p += m.lanes * kUnroll) {
+            uint4 r[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int pp = p + u * m.lanes;
+                r[u] = pp < p1 ? ld_raw<T>(xb + pix_off(d.x, n, pp, d.W)) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                float v[kVec];
+                unpack<T>(r[u], v);
+#pragma unroll
+                for (int i = 0; i < kVec; ++i) a[i] += v[i];
+            }
+        }
+    }
+    block_channel_sum<kVec>(m, a, s_red, s, C);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = s[c] * d.scale;
+        if (d.out_nc) atomicAdd(&d.out_nc[(int64_t)n * d.pitch + c], v);
+        if (d.out_c) atomicAdd(&d.out_c[c], v);
+    }
+}
+
 // ------------------------------------------------------------------ SiLU + global average pool (EnergyNet head)
 // models/energy_based.py:79-83:  pooled[n,c] = mean_p silu(x[n,p,c]);   backward: dx[n,p,c] = silu'(x) * g[n,c] * scale
 template <typename T>
@@ -1436,6 +1487,14 @@ int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C,
     }
     DISPATCH_T(t.dtype, colsum_kernel, grid, 256, as_stream(stream), t, Hh, Ww, C, out_nc, pitch, out_c, scale);
     return check_launch("dmu_colsum");
+}
+
+int dmu_colsum_multi(const dmu_colsum_desc* table_device, int32_t n_desc, int32_t total_ctas, int32_t dtype, dmu_stream_t stream) {
+    DMU_REQUIRE(table_device && n_desc > 0 && total_ctas > 0, "dmu_colsum_multi: bad arguments");
+    const dim3 grid(total_ctas);
+    if (dtype == DMU_BF16) launch_pdl(colsum_multi_kernel<__nv_bfloat16>, grid, dim3(256), 0, as_stream(stream), dim3(1, 1, 1), table_device, (int)n_desc);
+    else launch_pdl(colsum_multi_kernel<float>, grid, dim3(256), 0, as_stream(stream), dim3(1, 1, 1), table_device, (int)n_desc);
+    return check_launch("dmu_colsum_multi");
 }
 
 int dmu_silu_pool_fwd(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out, int64_t pitch, float scale, dmu_stream_t stream) {

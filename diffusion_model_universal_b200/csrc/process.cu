@@ -300,6 +300,7 @@ int dmu_sizeof(const char* name) {
     if (eq(name, "dmu_attn_params")) return (int)sizeof(dmu_attn_params);
     if (eq(name, "dmu_repack_desc")) return (int)sizeof(dmu_repack_desc);
     if (eq(name, "dmu_gn_bwd2_params")) return (int)sizeof(dmu_gn_bwd2_params);
+    if (eq(name, "dmu_colsum_desc")) return (int)sizeof(dmu_colsum_desc);
     return -1;
 }
 

@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _abi, ops
-from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, RepackDesc, GnPgDesc
+from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, RepackDesc, GnPgDesc, ColsumDesc
 
 
 def gn_groups(channels: int, num_groups: int = 32) -> int:
@@ -580,9 +580,13 @@ class Engine:
             plan.keep.append(sp)
             gn_pg += sub.gn_pg
 
+        skip = os.environ.get("DMU_EXPERIMENT_SKIP", "")    # timing experiments only: "side" / "main" lane of the backward
+
         def retag(ops_, k):
             out = []
             for op in ops_:
+                if skip and op[0] is not None and op[0] != "split" and ops_ is not sub.plan.fwd and ((len(op) == 3) == (skip == "side")):
+                    continue
                 if op[0] is None:
                     out.append((None, (), 2 * k))                        # join this sub-plan's side lane into its main lane
                 else:
@@ -672,6 +676,7 @@ class _PlanBuilder:
         self.gn_pg = []         # (red, dgamma, dbeta, C) of every GroupNorm backward: folded by one launch at the end
         self.gn_pg_split = []   # len(gn_pg) at each split marker of the backward
         self.side_lane = True   # weight-gradient / column-sum launches of the backward go to the graph's second branch
+        self.cs_pending = []    # column sums (bias gradients, time-projection sums) batched into one launch per backward part
 
     # ---- allocation helpers
     def act(self, H, W, Cc, want_grad=True) -> Buf:
@@ -694,6 +699,34 @@ class _PlanBuilder:
         """Gradient-arena address of a parameter."""
         return self.e.gaddr(name)
 
+    def colsum(self, t4: Tensor4, N, H, W, Cc, out_nc, pitch, out_c):
+        """Per-image (out_nc) and / or total (out_c) channel sums of an NHWC tensor.  While the side lane is open the request is
+        only recorded: flush_colsums() turns every request of a backward part into ONE dmu_colsum_multi launch."""
+        if not (self.side_lane and t4.sc == 1 and t4.dtype == self.code):
+            self.plan.keep.append(t4)
+            op = (self.lib.dmu_colsum, (C.byref(t4), N, H, W, Cc, out_nc, pitch, out_c, 1.0))
+            self.plan.bwd.append(op + (1,) if self.side_lane else op)
+            return
+        if out_nc is None and t4.sh == W * t4.sw and t4.sn == H * t4.sh:    # only the total: one flat pixel range
+            t4 = Tensor4(t4.ptr, N * H * W * t4.sw, N * H * W * t4.sw, t4.sw, 1, t4.dtype, 0)
+            N, H, W = 1, 1, N * H * W
+        chunks = max(1, min(148 if N == 1 else 8, (H * W * Cc) // 65536))
+        self.cs_pending.append(ColsumDesc(t4, out_nc, pitch, out_c, N, H, W, Cc, chunks, 1.0, 0, 0))
+
+    def flush_colsums(self):
+        if not self.cs_pending:
+            return
+        cta = 0
+        for d in self.cs_pending:
+            d.cta0 = cta
+            cta += d.N * d.chunks
+        arr = (ColsumDesc * len(self.cs_pending))(*self.cs_pending)
+        dev = self.e.device
+        tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self.plan.keep.append(tab)
+        self.plan.bwd.append((self.lib.dmu_colsum_multi, (tab.data_ptr(), len(self.cs_pending), cta, self.code), 1))
+        self.cs_pending = []
+
     def conv(self, lst, x: Tensor4, y: Tensor4, w, w_strides, w_code, dims, geom, bias=None, temb=None, temb_pitch=0, res=None, gather=0):
         N, Hi, Wi, Ck, Ho, Wo, Cj = dims
         R, S, stride, pad = geom
@@ -707,9 +740,13 @@ class _PlanBuilder:
     def wgrad(self, p4: Tensor4, q4: Tensor4, dw, dw_strides, dbias, dims, geom):
         N, Hp, Wp, Ca, Hq, Wq, Cb = dims
         R, S, stride, pad = geom
-        p = WgradParams(p4, q4, dw, dw_strides[0], dw_strides[1], dw_strides[2], dbias, N, Hp, Wp, Ca, Hq, Wq, Cb, R, S, stride, pad, self.e.impl)
+        batched = dbias is not None and self.side_lane and p4.sc == 1 and p4.dtype == self.code
+        p = WgradParams(p4, q4, dw, dw_strides[0], dw_strides[1], dw_strides[2], None if batched else dbias, N, Hp, Wp, Ca, Hq, Wq, Cb, R, S, stride, pad,
+                        self.e.impl)
         self.plan.bwd.append((self.lib.dmu_conv2d_wgrad, (C.byref(p),), 1) if self.side_lane else (self.lib.dmu_conv2d_wgrad, (C.byref(p),)))
         self.plan.keep.append(p)
+        if batched:
+            self.colsum(p4, N, Hp, Wp, Ca, None, 0, dbias)
         return p
 
     def gn(self, x: Buf, G, gamma_name, beta_name, silu: bool):
@@ -790,9 +827,7 @@ class _PlanBuilder:
             # norm2 + silu -> dh
             self.gn_bwd(rec2, h.grad)
             # time projection: per-image channel sums of dh
-            t4 = h.grad.t4()
-            self.plan.keep.append(t4)
-            self.plan.bwd.append((self.lib.dmu_colsum, (C.byref(t4), self.N, h.H, h.W, Co, self.dtproj + self.tp_off[pfx] * 4, self.tp_total, None, 1.0), 1))
+            self.colsum(h.grad.t4(), self.N, h.H, h.W, Co, self.dtproj + self.tp_off[pfx] * 4, self.tp_total, None)
             # conv1
             self.conv_layer_bwd(a1, h, pfx + "conv1.weight", pfx + "conv1.bias", 3, 1, 1, a1.grad)
             # shortcut
@@ -975,9 +1010,7 @@ class _PlanBuilder:
                     # dW[ci][co][r][s] (IOHW) += x[.., ci] * du[gathered, co]
                     self.wgrad(y.t4(), du.t4(), e.gsaddr(pfx + "upsample.weight"), (16 * co, 1, co), None,
                                (N, y.H, y.W, co, u.H, u.W, co), (4, 4, 2, 1))
-                    t4 = du.t4()
-                    plan.keep.append(t4)
-                    plan.bwd.append((lib.dmu_colsum, (C.byref(t4), N, u.H, u.W, co, None, 0, self.gp(pfx + "upsample.bias"), 1.0), 1))
+                    self.colsum(du.t4(), N, u.H, u.W, co, None, 0, self.gp(pfx + "upsample.bias"))
                 self.tape.append(up_bwd)
             x = u
         # -------- head: GroupNorm -> SiLU -> conv3x3 -> NCHW fp32
@@ -1006,6 +1039,7 @@ class _PlanBuilder:
                 # Everything emitted so far is the backward of (head + up path) or of (... + bottleneck + down 4, 3): the
                 # parameter gradients of those layers are final here (except their time projections and q/k/v, which live at
                 # the head of the arena), which is where a data-parallel step can start all-reducing them.
+                self.flush_colsums()
                 plan.bwd.append(("split", ()))
                 self.gn_pg_split.append(len(self.gn_pg))
             self.tape[i]()
@@ -1014,6 +1048,7 @@ class _PlanBuilder:
                    (9 * net.in_channels, 1, net.in_channels), self.gp("initial_conv.bias"), (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
         # time projections (one GEMM for all 22 blocks), then the embedding MLP: they consume the per-image column sums the
         # side lane produced, so the lanes join here
+        self.flush_colsums()
         plan.bwd.append((None, ()))
         self.side_lane = False
         dtemb = self.f32(N * T4)

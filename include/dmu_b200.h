@@ -211,6 +211,23 @@ int dmu_gn_bwd_apply(const dmu_gn_params* p, dmu_stream_t stream);
 int dmu_colsum(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C,
                float* out_nc, int64_t out_nc_pitch, float* out_c, float scale, dmu_stream_t stream);
 
+/* A whole table of dmu_colsum calls in one launch (all tensors of one dtype; the table lives in device memory).  Per entry:
+ * x is N images of H*W pixels of C channels, `chunks` CTAs per image; out_nc / out_c / scale as in dmu_colsum.
+ * Used for the bias gradients (trainers/ddpm_trainer.py:543-547: every conv / Linear bias) and the per-image time-projection
+ * sums (residual.py:61) of one part of the backward. */
+typedef struct {
+    dmu_tensor4 x;
+    float* out_nc;
+    int64_t pitch;
+    float* out_c;
+    int32_t N, H, W, C;
+    int32_t chunks;                  /* CTAs per image */
+    float scale;
+    int32_t cta0;                    /* first CTA of this entry: prefix sum of N * chunks over the table */
+    int32_t _pad;
+} dmu_colsum_desc;
+int dmu_colsum_multi(const dmu_colsum_desc* table_device, int32_t n_desc, int32_t total_ctas, int32_t dtype, dmu_stream_t stream);
+
 /* EnergyNet head, models/energy_based.py:79-83: out[n*pitch + c] += scale * sum_p silu(x[n,p,c])  (scale = 1/(H*W) gives the
  * mean; out is accumulated: zero it first) and its input gradient dx[n,p,c] = silu'(x[n,p,c]) * g[n*pitch + c] * scale. */
 int dmu_silu_pool_fwd(const dmu_tensor4* x, int32_t N, int32_t H, int32_t W, int32_t C, float* out, int64_t pitch, float scale,

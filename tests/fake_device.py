@@ -227,6 +227,18 @@ class FakeLib:
             _flat(_addr(out_c), Cc).add_(x.sum(0))
         return 0
 
+    def dmu_colsum_multi(self, table, n, total_ctas, dtype, stream):
+        from diffusion_model_universal_b200._abi import ColsumDesc
+        self._count()
+        arr = (ColsumDesc * n).from_address(_addr(table))
+        for d in arr:
+            x = _view4(d.x, d.N, d.H, d.W, d.C).float().sum(dim=(1, 2)) * d.scale
+            if d.out_nc:
+                _flat(d.out_nc, (d.N - 1) * d.pitch + d.C).as_strided((d.N, d.C), (d.pitch, 1)).add_(x)
+            if d.out_c:
+                _flat(d.out_c, d.C).add_(x.sum(0))
+        return 0
+
     # ---------------------------------------------------------------- attention
     def _qkv(self, p):
         rows = p.N * p.S
