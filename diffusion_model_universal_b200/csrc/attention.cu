@@ -54,6 +54,69 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(dmu_attn_params P) {
     if (P.lse) P.lse[((int64_t)n * P.heads + h) * S + i] = mx + logf(l);
 }
 
+// Forward, one CTA per (image, head): KSPLIT adjacent lanes share a query and each walks every KSPLIT-th key with its own
+// online softmax; the partial (max, sum, output) triples meet through warp shuffles.  The single-CTA-per-image version above
+// is one serial chain of S x ~100 instructions per thread (46 us at S = 64, batch 256: 2 waves of 256 CTAs); here the chain
+// is KSPLIT times shorter and 4x as many CTAs hide each other's latency.
+template <typename T, int D, int KSPLIT>
+__global__ void __launch_bounds__(256) attn_fwd_split_kernel(dmu_attn_params P) {
+    extern __shared__ __align__(16) float sm[];  // q|k|v of this head: [S][3D + 4]
+    constexpr int kRow = 3 * D + 4;
+    constexpr int kVec = Elem<T>::kVec;
+    const int n = blockIdx.x, h = blockIdx.y, S = P.S, C = P.C;
+    const T* qkv = reinterpret_cast<const T*>(P.qkv) + (int64_t)n * S * P.qkv_pitch;
+    constexpr int vpr = D / kVec;                 // 16-byte vectors per (row, q|k|v)
+    for (int idx = threadIdx.x; idx < S * 3 * vpr; idx += blockDim.x) {
+        const int r = idx / (3 * vpr), w = (idx / vpr) % 3, v = idx % vpr;
+        float tmp[kVec];
+        load_vec<T>(qkv + (int64_t)r * P.qkv_pitch + w * C + h * D + v * kVec, tmp);
+#pragma unroll
+        for (int k = 0; k < kVec; ++k) sm[r * kRow + w * D + v * kVec + k] = tmp[k];
+    }
+    __syncthreads();
+    const int i = threadIdx.x / KSPLIT, part = threadIdx.x % KSPLIT;
+    const bool valid = i < S;
+    const int iq = valid ? i : 0;
+    const float scale = rsqrtf((float)D);
+    float q[D], o[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { q[d] = sm[iq * kRow + d] * scale; o[d] = 0.f; }
+    float mx = -INFINITY, l = 0.f;
+    for (int j = part; j < S; j += KSPLIT) {
+        const float* kj = sm + j * kRow + D;
+        const float* vj = sm + j * kRow + 2 * D;
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) s = fmaf(q[d], kj[d], s);
+        const float mn = fmaxf(mx, s);
+        const float corr = expf(mx - mn);
+        const float p = expf(s - mn);
+        l = l * corr + p;
+#pragma unroll
+        for (int d = 0; d < D; ++d) o[d] = o[d] * corr + p * vj[d];
+        mx = mn;
+    }
+#pragma unroll
+    for (int off = 1; off < KSPLIT; off <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, mx, off), l2 = __shfl_xor_sync(0xffffffffu, l, off);
+        const float mn = fmaxf(mx, m2);
+        // a part that saw no key (S < KSPLIT) carries (-inf, 0, 0): its weight is exp(-inf) = 0
+        const float c1 = mn == -INFINITY ? 0.f : expf(mx - mn), c2 = mn == -INFINITY ? 0.f : expf(m2 - mn);
+        l = l * c1 + l2 * c2;
+#pragma unroll
+        for (int d = 0; d < D; ++d) o[d] = o[d] * c1 + __shfl_xor_sync(0xffffffffu, o[d], off) * c2;
+        mx = mn;
+    }
+    if (!valid) return;
+    const float inv = 1.f / l;
+    T* orow = reinterpret_cast<T*>(P.o) + ((int64_t)n * S + i) * P.o_pitch + h * D;
+    constexpr int kPer = D / KSPLIT;              // every part writes its slice of the (identical) merged row
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+        if (d / kPer == part) orow[d] = Elem<T>::from_f(o[d] * inv);
+    if (P.lse && part == 0) P.lse[((int64_t)n * P.heads + h) * S + i] = mx + logf(l);
+}
+
 template <typename T, int D>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(dmu_attn_params P) {
     extern __shared__ float sm[];
@@ -156,7 +219,10 @@ static int attn_launch(const dmu_attn_params* p, cudaStream_t s, bool bwd) {
             cudaFuncSetAttribute(bwd ? (const void*)kb : (const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         }                                                                                                           \
         if (bwd) kb<<<p->N, threads, smem, s>>>(*p);                                                                \
-        else kf<<<p->N, threads, smem, s>>>(*p);                                                                    \
+        else if (p->S * 4 <= 256 && DD >= 8) {                                                                      \
+            const int th = ((p->S * 4 + 31) / 32) * 32;                                                             \
+            attn_fwd_split_kernel<T, DD, 4><<<dim3(p->N, p->heads), th, (size_t)p->S * (3 * DD + 4) * sizeof(float), s>>>(*p); \
+        } else kf<<<p->N, threads, smem, s>>>(*p);                                                                  \
         break;                                                                                                      \
     }
     switch (D) {

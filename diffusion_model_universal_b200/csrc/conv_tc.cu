@@ -421,6 +421,9 @@ long long* g_debug_buffer = nullptr;
 // conv_halo.cu
 int halo_supported(const dmu_conv_params* p, int force);
 int halo_launch(const dmu_conv_params* p, cudaStream_t stream);
+// conv_stem.cu: few-channel input (stem fprop, head dgrad)
+int stem_supported(const dmu_conv_params* p);
+int stem_launch(const dmu_conv_params* p, cudaStream_t stream);
 
 static bool halo_enabled() {
     static int v = -1;
@@ -444,6 +447,7 @@ static int narrow_head_supported(const dmu_conv_params* p) {
 static int conv_supported(const dmu_conv_params* p) {
     if (!p || !p->x.ptr || !p->y.ptr || !p->w) return 0;
     if (narrow_head_supported(p)) return 1;
+    if (p->impl != 4 && p->impl != 5 && stem_supported(p)) return 1;
     if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y)) return 0;
     if (p->res.ptr && !nhwc_bf16_ok(p->res)) return 0;
     if (p->Ck % 64 != 0 || p->Cj % 64 != 0) return 0;
@@ -463,6 +467,7 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         return halo_launch(p, stream);
     }
     if (narrow_head_supported(p)) return halo_launch(p, stream);
+    if (p->impl != 4 && stem_supported(p)) return stem_launch(p, stream);
     if (p->impl != 4 && halo_enabled() && halo_supported(p, 0)) return halo_launch(p, stream);
     Maps maps;
     ConvArgs A;

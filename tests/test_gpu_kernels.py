@@ -252,6 +252,36 @@ def test_stem_and_head_layouts(dtype, impl):
     assert rel_l2(dbh, dout.sum(dim=(0, 2, 3))) < 5e-5
 
 
+@pytest.mark.parametrize("N,H,W,Cm", [(3, 32, 32, 64), (2, 8, 24, 128), (1, 5, 7, 64), (128, 32, 32, 64)])
+def test_stem_and_head_dgrad_tensor_core(N, H, W, Cm):
+    """conv_stem.cu: the tcgen05 im2col kernel for the 3-channel NCHW fp32 boundary tensors (stem fprop, head dgrad), incl.
+    pixel counts that are not a multiple of the 128-pixel tile."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N * 1000 + H)
+    dtype = torch.bfloat16
+    x = torch.randn(N, 3, H, W, generator=g).to(dev)
+    w = (torch.randn(Cm, 3, 3, 3, generator=g) / 5).to(dev)
+    b = torch.randn(Cm, generator=g).to(dev)
+    wk = _repack(w, False, dtype)
+    code = ops.dtype_code(wk)
+    y = torch.full((N, H, W, Cm), float("nan"), device=dev, dtype=dtype)
+    ops.conv2d_raw(ConvParams(ops.t4_nchw(x), ops.t4_nhwc(y), _null(), wk.data_ptr(), 27, 1, 3, b.data_ptr(), None, 0,
+                              N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 0, code, 2, 0))
+    xq, wq = x.to(dtype).float(), w.to(dtype).float()
+    assert rel_l2(y.float().permute(0, 3, 1, 2), F.conv2d(xq, wq, b, padding=1)) < TOL[dtype]
+    # head dgrad: dout [N,3,H,W] fp32 NCHW -> da [N,H,W,Cm], filters read from the fprop cache [3][9][Cm] through strides
+    wh = (torch.randn(3, Cm, 3, 3, generator=g) / 24).to(dev)
+    whk = _repack(wh, False, dtype)
+    dout = torch.randn(N, 3, H, W, generator=g).to(dev)
+    da = torch.full((N, H, W, Cm), float("nan"), device=dev, dtype=dtype)
+    ops.conv2d_raw(ConvParams(ops.t4_nchw(dout), ops.t4_nhwc(da), _null(), whk.data_ptr(), 1, 9 * Cm, Cm, None, None, 0,
+                              N, H, W, 3, H, W, Cm, 3, 3, 1, 1, 1, code, 2, 0))
+    ref = torch.nn.grad.conv2d_input((N, Cm, H, W), wh.to(dtype).float(), dout.to(dtype).float(), padding=1)
+    assert rel_l2(da.float().permute(0, 3, 1, 2), ref) < TOL[dtype]
+
+
 @pytest.mark.parametrize("M,I,O", [(128, 256, 3136), (7, 64, 256), (2048, 128, 384), (5, 1, 64)])
 def test_linear_via_conv(M, I, O):
     ops, _abi = _mods()
