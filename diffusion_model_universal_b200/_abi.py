@@ -30,6 +30,7 @@ class ConvParams(C.Structure):
         ("R", c_i32), ("S", c_i32), ("stride", c_i32), ("pad", c_i32),
         ("gather", c_i32), ("w_dtype", c_i32), ("impl", c_i32), ("_pad", c_i32),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
+        ("gn_coef", c_vp), ("gn_silu", c_i32), ("_pad2", c_i32), ("a_out", Tensor4),
     ]
 
 
@@ -106,6 +107,8 @@ _SIGS = {
     "dmu_diffusion_loss": (c_i32, [c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "dmu_conv2d": (c_i32, [P(ConvParams), c_vp]),
     "dmu_conv2d_workspace_bytes": (c_i64, []),
+    "dmu_conv2d_gn_supported": (c_i32, [P(ConvParams)]),
+    "dmu_gn_coef": (c_i32, [P(GnParams), c_vp, c_vp]),
     "dmu_conv2d_wgrad": (c_i32, [P(WgradParams), c_vp]),
     "dmu_gn_forward": (c_i32, [P(GnParams), c_vp]),
     "dmu_gn_backward": (c_i32, [P(GnParams), c_vp]),

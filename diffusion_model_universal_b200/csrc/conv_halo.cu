@@ -17,6 +17,7 @@
 //     MMAs of tile i+1.
 // Positions of the padded space that are padding themselves are computed and dropped (efficiency H*W/((H+2)(W+2)): 89 %
 // at 32x32, 79 % at 16x16, 64 % at 8x8); below 8x8 the per-tap kernel (with split-K) is used instead.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -40,18 +41,41 @@ struct HaloArgs {
     // boundary); the weight box still has NT rows, the rows past Cj are TMA out-of-bounds zeros
     float* yn; int64_t n_sn, n_sh, n_sw, n_sc; int narrow;
     long long* dbg;     // development aid: CTA 0 stamps clock64 per tile (8 slots per tile)
+    // fused GroupNorm(+SiLU) on the gathered operand: a = act(x * coef[n][k][0] + coef[n][k][1]) is applied to the halo tile
+    // in shared memory by four dedicated warps before the MMAs read it; a (the conv's real input) is optionally written out
+    // for the backward (weight gradient operand)
+    const float* gn_coef; int gn_silu;
+    __nv_bfloat16* a_out; int64_t a_sn, a_sh, a_sw;
+    int exp_flags;      // development aid (DMU_HALO_EXP): 1 = no proxy fence, 2 = no transform body (timing experiments only)
 };
 
 constexpr int kMaxAStages = 4, kMaxWStages = 8;
 
 __device__ __forceinline__ int floordiv_dev(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <int NT>
-__global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloArgs P) {
+// x * sigmoid(x) with one MUFU: sigmoid(x) = 0.5 * (1 + tanh(x / 2))
+__device__ __forceinline__ float silu_tanh(float t) {
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * t));
+    return 0.5f * t * (1.f + th);
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int NT, bool GN>
+__global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloArgs P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t a_full[kMaxAStages], a_empty[kMaxAStages], w_full[kMaxWStages], w_empty[kMaxWStages];
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t a_ready[kMaxAStages];      // GN: transform warps -> MMA warp
     __shared__ uint32_t s_tmem;
     __shared__ float s_bias[NT];
 
@@ -67,6 +91,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_const
         for (int i = 0; i < P.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < kMaxAStages; ++i) mbar_init(&a_ready[i], 8);
         fence_mbar_init();
         tma_prefetch_desc(&maps.a);
         tma_prefetch_desc(&maps.b);
@@ -137,7 +162,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_const
             const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
             const int base_off = Q0 - P.PW - 1 - L0 * P.PW;       // smem row of padded position (Q0 - PW - 1)
             for (int c = 0; c < P.chunks; ++c) {
-                mbar_wait(&a_full[sa], pa);
+                mbar_wait(GN ? &a_ready[sa] : &a_full[sa], pa);
                 tc_fence_after();
                 if (dbg && c == 0) dbg[2] = clock64();
                 const uint32_t a_base = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes) + (uint32_t)base_off * 128u;
@@ -179,6 +204,85 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo_kernel(const __grid_const
             if (elect_one()) umma_commit(&acc_full[buf]);
             __syncwarp();
             if (dbg) dbg[3] = clock64();
+        }
+    } else if (GN && warp >= 6) {
+        // ------------------------------------------------ GroupNorm(+SiLU) transform warps 6..13
+        // Tile row r is padded-flat position L0 * PW + r.  Rows that are padding (TMA zero fill) stay zero; every other row is
+        // normalised in place: thread = one 16-byte chunk (8 channels) of one pixel, the chunk's logical position follows the
+        // 128-byte swizzle (physical chunk ^ (row & 7); the stage base is 1024-byte aligned).
+        // Warp = every 8th row of the tile (uniform validity / image bookkeeping); lane = a fixed LOGICAL 16-byte chunk (8
+        // channels: its 16 coefficients stay in registers while the image does not change) of every 4th pixel, four pixels in
+        // flight.  The transform of a tile is a latency chain (LDS -> affine -> SiLU -> STS) that the MMA warp waits for, so it
+        // is spread over rows and unrolled rather than made instruction-lean only.  The affine part runs in fp32, SiLU on the
+        // bf16x2-rounded pair: 0.5 t (1 + tanh(0.5 t)) = HMUL2 + MUFU + HFMA2.
+        const int tw = warp - 6;                          // 0..7
+        const int j = lane & 7, pp = lane >> 3;           // logical chunk, pixel phase 0..3
+        int sa = 0, pa = 0;
+        int coef_key = -1;
+        float sc[8], sh[8];
+        for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+            const int Q0 = tile * 128;
+            const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
+            const int own0 = Q0 - L0 * P.PW;              // tile rows [own0, own0 + 128) are this tile's own output positions
+            for (int c = 0; c < P.chunks; ++c) {
+                mbar_wait(&a_full[sa], pa);
+                const uint32_t st = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes);
+                for (int i = tw; i < P.NR && !(P.exp_flags & 2); i += 8) {
+                    const int L = L0 + i;
+                    const int n = floordiv_dev(L, P.PH), hp = L - n * P.PH;
+                    if (n < 0 || n >= P.N || hp < 1 || hp > P.H) continue;
+                    if (n * P.chunks + c != coef_key) {
+                        const float4* cf = reinterpret_cast<const float4*>(P.gn_coef + ((size_t)n * P.Ck + c * 64 + j * 8) * 2);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 v = __ldg(cf + k);
+                            sc[2 * k] = v.x; sh[2 * k] = v.y; sc[2 * k + 1] = v.z; sh[2 * k + 1] = v.w;
+                        }
+                        coef_key = n * P.chunks + c;
+                    }
+                    __nv_bfloat16* arow = (P.a_out && blockIdx.y == 0) ? P.a_out + (int64_t)n * P.a_sn + (int64_t)(hp - 1) * P.a_sh + c * 64 + j * 8 - P.a_sw
+                                                                        : nullptr;
+                    const int rbase = i * P.PW;
+                    for (int wp0 = 1 + pp; wp0 <= P.W; wp0 += 16) {
+                        uint4 raw[4];
+                        uint32_t cell[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int r = rbase + wp0 + 4 * u;
+                            cell[u] = st + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+                            if (wp0 + 4 * u <= P.W) raw[u] = lds128(cell[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int wp = wp0 + 4 * u, r = rbase + wp;
+                            if (wp <= P.W) {
+                                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+                                uint4 outv;
+                                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float2 f = __bfloat1622float2(h2[k]);
+                                    __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaf(f.x, sc[2 * k], sh[2 * k]), fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]));
+                                    if (P.gn_silu) {
+                                        const __nv_bfloat162 hf = __hmul2(t2, __floats2bfloat162_rn(0.5f, 0.5f));
+                                        uint32_t th;
+                                        asm("tanh.approx.bf16x2 %0, %1;" : "=r"(th) : "r"(*reinterpret_cast<const uint32_t*>(&hf)));
+                                        t2 = __hfma2(hf, *reinterpret_cast<const __nv_bfloat162*>(&th), hf);
+                                    }
+                                    o2[k] = t2;
+                                }
+                                sts128(cell[u], outv);
+                                if (arow && r >= own0 && r < own0 + 128) *reinterpret_cast<uint4*>(arow + (int64_t)wp * P.a_sw) = outv;
+                            }
+                        }
+                    }
+                }
+                if (!(P.exp_flags & 1)) fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&a_ready[sa]);
+                __syncwarp();
+                if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
+            }
         }
     } else {
         // ---------------------------------------------------- epilogue warps 0..3: thread = one output position (TMEM lane)
@@ -352,12 +456,23 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
     dim3 grid(gx, ntiles_n);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(conv3x3_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-        cudaFuncSetAttribute(conv3x3_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(conv3x3_halo_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(conv3x3_halo_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(conv3x3_halo_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        cudaFuncSetAttribute(conv3x3_halo_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         attr_done = true;
     }
-    cudaError_t e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64>, grid, dim3(192), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
-                             : launch_pdl(conv3x3_halo_kernel<128>, grid, dim3(192), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
+    cudaError_t e;
+    if (p->gn_coef) {
+        A.gn_coef = p->gn_coef; A.gn_silu = p->gn_silu;
+        { const char* e = getenv("DMU_HALO_EXP"); A.exp_flags = e ? atoi(e) : 0; }
+        A.a_out = reinterpret_cast<__nv_bfloat16*>(p->a_out.ptr); A.a_sn = p->a_out.sn; A.a_sh = p->a_out.sh; A.a_sw = p->a_out.sw;
+        e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64, true>, grid, dim3(448), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
+                     : launch_pdl(conv3x3_halo_kernel<128, true>, grid, dim3(448), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
+    } else {
+        e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64, false>, grid, dim3(192), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
+                     : launch_pdl(conv3x3_halo_kernel<128, false>, grid, dim3(192), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
+    }
     if (e != cudaSuccess) return fail("dmu_conv2d/halo: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/halo");
 }

@@ -446,6 +446,10 @@ static int narrow_head_supported(const dmu_conv_params* p) {
 
 static int conv_supported(const dmu_conv_params* p) {
     if (!p || !p->x.ptr || !p->y.ptr || !p->w) return 0;
+    if (p->gn_coef) {   // fused GroupNorm: the halo kernel only (wide bf16 NHWC input, 3x3 stride 1, >= 8x8)
+        if (!nhwc_bf16_ok(p->x) || p->Ck % 64 != 0 || !halo_supported(p, 1) || encode_tiled_fn() == nullptr) return 0;
+        if (p->a_out.ptr && !nhwc_bf16_ok(p->a_out)) return 0;
+    }
     if (narrow_head_supported(p)) return 1;
     if (p->impl != 4 && p->impl != 5 && stem_supported(p)) return 1;
     if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y)) return 0;
@@ -467,6 +471,7 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         return halo_launch(p, stream);
     }
     if (narrow_head_supported(p)) return halo_launch(p, stream);
+    if (p->gn_coef) return halo_launch(p, stream);
     if (p->impl != 4 && stem_supported(p)) return stem_launch(p, stream);
     if (p->impl != 4 && halo_enabled() && halo_supported(p, 0)) return halo_launch(p, stream);
     Maps maps;
@@ -776,6 +781,12 @@ int64_t dmu_conv2d_workspace_bytes(void) { return tc::kSplitWsBytes; }
 // development aid, not part of include/dmu_b200.h: int64 device buffer (8 per CTA) receiving clock64 stamps of conv_tc_kernel
 void dmu_debug_set_buffer(void* p) { tc::g_debug_buffer = reinterpret_cast<long long*>(p); }
 int dmu_conv2d_tc_supported(const dmu_conv_params* p) { return tc::conv_supported(p); }
+int dmu_conv2d_gn_supported(const dmu_conv_params* p) {
+    if (!p || !p->x.ptr || !p->y.ptr || !p->w || p->impl == 1 || p->impl == 3 || p->impl == 4) return 0;
+    if (!tc::nhwc_bf16_ok(p->x) || p->Ck % 64 != 0 || tc::encode_tiled_fn() == nullptr || !tc::halo_enabled()) return 0;
+    if (!tc::conv_supported(p)) return 0;
+    return tc::halo_supported(p, p->impl == 5 ? 1 : 0);
+}
 int dmu_conv2d_tc(const dmu_conv_params* p, dmu_stream_t stream) { return tc::conv_launch(p, as_stream(stream)); }
 int dmu_wgrad_tc_supported(const dmu_wgrad_params* p) { return tc::wgrad_supported(p); }
 int dmu_wgrad_tc(const dmu_wgrad_params* p, dmu_stream_t stream) { return tc::wgrad_launch(p, as_stream(stream)); }

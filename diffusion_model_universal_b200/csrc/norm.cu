@@ -187,6 +187,24 @@ __device__ __forceinline__ float act_grad(float u, float dy, int silu) {
     return dy * (s * fmaf(u, 1.f - s, 1.f));
 }
 
+// per-image affine form of the normalisation for the conv kernels that apply it to their operand tile (conv_halo.cu)
+__global__ void __launch_bounds__(256) gn_coef_kernel(dmu_gn_params P, float* __restrict__ coef) {
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.x;
+    const int cpg = P.C / P.G;
+    const float cnt = (float)cpg * (float)P.H * (float)P.W;
+    for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float su = P.sums[((int64_t)n * P.G + g) * 2 + 0], sq = P.sums[((int64_t)n * P.G + g) * 2 + 1];
+        const float mean = su / cnt;
+        const float rstd = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + P.eps);
+        const float sc = rstd * P.gamma[c];
+        coef[((int64_t)n * P.C + c) * 2 + 0] = sc;
+        coef[((int64_t)n * P.C + c) * 2 + 1] = P.beta[c] - mean * sc;
+    }
+}
+
 // ------------------------------------------------------------------ bwd reduce
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(dmu_gn_params P) {
@@ -1382,6 +1400,12 @@ int dmu_gn_stats(const dmu_gn_params* p, dmu_stream_t stream) {
     const int vec = p->x.dtype == DMU_BF16 ? 8 : 4;
     DISPATCH_T(p->x.dtype, gn_stats_kernel, gn_grid(p->N, p->H * p->W, p->C, vec), 256, as_stream(stream), *p);
     return check_launch("dmu_gn_stats");
+}
+int dmu_gn_coef(const dmu_gn_params* p, float* coef, dmu_stream_t stream) {
+    if (int e = gn_check(p, "dmu_gn_coef", false, false)) return e;
+    DMU_REQUIRE(coef, "dmu_gn_coef: null output");
+    launch_pdl(gn_coef_kernel, dim3(p->N), dim3(256), 0, as_stream(stream), dim3(1, 1, 1), *p, coef);
+    return check_launch("dmu_gn_coef");
 }
 int dmu_gn_apply(const dmu_gn_params* p, dmu_stream_t stream) {
     if (int e = gn_check(p, "dmu_gn_apply", true, false)) return e;

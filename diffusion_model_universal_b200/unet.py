@@ -248,6 +248,10 @@ class Engine:
         # 1.48 / 1.48 ms forward at 1 / 2 / 4 lanes for 128x32x32 - a chain of latency-bound kernels is as long for half the
         # batch, so lanes over the batch buy nothing; the default stays 1 (the machinery also carries the dgrad | wgrad lanes).
         self.micro_batches = int(os.environ.get("DMU_MICROBATCHES", "1"))
+        # GroupNorm applied inside the halo conv kernel (dmu_conv_params.gn_coef).  Correct and tested, but measured slower than
+        # GroupNorm launch + plain halo conv on B200 so far (scripts/gnconv_time.py: 39.5 vs 37.8 us at 128x32x32, 268 vs 192 us
+        # at 256x64x64: the in-place transform is a latency chain in front of every tile's MMAs), so it is opt-in.
+        self.fuse_gn = os.environ.get("DMU_GN_FUSE", "0") == "1"
         self._lib = None
 
     # ------------------------------------------------------------------ parameters
@@ -727,15 +731,46 @@ class _PlanBuilder:
         self.plan.bwd.append((self.lib.dmu_colsum_multi, (tab.data_ptr(), len(self.cs_pending), cta, self.code), 1))
         self.cs_pending = []
 
-    def conv(self, lst, x: Tensor4, y: Tensor4, w, w_strides, w_code, dims, geom, bias=None, temb=None, temb_pitch=0, res=None, gather=0):
+    def conv(self, lst, x: Tensor4, y: Tensor4, w, w_strides, w_code, dims, geom, bias=None, temb=None, temb_pitch=0, res=None, gather=0,
+             gn_coef=None, gn_silu=0, a_out=None, emit=True):
         N, Hi, Wi, Ck, Ho, Wo, Cj = dims
         R, S, stride, pad = geom
         p = ConvParams(x, y, res if res is not None else _null_t4(), w, w_strides[0], w_strides[1], w_strides[2], bias, temb, temb_pitch,
                        N, Hi, Wi, Ck, Ho, Wo, Cj, R, S, stride, pad, gather, w_code, self.e.impl, 0,
-                       self.plan.ws.data_ptr() if self.plan.ws is not None else None, self.plan.ws.numel() if self.plan.ws is not None else 0)
-        lst.append((self.lib.dmu_conv2d, (C.byref(p),)))
-        self.plan.keep.append(p)
+                       self.plan.ws.data_ptr() if self.plan.ws is not None else None, self.plan.ws.numel() if self.plan.ws is not None else 0,
+                       gn_coef, gn_silu, 0, a_out if a_out is not None else _null_t4())
+        if emit:
+            lst.append((self.lib.dmu_conv2d, (C.byref(p),)))
+            self.plan.keep.append(p)
         return p
+
+    def gn_conv(self, x: Buf, G, gamma_name, beta_name, silu, y4: Tensor4, w, w_strides, dims, geom, bias=None, temb=None, temb_pitch=0, res=None):
+        """act(GroupNorm(x)) followed by a 3x3 convolution (residual.py:57-58,63-64; ddpm.py:88-90).  Where the persistent halo
+        kernel takes the layer, the normalisation is applied to its operand tile in shared memory (statistics pass +
+        coefficients + conv: the activation is neither written nor re-read, except as the weight-gradient operand when
+        training); elsewhere a GroupNorm launch writes the activation first.  Returns (a, gn-record) like gn()."""
+        fuse = False
+        if self.e.fuse_gn and self.code == BF16 and hasattr(self.lib, "dmu_conv2d_gn_supported"):
+            # the probe must not depend on this pass's addresses (the sizing pass runs at base 0): dummy aligned pointers
+            d4 = lambda t: Tensor4(1 << 20, t.sn, t.sh, t.sw, t.sc, t.dtype, 0)
+            probe = self.conv(None, d4(x.t4()), d4(y4), 1 << 20, w_strides, self.code, dims, geom, bias=(1 << 20) if bias else None,
+                              temb=(1 << 20) if temb else None, temb_pitch=temb_pitch, res=d4(res) if res is not None else None, emit=False)
+            fuse = self.lib.dmu_conv2d_gn_supported(C.byref(probe)) == 1
+        if not fuse:
+            a, rec = self.gn(x, G, gamma_name, beta_name, silu)
+            self.conv(self.plan.fwd, a.t4(), y4, w, w_strides, self.code, dims, geom, bias=bias, temb=temb, temb_pitch=temb_pitch, res=res)
+            return a, rec
+        sums = self.stats.take(self.N * G * 2 * 4, 16)
+        coef = self.f32(self.N * x.C * 2)
+        gp = GnParams(x.t4(), _null_t4(), _null_t4(), _null_t4(), _null_t4(), sums, self.e.paddr(gamma_name), self.e.paddr(beta_name),
+                      None, None, None, self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, 0)
+        self.plan.keep.append(gp)
+        self.plan.fwd.append((self.lib.dmu_gn_stats, (C.byref(gp),)))
+        self.plan.fwd.append((self.lib.dmu_gn_coef, (C.byref(gp), coef)))
+        a = self.act(x.H, x.W, x.C) if self.train else None      # only the backward reads the activation itself
+        self.conv(self.plan.fwd, x.t4(), y4, w, w_strides, self.code, dims, geom, bias=bias, temb=temb, temb_pitch=temb_pitch, res=res,
+                  gn_coef=coef, gn_silu=1 if silu else 0, a_out=a.t4() if a is not None else None)
+        return a, (x, a, sums, G, gamma_name, beta_name, silu)
 
     def wgrad(self, p4: Tensor4, q4: Tensor4, dw, dw_strides, dbias, dims, geom):
         N, Hp, Wp, Ca, Hq, Wq, Cb = dims
@@ -807,17 +842,17 @@ class _PlanBuilder:
         extra_add: an already-written gradient of x from another consumer (skip connection)."""
         e = self.e
         Ci, Co = x.C, y.C
-        a1, rec1 = self.gn(x, gn_groups(Ci), pfx + "norm1.weight", pfx + "norm1.bias", True)
         h = self.act(x.H, x.W, Co)
-        self.conv_layer(a1, h, pfx + "conv1.weight", pfx + "conv1.bias", 3, 1, 1, temb=tp_addr, temb_pitch=tp_pitch)
-        a2, rec2 = self.gn(h, gn_groups(Co), pfx + "norm2.weight", pfx + "norm2.bias", True)
+        a1, rec1 = self.gn_conv(x, gn_groups(Ci), pfx + "norm1.weight", pfx + "norm1.bias", True, h.t4(), e.waddr(pfx + "conv1.weight"),
+                                (9 * Ci, 1, Ci), (self.N, x.H, x.W, Ci, h.H, h.W, Co), (3, 3, 1, 1), bias=e.paddr(pfx + "conv1.bias"),
+                                temb=tp_addr, temb_pitch=tp_pitch)
         has_sc = Ci != Co
         if has_sc:
             sc = self.tmp(x.H, x.W, Co)
             self.conv_layer(x, sc, pfx + "shortcut.weight", pfx + "shortcut.bias", 1, 1, 0)
-            self.conv_layer(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, res=sc)
-        else:
-            self.conv_layer(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, res=x)
+        a2, rec2 = self.gn_conv(h, gn_groups(Co), pfx + "norm2.weight", pfx + "norm2.bias", True, y.t4(), e.waddr(pfx + "conv2.weight"),
+                                (9 * Co, 1, Co), (self.N, h.H, h.W, Co, y.H, y.W, Co), (3, 3, 1, 1), bias=e.paddr(pfx + "conv2.bias"),
+                                res=(sc if has_sc else x).t4())
         if not self.train:
             return
 
@@ -1014,9 +1049,9 @@ class _PlanBuilder:
                 self.tape.append(up_bwd)
             x = u
         # -------- head: GroupNorm -> SiLU -> conv3x3 -> NCHW fp32
-        a, rec = self.gn(x, 32, "output_conv.0.weight", "output_conv.0.bias", True)
-        self.conv(plan.fwd, a.t4(), _nchw_t4(out_ptr, net.out_channels, H, W), e.waddr("output_conv.2.weight"), (9 * Cm, 1, Cm), self.code,
-                              (N, H, W, Cm, H, W, net.out_channels), (3, 3, 1, 1), bias=e.paddr("output_conv.2.bias"))
+        a, rec = self.gn_conv(x, 32, "output_conv.0.weight", "output_conv.0.bias", True, _nchw_t4(out_ptr, net.out_channels, H, W),
+                              e.waddr("output_conv.2.weight"), (9 * Cm, 1, Cm), (N, H, W, Cm, H, W, net.out_channels), (3, 3, 1, 1),
+                              bias=e.paddr("output_conv.2.bias"))
         # one launch zeroes every GroupNorm statistics accumulator of the forward
         plan.fwd.insert(0, (lib.dmu_zero, (self.stats.base, max(self.stats.off, 4))))
 

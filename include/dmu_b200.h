@@ -142,8 +142,20 @@ typedef struct {
      * be shared by launches that may run concurrently.  NULL/0 = never split. */
     void* workspace;
     int64_t workspace_bytes;
+    /* Optional fused GroupNorm(+SiLU) on the INPUT (residual.py:57-58,63-64, ddpm.py:88-90: every conv of the network reads
+     * act(GroupNorm(x))):  the contraction runs over a[n,h,w,k] = act(x[n,h,w,k] * gn_coef[(n*Ck+k)*2] + gn_coef[(n*Ck+k)*2+1])
+     * instead of x (act = SiLU when gn_silu, identity otherwise; padding stays zero), coefficients from dmu_gn_coef.
+     * a_out (ptr NULL = skip) receives a, bf16 NHWC: the weight gradient needs it.  Only the persistent halo kernel
+     * implements this (ask dmu_conv2d_gn_supported); any other shape with gn_coef set is an error. */
+    const float* gn_coef;
+    int32_t gn_silu;
+    int32_t _pad2;
+    dmu_tensor4 a_out;
 } dmu_conv_params;
 int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream);
+/* 1 when dmu_conv2d would run this layer on the halo kernel by its own heuristics, i.e. when the GroupNorm of its input may be
+ * fused into it (gn_coef itself need not be set yet). */
+int dmu_conv2d_gn_supported(const dmu_conv_params* p);
 /* bytes of split-K scratch that let dmu_conv2d split every eligible layer (a constant upper bound) */
 int64_t dmu_conv2d_workspace_bytes(void);
 
@@ -199,6 +211,9 @@ int dmu_gn_backward(const dmu_gn_params* p, dmu_stream_t stream);
  * (run once after the backward of all layers, with dgamma/dbeta left NULL in their dmu_gn_params).  The table lives in
  * device memory: n_desc entries of { const float* red; float* dgamma; float* dbeta; int32_t C; int32_t pad; }. */
 int dmu_gn_param_grads(const void* table_device, int32_t n_desc, int32_t max_c, int32_t N, dmu_stream_t stream);
+/* Per-image, per-channel affine form of the normalisation, from the sums of dmu_gn_stats:
+ *   coef[(n*C+c)*2] = rstd[n,g]*gamma[c],  coef[(n*C+c)*2+1] = beta[c] - mean[n,g]*rstd[n,g]*gamma[c]   (for dmu_conv_params.gn_coef) */
+int dmu_gn_coef(const dmu_gn_params* p, float* coef, dmu_stream_t stream);
 int dmu_gn_stats(const dmu_gn_params* p, dmu_stream_t stream);
 int dmu_gn_apply(const dmu_gn_params* p, dmu_stream_t stream);
 int dmu_gn_bwd_reduce(const dmu_gn_params* p, dmu_stream_t stream);

@@ -282,6 +282,46 @@ def test_stem_and_head_dgrad_tensor_core(N, H, W, Cm):
     assert rel_l2(da.float().permute(0, 3, 1, 2), ref) < TOL[dtype]
 
 
+@pytest.mark.parametrize("N,H,W,Ci,Co,silu,res", [(8, 32, 32, 64, 64, 1, True), (6, 16, 16, 128, 64, 1, False), (5, 8, 24, 64, 128, 0, False),
+                                                   (70, 32, 32, 64, 64, 1, False), (3, 64, 64, 64, 64, 1, True)])
+def test_conv_with_fused_groupnorm(N, H, W, Ci, Co, silu, res):
+    """Halo kernel with GroupNorm(+SiLU) applied to its operand tile in shared memory (dmu_conv_params.gn_coef): y and the
+    side output a = act(GN(x)) against ATen on the same bf16-rounded operands; padding pixels must stay zero."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams, GnParams
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N * 100 + H + Ci)
+    dtype, G = torch.bfloat16, 32
+    x = (torch.randn(N, Ci, H, W, generator=g) * 1.7 + 0.4).to(dev)
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / math.sqrt(9 * Ci)).to(dev)
+    b = torch.randn(Co, generator=g).to(dev)
+    gamma, beta = (1 + 0.2 * torch.randn(Ci, generator=g)).to(dev), (0.1 * torch.randn(Ci, generator=g)).to(dev)
+    xh = ops.nchw_to_nhwc(x, dtype)
+    wk = _repack(w, False, dtype)
+    lib = _abi.lib()
+    sums = torch.zeros(N, G, 2, device=dev)
+    coef = torch.empty(N, Ci, 2, device=dev)
+    pg = GnParams(ops.t4_nhwc(xh), _null(), _null(), _null(), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                  None, None, None, N, H, W, Ci, G, silu, 1e-5, 0)
+    _abi.check(lib.dmu_gn_stats(C.byref(pg), _stream()))
+    _abi.check(lib.dmu_gn_coef(C.byref(pg), coef.data_ptr(), _stream()))
+    y = torch.full((N, H, W, Co), float("nan"), device=dev, dtype=dtype)
+    a = torch.full((N, H, W, Ci), float("nan"), device=dev, dtype=dtype)
+    r = torch.randn(N, H, W, Co, generator=g).to(dev).to(dtype) if res else None
+    p = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(y), ops.t4_nhwc(r) if res else _null(), wk.data_ptr(), 9 * Ci, 1, Ci, b.data_ptr(), None, 0,
+                   N, H, W, Ci, H, W, Co, 3, 3, 1, 1, 0, ops.dtype_code(wk), 5, 0, None, 0, coef.data_ptr(), silu, 0, ops.t4_nhwc(a))
+    assert lib.dmu_conv2d_gn_supported(C.byref(p)) == 1
+    ops.conv2d_raw(p)
+    xq = xh.float().permute(0, 3, 1, 2)
+    aref = F.group_norm(xq, G, gamma, beta, eps=1e-5)
+    aref = F.silu(aref) if silu else aref
+    assert rel_l2(a.float().permute(0, 3, 1, 2), aref) < TOL[dtype]
+    yref = F.conv2d(aref.to(dtype).float(), w.to(dtype).float(), b, padding=1)
+    if res:
+        yref = yref + r.float().permute(0, 3, 1, 2)
+    assert rel_l2(y.float().permute(0, 3, 1, 2), yref) < TOL[dtype]
+
+
 @pytest.mark.parametrize("M,I,O", [(128, 256, 3136), (7, 64, 256), (2048, 128, 384), (5, 1, 64)])
 def test_linear_via_conv(M, I, O):
     ops, _abi = _mods()
