@@ -14,6 +14,7 @@
 //   * the contraction runs over pixels, so both operands are MN-major (channels contiguous): the same TMA boxes
 //     (64 channels x 64 pixels) are consumed through MN-major UMMA descriptors; M = two (tap, 64-channel) blocks of Q,
 //     N = up to 128 channels of P; split over pixel ranges (blockIdx.z), fp32 atomics into the OIHW gradient.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -549,9 +550,14 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         if (kb < kb_min) kb_min = kb;
     }
     A.splits = 1;
-    if (p->workspace && p->workspace_bytes >= kSplitWsBytes && slots * 2 <= sm_count() && kb_min >= 40) {
+    static int split_min = -1, split_per = -1;
+    if (split_min < 0) {
+        const char* e1 = getenv("DMU_SPLITK_MIN"); const char* e2 = getenv("DMU_SPLITK_PER");
+        split_min = e1 ? atoi(e1) : 40; split_per = e2 ? atoi(e2) : 12;
+    }
+    if (p->workspace && p->workspace_bytes >= kSplitWsBytes && slots * 2 <= sm_count() && kb_min >= split_min) {
         int sp = 8;                                               // portable cluster limit
-        while (sp > 1 && (slots * sp > kMaxSplitCtas || slots * sp > sm_count() + sm_count() / 4 || kb_min / sp < 12)) sp >>= 1;
+        while (sp > 1 && (slots * sp > kMaxSplitCtas || slots * sp > sm_count() + sm_count() / 4 || kb_min / sp < split_per)) sp >>= 1;
         if (sp >= 2) {
             A.splits = sp;
             A.ws = reinterpret_cast<float*>(p->workspace);
@@ -751,7 +757,12 @@ static int wgrad_launch(const dmu_wgrad_params* p, cudaStream_t stream) {
     A.units = A.RS * (p->Cb / 64);
     A.dw = p->dw; A.dw_sa = p->dw_sa; A.dw_sb = p->dw_sb; A.dw_st = p->dw_st;
     const int mt = (A.units + 1) / 2, ntl = p->Ca / NT;
-    int splits = (2 * sm_count() + mt * ntl - 1) / (mt * ntl);
+    // Grid size: the weight gradients run on the side lane of the backward graph, next to the dgrad / GroupNorm chain.  Sized to
+    // two waves they held every SM and the chain's launches queued behind them; at ~3/4 of a wave (each CTA walks more pixel
+    // tiles, fewer partial tiles are folded with atomics) a quarter of the SMs stays free for the chain: 30.7k -> 31.5k img/s.
+    static int target_ctas = -1;
+    if (target_ctas < 0) { const char* e = getenv("DMU_WGRAD_CTAS"); target_ctas = e ? atoi(e) : 3 * sm_count() / 4; }
+    int splits = (target_ctas + mt * ntl - 1) / (mt * ntl);
     if (splits > A.tiles_total) splits = A.tiles_total;
     if (splits < 1) splits = 1;
     A.tiles_per_split = (A.tiles_total + splits - 1) / splits;

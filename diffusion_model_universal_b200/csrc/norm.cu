@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(dmu_gn_params P) {
 }
 
 // per-channel mean / rstd*gamma / beta staged in smem for image n
-__device__ __forceinline__ void stage_affine(const dmu_gn_params& P, int n, float* s_mean, float* s_scale, float* s_beta, float* s_rstd) {
+__device__ __forceinline__ void stage_affine(const dmu_gn_params& P, int n, float* s_mean, float* s_scale, float* s_beta, float* s_rstd,
+                                             float* s_gamma = nullptr) {
     const int cpg = P.C / P.G;
     const float cnt = (float)cpg * (float)P.H * (float)P.W;
     for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
@@ -129,10 +130,12 @@ __device__ __forceinline__ void stage_affine(const dmu_gn_params& P, int n, floa
         const float mean = su / cnt;
         const float var = fmaxf(sq / cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + P.eps);
+        const float gam = P.gamma[c];
         s_mean[c] = mean;
-        s_scale[c] = rstd * P.gamma[c];
+        s_scale[c] = rstd * gam;
         s_beta[c] = P.beta[c];
         if (s_rstd) s_rstd[c] = rstd;
+        if (s_gamma) s_gamma[c] = gam;
     }
 }
 
@@ -393,6 +396,7 @@ __global__ void __launch_bounds__(256) gn_fwd_fused_kernel(dmu_gn_params P) {
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s_a[kMaxC], s_b[kMaxC], s_ta[kMaxC], s_tb[kMaxC];
     __shared__ float s_red[256 * kVec];
+    __shared__ float s_gam[kMaxC], s_bet[kMaxC];
     const int n = blockIdx.y, HW = P.H * P.W, C = P.C, cs = gridDim.x;
     RowMap m(C, kVec);
     int p0, p1; chunk_range(HW, p0, p1);
@@ -406,6 +410,8 @@ __global__ void __launch_bounds__(256) gn_fwd_fused_kernel(dmu_gn_params P) {
         const int pp = p0 + m.lane + u * m.lanes;
         r[u] = (m.active && pp < p1) ? ld_raw<T>(xb + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
     }
+    // parameters staged while the tensor loads fly (read again only after the reductions' barriers)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { s_gam[c] = P.gamma[c]; s_bet[c] = P.beta[c]; }
 #pragma unroll
     for (int u = 0; u < kHold; ++u) {
         float v[kVec];
@@ -429,9 +435,9 @@ __global__ void __launch_bounds__(256) gn_fwd_fused_kernel(dmu_gn_params P) {
         const float mean = su / cnt;
         const float rstd = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + P.eps);
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            const float sc = rstd * P.gamma[c];
+            const float sc = rstd * s_gam[c];
             s_a[c] = sc;
-            s_b[c] = P.beta[c] - mean * sc;
+            s_b[c] = s_bet[c] - mean * sc;
         }
     }
     __syncthreads();
@@ -464,11 +470,12 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(dmu_gn_params P) {
     __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC], s_rstd[kMaxC];
     __shared__ float s_a[kMaxC], s_b[kMaxC], s_ta[kMaxC], s_tb[kMaxC];
     __shared__ float s_red[256 * kVec];
+    __shared__ float s_gam[kMaxC];
     const int n = blockIdx.y, HW = P.H * P.W, C = P.C, cs = gridDim.x;
-    stage_affine(P, n, s_mean, s_scale, s_beta, s_rstd);
-    __syncthreads();
     RowMap m(C, kVec);
     int p0, p1; chunk_range(HW, p0, p1);
+    // the tensor loads go out first: the statistics / affine staging below overlaps their latency (these launches are
+    // latency chains: every dependent global round trip is ~0.7 us of a ~6 us kernel)
     uint4 rx[kHold], rd[kHold];
     const T* xb = reinterpret_cast<const T*>(P.x.ptr) + m.v * kVec;
     const T* dyb = reinterpret_cast<const T*>(P.y.ptr) + m.v * kVec;
@@ -479,6 +486,8 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(dmu_gn_params P) {
         rx[u] = ok ? ld_raw<T>(xb + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
         rd[u] = ok ? ld_raw<T>(dyb + pix_off(P.y, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
     }
+    stage_affine(P, n, s_mean, s_scale, s_beta, s_rstd, s_gam);
+    __syncthreads();
     float mu[kVec], sc[kVec], be[kVec];
     const int cbase = m.active ? m.v * kVec : 0;
 #pragma unroll
@@ -520,7 +529,7 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(dmu_gn_params P) {
         const int g0 = (c / cpg) * cpg;
         float A = 0.f, B = 0.f;
         for (int k = g0; k < g0 + cpg; ++k) {
-            const float gam = P.gamma[k];
+            const float gam = s_gam[k];
             A += gam * s_ta[k];
             B += gam * s_tb[k];
         }
