@@ -225,7 +225,11 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
             const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
             const int own0 = Q0 - L0 * P.PW;              // tile rows [own0, own0 + 128) are this tile's own output positions
             for (int c = 0; c < P.chunks; ++c) {
+                long long* tdbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tw == 0 && lane == 0 && (tile - (int)blockIdx.x) / (int)gridDim.x < 64)
+                                      ? P.dbg + 8 * 64 + 8 * ((tile - (int)blockIdx.x) / (int)gridDim.x) : nullptr;
+                if (tdbg) tdbg[0] = clock64();
                 mbar_wait(&a_full[sa], pa);
+                if (tdbg) tdbg[1] = clock64();
                 const uint32_t st = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes);
                 for (int i = tw; i < P.NR && !(P.exp_flags & 2); i += 8) {
                     const int L = L0 + i;
@@ -277,9 +281,11 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
                         }
                     }
                 }
+                if (tdbg) tdbg[2] = clock64();
                 if (!(P.exp_flags & 1)) fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (elect_one()) mbar_arrive(&a_ready[sa]);
+                if (tdbg) tdbg[3] = clock64();
                 __syncwarp();
                 if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
             }
