@@ -577,6 +577,89 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(dmu_gn_params P) {
     }
 }
 
+// Single-pass forward for images too large for the register-held kernel: the CTA's slab of the image is parked in SHARED
+// memory (bf16 64x64x64: 64 KB per CTA of an 8-CTA cluster), statistics meet through DSMEM, and the normalised slab is written
+// from shared memory: one read + one write of the activation where the two-pass pair reads it twice (the second read only
+// comes from L2 while the whole tensor fits there, which a 134 MB activation does not).
+template <typename T>
+__global__ void __launch_bounds__(256, 3) gn_fwd_smem_kernel(dmu_gn_params P, int per) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int kVec = Elem<T>::kVec;
+    constexpr int kU2 = 4;
+    extern __shared__ __align__(16) uint8_t gn_smem[];
+    const int n = blockIdx.y, HW = P.H * P.W, C = P.C, cs = gridDim.x;
+    uint4* s_x = reinterpret_cast<uint4*>(gn_smem);
+    float* s_a = reinterpret_cast<float*>(s_x + (size_t)per * (C / kVec));
+    float *s_b = s_a + C, *s_ta = s_b + C, *s_tb = s_ta + C;
+    __shared__ float s_red[256 * kVec];
+    RowMap m(C, kVec);
+    const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+    const int cbase = m.active ? m.v * kVec : 0;
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr) + cbase;
+    {
+        float a[kVec], q[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) { a[i] = 0.f; q[i] = 0.f; }
+        if (m.active) {
+            for (int p = p0 + m.lane; p < p1; p += m.lanes * kU2) {
+                uint4 r[kU2];
+#pragma unroll
+                for (int u = 0; u < kU2; ++u) {
+                    const int pp = p + u * m.lanes;
+                    r[u] = pp < p1 ? ld_raw<T>(xb + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < kU2; ++u) {
+                    const int pp = p + u * m.lanes;
+                    if (pp >= p1) break;
+                    s_x[(size_t)(pp - p0) * m.V + m.v] = r[u];
+                    float v[kVec];
+                    unpack<T>(r[u], v);
+#pragma unroll
+                    for (int i = 0; i < kVec; ++i) { a[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+                }
+            }
+        }
+        block_channel_sum<kVec>(m, a, s_red, s_a, C);
+        block_channel_sum<kVec>(m, q, s_red, s_b, C);
+    }
+    cluster_channel_total(s_a, s_b, s_ta, s_tb, C, cs);
+    const int cpg = C / P.G;
+    const float cnt = (float)cpg * (float)HW;
+    for (int g = threadIdx.x; g < P.G; g += blockDim.x) {
+        float su = 0.f, sq = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { su += s_ta[c]; sq += s_tb[c]; }
+        if (blockIdx.x == 0) {
+            P.sums[((int64_t)n * P.G + g) * 2 + 0] = su;
+            P.sums[((int64_t)n * P.G + g) * 2 + 1] = sq;
+        }
+        const float mean = su / cnt;
+        const float rstd = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + P.eps);
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float sc = rstd * P.gamma[c];
+            s_a[c] = sc;
+            s_b[c] = P.beta[c] - mean * sc;
+        }
+    }
+    __syncthreads();
+    if (!m.active) return;
+    float sc[kVec], sh[kVec];
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) { sc[i] = s_a[cbase + i]; sh[i] = s_b[cbase + i]; }
+    T* yb = reinterpret_cast<T*>(P.y.ptr) + cbase;
+    for (int p = p0 + m.lane; p < p1; p += m.lanes) {
+        float v[kVec];
+        unpack<T>(s_x[(size_t)(p - p0) * m.V + m.v], v);       // this thread's own entries: no barrier needed
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const float t = fmaf(v[i], sc[i], sh[i]);
+            v[i] = P.silu ? silu_f(t) : t;
+        }
+        store_vec<T>(yb + pix_off(P.y, n, p, P.W), v);
+    }
+}
+
 // Single-pass backward for images too large for the register-held kernel above: the CTA's (x, dy) slab is parked in
 // SHARED memory (bf16 32x32x64: 2 x 32 KB per CTA of a 4-CTA cluster), so the kernel needs ~64 registers and several
 // CTAs share an SM.  One read of (x, dy), one write of dx; the two-pass pair it replaces read both tensors twice and ran
@@ -1445,6 +1528,29 @@ int dmu_gn_forward(const dmu_gn_params* p, dmu_stream_t stream) {
     const int64_t bytes = (int64_t)p->N * p->H * p->W * p->C * (p->x.dtype == DMU_BF16 ? 2 : 4);
     const int cs = bytes <= (12ll << 20) ? gn_fused_cluster(p->H * p->W, p->C, vec) : 0;
     if (cs == 0) {
+        // large tensors: shared-memory single pass when an image fits the shared memory of a cluster of <= 8 CTAs
+        static const int fwd_smem = [] { const char* e = getenv("DMU_GN_FWD_SMEM"); return e ? atoi(e) : 1; }();     // A/B aid
+        const int HW = p->H * p->W, V = p->C / vec;
+        // (measured, scripts/gn_time.py: 16.8 MB 10.7 vs 14.3 us, 33.6 MB 22.5 vs 26.3 us; from 67 MB the two streaming passes win)
+        if (fwd_smem && bytes <= (48ll << 20) && 256 / V >= 1) {
+            for (int c2 = 1; c2 <= 8 && c2 <= HW; c2 <<= 1) {
+                const int per = (HW + c2 - 1) / c2;
+                const size_t smem = (size_t)per * V * 16 + (size_t)4 * p->C * 4;
+                if (smem > 70 * 1024) continue;
+                cudaError_t e;
+                if (p->x.dtype == DMU_BF16) {
+                    static bool a1 = (cudaFuncSetAttribute(gn_fwd_smem_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024), true);
+                    (void)a1;
+                    e = launch_pdl(gn_fwd_smem_kernel<__nv_bfloat16>, dim3(c2, p->N), dim3(256), smem, as_stream(stream), dim3(c2, 1, 1), *p, per);
+                } else {
+                    static bool a2 = (cudaFuncSetAttribute(gn_fwd_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024), true);
+                    (void)a2;
+                    e = launch_pdl(gn_fwd_smem_kernel<float>, dim3(c2, p->N), dim3(256), smem, as_stream(stream), dim3(c2, 1, 1), *p, per);
+                }
+                if (e != cudaSuccess) return fail("dmu_gn_forward: cluster launch failed: %s", cudaGetErrorString(e));
+                return check_launch("dmu_gn_forward");
+            }
+        }
         if (int e = dmu_gn_stats(p, stream)) return e;
         return dmu_gn_apply(p, stream);
     }
