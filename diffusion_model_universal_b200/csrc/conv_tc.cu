@@ -485,7 +485,21 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         THmax = (p->Ho + st - 1) / st;
         TWmax = (p->Wo + st - 1) / st;
     }
-    const Box b = make_box(p->N, THmax, TWmax, 128);
+    // Tile shape.  A sub-wave layer (the <= 8x8 stages) is bound by ONE CTA's serial k-loop, which ingests ~64 B/clk from L2:
+    // 16 KB of activations + 16 KB of filters per k-block at 128 pixels x 128 channels.  While the CTAs still fit one wave
+    // the tile is therefore halved along channels (NT = 64) and then along pixels (a 64-pixel TMA box; the MMA still reads 128
+    // rows, the upper 64 accumulator rows are never stored): 4x the CTAs, half the bytes and k-loop time per CTA.
+    int NT = (p->Cj % 128 == 0) ? 128 : 64;
+    int pix = 128;
+    {
+        static const int small_tiles = [] { const char* e = getenv("DMU_SMALL_TILES"); return e ? atoi(e) : 1; }();    // A/B aid
+        const Box b0 = make_box(p->N, THmax, TWmax, 128);
+        int ctas = b0.tiles_n * b0.tiles_h * b0.tiles_w * (p->Cj / NT) * nph;
+        if (small_tiles && NT == 128 && ctas * 2 <= sm_count()) { NT = 64; ctas *= 2; }
+        if (small_tiles && ctas * 2 <= sm_count() && (int64_t)p->N * THmax * TWmax > 64) { pix = 64; ctas *= 2; }
+        if (small_tiles >= 2 && pix == 64 && ctas * 2 <= sm_count() && (int64_t)p->N * THmax * TWmax > 32) pix = 32;
+    }
+    const Box b = make_box(p->N, THmax, TWmax, pix);
     if (p->gather == 0) {
         A.os = 1;
         A.phases[0] = Phase{0, p->R * p->S, 0, 0, p->Ho, p->Wo};
@@ -516,7 +530,6 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         const uint32_t box[4] = {64, (uint32_t)b.BW, (uint32_t)b.BH, (uint32_t)b.BN};
         if (int rc = make_map_bf16(&maps.a[0], p->x.ptr, 4, dims, str, box, "dmu_conv2d/tc")) return rc;
     }
-    const int NT = (p->Cj % 128 == 0) ? 128 : 64;
     {
         const uint64_t dims[2] = {(uint64_t)p->R * p->S * p->Ck, (uint64_t)p->Cj};
         const uint64_t str[2] = {1, (uint64_t)p->w_sn};
