@@ -261,7 +261,51 @@ __global__ void __launch_bounds__(128) linear_splitk_kernel(dmu_conv_params P, i
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bool w_kcontig = P.w_sk == 1;
+    // fp32 operands with 16-byte aligned rows: every thread issues its 2 + 4 float4 loads of a k-step back to back (the
+    // element-wise loader below is one branch + one dependent load per element: ~30 us for the 128 x 3136 x 256 products of
+    // the time-embedding backward, which sit alone at the tail of the step)
+    const bool vec = P.x.dtype == DMU_F32 && P.w_dtype == DMU_F32 && P.x.sc == 1 && P.x.sn % 4 == 0 && (k_lo % 4) == 0 &&
+                     (reinterpret_cast<uintptr_t>(P.x.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(P.w) & 15) == 0 &&
+                     (w_kcontig ? P.w_sn % 4 == 0 : (P.w_sn == 1 && P.w_sk % 4 == 0 && j_base + LN <= P.Cj));
     for (int k0 = k_lo; k0 < k_hi; k0 += LK) {
+        if (vec && k0 + LK <= k_hi) {
+            const float* xp = reinterpret_cast<const float*>(P.x.ptr);
+            const float* wp = reinterpret_cast<const float*>(P.w);
+            float4 ra[2], rb[4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i4 = tid + 128 * u, mm = i4 >> 3, k4 = i4 & 7;
+                const int m = m_base + mm;
+                ra[u] = m < M ? __ldg(reinterpret_cast<const float4*>(xp + (int64_t)m * P.x.sn + k0 + 4 * k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i4 = tid + 128 * u;
+                if (w_kcontig) {
+                    const int jj = i4 >> 3, k4 = i4 & 7, j = j_base + jj;
+                    rb[u] = j < P.Cj ? __ldg(reinterpret_cast<const float4*>(wp + (int64_t)j * P.w_sn + k0 + 4 * k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    const int kk = i4 >> 4, j4 = i4 & 15;
+                    rb[u] = __ldg(reinterpret_cast<const float4*>(wp + (int64_t)(k0 + kk) * P.w_sk + j_base + 4 * j4));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i4 = tid + 128 * u, mm = i4 >> 3, k4 = i4 & 7;
+                As[4 * k4 + 0][mm] = ra[u].x; As[4 * k4 + 1][mm] = ra[u].y; As[4 * k4 + 2][mm] = ra[u].z; As[4 * k4 + 3][mm] = ra[u].w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i4 = tid + 128 * u;
+                if (w_kcontig) {
+                    const int jj = i4 >> 3, k4 = i4 & 7;
+                    Bs[4 * k4 + 0][jj] = rb[u].x; Bs[4 * k4 + 1][jj] = rb[u].y; Bs[4 * k4 + 2][jj] = rb[u].z; Bs[4 * k4 + 3][jj] = rb[u].w;
+                } else {
+                    const int kk = i4 >> 4, j4 = i4 & 15;
+                    *reinterpret_cast<float4*>(&Bs[kk][4 * j4]) = rb[u];
+                }
+            }
+        } else {
         // A tile: LM rows x LK k (k fastest across threads: x rows are k-contiguous)
         for (int i = tid; i < LM * LK; i += 128) {
             const int kk = i % LK, mm = i / LK;
@@ -273,6 +317,7 @@ __global__ void __launch_bounds__(128) linear_splitk_kernel(dmu_conv_params P, i
             const int kk = w_kcontig ? i % LK : i / LN, jj = w_kcontig ? i / LK : i % LN;
             const int j = j_base + jj, k = k0 + kk;
             Bs[kk][jj] = (j < P.Cj && k < k_hi) ? ld_as_float(P.w, (int64_t)j * P.w_sn + (int64_t)k * P.w_sk, P.w_dtype) : 0.f;
+        }
         }
         __syncthreads();
 #pragma unroll
@@ -340,6 +385,20 @@ __global__ void __launch_bounds__(256) wgrad_kernel(dmu_wgrad_params P, int pix_
 
     for (int p0 = pix0; p0 < pix1; p0 += WK) {
         // ---- load P tile [WK][BMw]
+        if (TM == 4 && P.p.sc == 1 && P.p.dtype == DMU_F32 && a_base + BMw <= P.Ca && P.p.sw % 4 == 0 && P.p.sh % 4 == 0 && P.p.sn % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(P.p.ptr) & 15) == 0) {
+            // one float4 per thread: pixel tid >> 4, channels (tid & 15) * 4 (the element-wise loader below costs three integer
+            // divisions, a dtype branch and a dependent load per element)
+            const int k = tid >> 4, a4 = (tid & 15) * 4;
+            const int pix = p0 + k;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pix < pix1) {
+                const int wo = pix % P.Wp, ho = (pix / P.Wp) % P.Hp, n = pix / (P.Wp * P.Hp);
+                v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.p.ptr) + (int64_t)n * P.p.sn + (int64_t)ho * P.p.sh +
+                                                          (int64_t)wo * P.p.sw + a_base + a4));
+            }
+            *reinterpret_cast<float4*>(&Ps[k][a4]) = v;
+        } else
         for (int i = tid; i < WK * BMw; i += 256) {
             const int k = i / BMw, a = i % BMw;
             const int pix = p0 + k;

@@ -493,11 +493,13 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     int pix = 128;
     {
         static const int small_tiles = [] { const char* e = getenv("DMU_SMALL_TILES"); return e ? atoi(e) : 1; }();    // A/B aid
+        static const int limit_pct = [] { const char* e = getenv("DMU_SMALL_TILES_LIMIT"); return e ? atoi(e) : 100; }();
+        const int cap = sm_count() * limit_pct / 100;
         const Box b0 = make_box(p->N, THmax, TWmax, 128);
         int ctas = b0.tiles_n * b0.tiles_h * b0.tiles_w * (p->Cj / NT) * nph;
-        if (small_tiles && NT == 128 && ctas * 2 <= sm_count()) { NT = 64; ctas *= 2; }
-        if (small_tiles && ctas * 2 <= sm_count() && (int64_t)p->N * THmax * TWmax > 64) { pix = 64; ctas *= 2; }
-        if (small_tiles >= 2 && pix == 64 && ctas * 2 <= sm_count() && (int64_t)p->N * THmax * TWmax > 32) pix = 32;
+        if (small_tiles && NT == 128 && ctas * 2 <= cap) { NT = 64; ctas *= 2; }
+        if (small_tiles && ctas * 2 <= cap && (int64_t)p->N * THmax * TWmax > 64) { pix = 64; ctas *= 2; }
+        if (small_tiles >= 2 && pix == 64 && ctas * 2 <= cap && (int64_t)p->N * THmax * TWmax > 32) pix = 32;
     }
     const Box b = make_box(p->N, THmax, TWmax, pix);
     if (p->gather == 0) {
