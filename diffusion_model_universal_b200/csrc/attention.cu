@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(256) attn_fwd_split_kernel(dmu_attn_params P) 
     if (P.lse && part == 0) P.lse[((int64_t)n * P.heads + h) * S + i] = mx + logf(l);
 }
 
-template <typename T, int D>
+// Backward, one CTA per image.  KS adjacent lanes share one (head, row): in phase 1 they split the keys of query i (dQ_i), in
+// phase 2 the queries of key j (dK_j, dV_j); partial vectors meet through warp shuffles.  With KS = 1 the CTA has only
+// S * heads threads (64 at 4x4) walking 2 x S x 7D dependent FMAs each; KS = 4 fills the CTA and cuts the chain fourfold.
+template <typename T, int D, int KS>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(dmu_attn_params P) {
     extern __shared__ float sm[];
     const int n = blockIdx.x, S = P.S, C = P.C, H = P.heads;
@@ -129,10 +132,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(dmu_attn_params P) {
     const T* dO = reinterpret_cast<const T*>(P.d_o) + (int64_t)n * S * P.do_pitch;
     stage_rows<T>(qkv, P.qkv_pitch, S, 3 * C, s_qkv);
     stage_rows<T>(dO, P.do_pitch, S, C, s_do);
-    const int h = threadIdx.x / S, i = threadIdx.x % S;
+    const int part = threadIdx.x % KS, hi = threadIdx.x / KS;
+    const int h = hi / S, i = hi % S;
     const bool act = h < H;
+    const int hh = act ? h : 0;        // idle lanes run the loops on head 0 (they take part in the shuffles) and store nothing
     const float scale = rsqrtf((float)D);
-    if (act) {
+    if (act && part == 0) {
         const T* orow = reinterpret_cast<const T*>(P.o) + ((int64_t)n * S + i) * P.o_pitch + h * D;
         const T* drow = dO + (int64_t)i * P.do_pitch + h * D;
         float dl = 0.f;
@@ -142,17 +147,16 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(dmu_attn_params P) {
         s_lse[h * S + i] = P.lse[((int64_t)n * H + h) * S + i];
     }
     __syncthreads();
-    if (!act) return;
     T* dq_row = reinterpret_cast<T*>(P.dqkv) + ((int64_t)n * S + i) * P.dqkv_pitch;
-    // phase 1: this thread is query i -> dQ_i
+    // phase 1: this lane group is query i -> dQ_i
     {
         float q[D], dov[D], dq[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) { q[d] = s_qkv[i * 3 * C + h * D + d]; dov[d] = s_do[i * C + h * D + d]; dq[d] = 0.f; }
-        const float lse = s_lse[h * S + i], dl = s_delta[h * S + i];
-        for (int j = 0; j < S; ++j) {
-            const float* kj = s_qkv + j * 3 * C + C + h * D;
-            const float* vj = s_qkv + j * 3 * C + 2 * C + h * D;
+        for (int d = 0; d < D; ++d) { q[d] = s_qkv[i * 3 * C + hh * D + d]; dov[d] = s_do[i * C + hh * D + d]; dq[d] = 0.f; }
+        const float lse = s_lse[hh * S + i], dl = s_delta[hh * S + i];
+        for (int j = part; j < S; j += KS) {
+            const float* kj = s_qkv + j * 3 * C + C + hh * D;
+            const float* vj = s_qkv + j * 3 * C + 2 * C + hh * D;
             float s = 0.f, dp = 0.f;
 #pragma unroll
             for (int d = 0; d < D; ++d) { s = fmaf(q[d], kj[d], s); dp = fmaf(dov[d], vj[d], dp); }
@@ -162,29 +166,47 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(dmu_attn_params P) {
             for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, kj[d], dq[d]);
         }
 #pragma unroll
-        for (int d = 0; d < D; ++d) dq_row[h * D + d] = Elem<T>::from_f(dq[d]);
+        for (int off = 1; off < KS; off <<= 1)
+#pragma unroll
+            for (int d = 0; d < D; ++d) dq[d] += __shfl_xor_sync(0xffffffffu, dq[d], off);
+        if (act) {
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                if (d % KS == part) dq_row[h * D + d] = Elem<T>::from_f(dq[d]);
+        }
     }
-    // phase 2: this thread is key/value j = i -> dK_j, dV_j
+    // phase 2: this lane group is key/value j = i -> dK_j, dV_j
     {
         const int j = i;
         float k[D], v[D], dk[D], dv[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) { k[d] = s_qkv[j * 3 * C + C + h * D + d]; v[d] = s_qkv[j * 3 * C + 2 * C + h * D + d]; dk[d] = 0.f; dv[d] = 0.f; }
-        for (int ii = 0; ii < S; ++ii) {
-            const float* qi = s_qkv + ii * 3 * C + h * D;
-            const float* doi = s_do + ii * C + h * D;
+        for (int d = 0; d < D; ++d) { k[d] = s_qkv[j * 3 * C + C + hh * D + d]; v[d] = s_qkv[j * 3 * C + 2 * C + hh * D + d]; dk[d] = 0.f; dv[d] = 0.f; }
+        for (int ii = part; ii < S; ii += KS) {
+            const float* qi = s_qkv + ii * 3 * C + hh * D;
+            const float* doi = s_do + ii * C + hh * D;
             float s = 0.f, dp = 0.f;
 #pragma unroll
             for (int d = 0; d < D; ++d) { s = fmaf(qi[d], k[d], s); dp = fmaf(doi[d], v[d], dp); }
-            const float p = expf(s * scale - s_lse[h * S + ii]);
-            const float ds = p * (dp - s_delta[h * S + ii]) * scale;
+            const float p = expf(s * scale - s_lse[hh * S + ii]);
+            const float ds = p * (dp - s_delta[hh * S + ii]) * scale;
 #pragma unroll
             for (int d = 0; d < D; ++d) { dv[d] = fmaf(p, doi[d], dv[d]); dk[d] = fmaf(ds, qi[d], dk[d]); }
         }
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            dq_row[C + h * D + d] = Elem<T>::from_f(dk[d]);
-            dq_row[2 * C + h * D + d] = Elem<T>::from_f(dv[d]);
+        for (int off = 1; off < KS; off <<= 1)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                dk[d] += __shfl_xor_sync(0xffffffffu, dk[d], off);
+                dv[d] += __shfl_xor_sync(0xffffffffu, dv[d], off);
+            }
+        if (act) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                if (d % KS == part) {
+                    dq_row[C + h * D + d] = Elem<T>::from_f(dk[d]);
+                    dq_row[2 * C + h * D + d] = Elem<T>::from_f(dv[d]);
+                }
+            }
         }
     }
 }
@@ -214,11 +236,12 @@ static int attn_launch(const dmu_attn_params* p, cudaStream_t s, bool bwd) {
 #define ATTN_CASE(DD)                                                                                               \
     case DD: {                                                                                                      \
         auto kf = attn_fwd_kernel<T, DD>;                                                                           \
-        auto kb = attn_bwd_kernel<T, DD>;                                                                           \
+        const bool split4 = bwd && p->S * p->heads * 4 <= 256;                                                      \
+        auto kb = split4 ? attn_bwd_kernel<T, DD, 4> : attn_bwd_kernel<T, DD, 1>;                                   \
         if (smem > 48 * 1024) {                                                                                     \
             cudaFuncSetAttribute(bwd ? (const void*)kb : (const void*)kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         }                                                                                                           \
-        if (bwd) kb<<<p->N, threads, smem, s>>>(*p);                                                                \
+        if (bwd) kb<<<p->N, split4 ? ((p->S * p->heads * 4 + 31) / 32) * 32 : threads, smem, s>>>(*p);              \
         else if (p->S * 4 <= 256 && DD >= 8) {                                                                      \
             const int th = ((p->S * 4 + 31) / 32) * 32;                                                             \
             attn_fwd_split_kernel<T, DD, 4><<<dim3(p->N, p->heads), th, (size_t)p->S * (3 * DD + 4) * sizeof(float), s>>>(*p); \

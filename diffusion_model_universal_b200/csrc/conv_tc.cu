@@ -140,6 +140,7 @@ struct ConvArgs {
     float* ws;
     long long* dbg;   // development aid (dmu_debug_set_buffer): per-CTA clock64 stamps of the pipeline phases
     int prefetch;     // epilogue operands fetched while the pipeline runs (DMU_EPI_PREFETCH=0 turns it off: A/B aid)
+    int prefetch_w;   // filter boxes prefetched into L2 before griddepcontrol.wait (DMU_W_PREFETCH=0: A/B aid)
 };
 
 constexpr int kBtImgs = 8;
@@ -202,6 +203,19 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
+    if (P.prefetch_w && warp == 0 && elect_one()) {
+        // the filter boxes of this CTA's first k-blocks go to L2 while the previous kernel still runs (they are parameters;
+        // after a forward + backward sweep over the 640 MB activation arena they would otherwise come from HBM)
+        const int chunks_ = P.Ck >> 6;
+        int n = 0;
+        for (int ti = 0; ti < ph.ntaps && n < kStages; ++ti) {
+            const Tap t = P.taps[ph.tap0 + ti];
+            const int h = th0 + t.dh, w = tw0 + t.dw;
+            if (!(h < P.map_h[t.map] && h + P.BH > 0 && w < P.map_w[t.map] && w + P.BW > 0)) continue;
+            for (int c = 0; c < chunks_ && n < kStages; ++c, ++n) tma_prefetch_l2_2d(&maps.b, t.wk + c * 64, j0);
+        }
+    }
+    __syncwarp();
     pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
     if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
@@ -548,6 +562,9 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         static int pf = -1;
         if (pf < 0) { const char* e = getenv("DMU_EPI_PREFETCH"); pf = (e && e[0] == '0') ? 0 : 1; }
         A.prefetch = pf;
+        static int pw = -1;
+        if (pw < 0) { const char* e = getenv("DMU_W_PREFETCH"); pw = (e && e[0] == '1') ? 1 : 0; }   // measured: no gain, off by default
+        A.prefetch_w = pw;
     }
     // split-K for layers with few output tiles and a long contraction (the <= 4x4 stages: K up to 4608, 1-16 tiles):
     // the splits of one tile are a thread-block cluster along z (co-scheduled by hardware, so the in-kernel barrier is safe)
