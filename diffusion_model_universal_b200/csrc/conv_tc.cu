@@ -141,6 +141,7 @@ struct ConvArgs {
     long long* dbg;   // development aid (dmu_debug_set_buffer): per-CTA clock64 stamps of the pipeline phases
     int prefetch;     // epilogue operands fetched while the pipeline runs (DMU_EPI_PREFETCH=0 turns it off: A/B aid)
     int prefetch_w;   // filter boxes prefetched into L2 before griddepcontrol.wait (DMU_W_PREFETCH=0: A/B aid)
+    int stages;       // ring depth actually used (<= ConvCfg::kStages): sub-wave launches leave room for a weight-gradient CTA
 };
 
 constexpr int kBtImgs = 8;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
                 }
                 __syncwarp();
                 ++it;
-                if (++st == kStages) { st = 0; par ^= 1; }
+                if (++st == P.stages) { st = 0; par ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
                 }
                 __syncwarp();
                 ++it;
-                if (++st == kStages) { st = 0; par ^= 1; }
+                if (++st == P.stages) { st = 0; par ^= 1; }
             }
         }
         if (dbg && lane == 0) { dbg[3] = clock64(); dbg[6] = it; }   // last MMA issued
@@ -606,11 +607,22 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     }
     const dim3 cluster(1, 1, (unsigned)A.splits);
     const bool deep = (int)(grid.x * grid.y * grid.z) <= sm_count();
+    // Ring depth of the sub-wave (1 CTA per SM) variants: DMU_CONV_STAGES caps it so that a CTA of the backward's other lane
+    // (a weight gradient, DMU_WGRAD_STAGES) can share the SM instead of the chain waiting for one to retire.
+    static const int deep_cap = [] { const char* e = getenv("DMU_CONV_STAGES"); return e ? atoi(e) : 4; }();
+    auto stages_of = [&](int full) { int v = deep ? (deep_cap < full ? deep_cap : full) : full; return v < 2 ? 2 : v; };
     cudaError_t e;
-    if (NT == 64) e = deep ? launch_pdl(conv_tc_kernel<64, 1>, grid, dim3(128), ConvCfg<64, 1>::kSmem, stream, cluster, maps, A)
-                           : launch_pdl(conv_tc_kernel<64, 0>, grid, dim3(128), ConvCfg<64, 0>::kSmem, stream, cluster, maps, A);
-    else e = deep ? launch_pdl(conv_tc_kernel<128, 1>, grid, dim3(128), ConvCfg<128, 1>::kSmem, stream, cluster, maps, A)
-                  : launch_pdl(conv_tc_kernel<128, 0>, grid, dim3(128), ConvCfg<128, 0>::kSmem, stream, cluster, maps, A);
+    if (NT == 64) {
+        A.stages = stages_of(deep ? ConvCfg<64, 1>::kStages : ConvCfg<64, 0>::kStages);
+        const size_t smem = (size_t)A.stages * ConvCfg<64, 1>::kStageBytes + 1024;
+        e = deep ? launch_pdl(conv_tc_kernel<64, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
+                 : launch_pdl(conv_tc_kernel<64, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
+    } else {
+        A.stages = stages_of(deep ? ConvCfg<128, 1>::kStages : ConvCfg<128, 0>::kStages);
+        const size_t smem = (size_t)A.stages * ConvCfg<128, 1>::kStageBytes + 1024;
+        e = deep ? launch_pdl(conv_tc_kernel<128, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
+                 : launch_pdl(conv_tc_kernel<128, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
+    }
     if (e != cudaSuccess) return fail("dmu_conv2d/tc: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/tc");
 }
@@ -622,6 +634,7 @@ struct WgradArgs {
     int N, Hp, Wp, Ca, Cb, RS;
     int BN, BH, BW, tiles_h, tiles_w, tiles_total, tiles_per_split;
     int units;                    // RS * Cb/64 (tap, 64-channel chunk) row blocks; two per CTA
+    int stages;                   // ring depth actually used (<= WgradCfg::kStages)
     float* dw; int64_t dw_sa, dw_sb, dw_st;
 };
 
@@ -696,7 +709,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ M
                     tma_load_4d(sa + Cfg::kABytes + q * Cfg::kBlk, &maps.b, &full_bar[st], a0 + q * 64, tw0, th0, n0);
             }
             __syncwarp();
-            if (++st == kStages) { st = 0; par ^= 1; }
+            if (++st == P.stages) { st = 0; par ^= 1; }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);   // both operands MN-major (channels contiguous, K = pixels)
@@ -719,7 +732,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ M
             }
             __syncwarp();
             ++it;
-            if (++st == kStages) { st = 0; par ^= 1; }
+            if (++st == P.stages) { st = 0; par ^= 1; }
         }
         if (elect_one()) {
             s_issued = (uint32_t)it;
@@ -806,8 +819,14 @@ static int wgrad_launch(const dmu_wgrad_params* p, cudaStream_t stream) {
         cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<128>::kSmem);
         attr_done = true;
     }
-    cudaError_t e = NT == 64 ? launch_pdl(wgrad_tc_kernel<64>, grid, dim3(128), WgradCfg<64>::kSmem, stream, dim3(1, 1, 1), maps, A)
-                             : launch_pdl(wgrad_tc_kernel<128>, grid, dim3(128), WgradCfg<128>::kSmem, stream, dim3(1, 1, 1), maps, A);
+    // Measured (B=128, 32x32 step): three stages (72-96 KB) instead of 8 / 6 (193 KB) cost the weight gradients nothing - they are
+    // L2-bound, not latency-bound - and let a CTA of the dgrad / GroupNorm chain share the SM: backward 2.18 -> 2.03 ms.
+    static const int wg_cap = [] { const char* e = getenv("DMU_WGRAD_STAGES"); return e ? atoi(e) : 3; }();
+    const int full = NT == 64 ? WgradCfg<64>::kStages : WgradCfg<128>::kStages;
+    A.stages = wg_cap < full ? (wg_cap < 2 ? 2 : wg_cap) : full;
+    const size_t smem = (size_t)A.stages * (NT == 64 ? WgradCfg<64>::kStageBytes : WgradCfg<128>::kStageBytes) + 1024;
+    cudaError_t e = NT == 64 ? launch_pdl(wgrad_tc_kernel<64>, grid, dim3(128), smem, stream, dim3(1, 1, 1), maps, A)
+                             : launch_pdl(wgrad_tc_kernel<128>, grid, dim3(128), smem, stream, dim3(1, 1, 1), maps, A);
     if (e != cudaSuccess) return fail("dmu_conv2d_wgrad/tc: launch failed: %s", cudaGetErrorString(e));
     if (int rc = check_launch("dmu_conv2d_wgrad/tc")) return rc;
     if (p->dbias) return dmu_colsum(&p->p, p->N, p->Hp, p->Wp, p->Ca, nullptr, 0, p->dbias, 1.0f, (dmu_stream_t)stream);
