@@ -1713,7 +1713,8 @@ int dmu_sinusoidal_embedding(const void* t, int32_t t_is_float, float* emb, int6
 
 int dmu_repack_weights(const dmu_repack_desc* descs_device, int32_t n_desc, int64_t max_numel, dmu_stream_t stream) {
     DMU_REQUIRE(descs_device && n_desc > 0 && max_numel > 0, "dmu_repack_weights: bad arguments");
-    int gx = (int)((max_numel + 2047) / 2048); if (gx > 64) gx = 64;
+    static const int gx_cap = [] { const char* e = getenv("DMU_REPACK_GX"); return e ? atoi(e) : 64; }();
+    int gx = (int)((max_numel + 2047) / 2048); if (gx > gx_cap) gx = gx_cap;
     repack_kernel<<<dim3(gx, n_desc), 256, 0, as_stream(stream)>>>(descs_device);
     return check_launch("dmu_repack_weights");
 }

@@ -681,6 +681,7 @@ class _PlanBuilder:
         self.gn_pg_split = []   # len(gn_pg) at each split marker of the backward
         self.side_lane = True   # weight-gradient / column-sum launches of the backward go to the graph's second branch
         self.cs_pending = []    # column sums (bias gradients, time-projection sums) batched into one launch per backward part
+        self.temb_join_pending = False
 
     # ---- allocation helpers
     def act(self, H, W, Cc, want_grad=True) -> Buf:
@@ -740,6 +741,9 @@ class _PlanBuilder:
                        self.plan.ws.data_ptr() if self.plan.ws is not None else None, self.plan.ws.numel() if self.plan.ws is not None else 0,
                        gn_coef, gn_silu, 0, a_out if a_out is not None else _null_t4())
         if emit:
+            if temb is not None and self.temb_join_pending and lst is self.plan.fwd:
+                lst.append((None, ()))       # the time-embedding lane joins before the first launch that reads its projections
+                self.temb_join_pending = False
             lst.append((self.lib.dmu_conv2d, (C.byref(p),)))
             self.plan.keep.append(p)
         return p
@@ -978,6 +982,10 @@ class _PlanBuilder:
         first = e.res_block_prefixes()[0]
         self.linear(plan.fwd, _rows_t4(temb, T4), _rows_t4(self.tproj, self.tp_total), N, T4, self.tp_total,
                     e.paddr(first + "time_mlp.weight"), e.paddr(first + "time_mlp.bias"))
+        # Everything emitted so far (embedding MLP + the 22-way projection: ~5 small launches) only feeds the `+ temb` of the
+        # first ResBlock's conv1: it runs on the side lane of the forward graph, next to the stem conv and the first GroupNorm.
+        plan.fwd[:] = [op + (1,) for op in plan.fwd]
+        self.temb_join_pending = True
         # per-image channel sums of dh (time-projection gradient): accumulated with atomics -> lives in the zeroed region
         self.dtproj = self.red.take(N * self.tp_total * 4, 16) if self.train else 0
 
