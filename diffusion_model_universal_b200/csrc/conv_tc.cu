@@ -142,6 +142,9 @@ struct ConvArgs {
     int prefetch;     // epilogue operands fetched while the pipeline runs (DMU_EPI_PREFETCH=0 turns it off: A/B aid)
     int prefetch_w;   // filter boxes prefetched into L2 before griddepcontrol.wait (DMU_W_PREFETCH=0: A/B aid)
     int stages;       // ring depth actually used (<= ConvCfg::kStages): sub-wave launches leave room for a weight-gradient CTA
+    int stage_bytes, a_off;   // stage stride and offset of the filter tile: a 64-pixel box only reserves 8 KB for the pixels
+    int kps, kb_bytes;   // k-blocks per ring stage and bytes of one k-block (pixels + filters)
+    int m64;             // 64-pixel tile computed by M = 64 MMAs
 };
 
 constexpr int kBtImgs = 8;
@@ -223,7 +226,9 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     // Epilogue operands are fetched NOW, while the pipeline below runs: this thread's residual row goes to registers and
     // (bias + temb[n]) of the tile's images to shared memory, so that after the last MMA only TMEM loads, adds and the
     // stores remain (they used to be four dependent rounds of L2 loads, ~2 us of a ~8 us sub-wave launch).
-    const int row = threadIdx.x;
+    // M = 128: accumulator row r sits in TMEM lane r.  M = 64 (the 64-pixel tiles): row r sits in lane (r / 16) * 32 + r % 16
+    // (scripts/probes/umma_m64_layout.cu), i.e. lanes 0-15 of every warp's quadrant hold 16 consecutive rows.
+    const int row = P.m64 ? (lane < 16 ? warp * 16 + lane : 128) : (int)threadIdx.x;
     const int wl = row % P.BW, hl = (row / P.BW) % P.BH, nl = row / (P.BW * P.BH);
     const int n = n0 + nl, th = th0 + hl, tw = tw0 + wl;
     const int ho = th * P.os + ph.oph, wo = tw * P.os + ph.opw;
@@ -254,61 +259,86 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     const int kb_per = (kb_total + P.splits - 1) / P.splits;
     const int kb_lo = split * kb_per, kb_hi = min(kb_total, kb_lo + kb_per);
 
-    // Both roles run as whole, converged warps; the asynchronous instructions sit under elect_one() (see tc_common.cuh).
+    // Each role is ONE elected lane of a converged warp that runs its whole loop inside a single elect_one() region (see
+    // tc_common.cuh; measured with scripts/probes/umma_rate.cu: re-entering the region, a whole-warp barrier wait and a
+    // __syncwarp per k-block cost ~105 clk per MMA against 48-65 for the loop below - these k-loops are issue-bound).
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
-        const uint32_t a_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
-        int it = 0, st = 0, par = 1;
-        for (int ti = 0; ti < ph.ntaps; ++ti) {
-            const Tap t = P.taps[ph.tap0 + ti];
-            if (!tap_live(t)) continue;
-            for (int c = 0; c < chunks; ++c) {
-                const int kb = ti * chunks + c;
-                if (kb < kb_lo || kb >= kb_hi) continue;
-                mbar_wait(&empty_bar[st], par);
-                if (elect_one()) {
-                    uint8_t* sa = smem + st * Cfg::kStageBytes;
-                    mbar_arrive_expect_tx(&full_bar[st], a_bytes + Cfg::kBBytes);
+        // A ring stage holds P.kps consecutive k-blocks (sub-wave launches: 2): one barrier wait and one commit per stage is
+        // what the issuer pays, and its loop is issue-bound (~105 clk per MMA with one k-block per stage, see above).
+        if (elect_one()) {
+            const uint32_t a_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
+            int st = 0, par = 1, slot = 0;
+            uint32_t tx = 0;
+            for (int ti = 0; ti < ph.ntaps; ++ti) {
+                const Tap t = P.taps[ph.tap0 + ti];
+                if (!tap_live(t)) continue;
+                for (int c = 0; c < chunks; ++c) {
+                    const int kb = ti * chunks + c;
+                    if (kb < kb_lo || kb >= kb_hi) continue;
+                    if (slot == 0) mbar_wait(&empty_bar[st], par);
+                    uint8_t* sa = smem + st * P.stage_bytes + slot * P.kb_bytes;
                     tma_load_4d(sa, &maps.a[t.map], &full_bar[st], c * 64, tw0 + t.dw, th0 + t.dh, n0);
-                    tma_load_2d(sa + Cfg::kABytes, &maps.b, &full_bar[st], t.wk + c * 64, j0);
+                    tma_load_2d(sa + P.a_off, &maps.b, &full_bar[st], t.wk + c * 64, j0);
+                    tx += a_bytes + Cfg::kBBytes;
+                    if (++slot == P.kps) {
+                        // posted after the loads: the barrier's pending arrival keeps the phase open, the transaction count may
+                        // run negative in between
+                        mbar_arrive_expect_tx(&full_bar[st], tx);
+                        slot = 0; tx = 0;
+                        if (++st == P.stages) { st = 0; par ^= 1; }
+                    }
                 }
-                __syncwarp();
-                ++it;
-                if (++st == P.stages) { st = 0; par ^= 1; }
             }
+            if (slot) mbar_arrive_expect_tx(&full_bar[st], tx);
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
-        int it = 0, st = 0, par = 0;
-        for (int ti = 0; ti < ph.ntaps; ++ti) {
-            const Tap t = P.taps[ph.tap0 + ti];
-            if (!tap_live(t)) continue;
-            for (int c = 0; c < chunks; ++c) {
-                const int kb = ti * chunks + c;
-                if (kb < kb_lo || kb >= kb_hi) continue;
+        if (elect_one()) {
+            // a 64-pixel tile runs as an M = 64 MMA: 32 instead of 48 clk at N = 64 (the SS-mode MMA is paced by its operand
+            // reads from shared memory, (M + N) x 32 B at 128 B/clk), and no read of rows the TMA box never wrote
+            const uint32_t idesc = P.m64 ? umma_idesc_bf16(64, NT, 0, 0) : umma_idesc_bf16(128, NT, 0, 0);
+            const uint32_t smem0 = smem_u32(smem);
+            int nkb = 0;                                  // live k-blocks of this CTA
+            for (int ti = 0; ti < ph.ntaps; ++ti) {
+                if (!tap_live(P.taps[ph.tap0 + ti])) continue;
+                for (int c = 0; c < chunks; ++c) {
+                    const int kb = ti * chunks + c;
+                    nkb += (kb >= kb_lo && kb < kb_hi) ? 1 : 0;
+                }
+            }
+            int st = 0, par = 0;
+            long long waited = 0;
+            // descriptors advance by plain 64-bit adds on the encoded start address (16-byte units; the ring stays far below
+            // the 256 KB the 14-bit field covers): the issue loop is latency-bound, every scalar instruction in it counts
+            const uint64_t d_ring = smem_desc_sw128(smem0, 16, 1024);
+            const uint64_t stage16 = (uint64_t)(P.stage_bytes >> 4), kb16 = (uint64_t)(P.kb_bytes >> 4), aoff16 = (uint64_t)(P.a_off >> 4);
+            uint64_t d_stage = d_ring;
+            for (int g = 0; g < nkb; g += P.kps) {
+                const int cnt = min(P.kps, nkb - g);
+                const long long w0 = dbg ? clock64() : 0;
                 mbar_wait(&full_bar[st], par);
                 tc_fence_after();
-                if (dbg && it == 0 && lane == 0) dbg[2] = clock64();      // first stage landed
-                const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
-                const uint64_t da = smem_desc_sw128(sa, 16, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, 16, 1024);
-                if (elect_one()) {
+                if (dbg) { waited += clock64() - w0; if (g == 0) dbg[2] = clock64(); }      // first stage landed
+                uint64_t da = d_stage;
+#pragma unroll 1
+                for (int j = 0; j < cnt; ++j, da += kb16) {
+                    const uint64_t db = da + aoff16;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)   // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
-                        umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
-                    umma_commit(&empty_bar[st]);
+                        umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (g | j | k) != 0);
                 }
-                __syncwarp();
-                ++it;
-                if (++st == P.stages) { st = 0; par ^= 1; }
+                umma_commit(&empty_bar[st]);
+                d_stage += stage16;
+                if (++st == P.stages) { st = 0; par ^= 1; d_stage = d_ring; }
             }
-        }
-        if (dbg && lane == 0) { dbg[3] = clock64(); dbg[6] = it; }   // last MMA issued
-        if (elect_one()) {
-            s_issued = (uint32_t)it;
+            if (dbg) { dbg[3] = clock64(); dbg[6] = nkb; dbg[7] = waited; }   // last MMA issued; cycles spent waiting for operands
+            s_issued = (uint32_t)nkb;
             umma_commit(&acc_bar);      // arrival 1: all MMAs retired
             mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
         }
+        __syncwarp();
     }
     __syncwarp();
 
@@ -607,22 +637,33 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     }
     const dim3 cluster(1, 1, (unsigned)A.splits);
     const bool deep = (int)(grid.x * grid.y * grid.z) <= sm_count();
-    // Ring depth of the sub-wave (1 CTA per SM) variants: DMU_CONV_STAGES caps it so that a CTA of the backward's other lane
-    // (a weight gradient, DMU_WGRAD_STAGES) can share the SM instead of the chain waiting for one to retire.
-    static const int deep_cap = [] { const char* e = getenv("DMU_CONV_STAGES"); return e ? atoi(e) : 4; }();
-    auto stages_of = [&](int full) { int v = deep ? (deep_cap < full ? deep_cap : full) : full; return v < 2 ? 2 : v; };
-    cudaError_t e;
-    if (NT == 64) {
-        A.stages = stages_of(deep ? ConvCfg<64, 1>::kStages : ConvCfg<64, 0>::kStages);
-        const size_t smem = (size_t)A.stages * ConvCfg<64, 1>::kStageBytes + 1024;
-        e = deep ? launch_pdl(conv_tc_kernel<64, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
-                 : launch_pdl(conv_tc_kernel<64, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
-    } else {
-        A.stages = stages_of(deep ? ConvCfg<128, 1>::kStages : ConvCfg<128, 0>::kStages);
-        const size_t smem = (size_t)A.stages * ConvCfg<128, 1>::kStageBytes + 1024;
-        e = deep ? launch_pdl(conv_tc_kernel<128, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
-                 : launch_pdl(conv_tc_kernel<128, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
+    // Ring geometry.  One TMA round trip is ~2000 clk here (scripts/conv_timeline.py), so a CTA's k-loop moves at most
+    // (bytes in flight) / 2000 clk: the sub-wave (1 CTA per SM) variants keep ~128 KB in flight - compact stages for the
+    // 64-pixel box, 8 KB + NT x 128 B each - which still leaves room on the SM for a weight-gradient CTA of the backward's other
+    // lane (3 x 24-32 KB, see wgrad_launch) instead of the chain waiting for one to retire.  DMU_CONV_RING_KB: A/B aid.
+    static const int ring_kb = [] { const char* e = getenv("DMU_CONV_RING_KB"); return e ? atoi(e) : 128; }();
+    static const int kps_env = [] { const char* e = getenv("DMU_CONV_KPS"); return e ? atoi(e) : 2; }();
+    // measured: the k-loop of these launches is issue-bound (~100 clk per MMA whatever its shape), M = 64 buys nothing: opt-in
+    static const int m64_env = [] { const char* e = getenv("DMU_CONV_M64"); return e ? atoi(e) : 0; }();
+    A.m64 = (pix == 64 && A.splits == 1 && m64_env) ? 1 : 0;
+    A.a_off = pix * 128;
+    A.kb_bytes = A.a_off + NT * 128;
+    A.kps = deep ? (kps_env < 1 ? 1 : kps_env) : 1;
+    A.stage_bytes = A.kps * A.kb_bytes;
+    const int max_stages = NT == 64 ? (deep ? ConvCfg<64, 1>::kStages : ConvCfg<64, 0>::kStages) : (deep ? ConvCfg<128, 1>::kStages : ConvCfg<128, 0>::kStages);
+    A.stages = max_stages;
+    if (deep) {
+        A.stages = ring_kb * 1024 / A.stage_bytes;
+        if (A.stages > max_stages) A.stages = max_stages;
+        if (A.stages < 2) A.stages = 2;
     }
+    // + 1 KB alignment slack + the rows past a 64-pixel box that the M = 128 MMA of the last stage still reads
+    const size_t smem = (size_t)A.stages * A.stage_bytes + 1024 + (128 * 128 - A.a_off);
+    cudaError_t e;
+    if (NT == 64) e = deep ? launch_pdl(conv_tc_kernel<64, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
+                           : launch_pdl(conv_tc_kernel<64, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
+    else e = deep ? launch_pdl(conv_tc_kernel<128, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
+                  : launch_pdl(conv_tc_kernel<128, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
     if (e != cudaSuccess) return fail("dmu_conv2d/tc: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/tc");
 }
@@ -689,16 +730,16 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ M
     };
 
     if (warp == 0) {
-        const uint32_t blk_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
-        int st = 0, par = 1;
-        for (int tile = tile_lo; tile < tile_hi; ++tile) {
-            const int tw0 = (tile % P.tiles_w) * P.BW;
-            const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
-            const int n0 = (tile / (P.tiles_w * P.tiles_h)) * P.BN;
-            const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
-            if (!l0 && !l1) continue;
-            mbar_wait(&empty_bar[st], par);
-            if (elect_one()) {
+        if (elect_one()) {
+            const uint32_t blk_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
+            int st = 0, par = 1;
+            for (int tile = tile_lo; tile < tile_hi; ++tile) {
+                const int tw0 = (tile % P.tiles_w) * P.BW;
+                const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
+                const int n0 = (tile / (P.tiles_w * P.tiles_h)) * P.BN;
+                const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
+                if (!l0 && !l1) continue;
+                mbar_wait(&empty_bar[st], par);
                 uint8_t* sa = smem + st * Cfg::kStageBytes;
                 mbar_arrive_expect_tx(&full_bar[st], blk_bytes * (2 + NT / 64));
                 // a dead tap still issues its (fully out-of-bounds, zero-filled) load so the block holds zeros, not stale data
@@ -707,38 +748,37 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ M
 #pragma unroll
                 for (int q = 0; q < NT / 64; ++q)
                     tma_load_4d(sa + Cfg::kABytes + q * Cfg::kBlk, &maps.b, &full_bar[st], a0 + q * 64, tw0, th0, n0);
+                if (++st == P.stages) { st = 0; par ^= 1; }
             }
-            __syncwarp();
-            if (++st == P.stages) { st = 0; par ^= 1; }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);   // both operands MN-major (channels contiguous, K = pixels)
-        const int ksteps = (P.BN * P.BH * P.BW + 15) >> 4;             // K = 16 pixels per MMA; a box holds <= 64 pixels
-        int it = 0, st = 0, par = 0;
-        for (int tile = tile_lo; tile < tile_hi; ++tile) {
-            const int tw0 = (tile % P.tiles_w) * P.BW;
-            const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
-            const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
-            if (!l0 && !l1) continue;
-            mbar_wait(&full_bar[st], par);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
-            const uint64_t da = smem_desc_sw128(sa, Cfg::kBlk, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, Cfg::kBlk, 1024);
-            if (elect_one()) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 1);   // both operands MN-major (channels contiguous, K = pixels)
+            const int ksteps = (P.BN * P.BH * P.BW + 15) >> 4;             // K = 16 pixels per MMA; a box holds <= 64 pixels
+            const uint32_t smem0 = smem_u32(smem);
+            int it = 0, st = 0, par = 0;
+            for (int tile = tile_lo; tile < tile_hi; ++tile) {
+                const int tw0 = (tile % P.tiles_w) * P.BW;
+                const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
+                const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
+                if (!l0 && !l1) continue;
+                mbar_wait(&full_bar[st], par);
+                tc_fence_after();
+                const uint32_t sa = smem0 + (uint32_t)(st * Cfg::kStageBytes);
+                const uint64_t da = smem_desc_sw128(sa, Cfg::kBlk, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, Cfg::kBlk, 1024);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)   // K = 16 pixels = 16 rows of 128 B = 2048 B per step
                     if (k < ksteps) umma_bf16(tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) != 0);
                 umma_commit(&empty_bar[st]);
+                ++it;
+                if (++st == P.stages) { st = 0; par ^= 1; }
             }
-            __syncwarp();
-            ++it;
-            if (++st == P.stages) { st = 0; par ^= 1; }
-        }
-        if (elect_one()) {
             s_issued = (uint32_t)it;
             umma_commit(&acc_bar);      // arrival 1: all MMAs retired
             mbar_arrive(&acc_bar);      // arrival 2: release-publishes s_issued to the epilogue threads
         }
+        __syncwarp();
     }
     __syncwarp();
 

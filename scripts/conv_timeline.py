@@ -40,7 +40,7 @@ def run(N, H, Ci, Co, R, ws=None, reps=3):
         return
     rel = (d[:, 1:6] - d[:, 0:1]).float()
     print(f"N={N} H={H} {Ci}->{Co} k{R}  ctas={len(d)} kblocks={int(d[0,6])}  avg cycles since start: setup {rel[:,0].mean():.0f}  first-stage {rel[:,1].mean():.0f}  "
-          f"last-mma-issued {rel[:,2].mean():.0f}  acc-ready {rel[:,3].mean():.0f}  epilogue-done {rel[:,4].mean():.0f}   | back-to-back {us:.1f} us/launch  {flops / us / 1e6:.0f} TFLOP/s", flush=True)
+          f"last-mma-issued {rel[:,2].mean():.0f}  acc-ready {rel[:,3].mean():.0f}  epilogue-done {rel[:,4].mean():.0f}  issuer-waited {d[:,7].float().mean():.0f}   | back-to-back {us:.1f} us/launch  {flops / us / 1e6:.0f} TFLOP/s", flush=True)
 
 ws = torch.zeros(int(lib.dmu_conv2d_workspace_bytes()), dtype=torch.uint8, device=dev)
 run(128, 32, 64, 64, 3)

@@ -18,7 +18,7 @@ using namespace dmu::tc;
 namespace dmu { char* err_buf() { static char b[256]; return b; } int fail(const char* f, ...) { printf("fail: %s\n", f); return 1; } int sm_count() { return 148; } bool pdl_enabled() { return false; }
 namespace tc { EncodeTiledFn encode_tiled_fn() { return nullptr; } } }
 
-struct Args { int N, ts, iters, stages, rowshift; long long* out; int M, nacc, mnmajor; };
+struct Args { int N, ts, iters, stages, rowshift; long long* out; int M, nacc, mnmajor, commit_every, loop_flags; };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -70,22 +70,16 @@ __global__ void __launch_bounds__(128) rate1(const Args P) {
 }
 
 
-__device__ __forceinline__ uint32_t elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred;
-}
-
 // Same work as rate1 in SS mode, but issued the CUTLASS way: warp 0 stays converged, one elected lane issues.
 __global__ void __launch_bounds__(128) rate1e(const Args P) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar, bar2[2];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5;
     const int a_bytes = (128 + 8) * 128, b_bytes = P.N * 128;
     for (int i = threadIdx.x; i < P.stages * (a_bytes + b_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i % 7;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2[0], 1); mbar_init(&bar2[1], 1); fence_mbar_init(); }
     if (warp == 1) tmem_alloc(&s_tmem, 512);
     fence_proxy_async();
     tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -103,11 +97,67 @@ __global__ void __launch_bounds__(128) rate1e(const Args P) {
             for (int it = 0; it < P.iters; it += 2) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(tmem, da0 + 2 * k, db0 + 2 * k, idesc, (it | k) != 0);
+                if (P.commit_every == 4) umma_commit(&bar2[0]);      // what a per-k-block pipeline does: one commit per 4 MMAs
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(d1, da1 + 2 * k, db1 + 2 * k, idesc, (it | k) != 0);
+                if (P.commit_every == 4 || P.commit_every == 8) umma_commit(&bar2[1]);
             }
         }
         __syncwarp();
+        long long t1 = clock64();
+        if (elect_one()) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        if (threadIdx.x == 0) { P.out[2 * blockIdx.x] = t1 - t0; P.out[2 * blockIdx.x + 1] = t2 - t0; }
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+
+// The per-k-block issue loop of the conv kernels, piece by piece: every iteration issues 4 MMAs; loop_flags adds
+//   1 = an mbarrier try_wait on an already-complete barrier,  2 = tcgen05.fence::after_thread_sync,
+//   4 = leaving / re-entering the elect.sync region (+ __syncwarp) every iteration,  8 = a tcgen05.commit every iteration.
+__global__ void __launch_bounds__(128) rate1f(const Args P) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar, ready, sink[8];
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5;
+    const int a_bytes = (128 + 8) * 128, b_bytes = P.N * 128;
+    for (int i = threadIdx.x; i < 2 * (a_bytes + b_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i % 7;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&ready, 1); for (int i = 0; i < 8; ++i) mbar_init(&sink[i], 1); fence_mbar_init(); }
+    if (warp == 1) tmem_alloc(&s_tmem, 512);
+    fence_proxy_async();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (warp == 0) {
+        const uint32_t idesc = umma_idesc_bf16(P.M, P.N, 0, 0);
+        const uint32_t base = smem_u32(smem);
+        long long t0 = clock64();
+        int st = 0;
+        for (int it = 0; it < P.iters; ++it) {
+            if (P.loop_flags & 1) mbar_wait(&ready, 1);           // fresh barrier: the phase before phase 0 counts as complete
+            if (P.loop_flags & 2) tc_fence_after();
+            const uint64_t da = smem_desc_sw128(base + st * (a_bytes + b_bytes), 16, 1024);
+            const uint64_t db = smem_desc_sw128(base + st * (a_bytes + b_bytes) + a_bytes, 16, 1024);
+            if (P.loop_flags & 4) {
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                    if (P.loop_flags & 8) umma_commit(&sink[it & 7]);
+                }
+                __syncwarp();
+            } else if (threadIdx.x == 0 || true) {
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                    if (P.loop_flags & 8) umma_commit(&sink[it & 7]);
+                }
+            }
+            st ^= 1;
+        }
         long long t1 = clock64();
         if (elect_one()) umma_commit(&bar);
         __syncwarp();
@@ -169,15 +219,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) rate2(const Arg
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
-static void run(const char* what, int pair, int N, int ts, int stages, int rowshift, int ctas, int smem_pad, int M = 128, int nacc = 1, int mnmajor = 0, int elect = 0) {
+static void run(const char* what, int pair, int N, int ts, int stages, int rowshift, int ctas, int smem_pad, int M = 128, int nacc = 1, int mnmajor = 0, int elect = 0, int commit_every = 0, int loop_flags = -1) {
     const int iters = 2048;
     long long* dout;
     cudaMalloc(&dout, sizeof(long long) * 2 * 1024);
     cudaMemset(dout, 0, sizeof(long long) * 2 * 1024);
-    Args A{N, ts, iters, stages, rowshift, dout, M, nacc, mnmajor};
+    Args A{N, ts, iters, stages, rowshift, dout, M, nacc, mnmajor, commit_every, loop_flags};
     const int per_stage = pair ? (128 * 128 + N / 2 * 128) : ((128 + 8) * 128 + N * 128);
     int smem = stages * per_stage + 1024 + smem_pad;
     if (pair) { cudaFuncSetAttribute(rate2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); rate2<<<ctas, 128, smem>>>(A); }
+    else if (loop_flags >= 0) { cudaFuncSetAttribute(rate1f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); rate1f<<<ctas, 128, smem>>>(A); }
     else if (elect) { cudaFuncSetAttribute(rate1e, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); rate1e<<<ctas, 128, smem>>>(A); }
     else { cudaFuncSetAttribute(rate1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); rate1<<<ctas, 128, smem>>>(A); }
     cudaError_t e = cudaDeviceSynchronize();
@@ -222,6 +273,15 @@ int main() {
     run("SS elect-issued M=64 N=256", 0, 256, 0, 2, 0, 148, pad256, 64, 1, 0, 1);
     run("SS elect-issued N=64, 296 CTAs (2/SM)", 0, 64, 0, 2, 0, 296, 0, 128, 1, 0, 1);
     run("SS elect-issued N=128, 296 CTAs (2/SM)", 0, 128, 0, 2, 0, 296, 0, 128, 1, 0, 1);
+    run("SS elect N=64, commit every 4 MMAs", 0, 64, 0, 2, 0, 148, pad64, 128, 1, 0, 1, 4);
+    run("SS elect N=64, commit every 8 MMAs", 0, 64, 0, 2, 0, 148, pad64, 128, 1, 0, 1, 8);
+    run("SS elect N=128, commit every 4 MMAs", 0, 128, 0, 2, 0, 148, pad128, 128, 1, 0, 1, 4);
+    run("SS elect N=128, commit every 8 MMAs", 0, 128, 0, 2, 0, 148, pad128, 128, 1, 0, 1, 8);
+    for (int f : {0, 1, 2, 4, 8, 12, 15}) {
+        char b[96];
+        snprintf(b, sizeof b, "k-block loop N=64 flags=%d", f);
+        run(b, 0, 64, 0, 2, 0, 148, pad64, 128, 1, 0, 1, 0, f);
+    }
     run("SS N=16", 0, 16, 0, 2, 0, 148, pad64);
     run("SS N=32", 0, 32, 0, 2, 0, 148, pad64);
     run("SS N=64  2 accumulators", 0, 64, 0, 2, 0, 148, pad64, 128, 2);
