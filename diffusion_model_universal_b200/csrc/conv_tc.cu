@@ -733,10 +733,11 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ M
         if (elect_one()) {
             const uint32_t blk_bytes = (uint32_t)(P.BN * P.BH * P.BW) * 128u;
             int st = 0, par = 1;
+            // tile coordinates advance incrementally (no divisions in the issue loops: they are latency chains of one lane)
+            int iw = tile_lo % P.tiles_w, ih = (tile_lo / P.tiles_w) % P.tiles_h, in_ = tile_lo / (P.tiles_w * P.tiles_h);
             for (int tile = tile_lo; tile < tile_hi; ++tile) {
-                const int tw0 = (tile % P.tiles_w) * P.BW;
-                const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
-                const int n0 = (tile / (P.tiles_w * P.tiles_h)) * P.BN;
+                const int tw0 = iw * P.BW, th0 = ih * P.BH, n0 = in_ * P.BN;
+                if (++iw == P.tiles_w) { iw = 0; if (++ih == P.tiles_h) { ih = 0; ++in_; } }
                 const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
                 if (!l0 && !l1) continue;
                 mbar_wait(&empty_bar[st], par);
@@ -758,21 +759,24 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ M
             const int ksteps = (P.BN * P.BH * P.BW + 15) >> 4;             // K = 16 pixels per MMA; a box holds <= 64 pixels
             const uint32_t smem0 = smem_u32(smem);
             int it = 0, st = 0, par = 0;
+            int iw = tile_lo % P.tiles_w, ih = (tile_lo / P.tiles_w) % P.tiles_h;
+            const uint64_t d_ring = smem_desc_sw128(smem0, Cfg::kBlk, 1024);
+            uint64_t da = d_ring;
             for (int tile = tile_lo; tile < tile_hi; ++tile) {
-                const int tw0 = (tile % P.tiles_w) * P.BW;
-                const int th0 = ((tile / P.tiles_w) % P.tiles_h) * P.BH;
+                const int tw0 = iw * P.BW, th0 = ih * P.BH;
+                if (++iw == P.tiles_w) { iw = 0; if (++ih == P.tiles_h) ih = 0; }
                 const bool l0 = live(t0, th0, tw0), l1 = has1 && live(t1, th0, tw0);
                 if (!l0 && !l1) continue;
                 mbar_wait(&full_bar[st], par);
                 tc_fence_after();
-                const uint32_t sa = smem0 + (uint32_t)(st * Cfg::kStageBytes);
-                const uint64_t da = smem_desc_sw128(sa, Cfg::kBlk, 1024), db = smem_desc_sw128(sa + Cfg::kABytes, Cfg::kBlk, 1024);
+                const uint64_t db = da + (uint64_t)(Cfg::kABytes >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)   // K = 16 pixels = 16 rows of 128 B = 2048 B per step
                     if (k < ksteps) umma_bf16(tmem, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (it | k) != 0);
                 umma_commit(&empty_bar[st]);
                 ++it;
-                if (++st == P.stages) { st = 0; par ^= 1; }
+                da += (uint64_t)(Cfg::kStageBytes >> 4);
+                if (++st == P.stages) { st = 0; par ^= 1; da = d_ring; }
             }
             s_issued = (uint32_t)it;
             umma_commit(&acc_bar);      // arrival 1: all MMAs retired
