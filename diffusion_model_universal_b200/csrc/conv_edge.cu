@@ -291,25 +291,12 @@ __global__ void __launch_bounds__(256) narrow_wgrad_kernel(NarrowWgradArgs A) {
         if (!active) continue;
         const int npix = rows * A.W;
         const TW* wb = reinterpret_cast<const TW*>(A.wide.ptr) + (int64_t)n * A.wide.sn + g * 8;
-        // software pipeline: the next pixel's vector is in flight while this one's 72 FMAs run (one dependent global load per
-        // iteration made the loop a ~700 clk latency chain per pixel)
-        float xn[8];
-        if (pl < npix) {
-            const TW* xp = wb + (int64_t)(h0 + pl / A.W) * A.wide.sh + (int64_t)(pl % A.W) * A.wide.sw;
-            load_vec<TW>(xp, xn);
-            if constexpr (sizeof(TW) == 4) load_vec<TW>(xp + 4, xn + 4);
-        }
         for (int p = pl; p < npix; p += lanes) {
             const int hl = p / A.W, w = p % A.W;
             float xv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) xv[k] = xn[k];
-            if (p + lanes < npix) {
-                const int pn = p + lanes;
-                const TW* xp = wb + (int64_t)(h0 + pn / A.W) * A.wide.sh + (int64_t)(pn % A.W) * A.wide.sw;
-                load_vec<TW>(xp, xn);
-                if constexpr (sizeof(TW) == 4) load_vec<TW>(xp + 4, xn + 4);
-            }
+            const TW* xp = wb + (int64_t)(h0 + hl) * A.wide.sh + (int64_t)w * A.wide.sw;
+            load_vec<TW>(xp, xv);
+            if constexpr (sizeof(TW) == 4) load_vec<TW>(xp + 4, xv + 4);
             if (r == 0) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) bsum[k] += xv[k];
