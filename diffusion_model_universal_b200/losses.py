@@ -63,8 +63,8 @@ class DiffusionLoss:
             return torch.cumprod(1 - betas, dim=0).index_select(0, timesteps)
         tmax = timesteps.max()
         i = torch.arange(int(self.max_t), device=dev)
-        start = torch.tensor(1e-4, device=dev, dtype=torch.float32)
-        end = torch.tensor(2e-2, device=dev, dtype=torch.float32)
+        start = torch.full((), 1e-4, device=dev, dtype=torch.float32)     # fill kernels, not host copies: capturable in a CUDA graph
+        end = torch.full((), 2e-2, device=dev, dtype=torch.float32)
         step = (end - start) / tmax.clamp(min=1).to(torch.float32)
         steps = tmax + 1
         lo = start + step * i.to(torch.float32)

@@ -13,6 +13,8 @@ Mirror of trainers/ddpm_trainer.py:539-555 (``images.to(device)`` ->
 
 from typing import Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -29,6 +31,14 @@ class TrainStep:
         self.reducer = GradAllReducer(model.model, bucket_mb=bucket_mb, group=group)
         self._stage = None
         self._works = None
+        # Single-GPU DDPM steps replay ONE CUDA graph of everything between the input batch and the gradient arena (RNG draws,
+        # time weights, q_sample, forward, loss, three-part backward): ~30 small eager launches and four graph launches per step
+        # become one.  DMU_STEP_GRAPH=0 keeps the piecewise path.
+        self._use_step_graph = os.environ.get("DMU_STEP_GRAPH", "1") != "0"
+        self._graph = None
+        self._g_in = self._g_loss = None
+        self._g_warm = 0
+        self._g_launches = 0
 
     def step(self, images: torch.Tensor) -> torch.Tensor:
         """images: fp32 [B,C,H,W] on the device, or a (pinned) host tensor which is
@@ -42,7 +52,10 @@ class TrainStep:
             images = self._stage
         m = self.model
         if isinstance(getattr(m, "loss_fn", None), DiffusionLoss) and hasattr(m, "alphas_cumprod"):
-            loss = self._ddpm_step(images)
+            if self._use_step_graph and self.reducer.world == 1 and images.is_cuda and m.model.engine.use_graphs:
+                loss = self._ddpm_step_graphed(images)
+            else:
+                loss = self._ddpm_step(images)
         else:   # generic route through autograd (score / energy variants)
             loss = m.loss_function(images)
             loss.backward()
@@ -54,6 +67,26 @@ class TrainStep:
         self._works = None
         self.opt.step(grad_scale=scale)
         return loss.detach()
+
+    def _ddpm_step_graphed(self, images: torch.Tensor) -> torch.Tensor:
+        if self._g_in is None or self._g_in.shape != images.shape:
+            self._g_in = torch.empty_like(images)
+            self._graph, self._g_warm = None, 0
+        self._g_in.copy_(images)
+        if self._graph is None:
+            if self._g_warm < 3:               # eager steps first: plans, lazy one-time initialisation, allocator warm-up
+                self._g_warm += 1
+                return self._ddpm_step(self._g_in)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(g):
+                self._g_loss = self._ddpm_step(self._g_in)
+            self._g_launches = ops.LAUNCHES - n0
+            ops.LAUNCHES = n0
+            self._graph = g
+        self._graph.replay()
+        ops.LAUNCHES += self._g_launches
+        return self._g_loss
 
     def _ddpm_step(self, images: torch.Tensor) -> torch.Tensor:
         """``DDPM.loss_function`` + ``backward`` (models/ddpm.py:207-235) straight on the engine: same RNG calls in the same

@@ -496,6 +496,10 @@ class Engine:
         """Run plan.fwd / plan.bwd: eagerly the first time (warms every lazy one-time initialisation), then captured once
         into a CUDA graph and replayed — ~250 launches (and their tensor-map encodes) become one host call."""
         oplist = plan.fwd if which == "fwd" else plan.bwd if which == "bwd" else plan.bwd_parts[int(which[3:])]
+        if self.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            # the caller is capturing (TrainStep's whole-step graph): record the launches, lanes included, into ITS graph
+            self._run_forked(oplist)
+            return
         g = plan.graphs.get(which)
         if g is not None:
             g.replay()

@@ -339,3 +339,25 @@ def test_fused_groupnorm_plan_matches_unfused():
         if e >= 1e-1:
             bad.append((k, e, g0.norm().item() / scale))
     assert not bad, bad
+
+
+def test_trainstep_whole_step_graph_matches_piecewise():
+    """TrainStep's single-GPU whole-step CUDA graph (RNG draws, time weights, q_sample, forward, loss, backward in one graph)
+    against the piecewise path from the same seed: same noise and timesteps step after step, same losses (bf16 noise)."""
+    import diffusion_model_universal_b200 as D
+    from diffusion_model_universal_b200.trainer import TrainStep
+    f = load_golden("ddpm_train.pt")
+    dev = torch.device("cuda:0")
+    x0 = f["x0"].to(dev)
+    runs = []
+    for graph in (False, True):
+        m = _load(D.DDPM(_cfg(f["C"], "bf16")), W.unet_param_spec(f["C"], 3, "model."), f["wseed"]).to(dev)
+        ts = TrainStep(m, lr=1e-4, ema_decay=0.999)
+        ts._use_step_graph = graph
+        torch.manual_seed(123)
+        losses = [ts.step(x0).item() for _ in range(7)]      # steps 0-2 eager warm-up, 3 = capture + replay, 4+ = replay
+        assert (ts._graph is not None) == graph
+        runs.append((losses, m.model.engine.flat.clone()))
+    for a, b in zip(*[r[0] for r in runs]):
+        assert abs(a - b) < 3e-2 * abs(a), (runs[0][0], runs[1][0])
+    assert rel_l2(runs[1][1], runs[0][1]) < 1e-3          # parameters after 7 Adam steps
