@@ -624,6 +624,7 @@ class Engine:
             plan.gn_pg_tables = []
             plan.bwd_parts = [[(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4), 0),
                                (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4), 0)], [], []]
+            tails = ([], [], [])       # per part: batch fold of the GroupNorm parameter gradients + staging unpack
             for h, lst in enumerate(plan.bwd_parts):
                 lst.append((None, (), -2))
                 lst.extend(parts[h])
@@ -632,14 +633,28 @@ class Engine:
                     arr = (GnPgDesc * len(pg[h]))(*pg[h])
                     tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
                     plan.gn_pg_tables.append(tab)
-                    lst.append((lib.dmu_gn_param_grads, (tab.data_ptr(), len(pg[h]), max(d.C for d in pg[h]), Ns), 0))
+                    tails[h].append((lib.dmu_gn_param_grads, (tab.data_ptr(), len(pg[h]), max(d.C for d in pg[h]), Ns), 0))
                 # filter gradients: staging layout -> the parameters' own layout inside the gradient arena
                 tab, n_un = self.unpack_tables[h]
                 if n_un:
-                    lst.append((lib.dmu_repack_weights, (tab.data_ptr(), n_un, self.repack_max), 0))
+                    tails[h].append((lib.dmu_repack_weights, (tab.data_ptr(), n_un, self.repack_max), 0))
+                lst.extend(tails[h])
             total = self.gflat.numel()
             plan.ranges = [(self.cuts[0], total), (self.cuts[1], self.cuts[0]), (0, self.cuts[1])]
-            plan.bwd = plan.bwd_parts[0] + plan.bwd_parts[1] + plan.bwd_parts[2]
+            # One-graph form (no all-reduce between the parts): the tail of part h only touches part h's gradients, so it rides
+            # on the side lane at the start of part h + 1 instead of standing between the two parts on lane 0.
+            plan.bwd = []
+            for h in range(3):
+                body = plan.bwd_parts[h][:len(plan.bwd_parts[h]) - len(tails[h])]
+                if h == 0:
+                    # the two arena memsets (128 MB) also move to the side lane: only weight gradients / column sums (side
+                    # lane, same stream order) and the tails accumulate into them before the lanes join
+                    i = body.index((None, (), -2)) + 1
+                    plan.bwd += [body[i - 1]] + [(fn, args, 1) for fn, args, _ in body[:i - 1]] + body[i:]
+                else:
+                    i = body.index((None, (), -2)) + 1
+                    plan.bwd += body[:i] + [(fn, args, 1) for fn, args, _ in tails[h - 1]] + body[i:]
+            plan.bwd += tails[2]
         plan.arena = arena
         plan.nbytes = nbytes
         plan.lanes = K
