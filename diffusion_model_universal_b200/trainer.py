@@ -36,7 +36,7 @@ class TrainStep:
         # become one.  DMU_STEP_GRAPH=0 keeps the piecewise path.
         self._use_step_graph = os.environ.get("DMU_STEP_GRAPH", "1") != "0"
         self._graph = None
-        self._g_in = self._g_loss = None
+        self._g_in = self._g_loss = self._g_dpred = self._g_plan = None
         self._g_warm = 0
         self._g_launches = 0
 
@@ -52,7 +52,7 @@ class TrainStep:
             images = self._stage
         m = self.model
         if isinstance(getattr(m, "loss_fn", None), DiffusionLoss) and hasattr(m, "alphas_cumprod"):
-            if self._use_step_graph and self.reducer.world == 1 and images.is_cuda and m.model.engine.use_graphs:
+            if self._use_step_graph and images.is_cuda and m.model.engine.use_graphs:
                 loss = self._ddpm_step_graphed(images)
             else:
                 loss = self._ddpm_step(images)
@@ -80,18 +80,29 @@ class TrainStep:
             g = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES
             with torch.cuda.graph(g):
-                self._g_loss = self._ddpm_step(self._g_in)
+                if self.reducer.world == 1:
+                    self._g_loss = self._ddpm_step(self._g_in)
+                else:      # data parallel: the graph ends at dL/d(eps); the three backward graphs alternate with the all-reduces
+                    self._g_loss, self._g_dpred, self._g_plan = self._ddpm_front(self._g_in)
             self._g_launches = ops.LAUNCHES - n0
             ops.LAUNCHES = n0
             self._graph = g
         self._graph.replay()
         ops.LAUNCHES += self._g_launches
+        if self.reducer.world > 1:
+            self._ddpm_back(self._g_plan, self._g_dpred)
         return self._g_loss
 
     def _ddpm_step(self, images: torch.Tensor) -> torch.Tensor:
         """``DDPM.loss_function`` + ``backward`` (models/ddpm.py:207-235) straight on the engine: same RNG calls in the same
         order and the same launches, without the autograd graph (314 AccumulateGrad nodes cost more host time than the
         GPU needs for the whole backward pass).  Gradients land in the engine's flat arena, which the optimizer reads."""
+        loss, dpred, plan = self._ddpm_front(images)
+        self._ddpm_back(plan, dpred)
+        return loss
+
+    def _ddpm_front(self, images: torch.Tensor):
+        """RNG draws, time weights, q_sample, forward, loss and dL/d(eps)."""
         m = self.model
         eng = m.model.engine
         t = torch.randint(0, m.num_timesteps, (images.shape[0],), device=images.device)
@@ -103,6 +114,10 @@ class TrainStep:
         eps = eng.run_forward(xt, t, plan)
         wm, wl, wh = m.loss_fn.coefficients()
         loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True)
+        return loss, dpred, plan
+
+    def _ddpm_back(self, plan, dpred):
+        eng = self.model.model.engine
         if self.reducer.world > 1:
             # all-reduce each third of the gradient arena as soon as its part of the backward has finished
             works = []
@@ -110,4 +125,3 @@ class TrainStep:
             self._works = works
         else:
             eng.run_backward(plan, dpred)
-        return loss
