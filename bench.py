@@ -276,6 +276,11 @@ def run_ours(args):
         return ms, launches
 
     losses = []
+    # one-time setup, outside the warm-up / timed steps: launch-plan construction, tensor-map encodes, CUDA-graph capture
+    # (TrainStep captures its step graph on its fourth call)
+    for i in range(6):
+        ts.step(devb[i % n_batches])
+    barrier()
     sampler = ClockSampler(local)
     sampler.start()
     ms_dev, launches = timed(lambda i: ts.step(devb[i % n_batches]), args.steps, args.warmup)
