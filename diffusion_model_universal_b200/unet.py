@@ -654,7 +654,14 @@ class Engine:
                 else:
                     i = body.index((None, (), -2)) + 1
                     plan.bwd += body[:i] + [(fn, args, 1) for fn, args, _ in tails[h - 1]] + body[i:]
-            plan.bwd += tails[2]
+            # the last tail runs next to the time-embedding backward (both only need the lanes joined): it goes on the side lane
+            # right after the join that precedes those launches (the second-to-last join marker of the part)
+            joins = [i for i, op in enumerate(plan.bwd) if op[0] is None and op[2] == 0]
+            if len(joins) >= 2 and K == 1:
+                i = joins[-2] + 1
+                plan.bwd[i:i] = [(fn, args, 1) for fn, args, _ in tails[2]]
+            else:
+                plan.bwd += tails[2]
         plan.arena = arena
         plan.nbytes = nbytes
         plan.lanes = K
