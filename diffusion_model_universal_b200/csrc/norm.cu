@@ -1585,14 +1585,17 @@ int dmu_gn_backward(const dmu_gn_params* p, dmu_stream_t stream) {
             for (int c2 = 1; c2 <= 8 && c2 <= HW; c2 <<= 1) {
                 const int per = (HW + c2 - 1) / c2;
                 const size_t smem = (size_t)2 * per * V * 16 + (size_t)8 * p->C * 4;
-                if (smem > 56 * 1024) continue;      // keep >= 3 CTAs per SM
+                static const int bwd_cap_kb = [] { const char* e = getenv("DMU_GN_BWD_SMEM_KB"); return e ? atoi(e) : 72; }();
+                // 72 KB (a 4-CTA cluster per 32x32x64 image, 3 CTAs per SM): slower than 8 smaller CTAs when timed alone (48.7 vs 37 us)
+                // but faster inside the backward graph next to the weight-gradient lane (step 3.19 -> 3.14 ms)
+                if (smem > (size_t)bwd_cap_kb * 1024) continue;
                 cudaError_t e;
                 if (p->x.dtype == DMU_BF16) {
-                    static bool a1 = (cudaFuncSetAttribute(gn_bwd_smem_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), true);
+                    static bool a1 = (cudaFuncSetAttribute(gn_bwd_smem_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024), true);
                     (void)a1;
                     e = launch_pdl(gn_bwd_smem_kernel<__nv_bfloat16>, dim3(c2, p->N), dim3(256), smem, as_stream(stream), dim3(c2, 1, 1), *p, per);
                 } else {
-                    static bool a2 = (cudaFuncSetAttribute(gn_bwd_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), true);
+                    static bool a2 = (cudaFuncSetAttribute(gn_bwd_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024), true);
                     (void)a2;
                     e = launch_pdl(gn_bwd_smem_kernel<float>, dim3(c2, p->N), dim3(256), smem, as_stream(stream), dim3(c2, 1, 1), *p, per);
                 }
