@@ -1526,7 +1526,8 @@ int dmu_gn_forward(const dmu_gn_params* p, dmu_stream_t stream) {
     // wins while the tensor is small enough that launch count matters; from ~12 MB upwards the two streaming passes
     // (the second one served from L2 when the tensor fits) are faster (33.6 MB: 26.5 vs 36.9 us, 67 MB: 47 vs 98 us)
     const int64_t bytes = (int64_t)p->N * p->H * p->W * p->C * (p->x.dtype == DMU_BF16 ? 2 : 4);
-    const int cs = bytes <= (12ll << 20) ? gn_fused_cluster(p->H * p->W, p->C, vec) : 0;
+    static const int fwd_fused_mb = [] { const char* e = getenv("DMU_GN_FWD_FUSED_MB"); return e ? atoi(e) : 12; }();
+    const int cs = bytes <= ((int64_t)fwd_fused_mb << 20) ? gn_fused_cluster(p->H * p->W, p->C, vec) : 0;
     if (cs == 0) {
         // large tensors: shared-memory single pass when an image fits the shared memory of a cluster of <= 8 CTAs
         static const int fwd_smem = [] { const char* e = getenv("DMU_GN_FWD_SMEM"); return e ? atoi(e) : 1; }();     // A/B aid
@@ -1572,8 +1573,13 @@ int dmu_gn_backward(const dmu_gn_params* p, dmu_stream_t stream) {
     const int64_t img_bytes = bytes / p->N;
     // measured (scripts/gn_time.py): register-held single pass up to ~3 MB (launch-bound sizes), shared-memory single pass for
     // images of >= 128 KB, the two-pass pair in between (4.2 MB: 11.0 vs 14.3 us, 8.4 MB: 20.5 vs 24.7 us)
-    const int cs = (bytes <= (3ll << 20) && gn_fused_cluster(p->H * p->W, p->C, vec) == 1) ? 1 : 0;
-    if (cs == 0 && img_bytes < (128 << 10)) {
+    // measured inside the backward graph: the register-held single pass (221 registers, one CTA per SM) is the faster kernel
+    // alone for small tensors but costs the step 2.4 % (41.6k vs 40.6k img/s with it off): its CTAs leave no room for the
+    // weight-gradient lane, the two-pass pair does.  DMU_GN_BWD_FUSED_MB > 0 re-enables it up to that size.
+    static const int bwd_fused_mb = [] { const char* e = getenv("DMU_GN_BWD_FUSED_MB"); return e ? atoi(e) : 0; }();
+    const int cs = (bytes <= ((int64_t)bwd_fused_mb << 20) && gn_fused_cluster(p->H * p->W, p->C, vec) == 1) ? 1 : 0;
+    static const int smem_min_kb = [] { const char* e = getenv("DMU_GN_BWD_SMEM_MIN_KB"); return e ? atoi(e) : 128; }();
+    if (cs == 0 && img_bytes < ((int64_t)smem_min_kb << 10)) {
         if (int e = dmu_gn_bwd_reduce(p, stream)) return e;
         return dmu_gn_bwd_apply(p, stream);
     }
