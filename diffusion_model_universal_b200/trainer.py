@@ -39,6 +39,7 @@ class TrainStep:
         self._g_in = self._g_loss = self._g_dpred = self._g_plan = None
         self._g_warm = 0
         self._g_launches = 0
+        self._g_arena = 0
 
     def step(self, images: torch.Tensor) -> torch.Tensor:
         """images: fp32 [B,C,H,W] on the device, or a (pinned) host tensor which is
@@ -69,9 +70,13 @@ class TrainStep:
         return loss.detach()
 
     def _ddpm_step_graphed(self, images: torch.Tensor) -> torch.Tensor:
-        if self._g_in is None or self._g_in.shape != images.shape:
+        eng = self.model.model.engine
+        arena = eng.flat.data_ptr() if eng.flat is not None else 0
+        if self._g_in is None or self._g_in.shape != images.shape or self._g_in.device != images.device or arena != self._g_arena:
+            # new batch shape / device, or the engine rebuilt its parameter arena (model.to(), first call): the captured graph
+            # holds the old addresses
             self._g_in = torch.empty_like(images)
-            self._graph, self._g_warm = None, 0
+            self._graph, self._g_warm, self._g_arena = None, 0, arena
         self._g_in.copy_(images)
         if self._graph is None:
             if self._g_warm < 3:               # eager steps first: plans, lazy one-time initialisation, allocator warm-up
