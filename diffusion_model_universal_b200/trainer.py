@@ -75,9 +75,11 @@ class TrainStep:
         if self._g_in is None or self._g_in.shape != images.shape or self._g_in.device != images.device or arena != self._g_arena:
             # new batch shape / device, or the engine rebuilt its parameter arena (model.to(), first call): the captured graph
             # holds the old addresses
-            self._g_in = torch.empty_like(images)
+            # a host batch has already been staged into self._stage: that buffer is the graph's static input (no second copy)
+            self._g_in = images if images is self._stage else torch.empty_like(images)
             self._graph, self._g_warm, self._g_arena = None, 0, arena
-        self._g_in.copy_(images)
+        if images is not self._g_in:
+            self._g_in.copy_(images)
         if self._graph is None:
             if self._g_warm < 3:               # eager steps first: plans, lazy one-time initialisation, allocator warm-up
                 self._g_warm += 1
