@@ -82,6 +82,77 @@ def q_sample(x0, t, noise, alphas_cumprod):
     return out
 
 
+def ingest_u8(img, mean=None, std=None, layout="NCHW", t=None, noise=None, alphas_cumprod=None, want_x0=True):
+    """datasets/dataset_utils.py:58-61 (ToTensor + Normalize) on the device, optionally fused with q_sample
+    (models/ddpm.py:286-296).  img: uint8 [B,C,H,W] (layout "NCHW") or [B,H,W,C] ("NHWC"); mean / std: fp32 [C] device
+    tensors or None.  Returns (x0, xt) as fp32 [B,C,H,W]; x0 is None when want_x0 is False, xt is None without noise."""
+    _need_cuda(img, mean, std, t, noise, alphas_cumprod)
+    if img.dtype != torch.uint8 or img.dim() != 4 or not img.is_contiguous():
+        raise TypeError("img must be a contiguous 4-D uint8 tensor")
+    if layout not in ("NCHW", "NHWC"):
+        raise ValueError(f"layout must be 'NCHW' or 'NHWC', got {layout!r}")
+    if layout == "NHWC":
+        b, h, w, c = img.shape
+    else:
+        b, c, h, w = img.shape
+    for v, name in ((mean, "mean"), (std, "std")):
+        if v is not None and (v.dtype != torch.float32 or v.numel() != c or not v.is_contiguous()):
+            raise TypeError(f"{name} must be a contiguous float32 tensor with one entry per channel")
+    fused = noise is not None
+    if fused:
+        if t is None or alphas_cumprod is None:
+            raise ValueError("the fused q_sample needs t, noise and alphas_cumprod")
+        _f32c(noise, "noise")
+        if tuple(noise.shape) != (b, c, h, w):
+            raise ValueError("noise must be [B,C,H,W]")
+        if t.dtype != torch.int64 or t.numel() != b:
+            raise TypeError("t must be int64 [B]")
+    elif not want_x0:
+        raise ValueError("nothing to compute: want_x0 is False and no noise was given")
+    x0 = torch.empty((b, c, h, w), device=img.device, dtype=torch.float32) if want_x0 else None
+    xt = torch.empty((b, c, h, w), device=img.device, dtype=torch.float32) if fused else None
+    ptr = lambda v: v.data_ptr() if v is not None else None
+    _launched()
+    check(_abi.lib().dmu_ingest_u8(img.data_ptr(), 1 if layout == "NHWC" else 0, ptr(mean), ptr(std), ptr(noise),
+                                   ptr(t) if fused else None, ptr(alphas_cumprod) if fused else None, ptr(x0), ptr(xt),
+                                   b, c, h * w, _stream()), "ingest_u8")
+    return x0, xt
+
+
+def image_grid_shape(n, c, h, w, nrow=8, padding=2):
+    """(grid_h, grid_w, grid_c) of torchvision.utils.make_grid for n images of [c,h,w]."""
+    gh, gw, gc = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    check(_abi.lib().dmu_image_grid_shape(n, c, h, w, nrow, padding, C.byref(gh), C.byref(gw), C.byref(gc)), "image_grid_shape")
+    return gh.value, gw.value, gc.value
+
+
+def image_grid_u8(x, nrow=8, padding=2, pad_value=0.0, transpose=False):
+    """trainers/ddpm_trainer.py:821-834: make_grid + save_image's 8-bit quantisation in one launch.
+    x: fp32 [N,C,H,W] (cells filled in order) or [A,B,C,H,W]; with transpose=True the 5-D tensor is read as
+    image k = x[k % A, k // A] — the trainer's "row per sample, column per saved step" view of a stacked list of
+    intermediates.  Returns uint8 [grid_h, grid_w, grid_c] on the device."""
+    _need_cuda(x)
+    _f32c(x, "x")
+    if x.dim() == 4:
+        n, c, h, w = x.shape
+        period, s_mod, s_div = max(n, 1), c * h * w, 0
+    elif x.dim() == 5:
+        a, b, c, h, w = x.shape
+        n = a * b
+        if transpose:
+            period, s_mod, s_div = a, b * c * h * w, c * h * w
+        else:
+            period, s_mod, s_div = max(n, 1), c * h * w, 0
+    else:
+        raise ValueError("x must be [N,C,H,W] or [A,B,C,H,W]")
+    gh, gw, gc = image_grid_shape(n, c, h, w, nrow, padding)
+    out = torch.empty((gh, gw, gc), device=x.device, dtype=torch.uint8)
+    _launched()
+    check(_abi.lib().dmu_image_grid_u8(x.data_ptr(), n, period, s_mod, s_div, c, h, w, nrow, padding, float(pad_value),
+                                       out.data_ptr(), _stream()), "image_grid_u8")
+    return out
+
+
 def ddpm_step(x, eps, t, noise, betas, alphas, alphas_cumprod, out=None):
     """models/ddpm.py:306-329 after the eps prediction (noise=None only when t == 0)."""
     _need_cuda(x, eps, t)

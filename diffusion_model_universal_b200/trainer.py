@@ -25,8 +25,17 @@ from .parallel import GradAllReducer
 
 class TrainStep:
     def __init__(self, model, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 ema_decay: Optional[float] = 0.9999, bucket_mb: float = 16.0, group=None):
+                 ema_decay: Optional[float] = 0.9999, bucket_mb: float = 16.0, group=None,
+                 input_norm=None, input_layout: str = "NCHW"):
+        """input_norm = (mean, std) per channel and input_layout ("NCHW" | "NHWC") describe uint8 batches: ``step`` then
+        takes the decoded image bytes and runs ToTensor + Normalize (datasets/dataset_utils.py:58-61) on the device, fused
+        into q_sample.  fp32 batches are used as they are."""
         self.model = model
+        if input_layout not in ("NCHW", "NHWC"):
+            raise ValueError(f"input_layout must be 'NCHW' or 'NHWC', got {input_layout!r}")
+        self.input_layout = input_layout
+        self._norm_host = None if input_norm is None else tuple(torch.as_tensor(v, dtype=torch.float32).flatten() for v in input_norm)
+        self._norm_dev = (None, None)
         self.opt = FusedAdamEMA(model.model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay)
         self.reducer = GradAllReducer(model.model, bucket_mb=bucket_mb, group=group)
         self._stage = None
@@ -43,16 +52,25 @@ class TrainStep:
 
     def step(self, images: torch.Tensor) -> torch.Tensor:
         """images: fp32 [B,C,H,W] on the device, or a (pinned) host tensor which is
-        copied asynchronously first (trainers/ddpm_trainer.py:539).  Returns the 0-dim
-        device loss tensor of this rank (no host sync)."""
+        copied asynchronously first (trainers/ddpm_trainer.py:539); or the uint8 image bytes
+        ([B,C,H,W] / [B,H,W,C] per ``input_layout``), normalised on the device.  Returns the
+        0-dim device loss tensor of this rank (no host sync)."""
+        if images.dtype not in (torch.float32, torch.uint8):
+            raise TypeError(f"images must be float32 or uint8, got {images.dtype}")
         if not images.is_cuda:
             dev = next(self.model.parameters()).device
-            if self._stage is None or self._stage.shape != images.shape:
-                self._stage = torch.empty(images.shape, device=dev, dtype=torch.float32)
+            if self._stage is None or self._stage.shape != images.shape or self._stage.dtype != images.dtype:
+                self._stage = torch.empty(images.shape, device=dev, dtype=images.dtype)
             self._stage.copy_(images, non_blocking=True)
             images = self._stage
         m = self.model
-        if isinstance(getattr(m, "loss_fn", None), DiffusionLoss) and hasattr(m, "alphas_cumprod"):
+        ddpm_like = isinstance(getattr(m, "loss_fn", None), DiffusionLoss) and hasattr(m, "alphas_cumprod")
+        if images.dtype == torch.uint8:
+            if self._norm_host is not None and (self._norm_dev[0] is None or self._norm_dev[0].device != images.device):
+                self._norm_dev = tuple(v.to(images.device) for v in self._norm_host)
+            if not ddpm_like:      # score / energy variants take the normalised batch
+                images, _ = ops.ingest_u8(images, self._norm_dev[0], self._norm_dev[1], self.input_layout)
+        if ddpm_like:
             if self._use_step_graph and images.is_cuda and m.model.engine.use_graphs:
                 loss = self._ddpm_step_graphed(images)
             else:
@@ -72,7 +90,8 @@ class TrainStep:
     def _ddpm_step_graphed(self, images: torch.Tensor) -> torch.Tensor:
         eng = self.model.model.engine
         arena = eng.flat.data_ptr() if eng.flat is not None else 0
-        if self._g_in is None or self._g_in.shape != images.shape or self._g_in.device != images.device or arena != self._g_arena:
+        if self._g_in is None or self._g_in.shape != images.shape or self._g_in.dtype != images.dtype \
+                or self._g_in.device != images.device or arena != self._g_arena:
             # new batch shape / device, or the engine rebuilt its parameter arena (model.to(), first call): the captured graph
             # holds the old addresses
             # a host batch has already been staged into self._stage: that buffer is the graph's static input (no second copy)
@@ -113,9 +132,18 @@ class TrainStep:
         m = self.model
         eng = m.model.engine
         t = torch.randint(0, m.num_timesteps, (images.shape[0],), device=images.device)
-        noise = torch.randn_like(images)
+        if images.dtype == torch.uint8:        # decoded bytes: ToTensor + Normalize + q_sample in one launch
+            b, d1, d2, d3 = images.shape
+            shape = (b, d3, d1, d2) if self.input_layout == "NHWC" else (b, d1, d2, d3)
+            noise = torch.randn(shape, device=images.device, dtype=torch.float32)
+        else:
+            noise = torch.randn_like(images)
         w = m.loss_fn.time_weights(t)          # [B]-sized torch ops, issued before the forward so nothing waits on them later
-        xt = m._add_noise(images, t, noise)
+        if images.dtype == torch.uint8:
+            _, xt = ops.ingest_u8(images, self._norm_dev[0], self._norm_dev[1], self.input_layout, t, noise, m.alphas_cumprod,
+                                  want_x0=False)
+        else:
+            xt = m._add_noise(images, t, noise)
         eng.prepare(images.device)
         plan = eng.get_plan(xt.shape, True)
         eps = eng.run_forward(xt, t, plan)

@@ -325,6 +325,34 @@ int dmu_adam_ema(float* p, const float* g, float* m, float* v, float* ema,
                  int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                  int64_t step, float ema_decay, float grad_scale, dmu_stream_t stream);
 
+/* ------------------------------------------------------------------ *
+ * Input ingest / sample formatting                   *
+ * ------------------------------------------------------------------ */
+
+/* datasets/dataset_utils.py:58-61 (T.ToTensor + T.Normalize) and trainers/ddpm_trainer.py:539 (`batch[0].to(device)`),
+ * optionally fused with models/ddpm.py:286-296 `_add_noise`:
+ *   x0 = (img / 255 - mean[c]) / std[c]          xt = sqrt(acp[t]) x0 + sqrt(1 - acp[t]) noise
+ * img: uint8 decoded pixels, [B,H,W,C] when hwc != 0 (PIL / numpy order) else [B,C,H,W]; outputs fp32 [B,C,H,W].
+ * mean / std: device pointers to `channels` floats, NULL = skip that step (ToTensor only).  x0_out or xt_out may be
+ * NULL (not both); xt_out needs noise, t, alphas_cumprod.  The host->device copy carries 1 byte per value. */
+int dmu_ingest_u8(const uint8_t* img, int32_t hwc, const float* mean, const float* std,
+                  const float* noise, const int64_t* t, const float* alphas_cumprod,
+                  float* x0_out, float* xt_out, int64_t batch, int32_t channels, int64_t hw, dmu_stream_t stream);
+
+/* trainers/ddpm_trainer.py:821-834: torchvision `make_grid(samples, nrow, padding, pad_value)` followed by
+ * `save_image`'s quantisation `mul(255).add_(0.5).clamp_(0,255).to(uint8)`, written as [grid_h, grid_w, grid_c] bytes
+ * (the array PIL encodes).  Image k (row-major cell order) is read from
+ *   x + (k % period) * stride_mod + (k / period) * stride_div        (fp32 [channels, height, width] each, contiguous)
+ * so the trainer's "one row per sample, one column per saved denoising step" arrangement of a stacked
+ * [steps, B, C, H, W] tensor is period = steps, stride_mod = B*C*H*W, stride_div = C*H*W without the cat/cat copies;
+ * a plain [N,C,H,W] batch is period = N, stride_mod = C*H*W.  One image => no border; 1 channel => replicated to 3
+ * (both as torchvision does).  dmu_image_grid_shape is host-only arithmetic. */
+int dmu_image_grid_shape(int64_t n_images, int32_t channels, int32_t height, int32_t width, int32_t nrow, int32_t padding,
+                         int64_t* grid_h, int64_t* grid_w, int32_t* grid_c);
+int dmu_image_grid_u8(const float* x, int64_t n_images, int64_t period, int64_t stride_mod, int64_t stride_div,
+                      int32_t channels, int32_t height, int32_t width, int32_t nrow, int32_t padding, float pad_value,
+                      uint8_t* out, dmu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,127 @@
+"""GPU parity for the ingest / sample-formatting row, through the C ABI: bit-exact against the oracle
+restatement of torchvision's ToTensor / Normalize / make_grid / save_image (pinned to torchvision in tests/test_pipeline_cpu.py)."""
+
+import pytest
+import torch
+
+from oracle import pipeline as OP, process as P
+
+pytestmark = pytest.mark.gpu
+
+MEAN, STD = (0.5, 0.4, 0.3), (0.5, 0.25, 0.2)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _ops():
+    from diffusion_model_universal_b200 import ops
+    return ops
+
+
+def _bytes(shape, seed):
+    return torch.randint(0, 256, shape, generator=torch.Generator().manual_seed(seed), dtype=torch.uint8)
+
+
+@pytest.mark.parametrize("shape,layout", [((5, 32, 32, 3), "NHWC"), ((5, 3, 32, 32), "NCHW"), ((3, 7, 5, 3), "NHWC"),
+                                          ((3, 3, 7, 5), "NCHW"), ((2, 6, 6, 1), "NHWC"), ((128, 32, 32, 3), "NHWC")])
+def test_ingest_u8_bit_exact(dev, shape, layout):
+    ops = _ops()
+    img = _bytes(shape, sum(shape))
+    c = shape[3] if layout == "NHWC" else shape[1]
+    mean, std = MEAN[:c], STD[:c]
+    ref = OP.ingest(img, mean, std, layout)
+    md, sd = torch.tensor(mean, device=dev), torch.tensor(std, device=dev)
+    x0, xt = ops.ingest_u8(img.to(dev), md, sd, layout)
+    assert xt is None and torch.equal(x0.cpu(), ref)
+    # ToTensor only / one of the two steps
+    assert torch.equal(ops.ingest_u8(img.to(dev), None, None, layout)[0].cpu(), OP.ingest(img, None, None, layout))
+    assert torch.equal(ops.ingest_u8(img.to(dev), md, None, layout)[0].cpu(), OP.ingest(img, mean, None, layout))
+    # fused with q_sample: same bits as normalise-then-dmu_q_sample and as the oracle
+    g = torch.Generator().manual_seed(1)
+    t = torch.randint(0, 1000, (shape[0],), generator=g)
+    noise = torch.randn(ref.shape, generator=g)
+    acp = P.linear_schedule(1e-4, 0.02, 1000)[2]
+    x0b, xt = ops.ingest_u8(img.to(dev), md, sd, layout, t.to(dev), noise.to(dev), acp.to(dev))
+    assert torch.equal(x0b, x0)
+    assert torch.equal(xt, ops.q_sample(x0, t.to(dev), noise.to(dev), acp.to(dev)))
+    assert torch.equal(xt.cpu(), P.q_sample(ref, t, noise, acp))
+    assert ops.ingest_u8(img.to(dev), md, sd, layout, t.to(dev), noise.to(dev), acp.to(dev), want_x0=False)[0] is None
+
+
+def test_ingest_u8_edges(dev):
+    ops = _ops()
+    ramp = torch.arange(256, dtype=torch.uint8).view(1, 16, 16, 1)               # every byte value; end points exact
+    h = torch.tensor([0.5], device=dev)
+    x = ops.ingest_u8(ramp.to(dev), h, h, "NHWC")[0]
+    assert torch.equal(x.cpu(), OP.ingest(ramp, (0.5,), (0.5,), "NHWC")) and x.min() == -1 and x.max() == 1
+    e = ops.ingest_u8(torch.empty((0, 4, 4, 3), dtype=torch.uint8, device=dev), None, None, "NHWC")[0]      # empty batch
+    assert e.shape == (0, 3, 4, 4)
+    odd = _bytes((2, 3, 4, 4), 9).to(dev)
+    view = odd.flatten()[1:1 + 48].view(1, 3, 4, 4)                                # byte pointer not 4-aligned: scalar route
+    assert torch.equal(ops.ingest_u8(view.contiguous(), None, None, "NCHW")[0], ops.ingest_u8(view.clone(), None, None, "NCHW")[0])
+    with pytest.raises(RuntimeError):
+        ops.ingest_u8(_bytes((1, 4, 4, 3), 0), None, None, "NHWC")                 # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("n,c,nrow,pad,pv", [(8, 3, 4, 2, 0.0), (7, 3, 3, 1, 0.5), (1, 3, 8, 2, 0.0), (5, 1, 8, 2, 1.0),
+                                             (6, 3, 11, 0, 0.0), (88, 3, 11, 2, 0.0)])
+def test_image_grid_u8_bit_exact(dev, n, c, nrow, pad, pv):
+    ops = _ops()
+    x = torch.randn(n, c, 32, 32, generator=torch.Generator().manual_seed(n)) * 0.7 + 0.5
+    x[0, 0, 0, :4] = torch.tensor([0.0, 1.0, -3.0, 7.0])
+    ref = OP.to_u8_hwc(OP.make_grid(x, nrow, pad, pv))
+    got = ops.image_grid_u8(x.to(dev), nrow, pad, pv)
+    assert got.dtype == torch.uint8 and got.shape == ref.shape
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_denoising_grid_matches_trainer_layout(dev):
+    """trainers/ddpm_trainer.py:815-834: rows = samples, columns = saved steps, read straight from the stacked intermediates."""
+    from diffusion_model_universal_b200 import pipeline
+    g = torch.Generator().manual_seed(2)
+    inter = [torch.rand(8, 3, 32, 32, generator=g) * 1.2 - 0.1 for _ in range(11)]
+    ref = OP.to_u8_hwc(OP.make_grid(OP.denoising_rows(inter), nrow=11, padding=2))
+    got = pipeline.denoising_grid([t.to(dev) for t in inter])
+    assert not got.is_cuda and torch.equal(got, ref)
+    ing = pipeline.DeviceIngest(MEAN, STD, dev)
+    b = _bytes((4, 32, 32, 3), 3)
+    assert torch.equal(ing(b).cpu(), OP.ingest(b, MEAN, STD, "NHWC"))
+    assert torch.equal(pipeline.image_grid(inter[0].to(dev), nrow=4).cpu(), OP.to_u8_hwc(OP.make_grid(inter[0], 4, 2)))
+
+
+def test_trainstep_image_bytes_equal_float_batches(dev):
+    """TrainStep fed the decoded bytes (pinned host memory, 1 byte per value over PCIe) takes the same steps as when fed the
+    fp32 batch the reference's DataLoader builds from them — through the eager warm-up steps and the captured step graph."""
+    import diffusion_model_universal_b200 as D
+    from diffusion_model_universal_b200.trainer import TrainStep
+    from oracle import weights as W
+    cfg = {"beta_start": 1e-4, "beta_end": 0.02, "image_size": 32, "image_channels": 3, "model_channels": 32, "loss_type": "mse",
+           "precision": "bf16",
+           "loss_config": {"use_time_weighting": True, "time_weight_type": "snr", "time_weight_params": {"min_weight": 0.1, "max_weight": 1.0}}}
+    batches = [_bytes((8, 32, 32, 3), 20 + i) for i in range(7)]     # steps 0-2 eager warm-up, 3 = capture + replay, 4+ = replay
+    res = []
+    for kind in ("u8", "f32"):
+        m = D.DDPM(cfg)
+        sd = m.state_dict()
+        sd.update(W.make_state_dict(W.unet_param_spec(32, 3, "model."), 7))
+        m.load_state_dict(sd)
+        m.to(dev)
+        ts = TrainStep(m, lr=1e-4, input_norm=(MEAN, STD), input_layout="NHWC")
+        torch.manual_seed(11)
+        losses = []
+        for b in batches:
+            src = b.pin_memory() if kind == "u8" else OP.ingest(b, MEAN, STD, "NHWC").pin_memory()
+            losses.append(ts.step(src).clone())
+        torch.cuda.synchronize()
+        assert ts._graph is not None and ts._g_in.dtype == (torch.uint8 if kind == "u8" else torch.float32)
+        res.append((torch.stack(losses).cpu(), m.model.engine.flat.clone().cpu()))
+    assert torch.isfinite(res[0][0]).all()
+    # the network input is bit-identical (test_ingest_u8_bit_exact); the weight-gradient atomics are not ordered, so compare
+    # like test_trainstep_whole_step_graph_matches_piecewise does
+    for a, b in zip(res[0][0].tolist(), res[1][0].tolist()):
+        assert abs(a - b) < 3e-2 * abs(b), (res[0][0], res[1][0])
+    from conftest import rel_l2
+    assert rel_l2(res[0][1], res[1][1]) < 1e-3
