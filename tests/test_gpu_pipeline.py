@@ -47,7 +47,10 @@ def test_ingest_u8_bit_exact(dev, shape, layout):
     x0b, xt = ops.ingest_u8(img.to(dev), md, sd, layout, t.to(dev), noise.to(dev), acp.to(dev))
     assert torch.equal(x0b, x0)
     assert torch.equal(xt, ops.q_sample(x0, t.to(dev), noise.to(dev), acp.to(dev)))
-    assert torch.equal(xt.cpu(), P.q_sample(ref, t, noise, acp))
+    # the CPU oracle's vectorised sqrt of the [B] coefficients is not correctly rounded on every host (MKL VML: <= 1 ulp), the
+    # device's is; dmu_q_sample itself is pinned bit-exactly to the reference fixture in test_gpu_process.py
+    from conftest import rel_l2
+    assert rel_l2(xt, P.q_sample(ref, t, noise, acp)) < 1e-6
     assert ops.ingest_u8(img.to(dev), md, sd, layout, t.to(dev), noise.to(dev), acp.to(dev), want_x0=False)[0] is None
 
 
