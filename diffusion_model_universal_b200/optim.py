@@ -48,3 +48,77 @@ class FusedAdamEMA:
         for k, (o, n) in eng.offs.items():
             out[prefix + k] = self.ema[o:o + n].view(eng.named[k].shape).clone()
         return out
+
+    # ------------------------------------------------------------------ checkpoint interop
+    def _order(self):
+        """Parameter names in ``model.parameters()`` order — the index space of torch.optim.Adam's state_dict."""
+        return [k for k, _ in self.unet.named_parameters()]
+
+    def state_dict(self):
+        """The dict ``torch.optim.Adam(model.parameters(), ...).state_dict()`` would hold at this point
+        (trainers/ddpm_trainer.py:139-143,873), so a checkpoint written here resumes in the reference trainer and
+        vice versa: per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` cut out of the flat moment arenas."""
+        names = self._order()
+        state = {}
+        if self.step_count > 0:
+            eng = self._ensure()
+            for i, k in enumerate(names):
+                o, n = eng.offs[k]
+                shape = eng.named[k].shape
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[o:o + n].view(shape).clone(),
+                            "exp_avg_sq": self.v[o:o + n].view(shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(names)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd, device=None):
+        """Inverse of ``state_dict``: accepts the reference trainer's ``optimizer_state_dict`` (trainers/ddpm_trainer.py:917)."""
+        groups = sd["param_groups"]
+        names = self._order()
+        if len(groups) != 1 or list(groups[0]["params"]) != list(range(len(names))):
+            raise ValueError(f"expected one parameter group over {len(names)} parameters (the reference's Adam), got "
+                             f"{[len(g['params']) for g in groups]}")
+        g = groups[0]
+        if g.get("amsgrad") or g.get("maximize") or g.get("decoupled_weight_decay"):
+            raise ValueError("amsgrad / maximize / decoupled weight decay are not implemented by the fused Adam")
+        self.lr, self.betas, self.eps, self.weight_decay = float(g["lr"]), tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"])
+        state = sd["state"]
+        if not state:
+            self.step_count, self.m, self.v = 0, None, None
+            return
+        if sorted(state) != list(range(len(names))):
+            raise ValueError("optimizer state must cover every parameter")
+        steps = {int(float(st["step"])) for st in state.values()}
+        if len(steps) != 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): one fused launch applies one bias correction")
+        eng = self.unet.engine
+        if eng.flat is None:
+            if device is None:
+                device = next(self.unet.parameters()).device
+            eng.prepare(device)
+        ema = self.ema
+        self.m = None
+        self._ensure()
+        if ema is not None and ema.numel() == eng.flat.numel() and ema.device == eng.flat.device:
+            self.ema = ema                      # keep EMA weights loaded before the optimizer state
+        for i, k in enumerate(names):
+            o, n = eng.offs[k]
+            for key, arena in (("exp_avg", self.m), ("exp_avg_sq", self.v)):
+                src = state[i][key]
+                if src.numel() != n:
+                    raise ValueError(f"{key} of parameter {i} ({k}) has {src.numel()} elements, expected {n}")
+                arena[o:o + n].copy_(src.reshape(-1))
+        self.step_count = steps.pop()
+
+    def load_ema_state_dict(self, sd, prefix=""):
+        """EMA weights from the reference's ``ema_model.state_dict()`` (trainers/ddpm_trainer.py:872,914-915); buffers and
+        other keys outside ``prefix`` + parameter name are ignored."""
+        if self.ema_decay is None:
+            return
+        eng = self._ensure()
+        for k, (o, n) in eng.offs.items():
+            if prefix + k not in sd:
+                raise KeyError(f"EMA state has no entry {prefix + k}")
+            self.ema[o:o + n].copy_(sd[prefix + k].reshape(-1))

@@ -160,3 +160,29 @@ class TrainStep:
             self._works = works
         else:
             eng.run_backward(plan, dpred)
+
+    # ------------------------------------------------------------------ checkpoint interop
+    def checkpoint(self, epoch: int, config=None, best_val_loss: float = float("inf")) -> dict:
+        """The dict ``DDPMTrainer.save_checkpoint`` writes (trainers/ddpm_trainer.py:869-877): model and EMA-model
+        ``state_dict``s under the reference's names and torch.optim.Adam's state layout, so ``torch.save`` of it resumes in
+        either implementation."""
+        m = self.model
+        ema_sd = None
+        if self.opt.ema_decay is not None and m.model.engine.flat is not None:
+            ema_sd = {k: v.detach().clone() for k, v in m.state_dict().items()}          # buffers as they are
+            ema_sd.update(self.opt.ema_state_dict(prefix="model."))
+        return {"epoch": epoch, "model_state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
+                "ema_model_state_dict": ema_sd, "optimizer_state_dict": self.opt.state_dict(), "config": config,
+                "best_val_loss": best_val_loss, "scheduler_state_dict": None}
+
+    def load_checkpoint(self, ckpt: dict) -> int:
+        """``DDPMTrainer.load_checkpoint`` (trainers/ddpm_trainer.py:897-925) for a dict read with ``torch.load``:
+        parameters, Adam moments and step count, EMA weights.  Returns the epoch."""
+        m = self.model
+        m.load_state_dict(ckpt["model_state_dict"])
+        dev = next(m.parameters()).device
+        m.model.engine.prepare(dev)
+        self.opt.load_state_dict(ckpt["optimizer_state_dict"], device=dev)
+        if ckpt.get("ema_model_state_dict") is not None:
+            self.opt.load_ema_state_dict(ckpt["ema_model_state_dict"], prefix="model.")
+        return int(ckpt["epoch"])

@@ -361,3 +361,43 @@ def test_trainstep_whole_step_graph_matches_piecewise():
     for a, b in zip(*[r[0] for r in runs]):
         assert abs(a - b) < 3e-2 * abs(a), (runs[0][0], runs[1][0])
     assert rel_l2(runs[1][1], runs[0][1]) < 1e-3          # parameters after 7 Adam steps
+
+
+def test_checkpoint_resumes_in_torch_adam_and_back():
+    """SURVEY.md §8 f4 / trainers/ddpm_trainer.py:869-925: the reference trainer's checkpoint dict written after real steps
+    loads into torch.optim.Adam (moments, step count, hyper-parameters) and back into a fresh fused optimizer."""
+    import diffusion_model_universal_b200 as D
+    from diffusion_model_universal_b200.trainer import TrainStep
+    f = load_golden("ddpm_train.pt")
+    dev = torch.device("cuda:0")
+    x0 = f["x0"].to(dev)
+    m = _load(D.DDPM(_cfg(f["C"], "bf16")), W.unet_param_spec(f["C"], 3, "model."), f["wseed"]).to(dev)
+    ts = TrainStep(m, lr=1e-4, ema_decay=0.999)
+    torch.manual_seed(5)
+    for _ in range(5):
+        ts.step(x0)
+    ck = ts.checkpoint(epoch=2)
+    sd = ck["optimizer_state_dict"]
+    assert len(sd["state"]) == 314 and all(float(s["step"]) == 5.0 for s in sd["state"].values())
+    ref = torch.nn.ParameterList([torch.nn.Parameter(p.detach().clone()) for p in m.parameters()])
+    ropt = torch.optim.Adam(ref.parameters(), lr=1.0)
+    ropt.load_state_dict(sd)
+    eng = m.model.engine
+    g = torch.randn(eng.gflat.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 1e-3
+    eng.gflat.copy_(g)
+    for (k, _), p in zip(m.model.named_parameters(), ref):
+        o, n = eng.offs[k]
+        p.grad = g[o:o + n].view(p.shape).clone()
+    ts.opt.step()
+    ropt.step()
+    for (k, p), q in zip(m.model.named_parameters(), ref):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7), k
+    m2 = _load(D.DDPM(_cfg(f["C"], "bf16")), W.unet_param_spec(f["C"], 3, "model."), f["wseed"] + 1).to(dev)
+    ts2 = TrainStep(m2, lr=3.0, ema_decay=0.999)
+    assert ts2.load_checkpoint(ck) == 2 and ts2.opt.step_count == 5 and ts2.opt.lr == 1e-4
+    for k, v in ck["model_state_dict"].items():
+        assert torch.equal(m2.state_dict()[k], v), k
+    e1, e2 = ck["ema_model_state_dict"], ts2.opt.ema_state_dict("model.")
+    assert all(torch.equal(e1[k], e2[k]) for k in e2)
+    torch.manual_seed(9)
+    assert torch.isfinite(ts2.step(x0))
