@@ -381,7 +381,8 @@ def test_checkpoint_resumes_in_torch_adam_and_back():
     assert len(sd["state"]) == 314 and all(float(s["step"]) == 5.0 for s in sd["state"].values())
     ref = torch.nn.ParameterList([torch.nn.Parameter(p.detach().clone()) for p in m.parameters()])
     ropt = torch.optim.Adam(ref.parameters(), lr=1.0)
-    ropt.load_state_dict(sd)
+    import copy
+    ropt.load_state_dict(copy.deepcopy(sd))        # torch keeps the dict's `step` tensors by reference and increments them
     eng = m.model.engine
     g = torch.randn(eng.gflat.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 1e-3
     eng.gflat.copy_(g)
