@@ -95,3 +95,25 @@ def test_trainstep_takes_image_bytes(monkeypatch):
         ts.step(b.to(torch.int32))
     with pytest.raises(ValueError):
         TrainStep(m, input_layout="HWC")
+
+
+def test_trainstep_image_bytes_on_the_generic_route(monkeypatch):
+    """Score-based model: TrainStep has no fused front end for it, so the bytes are normalised first (one launch) and the
+    model's own loss_function runs on the result — same step as with the float batch."""
+    import diffusion_model_universal_b200 as D
+    from diffusion_model_universal_b200.trainer import TrainStep
+    from conftest import load_golden
+    fake_device.install(monkeypatch)
+    f = load_golden("score.pt")
+    b = _bytes((2, 3, 32, 32), 8)
+    out = []
+    for kind in ("u8", "f32"):
+        m = D.ScoreBasedDiffusion(dict(f["cfg"]))
+        sd = m.state_dict()
+        sd.update(W.make_state_dict(W.scorenet_param_spec(f["C"], 3, "model."), f["wseed"]))
+        m.load_state_dict(sd)
+        ts = TrainStep(m, lr=1e-3, input_norm=(MEAN, STD), input_layout="NCHW", ema_decay=None)
+        torch.manual_seed(3)
+        loss = ts.step(b if kind == "u8" else OP.ingest(b, MEAN, STD, "NCHW"))
+        out.append((loss.clone(), m.model.engine.flat.clone()))
+    assert torch.isfinite(out[0][0]) and torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
