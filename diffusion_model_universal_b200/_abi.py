@@ -135,6 +135,8 @@ _SIGS = {
     "dmu_ingest_u8": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
     "dmu_image_grid_shape": (c_i32, [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, P(c_i64), P(c_i64), P(c_i32)]),
     "dmu_image_grid_u8": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
+    "dmu_image_grid_range_u8": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, C.c_double, C.c_double,
+                                        c_vp, c_vp]),
 }
 EXPORTS = tuple(_SIGS)
 

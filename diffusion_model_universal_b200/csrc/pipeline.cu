@@ -89,8 +89,11 @@ __device__ __forceinline__ uint8_t quantise(float v) {
 }
 
 // One thread per grid pixel: which cell, which image, then C plane reads and Cg byte writes.
+// NORM: make_grid(normalize=True, value_range=(lo, hi)) first maps every image value to (clamp(v, lo, hi) - lo) / den,
+// den = max(hi - lo, 1e-5) (torchvision's norm_ip); the padding value is not normalised.
+template <bool NORM>
 __global__ void __launch_bounds__(256) image_grid_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, GridGeom G,
-                                                            float pad_value) {
+                                                            float pad_value, float lo, float hi, float den) {
     const int64_t total = G.hg * G.wg;
     const uint8_t padq = quantise(pad_value);
     const int cell_h = G.h + G.pad, cell_w = G.w + G.pad;
@@ -106,7 +109,11 @@ __global__ void __launch_bounds__(256) image_grid_u8_kernel(const float* __restr
             continue;
         }
         const float* src = x + (k % G.period) * G.stride_mod + (k / G.period) * G.stride_div + (int64_t)iy * G.w + ix;
-        for (int c = 0; c < G.cg; ++c) dst[c] = quantise(src[(int64_t)(G.c == 1 ? 0 : c) * G.h * G.w]);
+        for (int c = 0; c < G.cg; ++c) {
+            float v = src[(int64_t)(G.c == 1 ? 0 : c) * G.h * G.w];
+            if constexpr (NORM) v = __fdiv_rn(__fsub_rn(fminf(fmaxf(v, lo), hi), lo), den);
+            dst[c] = quantise(v);
+        }
     }
 }
 
@@ -171,8 +178,25 @@ int dmu_image_grid_u8(const float* x, int64_t n_images, int64_t period, int64_t 
     DMU_REQUIRE(grid_geometry(n_images, channels, height, width, nrow, padding, G), "dmu_image_grid_u8: bad geometry");
     DMU_REQUIRE(period >= 1 && stride_mod >= 0 && stride_div >= 0, "dmu_image_grid_u8: bad image addressing");
     G.period = period; G.stride_mod = stride_mod; G.stride_div = stride_div;
-    image_grid_u8_kernel<<<pipe_grid(G.hg * G.wg, 256), 256, 0, as_stream(stream)>>>(x, out, G, pad_value);
+    image_grid_u8_kernel<false><<<pipe_grid(G.hg * G.wg, 256), 256, 0, as_stream(stream)>>>(x, out, G, pad_value, 0.f, 0.f, 1.f);
     return check_launch("dmu_image_grid_u8");
+}
+
+int dmu_image_grid_range_u8(const float* x, int64_t n_images, int64_t period, int64_t stride_mod, int64_t stride_div,
+                            int32_t channels, int32_t height, int32_t width, int32_t nrow, int32_t padding, float pad_value,
+                            double range_lo, double range_hi, uint8_t* out, dmu_stream_t stream) {
+    GridGeom G;
+    DMU_REQUIRE(x && out, "dmu_image_grid_range_u8: null pointer");
+    DMU_REQUIRE(grid_geometry(n_images, channels, height, width, nrow, padding, G), "dmu_image_grid_range_u8: bad geometry");
+    DMU_REQUIRE(period >= 1 && stride_mod >= 0 && stride_div >= 0, "dmu_image_grid_range_u8: bad image addressing");
+    DMU_REQUIRE(range_lo <= range_hi, "dmu_image_grid_range_u8: empty value range");
+    G.period = period; G.stride_mod = stride_mod; G.stride_div = stride_div;
+    // torchvision: python doubles; max(high - low, 1e-5) is taken in double and each scalar becomes a float operand
+    const double span = range_hi - range_lo;
+    const float den = (float)(span > 1e-5 ? span : 1e-5);
+    image_grid_u8_kernel<true><<<pipe_grid(G.hg * G.wg, 256), 256, 0, as_stream(stream)>>>(x, out, G, pad_value, (float)range_lo,
+                                                                                          (float)range_hi, den);
+    return check_launch("dmu_image_grid_range_u8");
 }
 
 }  // extern "C"

@@ -126,8 +126,9 @@ def image_grid_shape(n, c, h, w, nrow=8, padding=2):
     return gh.value, gw.value, gc.value
 
 
-def image_grid_u8(x, nrow=8, padding=2, pad_value=0.0, transpose=False):
+def image_grid_u8(x, nrow=8, padding=2, pad_value=0.0, transpose=False, value_range=None):
     """trainers/ddpm_trainer.py:821-834: make_grid + save_image's 8-bit quantisation in one launch.
+    value_range=(lo, hi) is make_grid's normalize=True, value_range=... (scripts/generate.py:119-133).
     x: fp32 [N,C,H,W] (cells filled in order) or [A,B,C,H,W]; with transpose=True the 5-D tensor is read as
     image k = x[k % A, k // A] — the trainer's "row per sample, column per saved step" view of a stacked list of
     intermediates.  Returns uint8 [grid_h, grid_w, grid_c] on the device."""
@@ -148,8 +149,13 @@ def image_grid_u8(x, nrow=8, padding=2, pad_value=0.0, transpose=False):
     gh, gw, gc = image_grid_shape(n, c, h, w, nrow, padding)
     out = torch.empty((gh, gw, gc), device=x.device, dtype=torch.uint8)
     _launched()
-    check(_abi.lib().dmu_image_grid_u8(x.data_ptr(), n, period, s_mod, s_div, c, h, w, nrow, padding, float(pad_value),
-                                       out.data_ptr(), _stream()), "image_grid_u8")
+    if value_range is None:
+        check(_abi.lib().dmu_image_grid_u8(x.data_ptr(), n, period, s_mod, s_div, c, h, w, nrow, padding, float(pad_value),
+                                           out.data_ptr(), _stream()), "image_grid_u8")
+    else:
+        lo, hi = (float(v) for v in value_range)
+        check(_abi.lib().dmu_image_grid_range_u8(x.data_ptr(), n, period, s_mod, s_div, c, h, w, nrow, padding, float(pad_value),
+                                                 lo, hi, out.data_ptr(), _stream()), "image_grid_range_u8")
     return out
 
 

@@ -43,9 +43,10 @@ class DeviceIngest:
         return x0
 
 
-def image_grid(samples: torch.Tensor, nrow: int = 8, padding: int = 2, pad_value: float = 0.0) -> torch.Tensor:
-    """``save_image(make_grid(samples, nrow, padding, pad_value))``'s pixel array: uint8 [Hg, Wg, 3] on the device."""
-    return ops.image_grid_u8(samples.contiguous(), nrow, padding, pad_value)
+def image_grid(samples: torch.Tensor, nrow: int = 8, padding: int = 2, pad_value: float = 0.0, value_range=None) -> torch.Tensor:
+    """``save_image(samples, nrow=, padding=, pad_value=[, normalize=True, value_range=])``'s pixel array: uint8
+    [Hg, Wg, 3] on the device (scripts/generate.py:119-133 passes value_range=(-1, 1))."""
+    return ops.image_grid_u8(samples.contiguous(), nrow, padding, pad_value, value_range=value_range)
 
 
 def denoising_grid(intermediates: List[torch.Tensor], padding: int = 2, path: Optional[str] = None) -> torch.Tensor:

@@ -352,6 +352,12 @@ int dmu_image_grid_shape(int64_t n_images, int32_t channels, int32_t height, int
 int dmu_image_grid_u8(const float* x, int64_t n_images, int64_t period, int64_t stride_mod, int64_t stride_div,
                       int32_t channels, int32_t height, int32_t width, int32_t nrow, int32_t padding, float pad_value,
                       uint8_t* out, dmu_stream_t stream);
+/* scripts/generate.py:119-133 `save_image(samples, nrow=..., normalize=True, value_range=(-1, 1))`: the same grid with
+ * every image value first mapped to (clamp(v, lo, hi) - lo) / max(hi - lo, 1e-5) (torchvision's norm_ip; the range is
+ * given in double like the Python scalars, the divisor is rounded to float once). */
+int dmu_image_grid_range_u8(const float* x, int64_t n_images, int64_t period, int64_t stride_mod, int64_t stride_div,
+                            int32_t channels, int32_t height, int32_t width, int32_t nrow, int32_t padding, float pad_value,
+                            double range_lo, double range_hi, uint8_t* out, dmu_stream_t stream);
 
 #ifdef __cplusplus
 }

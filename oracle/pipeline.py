@@ -38,10 +38,14 @@ def ingest(batch_u8: torch.Tensor, mean=None, std=None, layout="NHWC") -> torch.
     return torch.stack(out) if out else torch.empty((0,) + tuple(batch_u8.shape[1:]), dtype=torch.float32)
 
 
-def make_grid(x: torch.Tensor, nrow: int = 8, padding: int = 2, pad_value: float = 0.0) -> torch.Tensor:
-    """torchvision.utils.make_grid (normalize=False) for a [N,C,H,W] batch -> [C', Hg, Wg]."""
+def make_grid(x: torch.Tensor, nrow: int = 8, padding: int = 2, pad_value: float = 0.0, value_range=None) -> torch.Tensor:
+    """torchvision.utils.make_grid for a [N,C,H,W] batch -> [C', Hg, Wg]; value_range=(lo, hi) is normalize=True with
+    that range (norm_ip: clamp, subtract lo, divide by max(hi - lo, 1e-5)), as scripts/generate.py:119-133 calls it."""
     if x.size(1) == 1:
         x = torch.cat((x, x, x), 1)
+    if value_range is not None:
+        lo, hi = value_range
+        x = x.clone().clamp_(min=lo, max=hi).sub_(lo).div_(max(hi - lo, 1e-5))
     if x.size(0) == 1:
         return x.squeeze(0)
     n = x.size(0)

@@ -369,7 +369,10 @@ class FakeLib:
         _obj(gh).value, _obj(gw).value, _obj(gc).value = hg, wg, cg
         return 0
 
-    def dmu_image_grid_u8(self, x, n, period, s_mod, s_div, c, h, w, nrow, padding, pad_value, out, stream):
+    def dmu_image_grid_range_u8(self, x, n, period, s_mod, s_div, c, h, w, nrow, padding, pad_value, lo, hi, out, stream):
+        return self.dmu_image_grid_u8(x, n, period, s_mod, s_div, c, h, w, nrow, padding, pad_value, out, stream, rng=(lo, hi))
+
+    def dmu_image_grid_u8(self, x, n, period, s_mod, s_div, c, h, w, nrow, padding, pad_value, out, stream, rng=None):
         self._count()
         gh, gw, gc = C.c_int64(0), C.c_int64(0), C.c_int32(0)
         self.dmu_image_grid_shape(n, c, h, w, nrow, padding, gh, gw, gc)
@@ -381,6 +384,8 @@ class FakeLib:
         for k in range(n):
             img = _flat(_addr(x) + 4 * ((k % period) * s_mod + (k // period) * s_div), c * h * w).view(c, h, w)
             img = img.expand(3, h, w) if c == 1 else img
+            if rng is not None:
+                img = (img.clamp(rng[0], rng[1]) - rng[0]) / max(rng[1] - rng[0], 1e-5)
             y0, x0 = (k // xm) * (h + pad) + pad, (k % xm) * (w + pad) + pad
             grid[y0:y0 + h, x0:x0 + w] = quant(img.permute(1, 2, 0))
         _flat(_addr(out), grid.numel(), dtype=torch.uint8).copy_(grid.reshape(-1))

@@ -43,3 +43,13 @@ def test_error_reporting_without_a_device():
     p = _abi.ConvParams()
     assert h.dmu_conv2d(ctypes.byref(p), None) != 0
     assert h.dmu_sinusoidal_embedding(1, 0, 1, 1, 2, None) != 0   # dim 2 divides by zero in the reference formula
+    assert h.dmu_ingest_u8(None, 1, None, None, None, None, None, None, None, 2, 3, 16, None) != 0
+    assert b"null image pointer" in h.dmu_last_error()
+    assert h.dmu_ingest_u8(None, 1, None, None, None, None, None, None, None, 0, 3, 16, None) == 0    # empty batch
+    assert h.dmu_image_grid_u8(None, 4, 4, 48, 0, 3, 4, 4, 2, 2, 0.0, None, None) != 0
+    assert h.dmu_image_grid_range_u8(1, 4, 4, 48, 0, 3, 4, 4, 2, 2, 0.0, 1.0, -1.0, 1, None) != 0
+    assert b"empty value range" in h.dmu_last_error()
+    gh, gw, gc = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+    assert h.dmu_image_grid_shape(88, 3, 32, 32, 11, 2, ctypes.byref(gh), ctypes.byref(gw), ctypes.byref(gc)) == 0
+    assert (gh.value, gw.value, gc.value) == (8 * 34 + 2, 11 * 34 + 2, 3)          # trainers/ddpm_trainer.py:832 grid
+    assert h.dmu_image_grid_shape(0, 3, 32, 32, 11, 2, None, None, None) != 0

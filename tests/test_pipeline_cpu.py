@@ -45,6 +45,22 @@ def test_oracle_grid_matches_torchvision_bit_for_bit(n, c, nrow, pad, pv, tmp_pa
     assert torch.equal(OP.to_u8_hwc(g), torch.from_numpy(np.array(Image.open(path))))
 
 
+@pytest.mark.parametrize("rng", [(-1.0, 1.0), (0.0, 1.0), (-0.5, 2.0)])
+def test_oracle_normalised_grid_matches_torchvision(rng, tmp_path):
+    """scripts/generate.py:119-133: save_image(samples, nrow=, normalize=True, value_range=(-1, 1))."""
+    tvu = pytest.importorskip("torchvision.utils")
+    Image = pytest.importorskip("PIL.Image")
+    np = pytest.importorskip("numpy")
+    x = torch.randn(9, 3, 6, 5, generator=torch.Generator().manual_seed(4)) * 1.5
+    g = OP.make_grid(x, 3, 2, 0.0, value_range=rng)
+    assert torch.equal(g, tvu.make_grid(x, nrow=3, padding=2, normalize=True, value_range=rng))
+    path = tmp_path / "g.png"
+    tvu.save_image(x, path, nrow=3, normalize=True, value_range=rng)
+    assert torch.equal(OP.to_u8_hwc(g), torch.from_numpy(np.array(Image.open(path))))
+    one = tvu.make_grid(x[0], normalize=True, value_range=rng)          # single images, as generate.py's per-sample loop
+    assert torch.equal(OP.make_grid(x[:1], value_range=rng), one)
+
+
 def test_wrappers_address_images_like_the_trainer(monkeypatch):
     from diffusion_model_universal_b200 import ops
     fake_device.install(monkeypatch)
@@ -57,6 +73,8 @@ def test_wrappers_address_images_like_the_trainer(monkeypatch):
     x = torch.rand(7, 1, 4, 4, generator=g)
     assert torch.equal(ops.image_grid_u8(x, nrow=3, padding=1, pad_value=0.25), OP.to_u8_hwc(OP.make_grid(x, 3, 1, 0.25)))
     assert torch.equal(ops.image_grid_u8(x[:1]), OP.to_u8_hwc(OP.make_grid(x[:1])))
+    y = torch.randn(5, 3, 4, 4, generator=g)
+    assert torch.equal(ops.image_grid_u8(y, nrow=2, value_range=(-1, 1)), OP.to_u8_hwc(OP.make_grid(y, 2, 2, 0.0, (-1, 1))))
     b = _bytes((2, 6, 4, 3), 1)
     mean, std = torch.tensor(MEAN), torch.tensor(STD)
     x0, xt = ops.ingest_u8(b, mean, std, "NHWC")
