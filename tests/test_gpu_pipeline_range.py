@@ -1,6 +1,5 @@
 """GPU parity of the normalised sample grid (scripts/generate.py:119-133: save_image(..., normalize=True, value_range=(-1, 1)))
-against the torchvision-pinned oracle.  Collected last on purpose: this entry point was added after the round's GPU budget was
-spent and has not run on a B200 yet."""
+against the torchvision-pinned oracle (tests/test_pipeline_cpu.py)."""
 
 import pytest
 import torch
