@@ -10,6 +10,11 @@
 #include "common.cuh"
 
 namespace dmu {
+namespace tc {   // conv_edge_tc.cu
+int edge_wgrad_tc_supported(const dmu_tensor4* wide, const dmu_tensor4* narrow, int N, int H, int W, int Cw, int Cn);
+int edge_wgrad_tc_launch(const dmu_tensor4* wide, const dmu_tensor4* narrow, int N, int H, int W, int Cw, int Cn, int sgn, float* out,
+                         int64_t o_c, int64_t o_t, int64_t o_j, float* dbias, float* dbias_n, cudaStream_t stream);
+}  // namespace tc
 namespace edge {
 
 constexpr int kMaxNarrow = 4;    // channels on the thin side
@@ -453,6 +458,10 @@ int dmu_wgrad_edge(const dmu_wgrad_params* p, dmu_stream_t stream) {
         A.o_c = p->dw_sb; A.o_j = p->dw_sa; A.o_t = p->dw_st;
         A.dbias = nullptr; A.dbias_n = p->dbias;
     }
+    // opt-in tensor-core form (conv_edge_tc.cu, DMU_EDGE_WGRAD_TC=1): same contract, pixels as the contraction axis
+    if (A.R == 3 && A.S == 3 && A.pad == 1 && tc::edge_wgrad_tc_supported(&A.wide, &A.narrow, A.N, A.H, A.W, A.Cw, A.Cn))
+        return tc::edge_wgrad_tc_launch(&A.wide, &A.narrow, A.N, A.H, A.W, A.Cw, A.Cn, A.sgn, A.out, A.o_c, A.o_t, A.o_j, A.dbias,
+                                        A.dbias_n, as_stream(stream));
     const int threads = 256;
     const size_t smem = edge::narrow_wgrad_smem(A, threads);
     DMU_REQUIRE(smem <= 200 * 1024, "dmu_conv2d_wgrad/edge: tile does not fit shared memory");
