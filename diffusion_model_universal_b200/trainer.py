@@ -44,6 +44,9 @@ class TrainStep:
         # time weights, q_sample, forward, loss, three-part backward): ~30 small eager launches and four graph launches per step
         # become one.  DMU_STEP_GRAPH=0 keeps the piecewise path.
         self._use_step_graph = os.environ.get("DMU_STEP_GRAPH", "1") != "0"
+        # Opt-in (DMU_DP_GRAPH=1, not yet measured on GPUs): with several ranks, capture the three backward parts AND their NCCL
+        # all-reduces into the same graph instead of replaying the front and issuing the rest eagerly.
+        self._dp_in_graph = os.environ.get("DMU_DP_GRAPH", "0") == "1"
         self._graph = None
         self._g_in = self._g_loss = self._g_dpred = self._g_plan = None
         self._g_warm = 0
@@ -108,6 +111,10 @@ class TrainStep:
             with torch.cuda.graph(g):
                 if self.reducer.world == 1:
                     self._g_loss = self._ddpm_step(self._g_in)
+                elif self._dp_in_graph:      # backward parts and their bucketed all-reduces are graph nodes too
+                    self._g_loss = self._ddpm_step(self._g_in)
+                    self.reducer.finish(self._works)
+                    self._works = None
                 else:      # data parallel: the graph ends at dL/d(eps); the three backward graphs alternate with the all-reduces
                     self._g_loss, self._g_dpred, self._g_plan = self._ddpm_front(self._g_in)
             self._g_launches = ops.LAUNCHES - n0
@@ -116,7 +123,10 @@ class TrainStep:
         self._graph.replay()
         ops.LAUNCHES += self._g_launches
         if self.reducer.world > 1:
-            self._ddpm_back(self._g_plan, self._g_dpred)
+            if self._dp_in_graph:
+                self._works = []           # the replayed graph already holds the summed gradients
+            else:
+                self._ddpm_back(self._g_plan, self._g_dpred)
         return self._g_loss
 
     def _ddpm_step(self, images: torch.Tensor) -> torch.Tensor:
