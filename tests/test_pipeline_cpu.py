@@ -135,3 +135,20 @@ def test_trainstep_image_bytes_on_the_generic_route(monkeypatch):
         loss = ts.step(b if kind == "u8" else OP.ingest(b, MEAN, STD, "NCHW"))
         out.append((loss.clone(), m.model.engine.flat.clone()))
     assert torch.isfinite(out[0][0]) and torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
+def test_grid_shape_entry_point_matches_torchvision_for_random_geometries():
+    """dmu_image_grid_shape is host-only arithmetic in the real library: check it against make_grid's output shape."""
+    import ctypes
+    import random
+    tvu = pytest.importorskip("torchvision.utils")
+    from diffusion_model_universal_b200 import _abi
+    h = _abi.lib()
+    rnd = random.Random(0)
+    for _ in range(200):
+        n, c = rnd.randint(1, 40), rnd.choice([1, 3, 4])
+        hh, ww, nrow, pad = rnd.randint(1, 9), rnd.randint(1, 9), rnd.randint(1, 12), rnd.randint(0, 3)
+        ref = tvu.make_grid(torch.zeros(n, c, hh, ww), nrow=nrow, padding=pad)
+        gh, gw, gc = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+        assert h.dmu_image_grid_shape(n, c, hh, ww, nrow, pad, ctypes.byref(gh), ctypes.byref(gw), ctypes.byref(gc)) == 0
+        assert (gc.value, gh.value, gw.value) == tuple(ref.shape), (n, c, hh, ww, nrow, pad)
