@@ -97,7 +97,7 @@ _SIGS = {
     "dmu_last_error": (C.c_char_p, []),
     "dmu_sizeof": (c_i32, [C.c_char_p]),
     "dmu_q_sample": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
-    "dmu_ddpm_step": (c_i32, [c_vp] * 8 + [c_i64, c_i64, c_vp]),
+    "dmu_ddpm_step": (c_i32, [c_vp] * 7 + [c_i64, c_vp, c_i64, c_i64, c_vp]),
     "dmu_ddim_step": (c_i32, [c_vp] * 9 + [c_i64, c_i64, c_vp]),
     "dmu_langevin_score_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_i64, c_vp]),
     "dmu_langevin_energy_step": (c_i32, [c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_i64, c_vp]),

@@ -90,14 +90,14 @@ struct QSample {
 // ------------------------------------------------------------------ DDPM posterior step
 struct DdpmStep {
     const float* x; const float* eps; const float* noise; const int64_t* t;
-    const float* betas; const float* alphas; const float* acp; float* out;
+    const float* betas; const float* alphas; const float* acp; int64_t T; float* out;
     struct C { float inv_sqrt_alpha, k_eps, sd; bool add; };
     __device__ __forceinline__ C coef(int64_t b) const {
         const int64_t tb = t[b];
         const bool pos = t[0] > 0;  // ddpm.py:311,323: the whole batch follows t[0]
         const float alpha = alphas[tb], ac = acp[tb], beta = betas[tb];
-        // ddpm.py:311 indexes acp[t-1]; python's negative index wraps for t == 0 rows of a mixed batch
-        const float ac_prev = pos ? acp[tb > 0 ? tb - 1 : 0] : 1.f;
+        // ddpm.py:311 indexes acp[t-1]: the tensor index -1 of a t == 0 row in a mixed batch wraps to the last table entry
+        const float ac_prev = pos ? acp[tb > 0 ? tb - 1 : T - 1] : 1.f;
         C c;
         const float one_m = SUB(1.f, ac);
         const float beta_tilde = MUL(DIV(SUB(1.f, ac_prev), one_m), beta);
@@ -315,12 +315,13 @@ int dmu_q_sample(const float* x0, const float* noise, const int64_t* t, const fl
 }
 
 int dmu_ddpm_step(const float* x, const float* eps, const float* noise, const int64_t* t, const float* betas,
-                  const float* alphas, const float* acp, float* out, int64_t batch, int64_t inner, dmu_stream_t stream) {
+                  const float* alphas, const float* acp, int64_t num_timesteps, float* out, int64_t batch, int64_t inner,
+                  dmu_stream_t stream) {
     if (batch == 0 || inner == 0) return 0;  // empty batch: nothing to do (pointers may be NULL)
     DMU_REQUIRE(x && eps && t && betas && alphas && acp && out, "dmu_ddpm_step: null pointer");
-    DMU_REQUIRE(batch >= 0 && inner >= 0, "dmu_ddpm_step: negative size");
+    DMU_REQUIRE(batch >= 0 && inner >= 0 && num_timesteps >= 1, "dmu_ddpm_step: negative size / empty tables");
     DMU_REQUIRE(aligned16(x) && aligned16(eps) && aligned16(out) && aligned16(noise), "dmu_ddpm_step: buffers must be 16-byte aligned");
-    DdpmStep f{x, eps, noise, t, betas, alphas, acp, out};
+    DdpmStep f{x, eps, noise, t, betas, alphas, acp, num_timesteps, out};
     return launch_per_sample(f, batch, inner, as_stream(stream), "dmu_ddpm_step");
 }
 

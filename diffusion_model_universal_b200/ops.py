@@ -47,6 +47,14 @@ def _f32c(t, name):
     return t
 
 
+def _index_vec(t, batch, name):
+    """Timestep / table-index vectors are read as int64 [B] by the kernels: anything else would be reinterpreted, not cast."""
+    if t.dtype != torch.int64:
+        raise TypeError(f"{name} must be int64 (got {t.dtype}); cast with .long()")
+    if t.dim() != 1 or t.shape[0] != batch or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous [B] vector with B = {batch}, got shape {tuple(t.shape)}")
+
+
 def t4_nchw(t: torch.Tensor) -> Tensor4:
     """Describe a contiguous [N,C,H,W] tensor."""
     n, c, h, w = t.shape
@@ -74,6 +82,8 @@ def q_sample(x0, t, noise, alphas_cumprod):
     """models/ddpm.py:286-296."""
     _need_cuda(x0, t, noise, alphas_cumprod)
     x0, noise = _f32c(x0, "x0"), _f32c(noise, "noise")
+    _index_vec(t, x0.shape[0], "t")
+    _f32c(alphas_cumprod, "alphas_cumprod")
     out = torch.empty_like(x0)
     b = x0.shape[0]
     _launched()
@@ -165,13 +175,14 @@ def ddpm_step(x, eps, t, noise, betas, alphas, alphas_cumprod, out=None):
     x, eps = _f32c(x, "x"), _f32c(eps, "eps")
     if noise is not None:
         _f32c(noise, "noise")
-    if t.dtype != torch.int64:
-        raise TypeError("t must be int64")
+    _index_vec(t, x.shape[0], "t")
+    if not (betas.numel() == alphas.numel() == alphas_cumprod.numel()):
+        raise ValueError("betas, alphas and alphas_cumprod must have the same length")
     out = torch.empty_like(x) if out is None else out
     b = x.shape[0]
     _launched()
     check(_abi.lib().dmu_ddpm_step(x.data_ptr(), eps.data_ptr(), noise.data_ptr() if noise is not None else None, t.data_ptr(),
-                                   betas.data_ptr(), alphas.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
+                                   betas.data_ptr(), alphas.data_ptr(), alphas_cumprod.data_ptr(), betas.numel(), out.data_ptr(),
                                    b, x.numel() // max(b, 1), _stream()), "ddpm_step")
     return out
 
@@ -180,8 +191,7 @@ def ddim_step(x, eps, idx, noise, alphas, alphas_prev, sigmas, sqrt_one_minus_al
     """models/ddim.py:97-124 after the eps prediction; idx indexes the S-entry tables."""
     _need_cuda(x, eps, idx)
     x, eps = _f32c(x, "x"), _f32c(eps, "eps")
-    if idx.dtype != torch.int64:
-        raise TypeError("idx must be int64")
+    _index_vec(idx, x.shape[0], "idx")
     out = torch.empty_like(x) if out is None else out
     b = x.shape[0]
     _launched()

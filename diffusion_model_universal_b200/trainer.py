@@ -11,16 +11,70 @@ Mirror of trainers/ddpm_trainer.py:539-555 (``images.to(device)`` ->
   * the loss stays on the device — callers read it when they want it.
 """
 
+from collections import OrderedDict
 from typing import Optional
 
 import os
 
 import torch
+import torch.distributed as dist
 
 from . import ops
 from .losses import DiffusionLoss
 from .optim import FusedAdamEMA
 from .parallel import GradAllReducer
+
+
+class _FlatParams:
+    """Flat fp32 parameter / gradient arenas for a network that has no launch-plan engine of its own (EnergyNet,
+    models/energy_based.py:51-85): the parameters become views of ``flat`` and their ``.grad`` views of ``gflat`` (autograd
+    accumulates into an installed ``.grad`` in place), which is all FusedAdamEMA and GradAllReducer need of an engine."""
+
+    def __init__(self, module):
+        self.module = module
+        self.flat = self.gflat = None
+        self.named = OrderedDict(module.named_parameters())
+        self.offs = {}
+
+    def _in_arena(self):
+        if self.flat is None:
+            return False
+        lo, hi = self.flat.data_ptr(), self.flat.data_ptr() + self.flat.numel() * 4
+        return all(p.device == self.flat.device and lo <= p.data_ptr() < hi for p in self.named.values())
+
+    def prepare(self, device=None):
+        if self._in_arena():
+            return
+        device = device if device is not None else next(iter(self.named.values())).device
+        offs, total = {}, 0
+        for k, p in self.named.items():
+            offs[k] = (total, p.numel())
+            total += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(total, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for k, p in self.named.items():
+                o, n = offs[k]
+                flat[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = flat[o:o + n].view(p.shape)
+        self.flat, self.offs = flat, offs
+        self.gflat = torch.zeros_like(flat)
+
+    def install_grads(self):
+        """Zero the gradient arena and make every ``param.grad`` a view of it."""
+        self.prepare()
+        self.gflat.zero_()
+        for k, p in self.named.items():
+            o, n = self.offs[k]
+            p.grad = self.gflat[o:o + n].view(p.shape)
+
+
+class _EngineShim:
+    """What FusedAdamEMA / GradAllReducer take as ``unet``: an object with ``.engine`` and the module's parameter iterators."""
+
+    def __init__(self, module):
+        self.engine = _FlatParams(module)
+        self.named_parameters = module.named_parameters
+        self.parameters = module.parameters
 
 
 class TrainStep:
@@ -36,8 +90,13 @@ class TrainStep:
         self.input_layout = input_layout
         self._norm_host = None if input_norm is None else tuple(torch.as_tensor(v, dtype=torch.float32).flatten() for v in input_norm)
         self._norm_dev = (None, None)
-        self.opt = FusedAdamEMA(model.model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay)
-        self.reducer = GradAllReducer(model.model, bucket_mb=bucket_mb, group=group)
+        # the UNet-based models (DDPM / DDIM / score) own an Engine with flat arenas; any other network (EnergyNet) gets them here
+        self._net = model.model if hasattr(model.model, "engine") else _EngineShim(model.model)
+        self._own_arena = not hasattr(model.model, "engine")
+        self.opt = FusedAdamEMA(self._net, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay)
+        self.reducer = GradAllReducer(self._net, bucket_mb=bucket_mb, group=group)
+        self.group = group
+        self._synced = False
         self._stage = None
         self._works = None
         # Single-GPU DDPM steps replay ONE CUDA graph of everything between the input batch and the gradient arena (RNG draws,
@@ -67,7 +126,9 @@ class TrainStep:
             self._stage.copy_(images, non_blocking=True)
             images = self._stage
         m = self.model
-        ddpm_like = isinstance(getattr(m, "loss_fn", None), DiffusionLoss) and hasattr(m, "alphas_cumprod")
+        ddpm_like = isinstance(getattr(m, "loss_fn", None), DiffusionLoss) and hasattr(m, "alphas_cumprod") and not self._own_arena
+        if not self._synced:
+            self.sync_parameters(images.device if images.is_cuda else next(m.parameters()).device)
         if images.dtype == torch.uint8:
             if self._norm_host is not None and (self._norm_dev[0] is None or self._norm_dev[0].device != images.device):
                 self._norm_dev = tuple(v.to(images.device) for v in self._norm_host)
@@ -78,7 +139,11 @@ class TrainStep:
                 loss = self._ddpm_step_graphed(images)
             else:
                 loss = self._ddpm_step(images)
-        else:   # generic route through autograd (score / energy variants)
+        elif self._own_arena:   # EnergyNet: autograd accumulates straight into the views of the gradient arena
+            self._net.engine.install_grads()
+            loss = m.loss_function(images)
+            loss.backward()
+        else:   # generic route through autograd (score variant): _UNetFn.backward fills the engine's gradient arena
             loss = m.loss_function(images)
             loss.backward()
             for p in m.parameters():      # the arena holds this step's gradients; views must not accumulate into the next
@@ -89,6 +154,22 @@ class TrainStep:
         self._works = None
         self.opt.step(grad_scale=scale)
         return loss.detach()
+
+    def sync_parameters(self, device=None):
+        """What DDP does at construction (trainers/ddpm_trainer.py:130-136): every rank starts from rank 0's parameters; here
+        also the optimizer's moment and EMA arenas when they exist (after ``load_checkpoint``).  No-op on one rank."""
+        eng = self._net.engine
+        eng.prepare(device if device is not None else next(self.model.parameters()).device)
+        self._synced = True
+        if self.reducer.world == 1:
+            return
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        for t in (eng.flat, self.opt.m, self.opt.v, self.opt.ema):
+            if t is not None:
+                dist.broadcast(t, src=src, group=self.group)
+        steps = torch.tensor([self.opt.step_count], device=eng.flat.device, dtype=torch.int64)
+        dist.broadcast(steps, src=src, group=self.group)
+        self.opt.step_count = int(steps.item())
 
     def _ddpm_step_graphed(self, images: torch.Tensor) -> torch.Tensor:
         eng = self.model.model.engine
@@ -127,7 +208,8 @@ class TrainStep:
                 self._works = []           # the replayed graph already holds the summed gradients
             else:
                 self._ddpm_back(self._g_plan, self._g_dpred)
-        return self._g_loss
+        # the graph's static output is overwritten by the next replay: hand out a copy (one 4-byte device copy, no sync)
+        return self._g_loss.clone()
 
     def _ddpm_step(self, images: torch.Tensor) -> torch.Tensor:
         """``DDPM.loss_function`` + ``backward`` (models/ddpm.py:207-235) straight on the engine: same RNG calls in the same
@@ -178,7 +260,7 @@ class TrainStep:
         either implementation."""
         m = self.model
         ema_sd = None
-        if self.opt.ema_decay is not None and m.model.engine.flat is not None:
+        if self.opt.ema_decay is not None and self._net.engine.flat is not None:
             ema_sd = {k: v.detach().clone() for k, v in m.state_dict().items()}          # buffers as they are
             ema_sd.update(self.opt.ema_state_dict(prefix="model."))
         return {"epoch": epoch, "model_state_dict": {k: v.detach().clone() for k, v in m.state_dict().items()},
@@ -191,8 +273,9 @@ class TrainStep:
         m = self.model
         m.load_state_dict(ckpt["model_state_dict"])
         dev = next(m.parameters()).device
-        m.model.engine.prepare(dev)
+        self._net.engine.prepare(dev)
         self.opt.load_state_dict(ckpt["optimizer_state_dict"], device=dev)
         if ckpt.get("ema_model_state_dict") is not None:
             self.opt.load_ema_state_dict(ckpt["ema_model_state_dict"], prefix="model.")
+        self.sync_parameters(dev)      # ranks that loaded different files (or only rank 0 did) continue from rank 0's state
         return int(ckpt["epoch"])

@@ -57,9 +57,12 @@ int dmu_q_sample(const float* x0, const float* noise, const int64_t* t, const fl
 /* models/ddpm.py:306-329 `_reverse_diffusion_step` after the eps prediction.
  * `noise` is the randn_like draw of ddpm.py:324 (may be NULL when the caller
  * knows t == 0).  The t[0] > 0 branch of ddpm.py:311,323 is taken on device
- * from t[0]; no host sync.  out may alias x. */
+ * from t[0]; no host sync.  `num_timesteps` is the length of the three tables:
+ * a row with t == 0 inside a batch whose t[0] > 0 reads alphas_cumprod[t-1] =
+ * alphas_cumprod[num_timesteps-1], like the reference's tensor index -1 (ddpm.py:311).
+ * out may alias x. */
 int dmu_ddpm_step(const float* x, const float* eps, const float* noise, const int64_t* t,
-                  const float* betas, const float* alphas, const float* alphas_cumprod,
+                  const float* betas, const float* alphas, const float* alphas_cumprod, int64_t num_timesteps,
                   float* out, int64_t batch, int64_t inner, dmu_stream_t stream);
 
 /* models/ddim.py:97-124 `_ddim_sample` after the eps prediction; `idx`

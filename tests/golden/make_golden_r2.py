@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Round-2 golden fixtures from the LIVE reference: BASELINE configs[2]'s real shape and full sampling chains.
+
+    python tests/golden/make_golden_r2.py [--ref /root/reference]
+
+Run in the build container only.  Writes
+  * ``unet_forward_cfg3.pt`` — ``UNet.forward`` (models/ddpm.py:93-135) at C = 64, 64x64, B = 2 (the shape of
+    BASELINE configs[2]) with the deterministic parity weights AND with the benchmark's weights;
+  * ``chains_full.pt`` — free-running FULL chains with the benchmark's weights (the reference's default initialisation at
+    ``torch.manual_seed(1234)`` + N(0, 0.02) on the zero-initialised tensors, bench.reseed_zero_init(seed 7)):
+    ``DDPM.generate_samples_with_intermediates`` over all 1000 steps at 32x32 (models/ddpm.py:257-284) and the repaired
+    50-step DDIM driver (arithmetic of models/ddim.py:97-124 unchanged) at 64x64, eta = 0.
+The benchmark's weights are not stored (64 MB): the tests rebuild them from the same two seeds — tests/test_host_logic.py
+pins that our constructors reproduce the reference's default initialisation bit for bit.
+"""
+
+import argparse
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import weights as W  # noqa: E402
+from bench import reseed_zero_init, model_config  # noqa: E402
+
+INIT_SEED, ZERO_SEED = 1234, 7
+
+
+def bench_model(cls, cfg):
+    torch.manual_seed(INIT_SEED)
+    m = cls(cfg)
+    reseed_zero_init(m, ZERO_SEED)
+    return m
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    args = ap.parse_args()
+    sys.path.insert(0, args.ref)
+    from models import DDPM, DDIM  # noqa
+    from models.ddpm import UNet  # noqa
+
+    torch.set_num_threads(8)
+    ref_cfg = lambda size: {k: v for k, v in model_config(size, "fp32").items() if k != "precision"}
+
+    # ------------------------------------------------------------------ 1. UNet forward at configs[2]'s shape
+    out = {}
+    net = UNet(3, 64, 3)
+    net.load_state_dict(W.make_state_dict(W.unet_param_spec(64, 3, prefix=""), 14), strict=True)
+    g = torch.Generator().manual_seed(114)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    t = torch.randint(0, 1000, (2,), generator=g)
+    with torch.no_grad():
+        y = net(x, t)
+    out["parity_weights"] = {"C": 64, "seed": 14, "x": x, "t": t, "eps": y}
+    dm = bench_model(DDIM, ref_cfg(64))
+    with torch.no_grad():
+        yb = dm.forward(x, t)
+    out["bench_weights"] = {"init_seed": INIT_SEED, "zero_seed": ZERO_SEED, "x": x, "t": t, "eps": yb}
+    print("cfg3 eps std", y.std().item(), yb.std().item())
+    torch.save(out, os.path.join(HERE, "unet_forward_cfg3.pt"))
+
+    # ------------------------------------------------------------------ 2. DDPM-1000 free-running chain, 32x32, B = 2
+    chains = {"init_seed": INIT_SEED, "zero_seed": ZERO_SEED}
+    m = bench_model(DDPM, ref_cfg(32))
+    torch.manual_seed(5)
+    with torch.no_grad():
+        inter = m.generate_samples_with_intermediates(2, torch.device("cpu"), save_interval=50)
+    chains["ddpm1000"] = {"rng_seed": 5, "batch": 2, "save_interval": 50, "intermediates": torch.stack(inter), "final": inter[-1]}
+    print("ddpm-1000 final absmax", inter[-1].abs().max().item(), "std", inter[-1].std().item(), "snapshots", len(inter))
+
+    # ------------------------------------------------------------------ 3. DDIM-50 (eta 0) free-running chain, 64x64, B = 2
+    torch.manual_seed(8)
+    x = torch.randn(2, 3, 64, 64)
+    x_init = x.clone()
+    traj = []
+    with torch.no_grad():
+        for i in range(len(dm.ddim_timesteps) - 1, -1, -1):
+            tt = torch.full((2,), int(dm.ddim_timesteps[i]))
+            eps = dm.forward(x, tt)
+            x = dm._ddim_sample(x, torch.full((2,), i), None, pred_noise=eps)
+            if i % 5 == 0:
+                traj.append(x.clone())
+    chains["ddim50"] = {"rng_seed": 8, "batch": 2, "x_init": x_init, "every": 5, "traj": torch.stack(traj), "final": x}
+    print("ddim-50 final absmax", x.abs().max().item(), "std", x.std().item())
+    torch.save(chains, os.path.join(HERE, "chains_full.pt"))
+    print("written")
+
+
+if __name__ == "__main__":
+    main()

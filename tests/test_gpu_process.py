@@ -57,6 +57,29 @@ def test_ddpm_step_device_branch_and_sizes(dev):
     assert torch.equal(want, got)
 
 
+def test_ddpm_step_mixed_batch_and_index_dtype(dev):
+    """A batch whose rows carry different timesteps: the t[0] > 0 branch applies to every row (ddpm.py:311,323) and a t == 0 row
+    reads alphas_cumprod[-1] = alphas_cumprod[T-1] like the reference's tensor index.  int32 timesteps are rejected, not
+    reinterpreted."""
+    ops = _ops()
+    sched = P.linear_schedule(1e-4, 0.02, 1000)
+    b, a, acp = (t.to(dev) for t in sched)
+    g = torch.Generator().manual_seed(12)
+    x, e, z = (torch.randn(4, 3, 8, 8, generator=g) for _ in range(3))
+    for tv in ([5, 0, 999, 1], [0, 7, 0, 3]):
+        t = torch.tensor(tv, dtype=torch.long)
+        ref = P.ddpm_reverse_step(x, e, t, z, *sched)
+        out = ops.ddpm_step(x.to(dev), e.to(dev), t.to(dev), z.to(dev), b, a, acp)
+        assert rel_l2(out, ref) < 5e-7, tv
+    t = torch.tensor([5, 0, 999, 1], device=dev)
+    with pytest.raises(TypeError):
+        ops.q_sample(x.to(dev), t.int(), z.to(dev), acp)
+    with pytest.raises(TypeError):
+        ops.ddpm_step(x.to(dev), e.to(dev), t.int(), z.to(dev), b, a, acp)
+    with pytest.raises(ValueError):
+        ops.q_sample(x.to(dev), t[:3], z.to(dev), acp)
+
+
 def test_empty_batch(dev):
     ops = _ops()
     b, a, acp = (t.to(dev) for t in P.linear_schedule(1e-4, 0.02, 1000))

@@ -136,11 +136,10 @@ def test_ddim_and_ddpm_loops(monkeypatch):
     import oracle.process as P
     fake = D._abi.lib()
 
-    def ddpm_step(x, eps, noise, t, betas, alphas, acp, out, batch, inner, stream):
+    def ddpm_step(x, eps, noise, t, betas, alphas, acp, T, out, batch, inner, stream):
         n = batch * inner
         fl = fake_device._flat
         tv = fl(t, batch, dtype=torch.int64)
-        T = int(tv.max()) + 1
         z = fl(noise, n).view(batch, inner, 1, 1) if noise else None
         r = P.ddpm_reverse_step(fl(x, n).view(batch, inner, 1, 1), fl(eps, n).view(batch, inner, 1, 1), tv, z,
                                 fl(betas, T), fl(alphas, T), fl(acp, T))
