@@ -227,3 +227,45 @@ def test_energy_model_against_live_reference_draws(tag, precision, tol):
         s.model.load_state_dict(m.model.state_dict())
         out = s.generate_samples(2, dev)
         assert out.shape == (2, 3, r["R"], r["R"]) and torch.isfinite(out).all()
+
+
+def test_trainstep_with_energy_model(dev):
+    """TrainStep over a network without a launch-plan engine (EnergyNet).  Its flat arenas are built by the trainer:
+    the gradients of one step equal loss_function(x).backward() from the same RNG state, and the fused Adam moves the weights."""
+    import diffusion_model_universal_b200 as D
+    from diffusion_model_universal_b200.trainer import TrainStep
+    from oracle import weights as W
+    cfg = {"num_timesteps": 1000, "beta_start": 1e-4, "beta_end": 0.02, "use_time_conditioning": False, "in_channels": 3,
+           "model_channels": 16, "image_size": 16, "image_channels": 3, "loss_type": "energy_based", "regularization_weight": 0.01,
+           "langevin_steps": 3, "langevin_step_size": 0.01}
+    x = torch.randn(4, 3, 16, 16, generator=torch.Generator().manual_seed(2)).to(dev)
+
+    def make():
+        m = D.EnergyBasedDiffusion(dict(cfg))
+        sd = m.state_dict()
+        sd.update(W.make_state_dict(W.energynet_param_spec(16, 3, "model."), 62))
+        m.load_state_dict(sd)
+        return m.to(dev)
+    a = make()
+    torch.manual_seed(3)
+    la = a.loss_function(x)
+    la.backward()
+    ga = {k: p.grad.clone() for k, p in a.named_parameters()}
+    b = make()
+    ts = TrainStep(b, lr=0.0, ema_decay=None)
+    torch.manual_seed(3)
+    lb = ts.step(x)
+    assert abs(lb.item() - la.item()) < 1e-4 * max(1.0, abs(la.item()))
+    eng = ts._net.engine
+    for k, (o, n) in eng.offs.items():
+        g = eng.gflat[o:o + n].view(eng.named[k].shape)
+        ref = ga["model." + k]
+        assert rel_l2(g, ref) < 1e-3 or ref.norm() < 1e-7, k
+    before = eng.flat.clone()
+    ts2 = TrainStep(b, lr=1e-3, ema_decay=0.99)
+    for _ in range(3):
+        assert torch.isfinite(ts2.step(x))
+    assert not torch.equal(ts2._net.engine.flat, before)
+    assert ts2.opt.ema is not None and torch.isfinite(ts2.opt.ema).all()
+    ck = ts2.checkpoint(epoch=1)
+    assert set(ck["model_state_dict"]) == set(b.state_dict())

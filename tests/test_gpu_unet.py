@@ -463,7 +463,7 @@ def test_unet_forward_cfg3_shape_golden(precision):
 # Stated full-chain tolerances (BASELINE north_star: "final samples after a full 1000-step DDPM or 50-step DDIM chain within a
 # stated rel-L2"), free-running, same weights and same injected noise as the live reference; measured values and the per-snapshot
 # drift curves are committed under profiles/r02_chain_drift_*.json.
-CHAIN_TOL = {("ddpm1000", "fp32"): 5e-3, ("ddpm1000", "bf16"): 1e-1, ("ddim50", "fp32"): 5e-3, ("ddim50", "bf16"): 1e-1}
+CHAIN_TOL = {("ddpm1000", "fp32"): 1e-4, ("ddpm1000", "bf16"): 2e-2}      # measured: 3.9e-7 / 1.7e-3
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -498,10 +498,18 @@ def test_ddpm1000_full_chain_golden(precision):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_ddim50_full_chain_golden(precision):
-    """The repaired 50-step DDIM driver (models/ddim.py:97-124), eta = 0, at 64x64 with the benchmark's weights,
-    free-running from the reference's initial noise."""
+    """The repaired 50-step DDIM driver (models/ddim.py:97-124), eta = 0, at 64x64 with the benchmark's weights.
+
+    Measured (profiles/r02_chain_drift_*.json): free-running from the reference's initial noise, an fp32 implementation is at
+    2e-4 after 5 steps, 7e-3 after 10 and O(1) after 20 - and so is the reference's OWN eager GPU path (oracle/ = the same ATen
+    calls, on cuda) against its CPU run: with random weights eps is noise, x0 = (x - sqrt(1-a) eps) / sqrt(a) is divided by
+    sqrt(a) ~ 0.007 at the first steps and clamped, which turns rounding differences into sign flips.  The chain is chaotic, so
+    a final-sample rel-L2 has no meaning here; parity is stated per step instead, from EVERY state of the reference trajectory
+    (teacher-forced): one full step (UNet + fused update) lands within STEP_TOL of the reference's next state.  The free-running
+    drift of this implementation and of the eager GPU reference are recorded next to each other."""
     import diffusion_model_universal_b200 as D
     from diffusion_model_universal_b200 import ops
+    STEP_TOL = {"fp32": 1e-3, "bf16": 5e-2}[precision]
     f = load_golden("chains_full.pt")["ddim50"]
     m = _bench_model(D.DDIM, 64, precision)
     eng = m.model.engine
@@ -509,21 +517,59 @@ def test_ddim50_full_chain_golden(precision):
     torch.manual_seed(f["rng_seed"])
     x = torch.randn(B, 3, 64, 64)
     assert torch.equal(x, f["x_init"])
+
+    def step(xin, i):
+        b = xin.shape[0]
+        eps = m.forward(xin, torch.full((b,), int(m.ddim_timesteps[i]), device="cuda"))
+        eng.frozen = True
+        return ops.ddim_step(xin, eps, torch.full((b,), i, device="cuda"), None, m.ddim_alphas, m.ddim_alphas_prev, m.ddim_sigmas,
+                             m.ddim_sqrt_one_minus_alphas)
+    # (a) teacher-forced, every step, image 0 of the reference chain
+    tb = f["traj_b0"]
+    worst, forced = 0.0, []
+    with torch.no_grad():
+        for j, i in enumerate(range(49, -1, -1)):
+            src = f["x_init"][0:1] if j == 0 else tb[j - 1:j]
+            e = rel_l2(step(src.cuda(), i), tb[j:j + 1])
+            forced.append({"i": i, "rel_l2": e})
+            worst = max(worst, e)
+    print(f"ddim-50 {precision} teacher-forced: worst one-step rel-L2 {worst:.3e}")
+    # (b) free-running drift (recorded, asserted only over the first five steps in fp32 mode)
     x = x.cuda()
     curve, k = [], 0
     with torch.no_grad():
         for i in range(49, -1, -1):
-            eps = m.forward(x, torch.full((B,), int(m.ddim_timesteps[i]), device="cuda"))
-            eng.frozen = True
-            x = ops.ddim_step(x, eps, torch.full((B,), i, device="cuda"), None, m.ddim_alphas, m.ddim_alphas_prev, m.ddim_sigmas,
-                              m.ddim_sqrt_one_minus_alphas)
+            x = step(x, i)
             if i % f["every"] == 0:
                 curve.append({"i": i, "rel_l2": rel_l2(x, f["traj"][k])})
                 k += 1
     eng.frozen = False
-    _dump_drift(f"ddim50_{precision}", curve)
-    print(f"ddim-50 {precision} drift:", " ".join(f"{c['i']}:{c['rel_l2']:.2e}" for c in curve))
-    assert rel_l2(x, f["final"]) < CHAIN_TOL[("ddim50", precision)]
+    # (c) the reference's own eager path on this GPU (oracle = its ATen call sequence), free-running from the same noise
+    ref_curve = []
+    if precision == "fp32":
+        sd = {"model." + kk: v.detach() for kk, v in m.model.state_dict().items()}
+        _, _, acp = P.linear_schedule(1e-4, 0.02, 1000)
+        tables = tuple(t.cuda() for t in P.ddim_tables(acp, P.ddim_timesteps(1000, 50), 0.0))
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            xr, k = f["x_init"].cuda(), 0
+            with torch.no_grad():
+                for i in range(49, -1, -1):
+                    eps = U.unet_forward(sd, xr, torch.full((B,), int(m.ddim_timesteps[i]), device="cuda"))
+                    xr = P.ddim_step(xr, eps, torch.full((B,), i, device="cuda"), tables, 0.0)
+                    if i % f["every"] == 0:
+                        ref_curve.append({"i": i, "rel_l2": rel_l2(xr, f["traj"][k])})
+                        k += 1
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+        print("ddim-50 eager-GPU reference vs its CPU run:", " ".join(f"{c['i']}:{c['rel_l2']:.2e}" for c in ref_curve))
+    _dump_drift(f"ddim50_{precision}", {"free_running": curve, "teacher_forced": forced, "reference_eager_gpu_fp32_free_running": ref_curve})
+    print(f"ddim-50 {precision} free-running drift:", " ".join(f"{c['i']}:{c['rel_l2']:.2e}" for c in curve))
+    assert worst < STEP_TOL
+    assert torch.isfinite(x).all() and x.abs().max().item() <= 1.5       # x0 is clamped to [-1, 1] at every step
+    if precision == "fp32":
+        assert curve[0]["rel_l2"] < 1e-3       # five free-running steps
     # the public loop from the same seed on the device draws its own noise: shape / finiteness only
-    s = m.generate_samples(2, torch.device("cuda"))
-    assert s.shape == (2, 3, 64, 64) and torch.isfinite(s).all()
+    s2 = m.generate_samples(2, torch.device("cuda"))
+    assert s2.shape == (2, 3, 64, 64) and torch.isfinite(s2).all()
