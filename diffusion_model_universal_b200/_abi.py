@@ -31,6 +31,7 @@ class ConvParams(C.Structure):
         ("gather", c_i32), ("w_dtype", c_i32), ("impl", c_i32), ("_pad", c_i32),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
         ("gn_coef", c_vp), ("gn_silu", c_i32), ("_pad2", c_i32), ("a_out", Tensor4),
+        ("gn_fuse", c_vp), ("gn_fuse_mode", c_i32), ("_pad3", c_i32),
     ]
 
 
@@ -73,7 +74,7 @@ class AttnParams(C.Structure):
 
 
 class GnPgDesc(C.Structure):
-    _fields_ = [("red", c_vp), ("dgamma", c_vp), ("dbeta", c_vp), ("C", c_i32), ("_pad", c_i32)]
+    _fields_ = [("red", c_vp), ("dgamma", c_vp), ("dbeta", c_vp), ("C", c_i32), ("count", c_i32)]
 
 
 class RepackDesc(C.Structure):
@@ -108,6 +109,7 @@ _SIGS = {
     "dmu_conv2d": (c_i32, [P(ConvParams), c_vp]),
     "dmu_conv2d_workspace_bytes": (c_i64, []),
     "dmu_conv2d_gn_supported": (c_i32, [P(ConvParams)]),
+    "dmu_conv2d_gn_fuse_supported": (c_i32, [P(ConvParams)]),
     "dmu_gn_coef": (c_i32, [P(GnParams), c_vp, c_vp]),
     "dmu_conv2d_wgrad": (c_i32, [P(WgradParams), c_vp]),
     "dmu_gn_forward": (c_i32, [P(GnParams), c_vp]),

@@ -46,7 +46,6 @@ struct HaloArgs {
     // for the backward (weight gradient operand)
     const float* gn_coef; int gn_silu;
     __nv_bfloat16* a_out; int64_t a_sn, a_sh, a_sw;
-    int exp_flags;      // development aid (DMU_HALO_EXP): 1 = no proxy fence, 2 = no transform body (timing experiments only)
 };
 
 constexpr int kMaxAStages = 4, kMaxWStages = 8;
@@ -231,7 +230,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
                 mbar_wait(&a_full[sa], pa);
                 if (tdbg) tdbg[1] = clock64();
                 const uint32_t st = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes);
-                for (int i = tw; i < P.NR && !(P.exp_flags & 2); i += 8) {
+                for (int i = tw; i < P.NR; i += 8) {
                     const int L = L0 + i;
                     const int n = floordiv_dev(L, P.PH), hp = L - n * P.PH;
                     if (n < 0 || n >= P.N || hp < 1 || hp > P.H) continue;
@@ -282,7 +281,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
                     }
                 }
                 if (tdbg) tdbg[2] = clock64();
-                if (!(P.exp_flags & 1)) fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async proxy
+                fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (elect_one()) mbar_arrive(&a_ready[sa]);
                 if (tdbg) tdbg[3] = clock64();
@@ -471,7 +470,6 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
     cudaError_t e;
     if (p->gn_coef) {
         A.gn_coef = p->gn_coef; A.gn_silu = p->gn_silu;
-        { const char* e = getenv("DMU_HALO_EXP"); A.exp_flags = e ? atoi(e) : 0; }
         A.a_out = reinterpret_cast<__nv_bfloat16*>(p->a_out.ptr); A.a_sn = p->a_out.sn; A.a_sh = p->a_out.sh; A.a_sw = p->a_out.sw;
         e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64, true>, grid, dim3(448), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
                      : launch_pdl(conv3x3_halo_kernel<128, true>, grid, dim3(448), (size_t)smem, stream, dim3(1, 1, 1), maps, A);

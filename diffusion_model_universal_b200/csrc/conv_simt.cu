@@ -505,6 +505,11 @@ int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream) {
     DMU_REQUIRE(p->R > 0 && p->S > 0 && p->stride > 0 && p->pad >= 0, "dmu_conv2d: bad filter geometry");
     DMU_REQUIRE(p->gather == 0 || p->gather == 1, "dmu_conv2d: gather must be 0 or 1");
     DMU_REQUIRE((int64_t)p->N * p->Ho * p->Wo < (1ll << 31), "dmu_conv2d: too many output pixels");
+    if (p->gn_fuse_mode) {
+        DMU_REQUIRE(dmu_conv2d_gn_fuse_supported(p) > 0,
+                    "dmu_conv2d: gn_fuse is set but this launch cannot take the GroupNorm in its epilogue (dmu_conv2d_gn_fuse_supported == 0)");
+        return dmu_conv2d_tc(p, stream);
+    }
     if (p->gn_coef) {
         DMU_REQUIRE(p->impl != 1 && p->impl != 3 && p->impl != 4 && dmu_conv2d_tc_supported(p),
                     "dmu_conv2d: fused GroupNorm (gn_coef) needs the halo kernel: bf16 NHWC, channels %% 64 == 0, 3x3 stride 1 pad 1, >= 8x8");

@@ -117,10 +117,29 @@ static int build_gather0(const dmu_tensor4& x, int N, int Hi, int Wi, int C, int
         const uint64_t str[4] = {1, (uint64_t)x.sw * stride, (uint64_t)x.sh * stride, (uint64_t)x.sn};
         const uint32_t box[4] = {64, (uint32_t)b.BW, (uint32_t)b.BH, (uint32_t)b.BN};
         const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(x.ptr) + (int64_t)ph * x.sh + (int64_t)pw * x.sw;
-        if (int rc = make_map_bf16(&maps->a[m], base, 4, dims, str, box, what)) return rc;
+        if (maps) {      // nullptr: geometry only
+            if (int rc = make_map_bf16(&maps->a[m], base, 4, dims, str, box, what)) return rc;
+        }
     }
     return 0;
 }
+
+// GroupNorm fused into the epilogue (dmu_conv_params.gn_fuse), device view.  The tile of a CTA then holds whole images
+// (tiles_h == tiles_w == 1) and whole groups (64 % cpg == 0), so the statistics never leave the CTA.
+struct GnEpi {
+    int mode;                 // 0 none, 1 forward (normalise this launch's output), 2 backward (the accumulator is dy of the norm)
+    int G, cpg, silu, C;
+    float eps, cnt;           // cnt = cpg * H * W
+    const float* gamma; const float* beta;
+    float* sums;              // [N][G][2] raw (sum, sum of squares): written in mode 1, read in mode 2
+    __nv_bfloat16* a; int64_t a_sn, a_sh, a_sw;              // mode 1: normalised (+SiLU) output
+    const __nv_bfloat16* x; int64_t x_sn, x_sh, x_sw;        // mode 2: input of the norm
+    __nv_bfloat16* dx; int64_t dx_sn, dx_sh, dx_sw;          // mode 2: result
+    const __nv_bfloat16* add0; int64_t a0_sn, a0_sh, a0_sw;
+    const __nv_bfloat16* add1; int64_t a1_sn, a1_sh, a1_sw;
+    float* red;               // mode 2: [tiles][C][2] per-tile channel sums (sum du, sum du * xhat)
+    int epi_off;              // byte offset from the ring base of a region that is NOT part of the ring (written while the pipeline runs)
+};
 
 // ================================================================================================ fprop / dgrad kernel
 struct ConvArgs {
@@ -145,6 +164,7 @@ struct ConvArgs {
     int stage_bytes, a_off;   // stage stride and offset of the filter tile: a 64-pixel box only reserves 8 KB for the pixels
     int kps, kb_bytes;   // k-blocks per ring stage and bytes of one k-block (pixels + filters)
     int m64;             // 64-pixel tile computed by M = 64 MMAs
+    GnEpi gn;
 };
 
 constexpr int kBtImgs = 8;
@@ -155,6 +175,109 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+
+
+// ---------------------------------------------------------------------------- GroupNorm epilogue helpers (GnEpi)
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void unpack_bf16x8(const uint4& r, float* out) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ float gn_silu(float u) { return __fdividef(u, 1.f + __expf(-u)); }
+// du = dy * act'(u)   (same arithmetic as norm.cu's act_grad: the fused and the stand-alone GroupNorm must agree)
+__device__ __forceinline__ float gn_act_grad(float u, float dy, int silu) {
+    if (!silu) return dy;
+    const float sg = __fdividef(1.f, 1.f + __expf(-u));
+    return dy * (sg * fmaf(u, 1.f - sg, 1.f));
+}
+// Sum over the 32 lanes of a warp of a 32-vector held by every lane: on return lane l holds the total of element l.
+// Recursive halving: 31 shuffles, against 160 for element-wise butterflies.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float keep = up ? v[i + o] : v[i];
+            const float send = up ? v[i] : v[i + o];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    return v[0];
+}
+// (sum, sum of squares) of every W consecutive channels of a 32-channel chunk
+template <int W>
+__device__ __forceinline__ void gn_group_sums(const float* v, float* dst) {
+#pragma unroll
+    for (int k = 0; k < 32 / W; ++k) {
+        float su = 0.f, sq = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) { const float t = v[k * W + w]; su += t; sq = fmaf(t, t, sq); }
+        dst[2 * k] = su; dst[2 * k + 1] = sq;
+    }
+}
+// v <- act((v - mean) * rstd * gamma + beta); stat = (mean, rstd) of the chunk's first group onwards, gam / bet at the chunk's first channel
+template <int W>
+__device__ __forceinline__ void gn_apply32(float* v, const float* stat, const float* gam, const float* bet, int silu) {
+#pragma unroll
+    for (int k = 0; k < 32 / W; ++k) {
+        const float mean = stat[2 * k], rstd = stat[2 * k + 1];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int i = k * W + w;
+            const float sc = rstd * gam[i];
+            const float t = fmaf(v[i], sc, bet[i] - mean * sc);
+            v[i] = silu ? gn_silu(t) : t;
+        }
+    }
+}
+// backward, first pass over a chunk: t1 = du, t2 = du * xhat per element; part = per-group (sum gamma du, sum gamma du xhat) of this row
+template <int W>
+__device__ __forceinline__ void gn_bwd_pass1(const float* dy, const float* xv, const float* mr, const float* gam, const float* bet, int silu,
+                                             float* t1, float* t2, float* part) {
+#pragma unroll
+    for (int k = 0; k < 32 / W; ++k) {
+        const float mean = mr[2 * k], rstd = mr[2 * k + 1];
+        float ga = 0.f, gb = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int i = k * W + w;
+            const float d = xv[i] - mean, g = gam[i];
+            const float du = gn_act_grad(fmaf(d, rstd * g, bet[i]), dy[i], silu);
+            const float e = du * d * rstd;
+            t1[i] = du; t2[i] = e;
+            ga = fmaf(g, du, ga); gb = fmaf(g, e, gb);
+        }
+        part[2 * k] = ga; part[2 * k + 1] = gb;
+    }
+}
+// backward, second pass: o = rstd (gamma du - A - xhat B) with ab = (A, B) / cnt of the row's image and group
+template <int W>
+__device__ __forceinline__ void gn_bwd_pass2(const float* dy, const float* xv, const float* mr, const float* ab, const float* gam, const float* bet,
+                                             int silu, float* o) {
+#pragma unroll
+    for (int k = 0; k < 32 / W; ++k) {
+        const float mean = mr[2 * k], rstd = mr[2 * k + 1];
+        const float k1 = -rstd * rstd * ab[2 * k + 1];
+        const float k0 = -rstd * ab[2 * k] - mean * k1;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int i = k * W + w;
+            const float sc = rstd * gam[i];
+            const float du = gn_act_grad(fmaf(xv[i] - mean, sc, bet[i]), dy[i], silu);
+            o[i] = fmaf(du, sc, fmaf(xv[i], k1, k0));
+        }
+    }
+}
+#define GN_DISPATCH_W(cpg_, ...)                                      \
+    switch (cpg_) {                                                   \
+        case 2: { constexpr int W = 2; __VA_ARGS__; } break;          \
+        case 4: { constexpr int W = 4; __VA_ARGS__; } break;          \
+        case 8: { constexpr int W = 8; __VA_ARGS__; } break;          \
+        case 16: { constexpr int W = 16; __VA_ARGS__; } break;        \
+        default: { constexpr int W = 32; __VA_ARGS__; } break;        \
+    }
 
 // DEEP = 0: 2 CTAs per SM with a short ring (grids of several waves: the co-resident CTA hides the pipeline bubbles);
 // DEEP = 1: 1 CTA per SM with as many stages as shared memory holds.  One TMA round trip is ~1 us, so a CTA moves at most
@@ -168,7 +291,8 @@ struct ConvCfg {
     static constexpr int kSmem = kStages * kStageBytes + 1024;   // + alignment slack
 };
 
-template <int NT, int DEEP>
+// GN = 1: the instantiation with the fused GroupNorm epilogues (GnEpi); the plain kernels stay lean (registers / code size)
+template <int NT, int DEEP, int GN>
 __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
     using Cfg = ConvCfg<NT, DEEP>;
     constexpr int kStages = Cfg::kStages;
@@ -177,6 +301,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
     __shared__ uint32_t s_tmem, s_issued;
     __shared__ __align__(16) float s_bt[kBtImgs * NT];     // bias + temb[n] of the (<= kBtImgs) images this tile touches
+    __shared__ __align__(16) float s_gb[GN ? 2 * NT : 4];  // GroupNorm gamma | beta of this CTA's channels
 
     const int split = (int)blockIdx.z % P.splits;
     const Phase ph = P.phases[blockIdx.z / P.splits];
@@ -236,9 +361,37 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     const bool stage_bt = P.prefetch && P.splits == 1 && P.BN <= kBtImgs && (P.bias || P.temb);
     const __nv_bfloat16* rp = (P.res && valid && P.splits == 1) ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
     uint4 rpre[NT / 8];
-    if (rp && P.prefetch) {
+    if constexpr (GN) {
+        // backward mode: the same registers hold this row of the norm's input x (a dgrad has no residual)
+        if (P.gn.mode == 2) rp = valid ? P.gn.x + (int64_t)n * P.gn.x_sn + (int64_t)ho * P.gn.x_sh + (int64_t)wo * P.gn.x_sw + j0 : nullptr;
+#pragma unroll
+        for (int i = 0; i < NT / 8; ++i) rpre[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (rp && (P.prefetch || GN)) {
 #pragma unroll
         for (int i = 0; i < NT / 8; ++i) rpre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+    }
+    if constexpr (GN) {
+        if (warp >= 2) {
+            for (int i = threadIdx.x - 64; i < NT; i += 64) {
+                s_gb[i] = __ldg(P.gn.gamma + j0 + i);
+                s_gb[NT + i] = __ldg(P.gn.beta + j0 + i);
+            }
+            if (P.gn.mode == 2) {      // (mean, rstd) of every (image, group) of the tile, same arithmetic as norm.cu's stage_affine
+                float* s_mr = reinterpret_cast<float*>(smem + P.gn.epi_off);
+                const int GT = NT / P.gn.cpg;
+                for (int i = threadIdx.x - 64; i < P.BN * GT; i += 64) {
+                    const int img = i / GT, g = i - img * GT;
+                    float mean = 0.f, rstd = 0.f;
+                    if (n0 + img < P.N) {
+                        const float* sp = P.gn.sums + ((int64_t)(n0 + img) * P.gn.G + j0 / P.gn.cpg + g) * 2;
+                        mean = sp[0] / P.gn.cnt;
+                        rstd = rsqrtf(fmaxf(sp[1] / P.gn.cnt - mean * mean, 0.f) + P.gn.eps);
+                    }
+                    s_mr[2 * i] = mean; s_mr[2 * i + 1] = rstd;
+                }
+            }
+        }
     }
     if (stage_bt && warp >= 2) {
         for (int i = threadIdx.x - 64; i < P.BN * NT; i += 64) {
@@ -343,11 +496,180 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     __syncwarp();
 
     // ---------------------------------------------------- epilogue: all 4 warps, thread = one output pixel (TMEM lane)
-    if (stage_bt) __syncthreads();     // s_bt written by warps 2-3 while the pipeline ran
+    if (stage_bt || GN) __syncthreads();     // s_bt (and the GroupNorm staging) written by warps 2-3 while the pipeline ran
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
     if (dbg && threadIdx.x == 0) dbg[4] = clock64();   // accumulator complete
     const bool have_acc = *reinterpret_cast<volatile uint32_t*>(&s_issued) != 0;
+    if constexpr (GN) {
+        // ------------------------------------------------ fused GroupNorm epilogue (splits == 1, whole images per tile)
+        // Two passes over the accumulator (TMEM reads are cheap) around one CTA-local reduction; the pipeline ring is idle by now
+        // (every MMA has retired) and serves as scratch: s_part [128 rows][2 GT + 1] per-row group partials, s_stat [BN][GT][2]
+        // per (image, group) results, s_col [4 warps][NT][2] per-warp channel sums (backward only).
+        const GnEpi& Gn = P.gn;
+        const int cpg = Gn.cpg, GT = NT / cpg, HWt = P.BH * P.BW, pstr = 2 * GT + 1;
+        float* s_part = reinterpret_cast<float*>(smem);
+        float* s_stat = s_part + 128 * pstr;
+        float* s_col = s_stat + P.BN * GT * 2;
+        const float* s_mr = reinterpret_cast<const float*>(smem + Gn.epi_off);
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const int nlc = valid ? nl : 0;
+        float* my_part = s_part + threadIdx.x * pstr;
+        const float* tp = (P.temb && valid) ? P.temb + (int64_t)n * P.temb_pitch + j0 : nullptr;
+        // accumulator chunk -> the value the stored tensor holds (bias, temb, residual, rounded to bf16); zeros for rows outside the problem
+        auto finalize = [&](int c, float* v, bool with_res) {
+            if (!have_acc || !valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (!valid) return;
+            if (stage_bt) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(&s_bt[nl * NT + c + i]);
+                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                }
+            } else {
+                if (P.bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c + i));
+                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    }
+                }
+                if (tp) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(tp + c + i));
+                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    }
+                }
+            }
+            if (with_res && rp) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rpre[(c + i) >> 3]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[i + 2 * k] += f.x; v[i + 2 * k + 1] += f.y; }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+        };
+        // (image, group) totals of the per-row partials; f(pair, image, group, total0, total1) stores what the second pass needs
+        auto reduce_pairs = [&](auto&& f) {
+            __syncthreads();
+            for (int pair = threadIdx.x; pair < P.BN * GT; pair += 128) {
+                const int img = pair / GT, g = pair - img * GT;
+                const float* pp = s_part + img * HWt * pstr + 2 * g;
+                float t0 = 0.f, t1 = 0.f;
+                for (int r = 0; r < HWt; ++r) { t0 += pp[r * pstr]; t1 += pp[r * pstr + 1]; }
+                f(pair, img, g, t0, t1);
+            }
+            __syncthreads();
+        };
+        if (Gn.mode == 1) {
+            __nv_bfloat16* yp1 = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0;
+            __nv_bfloat16* ap = Gn.a + (int64_t)n * Gn.a_sn + (int64_t)ho * Gn.a_sh + (int64_t)wo * Gn.a_sw + j0;
+#pragma unroll
+            for (int c = 0; c < NT; c += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c, v);
+                tmem_ld_wait();
+                finalize(c, v, true);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp1 + c + i, v + i);
+                }
+                GN_DISPATCH_W(cpg, gn_group_sums<W>(v, my_part + 2 * (c / W)));
+            }
+            reduce_pairs([&](int pair, int img, int g, float su, float sq) {
+                if (n0 + img < P.N) {
+                    float* sp = Gn.sums + ((int64_t)(n0 + img) * Gn.G + j0 / cpg + g) * 2;
+                    sp[0] = su; sp[1] = sq;
+                }
+                const float mean = su / Gn.cnt;
+                s_stat[2 * pair] = mean;
+                s_stat[2 * pair + 1] = rsqrtf(fmaxf(sq / Gn.cnt - mean * mean, 0.f) + Gn.eps);
+            });
+#pragma unroll
+            for (int c = 0; c < NT; c += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c, v);
+                tmem_ld_wait();
+                finalize(c, v, true);
+                GN_DISPATCH_W(cpg, gn_apply32<W>(v, s_stat + 2 * (nlc * GT + c / W), s_gb + c, s_gb + NT + c, Gn.silu));
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(ap + c + i, v + i);
+                }
+            }
+        } else {
+            // backward: the accumulator is dy (gradient w.r.t. the normalised activation), rpre holds this row of x
+#pragma unroll
+            for (int c = 0; c < NT; c += 32) {
+                float v[32], xv[32], t1[32], t2[32];
+                tmem_ld32(trow + (uint32_t)c, v);
+                tmem_ld_wait();
+                finalize(c, v, false);
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) unpack_bf16x8(rpre[(c + i) >> 3], xv + i);
+                GN_DISPATCH_W(cpg, gn_bwd_pass1<W>(v, xv, s_mr + 2 * (nlc * GT + c / W), s_gb + c, s_gb + NT + c, Gn.silu, t1, t2, my_part + 2 * (c / W)));
+                const float c1 = warp_transpose_sum(t1, lane), c2 = warp_transpose_sum(t2, lane);
+                s_col[(warp * NT + c + lane) * 2] = c1;
+                s_col[(warp * NT + c + lane) * 2 + 1] = c2;
+            }
+            reduce_pairs([&](int pair, int, int, float A, float B) {
+                s_stat[2 * pair] = A / Gn.cnt;
+                s_stat[2 * pair + 1] = B / Gn.cnt;
+            });
+            // per-tile channel sums for the affine-parameter gradients (folded over the tiles by dmu_gn_param_grads)
+            for (int e = threadIdx.x; e < NT * 2; e += 128)
+                Gn.red[((int64_t)tile * Gn.C + j0) * 2 + e] = (s_col[e] + s_col[NT * 2 + e]) + (s_col[2 * NT * 2 + e] + s_col[3 * NT * 2 + e]);
+            __nv_bfloat16* dxp = Gn.dx + (int64_t)n * Gn.dx_sn + (int64_t)ho * Gn.dx_sh + (int64_t)wo * Gn.dx_sw + j0;
+            const __nv_bfloat16* a0p = (Gn.add0 && valid) ? Gn.add0 + (int64_t)n * Gn.a0_sn + (int64_t)ho * Gn.a0_sh + (int64_t)wo * Gn.a0_sw + j0 : nullptr;
+            const __nv_bfloat16* a1p = (Gn.add1 && valid) ? Gn.add1 + (int64_t)n * Gn.a1_sn + (int64_t)ho * Gn.a1_sh + (int64_t)wo * Gn.a1_sw + j0 : nullptr;
+#pragma unroll
+            for (int c = 0; c < NT; c += 32) {
+                float v[32], xv[32], o[32];
+                uint4 r0[4], r1[4];
+                if (a0p) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r0[i] = *reinterpret_cast<const uint4*>(a0p + c + i * 8);
+                }
+                if (a1p) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r1[i] = *reinterpret_cast<const uint4*>(a1p + c + i * 8);
+                }
+                tmem_ld32(trow + (uint32_t)c, v);
+                tmem_ld_wait();
+                finalize(c, v, false);
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) unpack_bf16x8(rpre[(c + i) >> 3], xv + i);
+                GN_DISPATCH_W(cpg, gn_bwd_pass2<W>(v, xv, s_mr + 2 * (nlc * GT + c / W), s_stat + 2 * (nlc * GT + c / W), s_gb + c, s_gb + NT + c, Gn.silu, o));
+                if (a0p) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { float t[8]; unpack_bf16x8(r0[i], t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[i * 8 + k] += t[k]; }
+                }
+                if (a1p) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { float t[8]; unpack_bf16x8(r1[i], t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[i * 8 + k] += t[k]; }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(dxp + c + i, o + i);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem, NT);
+        return;
+    }
     if (P.splits > 1) {
         // ---- split-K: park the partial tile, cluster barrier, then fold + finish this CTA's share of the rows
         const int slot = ((int)(blockIdx.z / P.splits) * (int)gridDim.y + (int)blockIdx.y) * (int)gridDim.x + tile;
@@ -490,8 +812,10 @@ static int narrow_head_supported(const dmu_conv_params* p) {
     return halo_supported(p, 0);
 }
 
+static int conv_gn_fuse_tiles(const dmu_conv_params* p);
 static int conv_supported(const dmu_conv_params* p) {
     if (!p || !p->x.ptr || !p->y.ptr || !p->w) return 0;
+    if (p->gn_fuse_mode) return conv_gn_fuse_tiles(p) > 0 ? 1 : 0;
     if (p->gn_coef) {   // fused GroupNorm: the halo kernel only (wide bf16 NHWC input, 3x3 stride 1, >= 8x8)
         if (!nhwc_bf16_ok(p->x) || p->Ck % 64 != 0 || !halo_supported(p, 1) || encode_tiled_fn() == nullptr) return 0;
         if (p->a_out.ptr && !nhwc_bf16_ok(p->a_out)) return 0;
@@ -509,20 +833,19 @@ static int conv_supported(const dmu_conv_params* p) {
     return 1;
 }
 
-static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
-    // 3x3 stride-1 layers of 8x8 pixels and up: the persistent halo kernel (each input pixel fetched once per CTA);
-    // impl 4 forces the per-tap kernel below
-    if (p->impl == 5) {
-        DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3, stride 1, pad 1, >= 8x8)");
-        return halo_launch(p, stream);
-    }
-    if (narrow_head_supported(p)) return halo_launch(p, stream);
-    if (p->gn_coef) return halo_launch(p, stream);
-    if (p->impl != 4 && stem_supported(p)) return stem_launch(p, stream);
-    if (p->impl != 4 && halo_enabled() && halo_supported(p, 0)) return halo_launch(p, stream);
-    Maps maps;
-    ConvArgs A;
+// Geometry of one per-tap launch: everything conv_launch needs that does not depend on the tensor maps' contents.  With
+// maps == nullptr nothing is encoded (dmu_conv2d_gn_fuse_supported asks "what would this launch look like" with pointers that
+// may not be mapped yet).
+struct ConvGeom { int NT, pix, nph; Box b; dim3 grid; bool deep; size_t smem; int gn_tiles; };
+
+static bool gn_tensor_ok(const dmu_tensor4& t) {
+    return t.dtype == DMU_BF16 && t.sc == 1 && aligned16(t.ptr) && t.sw % 8 == 0 && t.sh % 8 == 0 && t.sn % 8 == 0;
+}
+
+static int conv_prepare(const dmu_conv_params* p, Maps* maps, ConvArgs& A, ConvGeom& G) {
     memset(&A, 0, sizeof(A));
+    const dmu_gn_params* gn = p->gn_fuse_mode ? reinterpret_cast<const dmu_gn_params*>(p->gn_fuse) : nullptr;
+    DMU_REQUIRE(p->gn_fuse_mode == 0 || (gn && (p->gn_fuse_mode == 1 || p->gn_fuse_mode == 2)), "dmu_conv2d/tc: gn_fuse_mode %d without a valid gn_fuse", p->gn_fuse_mode);
     const int st = p->stride;
     int nph = 1, THmax = p->Ho, TWmax = p->Wo;
     if (p->gather == 1) {
@@ -536,6 +859,8 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     // rows, the upper 64 accumulator rows are never stored): 4x the CTAs, half the bytes and k-loop time per CTA.
     int NT = (p->Cj % 128 == 0) ? 128 : 64;
     int pix = 128;
+    const int img_rows = pow2_ceil(THmax) * pow2_ceil(TWmax);      // tile rows one whole image occupies
+    if (gn) NT = 64;        // the fused GroupNorm epilogues exist for 64-channel tiles (register budget of two passes over the tile)
     {
         static const int small_tiles = [] { const char* e = getenv("DMU_SMALL_TILES"); return e ? atoi(e) : 1; }();    // A/B aid
         static const int limit_pct = [] { const char* e = getenv("DMU_SMALL_TILES_LIMIT"); return e ? atoi(e) : 100; }();
@@ -543,14 +868,14 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         const Box b0 = make_box(p->N, THmax, TWmax, 128);
         int ctas = b0.tiles_n * b0.tiles_h * b0.tiles_w * (p->Cj / NT) * nph;
         if (small_tiles && NT == 128 && ctas * 2 <= cap) { NT = 64; ctas *= 2; }
-        if (small_tiles && ctas * 2 <= cap && (int64_t)p->N * THmax * TWmax > 64) { pix = 64; ctas *= 2; }
-        if (small_tiles >= 2 && pix == 64 && ctas * 2 <= cap && (int64_t)p->N * THmax * TWmax > 32) pix = 32;
+        if (small_tiles && ctas * 2 <= cap && (int64_t)p->N * THmax * TWmax > 64 && !(gn && img_rows > 64)) { pix = 64; ctas *= 2; }
+        if (small_tiles >= 2 && pix == 64 && ctas * 2 <= cap && (int64_t)p->N * THmax * TWmax > 32 && !gn) pix = 32;
     }
     const Box b = make_box(p->N, THmax, TWmax, pix);
     if (p->gather == 0) {
         A.os = 1;
         A.phases[0] = Phase{0, p->R * p->S, 0, 0, p->Ho, p->Wo};
-        if (int rc = build_gather0(p->x, p->N, p->Hi, p->Wi, p->Ck, p->R, p->S, st, p->pad, b, A.taps, &maps, A.map_h, A.map_w, "dmu_conv2d/tc"))
+        if (int rc = build_gather0(p->x, p->N, p->Hi, p->Wi, p->Ck, p->R, p->S, st, p->pad, b, A.taps, maps, A.map_h, A.map_w, "dmu_conv2d/tc"))
             return rc;
     } else {
         // transposed gather: output parity class (oph, opw) uses the taps with (oph + pad - r) divisible by stride
@@ -572,16 +897,18 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
                 ph.ntaps = nt - ph.tap0;
             }
         A.map_h[0] = p->Hi; A.map_w[0] = p->Wi;
-        const uint64_t dims[4] = {(uint64_t)p->Ck, (uint64_t)p->Wi, (uint64_t)p->Hi, (uint64_t)p->N};
-        const uint64_t str[4] = {1, (uint64_t)p->x.sw, (uint64_t)p->x.sh, (uint64_t)p->x.sn};
-        const uint32_t box[4] = {64, (uint32_t)b.BW, (uint32_t)b.BH, (uint32_t)b.BN};
-        if (int rc = make_map_bf16(&maps.a[0], p->x.ptr, 4, dims, str, box, "dmu_conv2d/tc")) return rc;
+        if (maps) {
+            const uint64_t dims[4] = {(uint64_t)p->Ck, (uint64_t)p->Wi, (uint64_t)p->Hi, (uint64_t)p->N};
+            const uint64_t str[4] = {1, (uint64_t)p->x.sw, (uint64_t)p->x.sh, (uint64_t)p->x.sn};
+            const uint32_t box[4] = {64, (uint32_t)b.BW, (uint32_t)b.BH, (uint32_t)b.BN};
+            if (int rc = make_map_bf16(&maps->a[0], p->x.ptr, 4, dims, str, box, "dmu_conv2d/tc")) return rc;
+        }
     }
-    {
+    if (maps) {
         const uint64_t dims[2] = {(uint64_t)p->R * p->S * p->Ck, (uint64_t)p->Cj};
         const uint64_t str[2] = {1, (uint64_t)p->w_sn};
         const uint32_t box[2] = {64, (uint32_t)NT};
-        if (int rc = make_map_bf16(&maps.b, p->w, 2, dims, str, box, "dmu_conv2d/tc weights")) return rc;
+        if (int rc = make_map_bf16(&maps->b, p->w, 2, dims, str, box, "dmu_conv2d/tc weights")) return rc;
     }
     A.N = p->N; A.Ho = p->Ho; A.Wo = p->Wo; A.Ck = p->Ck; A.Cj = p->Cj;
     A.BN = b.BN; A.BH = b.BH; A.BW = b.BW; A.tiles_h = b.tiles_h; A.tiles_w = b.tiles_w;
@@ -626,17 +953,9 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
             A.ws = reinterpret_cast<float*>(p->workspace);
         }
     }
-    dim3 grid(b.tiles_n * b.tiles_h * b.tiles_w, p->Cj / NT, nph * A.splits);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(conv_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 0>::kSmem);
-        cudaFuncSetAttribute(conv_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 0>::kSmem);
-        cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 1>::kSmem);
-        cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 1>::kSmem);
-        attr_done = true;
-    }
-    const dim3 cluster(1, 1, (unsigned)A.splits);
-    const bool deep = (int)(grid.x * grid.y * grid.z) <= sm_count();
+    G.grid = dim3(b.tiles_n * b.tiles_h * b.tiles_w, p->Cj / NT, nph * A.splits);
+    G.deep = (int)(G.grid.x * G.grid.y * G.grid.z) <= sm_count();
+    const bool deep = G.deep;
     // Ring geometry.  One TMA round trip is ~2000 clk here (scripts/conv_timeline.py), so a CTA's k-loop moves at most
     // (bytes in flight) / 2000 clk: the sub-wave (1 CTA per SM) variants keep ~128 KB in flight - compact stages for the
     // 64-pixel box, 8 KB + NT x 128 B each - which still leaves room on the SM for a weight-gradient CTA of the backward's other
@@ -645,27 +964,123 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     static const int kps_env = [] { const char* e = getenv("DMU_CONV_KPS"); return e ? atoi(e) : 2; }();
     // measured: the k-loop of these launches is issue-bound (~100 clk per MMA whatever its shape), M = 64 buys nothing: opt-in
     static const int m64_env = [] { const char* e = getenv("DMU_CONV_M64"); return e ? atoi(e) : 0; }();
-    A.m64 = (pix == 64 && A.splits == 1 && m64_env) ? 1 : 0;
+    A.m64 = (pix == 64 && A.splits == 1 && m64_env && !gn) ? 1 : 0;
     A.a_off = pix * 128;
     A.kb_bytes = A.a_off + NT * 128;
     A.kps = deep ? (kps_env < 1 ? 1 : kps_env) : 1;
     A.stage_bytes = A.kps * A.kb_bytes;
     const int max_stages = NT == 64 ? (deep ? ConvCfg<64, 1>::kStages : ConvCfg<64, 0>::kStages) : (deep ? ConvCfg<128, 1>::kStages : ConvCfg<128, 0>::kStages);
     A.stages = max_stages;
+    // mode-2 GroupNorm statistics are staged while the pipeline runs, in a region behind the ring that comes out of the ring's budget
+    int gn_pre = 0;
+    if (gn && p->gn_fuse_mode == 2) gn_pre = (b.BN * (NT / (gn->C / gn->G)) * 2 * 4 + 1023) / 1024 * 1024;
     if (deep) {
-        A.stages = ring_kb * 1024 / A.stage_bytes;
+        A.stages = (ring_kb * 1024 - gn_pre) / A.stage_bytes;
         if (A.stages > max_stages) A.stages = max_stages;
         if (A.stages < 2) A.stages = 2;
     }
     // + 1 KB alignment slack + the rows past a 64-pixel box that the M = 128 MMA of the last stage still reads
-    const size_t smem = (size_t)A.stages * A.stage_bytes + 1024 + (128 * 128 - A.a_off);
+    const size_t ring = (size_t)A.stages * A.stage_bytes + (128 * 128 - A.a_off);
+    G.smem = ring + 1024 + gn_pre;
+    G.NT = NT; G.pix = pix; G.nph = nph; G.b = b; G.gn_tiles = 0;
+    if (gn) {
+        // ---- can this launch take the GroupNorm in its epilogue?
+        const int cpg = gn->G > 0 ? gn->C / gn->G : 0;
+        const bool shape_ok = gn->C == p->Cj && gn->G > 0 && gn->C % gn->G == 0 && gn->N == p->N && gn->H == p->Ho && gn->W == p->Wo &&
+                              (cpg == 2 || cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && p->Cj % 64 == 0;
+        const bool tile_ok = nph == 1 && A.os == 1 && b.tiles_h == 1 && b.tiles_w == 1 && A.splits == 1;
+        bool ok = shape_ok && tile_ok && gn->gamma && gn->beta && gn->sums;
+        if (ok && p->gn_fuse_mode == 1) ok = gn_tensor_ok(gn->y);
+        if (ok && p->gn_fuse_mode == 2)
+            ok = gn_tensor_ok(gn->x) && gn_tensor_ok(gn->dx) && gn->red && !p->res.ptr && !p->bias && !p->temb &&
+                 (!gn->add0.ptr || gn_tensor_ok(gn->add0)) && (!gn->add1.ptr || gn_tensor_ok(gn->add1));
+        if (ok) {
+            const int GT = NT / cpg;
+            const size_t need = ((size_t)128 * (2 * GT + 1) + (size_t)b.BN * GT * 2 + (size_t)4 * NT * 2) * 4;
+            ok = need <= ring;
+        }
+        if (!ok) return -1;      // not an error by itself: dmu_conv2d_gn_fuse_supported reports 0, dmu_conv2d fails loudly
+        GnEpi& E = A.gn;
+        E.mode = p->gn_fuse_mode; E.G = gn->G; E.cpg = cpg; E.silu = gn->silu; E.C = gn->C;
+        E.eps = gn->eps; E.cnt = (float)cpg * (float)p->Ho * (float)p->Wo;
+        E.gamma = gn->gamma; E.beta = gn->beta; E.sums = gn->sums;
+        E.a = reinterpret_cast<__nv_bfloat16*>(gn->y.ptr); E.a_sn = gn->y.sn; E.a_sh = gn->y.sh; E.a_sw = gn->y.sw;
+        E.x = reinterpret_cast<const __nv_bfloat16*>(gn->x.ptr); E.x_sn = gn->x.sn; E.x_sh = gn->x.sh; E.x_sw = gn->x.sw;
+        E.dx = reinterpret_cast<__nv_bfloat16*>(gn->dx.ptr); E.dx_sn = gn->dx.sn; E.dx_sh = gn->dx.sh; E.dx_sw = gn->dx.sw;
+        E.add0 = reinterpret_cast<const __nv_bfloat16*>(gn->add0.ptr); E.a0_sn = gn->add0.sn; E.a0_sh = gn->add0.sh; E.a0_sw = gn->add0.sw;
+        E.add1 = reinterpret_cast<const __nv_bfloat16*>(gn->add1.ptr); E.a1_sn = gn->add1.sn; E.a1_sh = gn->add1.sh; E.a1_sw = gn->add1.sw;
+        E.red = gn->red;
+        E.epi_off = (int)ring;
+        G.gn_tiles = b.tiles_n;
+    }
+    return 0;
+}
+
+static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
+    // 3x3 stride-1 layers of 8x8 pixels and up: the persistent halo kernel (each input pixel fetched once per CTA);
+    // impl 4 forces the per-tap kernel below
+    if (!p->gn_fuse_mode) {
+        if (p->impl == 5) {
+            DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3, stride 1, pad 1, >= 8x8)");
+            return halo_launch(p, stream);
+        }
+        if (narrow_head_supported(p)) return halo_launch(p, stream);
+        if (p->gn_coef) return halo_launch(p, stream);
+        if (p->impl != 4 && stem_supported(p)) return stem_launch(p, stream);
+        if (p->impl != 4 && halo_enabled() && halo_supported(p, 0)) return halo_launch(p, stream);
+    }
+    Maps maps;
+    ConvArgs A;
+    ConvGeom G;
+    if (int rc = conv_prepare(p, &maps, A, G)) {
+        if (rc == -1) return fail("dmu_conv2d/tc: this launch cannot take the GroupNorm of gn_fuse in its epilogue (ask dmu_conv2d_gn_fuse_supported first)");
+        return rc;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv_tc_kernel<64, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 0>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<128, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 0>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 1>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 1>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<64, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 0>::kSmem + 32 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 1>::kSmem + 32 * 1024);
+        attr_done = true;
+    }
+    const dim3 cluster(1, 1, (unsigned)A.splits);
+    const dim3 grid = G.grid;
+    const size_t smem = G.smem;
+    const bool deep = G.deep;
     cudaError_t e;
-    if (NT == 64) e = deep ? launch_pdl(conv_tc_kernel<64, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
-                           : launch_pdl(conv_tc_kernel<64, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
-    else e = deep ? launch_pdl(conv_tc_kernel<128, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
-                  : launch_pdl(conv_tc_kernel<128, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
+    if (A.gn.mode) e = deep ? launch_pdl(conv_tc_kernel<64, 1, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
+                            : launch_pdl(conv_tc_kernel<64, 0, 1>, grid, dim3(128), smem, stream, cluster, maps, A);
+    else if (G.NT == 64) e = deep ? launch_pdl(conv_tc_kernel<64, 1, 0>, grid, dim3(128), smem, stream, cluster, maps, A)
+                                  : launch_pdl(conv_tc_kernel<64, 0, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
+    else e = deep ? launch_pdl(conv_tc_kernel<128, 1, 0>, grid, dim3(128), smem, stream, cluster, maps, A)
+                  : launch_pdl(conv_tc_kernel<128, 0, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
     if (e != cudaSuccess) return fail("dmu_conv2d/tc: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/tc");
+}
+
+// what dmu_conv2d_gn_fuse_supported answers: would dmu_conv2d run this layer on the per-tap kernel with the norm in its epilogue?
+static int conv_gn_fuse_tiles(const dmu_conv_params* p) {
+    if (!p || !p->gn_fuse || (p->gn_fuse_mode != 1 && p->gn_fuse_mode != 2)) return 0;
+    if (p->impl == 1 || p->impl == 3 || p->impl == 5 || p->gn_coef) return 0;
+    if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y)) return 0;
+    if (p->res.ptr && !nhwc_bf16_ok(p->res)) return 0;
+    if (p->Ck % 64 != 0 || p->Cj % 64 != 0) return 0;
+    if (p->w_sk != 1 || (p->R * p->S > 1 && p->w_st != p->Ck) || p->w_sn != (int64_t)p->R * p->S * p->Ck || !aligned16(p->w)) return 0;
+    if (p->stride < 1 || p->stride > 2 || p->R * p->S > kMaxTaps) return 0;
+    if (p->bias && !aligned16(p->bias)) return 0;
+    if (p->temb && (!aligned16(p->temb) || p->temb_pitch % 4 != 0)) return 0;
+    if (encode_tiled_fn() == nullptr) return 0;
+    // the layers the halo kernel would take by its own heuristics keep their stand-alone GroupNorm
+    dmu_conv_params q = *p;
+    q.gn_fuse = nullptr; q.gn_fuse_mode = 0;
+    if (q.impl != 4 && halo_enabled() && halo_supported(&q, 0)) return 0;
+    ConvArgs A;
+    ConvGeom G;
+    if (conv_prepare(p, nullptr, A, G) != 0) return 0;
+    return G.gn_tiles;
 }
 
 // ================================================================================================ wgrad kernel
@@ -894,6 +1309,7 @@ int dmu_conv2d_gn_supported(const dmu_conv_params* p) {
     return tc::halo_supported(p, p->impl == 5 ? 1 : 0);
 }
 int dmu_conv2d_tc(const dmu_conv_params* p, dmu_stream_t stream) { return tc::conv_launch(p, as_stream(stream)); }
+int dmu_conv2d_gn_fuse_supported(const dmu_conv_params* p) { return tc::conv_gn_fuse_tiles(p); }
 int dmu_wgrad_tc_supported(const dmu_wgrad_params* p) { return tc::wgrad_supported(p); }
 int dmu_wgrad_tc(const dmu_wgrad_params* p, dmu_stream_t stream) { return tc::wgrad_launch(p, as_stream(stream)); }
 }

@@ -802,9 +802,10 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_smem_kernel(dmu_gn_params P, in
 // dgamma[c] += sum_n red[n,c,1], dbeta[c] += sum_n red[n,c,0] for a whole table of GroupNorm layers in one launch:
 // the batch reduction of the affine-parameter gradients, kept out of the per-layer kernels (where it was a same-address
 // atomic from every CTA of every image).
-struct GnPgDesc { const float* red; float* dgamma; float* dbeta; int32_t C; int32_t _pad; };
+struct GnPgDesc { const float* red; float* dgamma; float* dbeta; int32_t C; int32_t count; };
 __global__ void __launch_bounds__(256) gn_param_grads_kernel(const GnPgDesc* __restrict__ table, int N) {
     const GnPgDesc d = table[blockIdx.y];
+    if (d.count > 0) N = d.count;      // rows of per-tile sums written by a fused dgrad epilogue (conv_tc.cu)
     // thread = (channel, quantity); 256 threads cover 128 channels x 2
     const int e0 = blockIdx.x * 256 + threadIdx.x;
     if (e0 >= d.C * 2) return;

@@ -252,6 +252,10 @@ class Engine:
         # GroupNorm launch + plain halo conv on B200 so far (scripts/gnconv_time.py: 39.5 vs 37.8 us at 128x32x32, 268 vs 192 us
         # at 256x64x64: the in-place transform is a latency chain in front of every tile's MMAs), so it is opt-in.
         self.fuse_gn = os.environ.get("DMU_GN_FUSE", "0") == "1"
+        # GroupNorm in the EPILOGUE of the conv that produces its input (forward) / of the dgrad that produces its upstream
+        # gradient (backward): the <= 8x8 stages, where one output tile holds whole images (dmu_conv_params.gn_fuse).  The library
+        # decides per layer (dmu_conv2d_gn_fuse_supported); DMU_GN_EPI=0 keeps every GroupNorm a launch of its own (A/B aid).
+        self.fuse_gn_epi = os.environ.get("DMU_GN_EPI", "1") != "0"
         self._lib = None
 
     # ------------------------------------------------------------------ parameters
@@ -408,7 +412,10 @@ class Engine:
         if t.dim() != 1 or t.shape[0] != x.shape[0]:
             raise ValueError("t must have shape [B]")
         self.prepare(x.device)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.net.parameters()))
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("the gradient with respect to the network INPUT is not computed on this path (the recorded backward "
+                                      "stops at the stem's weight gradient, like the reference's training loop needs); detach x")
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.net.parameters())
         x = x.contiguous().float()
         if need_grad:
             params = [self.named[k] for k in self.offs]
@@ -588,13 +595,9 @@ class Engine:
             plan.keep.append(sp)
             gn_pg += sub.gn_pg
 
-        skip = os.environ.get("DMU_EXPERIMENT_SKIP", "")    # timing experiments only: "side" / "main" lane of the backward
-
         def retag(ops_, k):
             out = []
             for op in ops_:
-                if skip and op[0] is not None and op[0] != "split" and ops_ is not sub.plan.fwd and ((len(op) == 3) == (skip == "side")):
-                    continue
                 if op[0] is None:
                     out.append((None, (), 2 * k))                        # join this sub-plan's side lane into its main lane
                 else:
@@ -665,14 +668,33 @@ class Engine:
         plan.arena = arena
         plan.nbytes = nbytes
         plan.lanes = K
+        plan.gn_fused = [sum(sb.n_gn_fused[i] for sb in subs) for i in (0, 1)]   # GroupNorms riding in conv epilogues (fwd, bwd)
         return plan
+
+
+class _PlanLease:
+    """Marks a training plan busy (its activation arena holds what a pending backward needs) until the backward has run OR
+    the autograd node that owns the lease is collected - a grad-enabled forward whose graph is dropped (an evaluation loss
+    outside no_grad, an exception) must not strand the plan: get_plan would then allocate a new arena on every such call."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        plan.busy = True
+
+    def release(self):
+        if self.plan is not None:
+            self.plan.busy = False
+            self.plan = None
+
+    def __del__(self):
+        self.release()
 
 
 class _UNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng: Engine, x, t, *params):
         plan = eng.get_plan(x.shape, True)
-        plan.busy = True
+        ctx.lease = _PlanLease(plan)
         out = eng.run_forward(x, t, plan)
         ctx.eng, ctx.plan = eng, plan
         return out
@@ -683,7 +705,7 @@ class _UNetFn(torch.autograd.Function):
         try:
             g = eng.run_backward(plan, dout)
         finally:
-            plan.busy = False
+            ctx.lease.release()
         grads = []
         for k in eng.offs:
             o, n = eng.offs[k]
@@ -708,6 +730,8 @@ class _PlanBuilder:
         self.side_lane = True   # weight-gradient / column-sum launches of the backward go to the graph's second branch
         self.cs_pending = []    # column sums (bias gradients, time-projection sums) batched into one launch per backward part
         self.temb_join_pending = False
+        self.prod = {}          # output address -> ConvParams of the forward conv that writes it (candidates for a fused GroupNorm)
+        self.n_gn_fused = [0, 0]   # GroupNorms that ride in a conv epilogue: [forward, backward]
 
     # ---- allocation helpers
     def act(self, H, W, Cc, want_grad=True) -> Buf:
@@ -772,7 +796,22 @@ class _PlanBuilder:
                 self.temb_join_pending = False
             lst.append((self.lib.dmu_conv2d, (C.byref(p),)))
             self.plan.keep.append(p)
+            if lst is self.plan.fwd and gn_coef is None:
+                self.prod[(y.ptr, y.sw, Cj)] = p
         return p
+
+    def _try_fuse(self, conv_p, gn_p, mode) -> int:
+        """Ask the library whether `conv_p` can take the GroupNorm `gn_p` in its epilogue (mode 1 forward, 2 backward); leaves
+        the conv parameters armed when it can.  Returns the launch's pixel-tile count (0 = no)."""
+        if not (self.e.fuse_gn_epi and hasattr(self.lib, "dmu_conv2d_gn_fuse_supported")):
+            return 0
+        conv_p.gn_fuse = C.cast(C.pointer(gn_p), C.c_void_p)
+        conv_p.gn_fuse_mode = mode
+        tiles = int(self.lib.dmu_conv2d_gn_fuse_supported(C.byref(conv_p)))
+        if tiles <= 0:
+            conv_p.gn_fuse, conv_p.gn_fuse_mode = None, 0
+            return 0
+        return tiles
 
     def gn_conv(self, x: Buf, G, gamma_name, beta_name, silu, y4: Tensor4, w, w_strides, dims, geom, bias=None, temb=None, temb_pitch=0, res=None):
         """act(GroupNorm(x)) followed by a 3x3 convolution (residual.py:57-58,63-64; ddpm.py:88-90).  Where the persistent halo
@@ -814,27 +853,46 @@ class _PlanBuilder:
             self.colsum(p4, N, Hp, Wp, Ca, None, 0, dbias)
         return p
 
-    def gn(self, x: Buf, G, gamma_name, beta_name, silu: bool):
+    def gn(self, x: Buf, G, gamma_name, beta_name, silu: bool, out: Buf = None):
         """Forward GroupNorm(+SiLU): returns (y, gn-record)."""
         sums = self.stats.take(self.N * G * 2 * 4, 16)
-        y = self.act(x.H, x.W, x.C)
+        y = out if out is not None else self.act(x.H, x.W, x.C)
         p = GnParams(x.t4(), y.t4(), _null_t4(), _null_t4(), _null_t4(), sums, self.e.paddr(gamma_name), self.e.paddr(beta_name),
                      None, None, None, self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, 0)
         self.plan.keep.append(p)
-        self.plan.fwd.append((self.lib.dmu_gn_forward, (C.byref(p),)))
+        # the conv that wrote x (and nothing else has normalised yet) may carry this norm in its epilogue: no launch then
+        prod = self.prod.pop((x.addr, x.pitch, x.C), None)
+        if prod is not None and self._try_fuse(prod, p, 1):
+            self.n_gn_fused[0] += 1
+        else:
+            self.plan.fwd.append((self.lib.dmu_gn_forward, (C.byref(p),)))
         return y, (x, y, sums, G, gamma_name, beta_name, silu)
 
-    def gn_bwd(self, rec, dx: Buf, add0: Buf = None, add1: Buf = None):
-        """Backward of gn(): reads rec.y.grad, writes dx (+ addends)."""
+    def gn_bwd(self, rec, dx: Buf, add0: Buf = None, add1: Buf = None, dgrad=None, after_dgrad=None):
+        """Backward of gn(): reads rec.y.grad, writes dx (+ addends).  `dgrad` = emitter of the dgrad conv that PRODUCES rec.y.grad
+        (called with no argument, returns its ConvParams without emitting): where the library can, the norm's backward runs in that
+        conv's epilogue and rec.y.grad is never stored."""
         x, y, sums, G, gname, bname, silu = rec
         red = self.red.take(self.N * x.C * 2 * 4, 16)
         # dgamma/dbeta are left out here: one dmu_gn_param_grads launch folds every layer's per-image sums at the end
         p = GnParams(x.t4(), y.grad.t4(), dx.t4(), add0.t4() if add0 is not None else _null_t4(), add1.t4() if add1 is not None else _null_t4(),
                      sums, self.e.paddr(gname), self.e.paddr(bname), red, None, None,
                      self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, 0)
-        self.gn_pg.append(GnPgDesc(red, self.gp(gname), self.gp(bname), x.C, 0))
         self.plan.keep.append(p)
-        self.plan.bwd.append((self.lib.dmu_gn_backward, (C.byref(p),)))
+        tiles = 0
+        if dgrad is not None:
+            cp = dgrad()
+            tiles = self._try_fuse(cp, p, 2)
+            self.plan.bwd.append((self.lib.dmu_conv2d, (C.byref(cp),)))
+            self.plan.keep.append(cp)
+        if after_dgrad is not None:
+            after_dgrad()          # the weight gradient keeps its place right behind the dgrad (side lane)
+        # fused: red holds per-tile channel sums ([tiles][C][2]) instead of per-image ones
+        self.gn_pg.append(GnPgDesc(red, self.gp(gname), self.gp(bname), x.C, tiles))
+        if tiles:
+            self.n_gn_fused[1] += 1
+        else:
+            self.plan.bwd.append((self.lib.dmu_gn_backward, (C.byref(p),)))
 
     # ---- conv layer helpers (filters repacked [O][R][S][I])
     def conv_layer(self, x: Buf, y: Buf, wname, bname, R, stride, pad, temb=None, temb_pitch=0, res: Buf = None):
@@ -843,16 +901,23 @@ class _PlanBuilder:
                   (self.N, x.H, x.W, Ci, y.H, y.W, Co), (R, R, stride, pad), bias=self.e.paddr(bname), temb=temb, temb_pitch=temb_pitch,
                   res=res.t4() if res is not None else None)
 
-    def conv_layer_bwd(self, x: Buf, y: Buf, wname, bname, R, stride, pad, dx: Buf, need_dx=True):
-        """dgrad into dx (plain write) and wgrad/dbias into the arena.  dy = y.grad."""
+    def conv_layer_bwd(self, x: Buf, y: Buf, wname, bname, R, stride, pad, dx: Buf, need_dx=True, gn=None):
+        """dgrad into dx (plain write) and wgrad/dbias into the arena.  dy = y.grad.  gn = (rec, out, add0, add1): x is the output
+        of the GroupNorm `rec`, whose backward follows immediately (into `out`) - in the dgrad's epilogue where possible."""
         Ci, Co = x.C, y.C
         dy = y.grad
+        # dx[n,hi,wi,ci] = sum dy[n,(hi+pad-r)/s,..,co] w[co][r][s][ci]
+        dgrad = lambda emit: self.conv(self.plan.bwd, dy.t4(), dx.t4(), self.e.waddr_t(wname), (R * R * Co, 1, Co), self.code,
+                                       (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad), gather=1, emit=emit)
+        wgrad = lambda: self.wgrad(dy.t4(), x.t4(), self.e.gsaddr(wname), (R * R * Ci, 1, Ci), self.gp(bname),
+                                   (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad))
+        if gn is not None:
+            rec, out, add0, add1 = gn
+            self.gn_bwd(rec, out, add0=add0, add1=add1, dgrad=lambda: dgrad(False), after_dgrad=wgrad)
+            return
         if need_dx:
-            # dx[n,hi,wi,ci] = sum dy[n,(hi+pad-r)/s,..,co] w[co][r][s][ci]
-            self.conv(self.plan.bwd, dy.t4(), dx.t4(), self.e.waddr_t(wname), (R * R * Co, 1, Co), self.code,
-                      (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad), gather=1)
-        self.wgrad(dy.t4(), x.t4(), self.e.gsaddr(wname), (R * R * Ci, 1, Ci), self.gp(bname),
-                   (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad))
+            dgrad(True)
+        wgrad()
 
     def linear(self, lst, x4: Tensor4, y4: Tensor4, M, I, O, w_addr, b_addr, res4=None, w_code=F32):
         self.conv(lst, x4, y4, w_addr, (I, 1, 0), w_code, (M, 1, 1, I, 1, 1, O), (1, 1, 1, 0), bias=b_addr, res=res4)
@@ -887,15 +952,11 @@ class _PlanBuilder:
             return
 
         def bwd():
-            # conv2
-            self.conv_layer_bwd(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, a2.grad)
-            # norm2 + silu -> dh
-            self.gn_bwd(rec2, h.grad)
+            # conv2, then norm2 + silu -> dh (in the dgrad's epilogue where one tile holds whole images)
+            self.conv_layer_bwd(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, a2.grad, gn=(rec2, h.grad, None, None))
             # time projection: per-image channel sums of dh
             self.colsum(h.grad.t4(), self.N, h.H, h.W, Co, self.dtproj + self.tp_off[pfx] * 4, self.tp_total, None)
-            # conv1
-            self.conv_layer_bwd(a1, h, pfx + "conv1.weight", pfx + "conv1.bias", 3, 1, 1, a1.grad)
-            # shortcut
+            # shortcut (before conv1: its input gradient is an addend of norm1's backward)
             if has_sc:
                 dxs = self.tmp(x.H, x.W, Ci)
                 scb = Buf(0, self.N, x.H, x.W, Co, Co, self.code)
@@ -904,7 +965,8 @@ class _PlanBuilder:
             else:
                 dxs = y.grad
             prev = x.grad if x.grad_written else None
-            self.gn_bwd(rec1, x.grad, add0=dxs, add1=prev)
+            # conv1, then norm1 + silu (+ shortcut / skip gradients) -> dx
+            self.conv_layer_bwd(a1, h, pfx + "conv1.weight", pfx + "conv1.bias", 3, 1, 1, a1.grad, gn=(rec1, x.grad, dxs, prev))
             x.grad_written = True
         self.tape.append(bwd)
 
@@ -926,15 +988,10 @@ class _PlanBuilder:
         z = self.act(x.H, x.W, Cc)
         bf = e.paddr(pfx + "final_projection.bias")
         wf, wf_t = (e.waddr(pfx + "final_projection.weight"), e.waddr_t(pfx + "final_projection.weight")) if tc else (e.paddr(pfx + "final_projection.weight"), None)
-        self.linear(self.plan.fwd, _rows_t4(o.addr, Cc, self.code), _rows_t4(z.addr, Cc, self.code), M, Cc, Cc, wf, bf,
-                    res4=_rows_t4(x.addr, x.pitch, self.code), w_code=wcode)
-        G = gn_groups(Cc)
-        sums = self.stats.take(self.N * G * 2 * 4, 16)
-        gp_ = GnParams(z.t4(), y.t4(), _null_t4(), _null_t4(), _null_t4(), sums, e.paddr(pfx + "norm.weight"), e.paddr(pfx + "norm.bias"),
-                       None, None, None, self.N, x.H, x.W, Cc, G, 0, 1e-5, 0)
-        self.plan.keep.append(gp_)
-        self.plan.fwd.append((self.lib.dmu_gn_forward, (C.byref(gp_),)))
-        rec = (z, y, sums, G, pfx + "norm.weight", pfx + "norm.bias", False)
+        # final projection (+ x) as a 1x1 convolution over (N, H, W) - the same rows as the [M, C] Linear - so that an output tile
+        # holds whole images and the post-norm of attention.py:68 can ride in its epilogue
+        self.conv(self.plan.fwd, o.t4(), z.t4(), wf, (Cc, 1, 0), wcode, (self.N, x.H, x.W, Cc, x.H, x.W, Cc), (1, 1, 1, 0), bias=bf, res=x.t4())
+        _, rec = self.gn(z, gn_groups(Cc), pfx + "norm.weight", pfx + "norm.bias", False, out=y)
         if not self.train:
             return
 

@@ -154,8 +154,27 @@ typedef struct {
     int32_t gn_silu;
     int32_t _pad2;
     dmu_tensor4 a_out;
+    /* Optional GroupNorm fused into the EPILOGUE (the <= 8x8 stages, where one output tile of a CTA holds whole images and whole
+     * groups; ask dmu_conv2d_gn_fuse_supported).  gn_fuse points to a dmu_gn_params (declared below) with N, H, W = the conv's
+     * output, C = Cj:
+     *   gn_fuse_mode 1, forward (residual.py:57,63, attention.py:68: the next layer normalises this output):  y is written as
+     *     usual and additionally gn->y = act(GroupNorm(y)); gn->sums[n, g, 0..1] receives the raw sums (plain stores).
+     *     gn->x, dx, add0, add1, red are ignored.
+     *   gn_fuse_mode 2, backward (this launch is the dgrad that produces dy of a GroupNorm): the convolution result is NOT
+     *     stored; the epilogue applies dmu_gn_backward's arithmetic to it:  gn->dx = gn_backward(gn->x, dy; gn->sums, gamma,
+     *     beta) + add0 + add1, and gn->red receives PER-TILE channel sums [tiles][C][2] = (sum du, sum du*xhat) over the
+     *     images of each pixel tile (tiles = the return value of dmu_conv2d_gn_fuse_supported; fold them with
+     *     dmu_gn_param_grads, desc.count = tiles).  res / bias / temb must be NULL; gn->y is ignored.
+     * Any shape dmu_conv2d_gn_fuse_supported rejects is an error with gn_fuse set. */
+    const void* gn_fuse;
+    int32_t gn_fuse_mode;
+    int32_t _pad3;
 } dmu_conv_params;
 int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream);
+/* 0 when the launch cannot take p->gn_fuse (set, with its mode) in its epilogue; otherwise the number of pixel tiles of the
+ * launch (>= 1; mode 2 writes that many rows of per-tile channel sums).  Pure host logic: no pointer is dereferenced except
+ * p and p->gn_fuse themselves. */
+int dmu_conv2d_gn_fuse_supported(const dmu_conv_params* p);
 /* 1 when dmu_conv2d would run this layer on the halo kernel by its own heuristics, i.e. when the GroupNorm of its input may be
  * fused into it (gn_coef itself need not be set yet). */
 int dmu_conv2d_gn_supported(const dmu_conv_params* p);
@@ -212,7 +231,8 @@ int dmu_gn_backward(const dmu_gn_params* p, dmu_stream_t stream);
 /* Batch reduction of the affine-parameter gradients for a table of layers in one launch:
  *   dgamma[c] += sum_n red[n,c,1];  dbeta[c] += sum_n red[n,c,0]
  * (run once after the backward of all layers, with dgamma/dbeta left NULL in their dmu_gn_params).  The table lives in
- * device memory: n_desc entries of { const float* red; float* dgamma; float* dbeta; int32_t C; int32_t pad; }. */
+ * device memory: n_desc entries of { const float* red; float* dgamma; float* dbeta; int32_t C; int32_t count; } where
+ * count > 0 overrides N for that entry (rows of per-tile sums written by a fused dgrad epilogue, dmu_conv_params.gn_fuse). */
 int dmu_gn_param_grads(const void* table_device, int32_t n_desc, int32_t max_c, int32_t N, dmu_stream_t stream);
 /* Per-image, per-channel affine form of the normalisation, from the sums of dmu_gn_stats:
  *   coef[(n*C+c)*2] = rstd[n,g]*gamma[c],  coef[(n*C+c)*2+1] = beta[c] - mean[n,g]*rstd[n,g]*gamma[c]   (for dmu_conv_params.gn_coef) */

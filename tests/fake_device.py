@@ -114,8 +114,47 @@ class FakeLib:
             y = y + te[:, :, None, None]
         if p.res.ptr:
             y = y + _view4(p.res, p.N, p.Ho, p.Wo, p.Cj).float().permute(0, 3, 1, 2)
+        if p.gn_fuse_mode == 2:
+            # GroupNorm backward in the dgrad's epilogue: the result is dy, which is never stored (include/dmu_b200.h)
+            assert self.dmu_conv2d_gn_fuse_supported(ref) > 0
+            g = _abi.GnParams.from_address(p.gn_fuse)
+            dy = y.permute(0, 2, 3, 1).to(_DT[p.y.dtype]).float()
+            du, xhat, rstd_c, gamma, cpg, cnt = self._du(g, dy)
+            a, b = du.sum(dim=(1, 2)), (du * xhat).sum(dim=(1, 2))          # one pixel tile per image here
+            red = _flat(g.red, g.N * g.C * 2).view(g.N, g.C, 2)
+            red[..., 0] = a
+            red[..., 1] = b
+            self._gn_dx(g, du, xhat, rstd_c, gamma, cpg, cnt, red)
+            return 0
         _view4(p.y, p.N, p.Ho, p.Wo, p.Cj).copy_(y.permute(0, 2, 3, 1))
+        if p.gn_fuse_mode == 1:
+            assert self.dmu_conv2d_gn_fuse_supported(ref) > 0
+            g = _abi.GnParams.from_address(p.gn_fuse)
+            yv = _view4(p.y, p.N, p.Ho, p.Wo, p.Cj).float()
+            ys = yv.reshape(g.N, g.H * g.W, g.G, g.C // g.G)
+            sums = _flat(g.sums, g.N * g.G * 2).view(g.N, g.G, 2)
+            sums[..., 0] = ys.sum(dim=(1, 3))
+            sums[..., 1] = (ys * ys).sum(dim=(1, 3))
+            gg = _abi.GnParams.from_buffer_copy(g)
+            gg.x = p.y
+            self.launches -= 1
+            self.dmu_gn_apply(gg, stream)
         return 0
+
+    def dmu_conv2d_gn_fuse_supported(self, ref):
+        """Host-logic stand-in for the library's rule: whole images per 128-pixel tile, whole groups per 64-channel tile, one phase."""
+        p = _obj(ref)
+        if not p.gn_fuse or p.gn_fuse_mode not in (1, 2):
+            return 0
+        g = _abi.GnParams.from_address(p.gn_fuse)
+        cpg = g.C // g.G if g.G else 0
+        if g.C != p.Cj or p.Cj % 64 or cpg not in (2, 4, 8, 16, 32) or (g.N, g.H, g.W) != (p.N, p.Ho, p.Wo):
+            return 0
+        if (p.gather == 1 and p.stride != 1) or p.Ho * p.Wo > 128:
+            return 0
+        if p.gn_fuse_mode == 2 and (p.res.ptr or p.bias or p.temb):
+            return 0
+        return p.N
 
     def dmu_conv2d_wgrad(self, ref, stream):
         self._count()
@@ -162,9 +201,10 @@ class FakeLib:
         _view4(p.y, p.N, p.H, p.W, p.C).copy_(F.silu(u) if p.silu else u)
         return 0
 
-    def _du(self, p):
+    def _du(self, p, dy=None):
         x, mean_c, rstd_c, gamma, beta, cpg, cnt = self._gn_common(p)
-        dy = _view4(p.y, p.N, p.H, p.W, p.C).float()
+        if dy is None:
+            dy = _view4(p.y, p.N, p.H, p.W, p.C).float()
         xhat = (x - mean_c) * rstd_c
         u = xhat * gamma + beta
         if p.silu:
@@ -193,6 +233,10 @@ class FakeLib:
         p = _obj(ref)
         du, xhat, rstd_c, gamma, cpg, cnt = self._du(p)
         red = _flat(p.red, p.N * p.C * 2).view(p.N, p.C, 2)
+        self._gn_dx(p, du, xhat, rstd_c, gamma, cpg, cnt, red)
+        return 0
+
+    def _gn_dx(self, p, du, xhat, rstd_c, gamma, cpg, cnt, red):
         A = (red[..., 0] * gamma).view(p.N, p.G, cpg).sum(-1).repeat_interleave(cpg, dim=1)[:, None, None, :] / cnt
         B = (red[..., 1] * gamma).view(p.N, p.G, cpg).sum(-1).repeat_interleave(cpg, dim=1)[:, None, None, :] / cnt
         dx = du * (rstd_c * gamma) - rstd_c * (A + xhat * B)
@@ -207,7 +251,8 @@ class FakeLib:
         self._count()
         arr = (GnPgDesc * n).from_address(_addr(table))
         for d in arr:
-            red = _flat(d.red, N * d.C * 2, F32).view(N, d.C, 2).sum(0)
+            rows = d.count if d.count > 0 else N       # per-tile sums of a fused dgrad epilogue
+            red = _flat(d.red, rows * d.C * 2, F32).view(rows, d.C, 2).sum(0)
             _flat(d.dbeta, d.C, F32).add_(red[:, 0])
             _flat(d.dgamma, d.C, F32).add_(red[:, 1])
         return 0

@@ -550,3 +550,152 @@ def test_head_conv_on_halo_kernel():
         outs.append(out)
     ref = F.conv2d(ah.float().permute(0, 3, 1, 2), wh.to(torch.bfloat16).float(), bh, padding=1)
     assert rel_l2(outs[0], ref) < 1e-5 and rel_l2(outs[1], ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm in the conv epilogue
+GN_EPI_CASES = [
+    # N, H, W, Ci, Co, R, stride, G of the norm over the conv's OUTPUT channels, has_res
+    (6, 8, 8, 64, 128, 3, 1, 32, True),       # 2 images per 128-pixel tile, cpg 4
+    (128, 8, 8, 128, 128, 3, 1, 32, False),   # the bench's 8x8 stage
+    (5, 8, 8, 64, 64, 3, 1, 32, True),        # cpg 2, batch not a multiple of the images per tile
+    (37, 4, 4, 128, 128, 3, 1, 32, True),     # 8 images per tile, ragged batch
+    (128, 2, 2, 256, 256, 3, 1, 32, True),    # cpg 8, 32 images per tile
+    (128, 1, 1, 256, 256, 3, 1, 32, False),   # one pixel per image: 8 of 9 taps dead
+    (16, 16, 16, 64, 128, 4, 2, 32, False),   # the 4x4 stride-2 downsample feeding the next stage's norm1 (output 8x8)
+    (9, 4, 4, 128, 128, 1, 1, 32, True),      # attention final projection (+ x) followed by its post-norm
+    (8, 1, 1, 256, 512, 3, 1, 32, False),     # cpg 16
+    (4, 8, 8, 64, 64, 3, 1, 2, False),        # cpg 32
+]
+
+
+def _gn_epi_setup(case, g, dev):
+    ops, _abi = _mods()
+    N, H, W, Ci, Co, R, stride, G, has_res = case
+    pad = 1 if R > 1 else 0
+    Ho, Wo = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev)
+    w = (torch.randn(Co, Ci, R, R, generator=g) / math.sqrt(Ci * R * R)).to(dev)
+    return N, H, W, Ci, Co, R, stride, pad, G, has_res, Ho, Wo, x, w
+
+
+@pytest.mark.parametrize("silu", [1, 0])
+@pytest.mark.parametrize("case", GN_EPI_CASES)
+def test_conv_gn_epilogue_forward(case, silu):
+    """dmu_conv_params.gn_fuse mode 1: y = conv(x) + bias + temb + res and a = act(GroupNorm(y)) from ONE launch, against ATen
+    on the bf16-rounded operands and against this library's own conv launch followed by dmu_gn_forward."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams, GnParams
+    dev = torch.device("cuda:0")
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(sum(case[:8]))
+    N, H, W, Ci, Co, R, stride, pad, G, has_res, Ho, Wo, x, w = _gn_epi_setup(case, g, dev)
+    bias = torch.randn(Co, generator=g).to(dev)
+    temb = torch.randn(N, Co, generator=g).to(dev)
+    res = torch.randn(N, Ho, Wo, Co, generator=g).to(dev).to(dtype) if has_res else None
+    gamma, beta = (1 + 0.2 * torch.randn(Co, generator=g)).to(dev), (0.1 * torch.randn(Co, generator=g)).to(dev)
+    xh = ops.nchw_to_nhwc(x, dtype)
+    wk = _repack(w, False, dtype)
+    code = ops.dtype_code(xh)
+    lib = _abi.lib()
+
+    def run(fused):
+        y = torch.zeros(N, Ho, Wo, Co, device=dev, dtype=dtype)
+        a = torch.zeros(N, Ho, Wo, Co + 8, device=dev, dtype=dtype)       # normalised output into a channel slice
+        sums = torch.full((N, G, 2), float("nan"), device=dev) if fused else torch.zeros(N, G, 2, device=dev)
+        gp = GnParams(ops.t4_nhwc(y), ops.t4_nhwc(a, 8, Co), _null(), _null(), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                      None, None, None, N, Ho, Wo, Co, G, silu, 1e-5, 0)
+        p = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(y), ops.t4_nhwc(res) if has_res else _null(), wk.data_ptr(), R * R * Ci, 1, Ci,
+                       bias.data_ptr(), temb.data_ptr(), Co, N, H, W, Ci, Ho, Wo, Co, R, R, stride, pad, 0, code, 0, 0, None, 0)
+        if fused:
+            p.gn_fuse = C.cast(C.pointer(gp), C.c_void_p)
+            p.gn_fuse_mode = 1
+            tiles = lib.dmu_conv2d_gn_fuse_supported(C.byref(p))
+            assert tiles > 0, "the library refused a shape the plan builder relies on"
+        ops.conv2d_raw(p)
+        if not fused:
+            _abi.check(lib.dmu_gn_forward(C.byref(gp), _stream()))
+        torch.cuda.synchronize()
+        assert a[..., :8].abs().max() == 0
+        return y, a[..., 8:], sums
+    y1, a1, s1 = run(True)
+    y0, a0, s0 = run(False)
+    ref = F.conv2d(xh.float().permute(0, 3, 1, 2), w.to(dtype).float(), bias, stride=stride, padding=pad) + temb[:, :, None, None]
+    if has_res:
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    assert rel_l2(y1.float().permute(0, 3, 1, 2), ref) < TOL[dtype], "conv output"
+    yq = y1.float().permute(0, 3, 1, 2)           # the norm sees the stored (bf16) tensor
+    aref = F.group_norm(yq, G, gamma, beta, eps=1e-5)
+    aref = F.silu(aref) if silu else aref
+    assert rel_l2(a1.float().permute(0, 3, 1, 2), aref) < TOL[dtype], "normalised output vs ATen"
+    assert rel_l2(y1, y0) < 1e-3, "the fused launch must store the same conv output"
+    assert rel_l2(a1, a0) < 2e-3, "fused vs stand-alone GroupNorm"
+    assert rel_l2(s1, s0) < 1e-5, "raw sums handed to the backward"
+
+
+@pytest.mark.parametrize("silu", [1, 0])
+@pytest.mark.parametrize("adds", [0, 2])
+@pytest.mark.parametrize("case", [c for c in GN_EPI_CASES if c[5] != 4])
+def test_conv_gn_epilogue_backward(case, adds, silu):
+    """dmu_conv_params.gn_fuse mode 2: a layer y = conv(act(GroupNorm(x))).  One launch computes dgrad(dy) and, in its epilogue,
+    the GroupNorm(+SiLU) backward (+ addends), against autograd of the ATen composition and against this library's own
+    dgrad launch followed by dmu_gn_backward; the per-tile channel sums fold to dgamma / dbeta."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams, GnParams, GnPgDesc
+    dev = torch.device("cuda:0")
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(sum(case[:8]) + 1)
+    # here Ci is the channel count of the NORM (the conv's input), Co the conv's output; the dgrad maps Co -> Ci
+    N, H, W, Co, Ci, R, stride, pad, G, _, _, _, _, _ = _gn_epi_setup(case, g, dev)
+    x = (torch.randn(N, Ci, H, W, generator=g) * 1.5 + 0.3).to(dev)
+    w = (torch.randn(Co, Ci, R, R, generator=g) / math.sqrt(Ci * R * R)).to(dev)
+    gamma, beta = (1 + 0.2 * torch.randn(Ci, generator=g)).to(dev), (0.1 * torch.randn(Ci, generator=g)).to(dev)
+    dy = torch.randn(N, Co, H, W, generator=g).to(dev)
+    add_t = [torch.randn(N, H, W, Ci, generator=g).to(dev).to(dtype) for _ in range(adds)]
+    xh, dyh = ops.nchw_to_nhwc(x, dtype), ops.nchw_to_nhwc(dy, dtype)
+    wkt = _repack(w, False, dtype, dgrad=True)
+    code = ops.dtype_code(xh)
+    lib = _abi.lib()
+    # forward statistics from the library's own norm
+    ah = torch.empty_like(xh)
+    sums = torch.zeros(N, G, 2, device=dev)
+    gf = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(ah), _null(), _null(), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                  None, None, None, N, H, W, Ci, G, silu, 1e-5, 0)
+    _abi.check(lib.dmu_gn_forward(C.byref(gf), _stream()))
+
+    def run(fused):
+        da = torch.zeros(N, H, W, Ci, device=dev, dtype=dtype)
+        dx = torch.zeros(N, H, W, Ci, device=dev, dtype=dtype)
+        red = torch.zeros(N, Ci, 2, device=dev)
+        dgam, dbet = torch.zeros(Ci, device=dev), torch.zeros(Ci, device=dev)
+        t4s = [ops.t4_nhwc(t) for t in add_t] + [_null(), _null()]
+        gp = GnParams(ops.t4_nhwc(xh), ops.t4_nhwc(da), ops.t4_nhwc(dx), t4s[0], t4s[1], sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                      red.data_ptr(), None, None, N, H, W, Ci, G, silu, 1e-5, 0)
+        p = ConvParams(ops.t4_nhwc(dyh), ops.t4_nhwc(da), _null(), wkt.data_ptr(), R * R * Co, 1, Co, None, None, 0,
+                       N, H, W, Co, H, W, Ci, R, R, 1, pad, 1, code, 0, 0, None, 0)
+        tiles = 0
+        if fused:
+            p.gn_fuse = C.cast(C.pointer(gp), C.c_void_p)
+            p.gn_fuse_mode = 2
+            tiles = lib.dmu_conv2d_gn_fuse_supported(C.byref(p))
+            assert tiles > 0, "the library refused a shape the plan builder relies on"
+        ops.conv2d_raw(p)
+        if not fused:
+            _abi.check(lib.dmu_gn_backward(C.byref(gp), _stream()))
+        d = GnPgDesc(red.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), Ci, tiles)
+        tab = torch.frombuffer(bytearray(bytes(d)), dtype=torch.uint8).cuda()
+        _abi.check(lib.dmu_gn_param_grads(tab.data_ptr(), 1, Ci, N, _stream()))
+        torch.cuda.synchronize()
+        return dx, dgam, dbet
+    dx1, dg1, db1 = run(True)
+    dx0, dg0, db0 = run(False)
+    xq = xh.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gq, bq = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    a = F.group_norm(xq, G, gq, bq, eps=1e-5)
+    a = F.silu(a) if silu else a
+    y = F.conv2d(a, w.to(dtype).float(), padding=pad)
+    y.backward(dyh.float().permute(0, 3, 1, 2))
+    want = xq.grad + sum(t.float().permute(0, 3, 1, 2) for t in add_t) if adds else xq.grad
+    assert rel_l2(dx1.float().permute(0, 3, 1, 2), want) < 1.2e-2, "dx vs autograd (bf16 dy rounding included)"
+    assert rel_l2(dx1, dx0) < 4e-3, "fused vs dgrad + stand-alone GroupNorm backward"
+    assert rel_l2(dg1, gq.grad) < 1e-2 and rel_l2(db1, bq.grad) < 1e-2
+    assert rel_l2(dg1, dg0) < 2e-3 and rel_l2(db1, db0) < 2e-3

@@ -172,3 +172,28 @@ def test_snr_time_weights_without_host_sync_match_the_reference_formula():
         assert torch.allclose(wa, wb, rtol=2e-6, atol=1e-7), (t, wa, wb)
         ref = OL.time_weights(t, "snr", 0.1, 1.0).reshape(-1)
         assert torch.allclose(wb, ref, rtol=2e-6, atol=1e-7)
+
+
+def test_groupnorm_epilogue_fusion_plan_equals_unfused(monkeypatch):
+    """Host logic of dmu_conv_params.gn_fuse: with the library answering "yes" for the <= 8x8 layers, the plan drops those
+    GroupNorm launches (forward: armed on the producing conv; backward: armed on the dgrad, weight gradient kept behind it,
+    shortcut gradient computed first) and computes exactly what the unfused plan computes."""
+    import diffusion_model_universal_b200 as D
+    fake_device.install(monkeypatch)
+    outs = []
+    for fuse in (False, True):
+        net = D.UNet(3, 64, 3, precision="fp32")
+        net.load_state_dict(W.make_state_dict(W.unet_param_spec(64, 3, ""), 3))
+        net.engine.fuse_gn_epi = fuse
+        g = torch.Generator().manual_seed(5)
+        x, t, dout = torch.randn(2, 3, 32, 32, generator=g), torch.randint(0, 1000, (2,), generator=g), torch.randn(2, 3, 32, 32, generator=g)
+        y = net(x, t)
+        y.backward(dout)
+        plan = net.engine.get_plan(x.shape, True)
+        assert (plan.gn_fused[0] > 20 and plan.gn_fused[1] > 20) == fuse
+        n_gn = sum(1 for op in plan.fwd if op[0] is not None and getattr(op[0], "__name__", "") == "dmu_gn_forward")
+        assert n_gn == 50 - plan.gn_fused[0]
+        outs.append((y.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}))
+    assert rel_l2(outs[1][0], outs[0][0]) < 1e-6
+    for k, g0 in outs[0][1].items():
+        assert rel_l2(outs[1][1][k], g0) < 1e-5 or g0.norm() < 1e-9, k
