@@ -104,6 +104,7 @@ _SIGS = {
     "dmu_langevin_energy_step": (c_i32, [c_vp, c_vp, c_vp, c_f32, c_f32, c_vp, c_i64, c_vp]),
     "dmu_energy_renoise": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "dmu_scale_add": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "dmu_snr_time_weights": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_f32, c_f32, c_vp, c_vp]),
     "dmu_loss_workspace_floats": (c_i64, [c_i64]),
     "dmu_diffusion_loss": (c_i32, [c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "dmu_conv2d": (c_i32, [P(ConvParams), c_vp]),

@@ -184,101 +184,18 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& r, float* out) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
 }
-__device__ __forceinline__ float gn_silu(float u) { return __fdividef(u, 1.f + __expf(-u)); }
+// The GroupNorm epilogue runs on the four warps of one CTA: every loop below is latency-bound, so the activations are
+// branch-free (a select, not a jump: eight independent elements stay interleaved) and the loops carry 4-8 independent chains.
+__device__ __forceinline__ float gn_act(float u, int silu) {
+    const float v = __fdividef(u, 1.f + __expf(-u));
+    return silu ? v : u;
+}
 // du = dy * act'(u)   (same arithmetic as norm.cu's act_grad: the fused and the stand-alone GroupNorm must agree)
 __device__ __forceinline__ float gn_act_grad(float u, float dy, int silu) {
-    if (!silu) return dy;
     const float sg = __fdividef(1.f, 1.f + __expf(-u));
-    return dy * (sg * fmaf(u, 1.f - sg, 1.f));
+    const float r = dy * (sg * fmaf(u, 1.f - sg, 1.f));
+    return silu ? r : dy;
 }
-// Sum over the 32 lanes of a warp of a 32-vector held by every lane: on return lane l holds the total of element l.
-// Recursive halving: 31 shuffles, against 160 for element-wise butterflies.
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < o; ++i) {
-            const float keep = up ? v[i + o] : v[i];
-            const float send = up ? v[i] : v[i + o];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    return v[0];
-}
-// (sum, sum of squares) of every W consecutive channels of a 32-channel chunk
-template <int W>
-__device__ __forceinline__ void gn_group_sums(const float* v, float* dst) {
-#pragma unroll
-    for (int k = 0; k < 32 / W; ++k) {
-        float su = 0.f, sq = 0.f;
-#pragma unroll
-        for (int w = 0; w < W; ++w) { const float t = v[k * W + w]; su += t; sq = fmaf(t, t, sq); }
-        dst[2 * k] = su; dst[2 * k + 1] = sq;
-    }
-}
-// v <- act((v - mean) * rstd * gamma + beta); stat = (mean, rstd) of the chunk's first group onwards, gam / bet at the chunk's first channel
-template <int W>
-__device__ __forceinline__ void gn_apply32(float* v, const float* stat, const float* gam, const float* bet, int silu) {
-#pragma unroll
-    for (int k = 0; k < 32 / W; ++k) {
-        const float mean = stat[2 * k], rstd = stat[2 * k + 1];
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const int i = k * W + w;
-            const float sc = rstd * gam[i];
-            const float t = fmaf(v[i], sc, bet[i] - mean * sc);
-            v[i] = silu ? gn_silu(t) : t;
-        }
-    }
-}
-// backward, first pass over a chunk: t1 = du, t2 = du * xhat per element; part = per-group (sum gamma du, sum gamma du xhat) of this row
-template <int W>
-__device__ __forceinline__ void gn_bwd_pass1(const float* dy, const float* xv, const float* mr, const float* gam, const float* bet, int silu,
-                                             float* t1, float* t2, float* part) {
-#pragma unroll
-    for (int k = 0; k < 32 / W; ++k) {
-        const float mean = mr[2 * k], rstd = mr[2 * k + 1];
-        float ga = 0.f, gb = 0.f;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const int i = k * W + w;
-            const float d = xv[i] - mean, g = gam[i];
-            const float du = gn_act_grad(fmaf(d, rstd * g, bet[i]), dy[i], silu);
-            const float e = du * d * rstd;
-            t1[i] = du; t2[i] = e;
-            ga = fmaf(g, du, ga); gb = fmaf(g, e, gb);
-        }
-        part[2 * k] = ga; part[2 * k + 1] = gb;
-    }
-}
-// backward, second pass: o = rstd (gamma du - A - xhat B) with ab = (A, B) / cnt of the row's image and group
-template <int W>
-__device__ __forceinline__ void gn_bwd_pass2(const float* dy, const float* xv, const float* mr, const float* ab, const float* gam, const float* bet,
-                                             int silu, float* o) {
-#pragma unroll
-    for (int k = 0; k < 32 / W; ++k) {
-        const float mean = mr[2 * k], rstd = mr[2 * k + 1];
-        const float k1 = -rstd * rstd * ab[2 * k + 1];
-        const float k0 = -rstd * ab[2 * k] - mean * k1;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const int i = k * W + w;
-            const float sc = rstd * gam[i];
-            const float du = gn_act_grad(fmaf(xv[i] - mean, sc, bet[i]), dy[i], silu);
-            o[i] = fmaf(du, sc, fmaf(xv[i], k1, k0));
-        }
-    }
-}
-#define GN_DISPATCH_W(cpg_, ...)                                      \
-    switch (cpg_) {                                                   \
-        case 2: { constexpr int W = 2; __VA_ARGS__; } break;          \
-        case 4: { constexpr int W = 4; __VA_ARGS__; } break;          \
-        case 8: { constexpr int W = 8; __VA_ARGS__; } break;          \
-        case 16: { constexpr int W = 16; __VA_ARGS__; } break;        \
-        default: { constexpr int W = 32; __VA_ARGS__; } break;        \
-    }
-
 // DEEP = 0: 2 CTAs per SM with a short ring (grids of several waves: the co-resident CTA hides the pipeline bubbles);
 // DEEP = 1: 1 CTA per SM with as many stages as shared memory holds.  One TMA round trip is ~1 us, so a CTA moves at most
 // (stages x stage bytes) per us: layers whose whole grid is under one wave (the <= 8x8 stages) are bound by exactly that.
@@ -292,8 +209,10 @@ struct ConvCfg {
 };
 
 // GN = 1: the instantiation with the fused GroupNorm epilogues (GnEpi); the plain kernels stay lean (registers / code size)
+// The GN = 1 kernels run 256 threads: warps 4-7 idle through the pipeline and then take the upper 32 channels of every tile row in the
+// epilogue (a warp reads the TMEM lane quarter warp % 4), which halves every latency-bound phase of the norm.
 template <int NT, int DEEP, int GN>
-__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
+__global__ void __launch_bounds__(GN ? 256 : 128) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
     using Cfg = ConvCfg<NT, DEEP>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -353,7 +272,9 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     // stores remain (they used to be four dependent rounds of L2 loads, ~2 us of a ~8 us sub-wave launch).
     // M = 128: accumulator row r sits in TMEM lane r.  M = 64 (the 64-pixel tiles): row r sits in lane (r / 16) * 32 + r % 16
     // (scripts/probes/umma_m64_layout.cu), i.e. lanes 0-15 of every warp's quadrant hold 16 consecutive rows.
-    const int row = P.m64 ? (lane < 16 ? warp * 16 + lane : 128) : (int)threadIdx.x;
+    const int row = P.m64 ? (lane < 16 ? warp * 16 + lane : 128) : (int)(threadIdx.x & 127);
+    const int c0 = GN ? (int)(threadIdx.x >> 7) * 32 : 0;       // GN: this thread's 32-channel half of the row
+    const int nstage = (int)blockDim.x - 64;                    // threads of warps >= 2 (staging helpers)
     const int wl = row % P.BW, hl = (row / P.BW) % P.BH, nl = row / (P.BW * P.BH);
     const int n = n0 + nl, th = th0 + hl, tw = tw0 + wl;
     const int ho = th * P.os + ph.oph, wo = tw * P.os + ph.opw;
@@ -366,35 +287,39 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
         if (P.gn.mode == 2) rp = valid ? P.gn.x + (int64_t)n * P.gn.x_sn + (int64_t)ho * P.gn.x_sh + (int64_t)wo * P.gn.x_sw + j0 : nullptr;
 #pragma unroll
         for (int i = 0; i < NT / 8; ++i) rpre[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    if (rp && (P.prefetch || GN)) {
+        if (rp) {      // this thread's 32 channels only
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rpre[i] = *reinterpret_cast<const uint4*>(rp + c0 + i * 8);
+        }
+    } else if (rp && P.prefetch) {
 #pragma unroll
         for (int i = 0; i < NT / 8; ++i) rpre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
     }
     if constexpr (GN) {
         if (warp >= 2) {
-            for (int i = threadIdx.x - 64; i < NT; i += 64) {
+            for (int i = threadIdx.x - 64; i < NT; i += nstage) {
                 s_gb[i] = __ldg(P.gn.gamma + j0 + i);
                 s_gb[NT + i] = __ldg(P.gn.beta + j0 + i);
             }
             if (P.gn.mode == 2) {      // (mean, rstd) of every (image, group) of the tile, same arithmetic as norm.cu's stage_affine
                 float* s_mr = reinterpret_cast<float*>(smem + P.gn.epi_off);
                 const int GT = NT / P.gn.cpg;
-                for (int i = threadIdx.x - 64; i < P.BN * GT; i += 64) {
+                for (int i = threadIdx.x - 64; i < P.BN * GT; i += nstage) {
                     const int img = i / GT, g = i - img * GT;
                     float mean = 0.f, rstd = 0.f;
                     if (n0 + img < P.N) {
                         const float* sp = P.gn.sums + ((int64_t)(n0 + img) * P.gn.G + j0 / P.gn.cpg + g) * 2;
-                        mean = sp[0] / P.gn.cnt;
-                        rstd = rsqrtf(fmaxf(sp[1] / P.gn.cnt - mean * mean, 0.f) + P.gn.eps);
+                        const float inv_cnt = 1.f / P.gn.cnt;
+                        mean = sp[0] * inv_cnt;
+                        rstd = rsqrtf(fmaxf(fmaf(sp[1], inv_cnt, -mean * mean), 0.f) + P.gn.eps);
                     }
-                    s_mr[2 * i] = mean; s_mr[2 * i + 1] = rstd;
+                    s_mr[img * (2 * GT + 1) + 2 * g] = mean; s_mr[img * (2 * GT + 1) + 2 * g + 1] = rstd;     // odd image stride: no bank conflicts
                 }
             }
         }
     }
     if (stage_bt && warp >= 2) {
-        for (int i = threadIdx.x - 64; i < P.BN * NT; i += 64) {
+        for (int i = threadIdx.x - 64; i < P.BN * NT; i += nstage) {
             const int img = i / NT, c = i % NT;
             float v = P.bias ? __ldg(P.bias + j0 + c) : 0.f;
             if (P.temb && n0 + img < P.N) v += __ldg(P.temb + (int64_t)(n0 + img) * P.temb_pitch + j0 + c);
@@ -503,168 +428,214 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Ma
     const bool have_acc = *reinterpret_cast<volatile uint32_t*>(&s_issued) != 0;
     if constexpr (GN) {
         // ------------------------------------------------ fused GroupNorm epilogue (splits == 1, whole images per tile)
-        // Two passes over the accumulator (TMEM reads are cheap) around one CTA-local reduction; the pipeline ring is idle by now
-        // (every MMA has retired) and serves as scratch: s_part [128 rows][2 GT + 1] per-row group partials, s_stat [BN][GT][2]
-        // per (image, group) results, s_col [4 warps][NT][2] per-warp channel sums (backward only).
+        // The finished tile is parked in shared memory (the pipeline ring is idle: every MMA has retired) and the norm runs over
+        // it in ROLLED loops with their own thread mappings, 256 threads.  (A first version kept the TMEM-lane mapping in
+        // registers and unrolled per channels-per-group case: 411 KB of SASS per kernel and +14 us per launch.)
+        //   tileV [128][TS] fp32: conv output y (forward) | dy, then du (backward);   tileX [128][TS]: x, then xhat (backward)
+        //   s_stat [BN][IS]: (mean, rstd) per group forward | (A, B) / cnt backward;   s_tmp: partial sums of the reductions
         const GnEpi& Gn = P.gn;
-        const int cpg = Gn.cpg, GT = NT / cpg, HWt = P.BH * P.BW, pstr = 2 * GT + 1;
-        float* s_part = reinterpret_cast<float*>(smem);
-        float* s_stat = s_part + 128 * pstr;
-        float* s_col = s_stat + P.BN * GT * 2;
+        constexpr int TS = NT + 1;
+        const int cpg = Gn.cpg, sh = 31 - __clz(cpg), GT = NT >> sh, IS = 2 * GT + 1, HWt = P.BH * P.BW, npairs = P.BN * GT;
+        float* tileV = reinterpret_cast<float*>(smem);
+        float* tileX = tileV + 128 * TS;
+        float* s_stat = tileX + 128 * TS;
+        float* s_tmp = s_stat + P.BN * IS;
         const float* s_mr = reinterpret_cast<const float*>(smem + Gn.epi_off);
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        const int nlc = valid ? nl : 0;
-        float* my_part = s_part + threadIdx.x * pstr;
-        const float* tp = (P.temb && valid) ? P.temb + (int64_t)n * P.temb_pitch + j0 : nullptr;
-        // accumulator chunk -> the value the stored tensor holds (bias, temb, residual, rounded to bf16); zeros for rows outside the problem
-        auto finalize = [&](int c, float* v, bool with_res) {
-            if (!have_acc || !valid) {
+        const int tid = threadIdx.x;
+        const int silu = Gn.silu;
+        const float inv_cnt = 1.f / Gn.cnt;
+        float* myV = tileV + row * TS + c0;
+        float* myX = tileX + row * TS + c0;
+        const float* gam = s_gb + c0;
+        const float* bet = s_gb + NT + c0;
+        // Few phases, few barriers (every phase of a 256-thread CTA costs ~1-2k cycles of latency whatever its size):
+        //   1. this thread's 32 channels of its row -> registers: finalised conv output (forward) or du / xhat (backward), parked
+        //      in the shared tiles for the cross-row sums;                                              barrier
+        //   2. (image, group) sums - the threads of one pair are adjacent lanes, combined by shuffles - and, backward, the
+        //      per-tile channel sums;                                                                     barrier
+        //   3. the result from the registers of phase 1.
+        float v[32], xh[32];
+        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!have_acc || !valid) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            }
-            if (!valid) return;
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (valid) {
             if (stage_bt) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(&s_bt[nl * NT + c + i]);
+                    const float4 b = *reinterpret_cast<const float4*>(&s_bt[nl * NT + c0 + i]);
                     v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
                 }
             } else {
                 if (P.bias) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c + i));
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c0 + i));
                         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
                     }
                 }
-                if (tp) {
+                if (P.temb) {
+                    const float* tp = P.temb + (int64_t)n * P.temb_pitch + j0 + c0;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(tp + c + i));
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(tp + i));
                         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
                     }
                 }
             }
-            if (with_res && rp) {
+            if (Gn.mode == 1 && rp) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rpre[(c + i) >> 3]);
+                for (int i = 0; i < 4; ++i) {
+                    float r8[8];
+                    unpack_bf16x8(rpre[i], r8);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); v[i + 2 * k] += f.x; v[i + 2 * k + 1] += f.y; }
+                    for (int k = 0; k < 8; ++k) v[i * 8 + k] += r8[k];
                 }
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
-        };
-        // (image, group) totals of the per-row partials; f(pair, image, group, total0, total1) stores what the second pass needs
-        auto reduce_pairs = [&](auto&& f) {
-            __syncthreads();
-            for (int pair = threadIdx.x; pair < P.BN * GT; pair += 128) {
-                const int img = pair / GT, g = pair - img * GT;
-                const float* pp = s_part + img * HWt * pstr + 2 * g;
-                float t0 = 0.f, t1 = 0.f;
-                for (int r = 0; r < HWt; ++r) { t0 += pp[r * pstr]; t1 += pp[r * pstr + 1]; }
-                f(pair, img, g, t0, t1);
+            if (Gn.mode == 1) {
+                __nv_bfloat16* yp1 = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0 + c0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp1 + i, v + i);
             }
-            __syncthreads();
+        }
+        if (Gn.mode == 2) {
+            // du = dy act'(u), xhat: rpre holds this thread's part of row x (zeros, like dy, for rows outside the problem)
+            const float* mr = s_mr + (valid ? nl : 0) * IS;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) unpack_bf16x8(rpre[i], xh + i * 8);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int g = (c0 + i) >> sh;
+                const float mean = mr[2 * g], rstd = mr[2 * g + 1];
+                const float d = xh[i] - mean;
+                v[i] = gn_act_grad(fmaf(d, rstd * gam[i], bet[i]), v[i], silu);
+                xh[i] = d * rstd;
+                myX[i] = xh[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) myV[i] = v[i];
+        if (dbg && threadIdx.x == 0) dbg[6] = clock64();   // (GroupNorm epilogue) tile parked in shared memory
+        __syncthreads();
+        // ---- phase 2: `parts` adjacent lanes share one (image, group) pair, rows interleaved
+        int parts = 1;
+        while (parts < 32 && parts * 2 * npairs <= 256 && parts * 2 <= HWt) parts *= 2;
+        const int pair = tid / parts, part = tid - pair * parts;
+        // f(offset into the tiles, channel of the group, two accumulators); two independent accumulator pairs (even / odd channels)
+        auto pair_sum = [&](int pr, auto&& f, float& r0, float& r1) {
+            const int img = pr / GT, g = pr - img * GT;
+            float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+            if (pr < npairs) {
+                for (int r = part; r < HWt; r += parts) {
+                    const int off = (img * HWt + r) * TS + (g << sh);
+#pragma unroll 2
+                    for (int k = 0; k < cpg; k += 2) {
+                        f(off + k, (g << sh) + k, a0, b0);
+                        f(off + k + 1, (g << sh) + k + 1, a1, b1);
+                    }
+                }
+            }
+            r0 = a0 + a1; r1 = b0 + b1;
+            for (int o = parts >> 1; o > 0; o >>= 1) {        // the pair's threads are `parts` adjacent lanes (parts divides 32)
+                r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+                r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+            }
         };
+        const int pair_stride = 256 / parts;
+        const int pair_rounds = (npairs + pair_stride - 1) / pair_stride;      // uniform trip count: the shuffles need whole warps
         if (Gn.mode == 1) {
-            __nv_bfloat16* yp1 = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0;
-            __nv_bfloat16* ap = Gn.a + (int64_t)n * Gn.a_sn + (int64_t)ho * Gn.a_sh + (int64_t)wo * Gn.a_sw + j0;
-#pragma unroll
-            for (int c = 0; c < NT; c += 32) {
-                float v[32];
-                tmem_ld32(trow + (uint32_t)c, v);
-                tmem_ld_wait();
-                finalize(c, v, true);
-                if (valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp1 + c + i, v + i);
+            for (int it = 0; it < pair_rounds; ++it) {
+                const int pr = pair + it * pair_stride;
+                float su, sq;
+                pair_sum(pr, [&](int o, int, float& a, float& b) { const float t = tileV[o]; a += t; b = fmaf(t, t, b); }, su, sq);
+                if (part == 0 && pr < npairs) {
+                    const int img = pr / GT, g = pr - img * GT;
+                    if (n0 + img < P.N) {
+                        float* sp = Gn.sums + ((int64_t)(n0 + img) * Gn.G + (j0 >> sh) + g) * 2;
+                        sp[0] = su; sp[1] = sq;
+                    }
+                    const float mean = su * inv_cnt;
+                    s_stat[img * IS + 2 * g] = mean;
+                    s_stat[img * IS + 2 * g + 1] = rsqrtf(fmaxf(fmaf(sq, inv_cnt, -mean * mean), 0.f) + Gn.eps);
                 }
-                GN_DISPATCH_W(cpg, gn_group_sums<W>(v, my_part + 2 * (c / W)));
             }
-            reduce_pairs([&](int pair, int img, int g, float su, float sq) {
-                if (n0 + img < P.N) {
-                    float* sp = Gn.sums + ((int64_t)(n0 + img) * Gn.G + j0 / cpg + g) * 2;
-                    sp[0] = su; sp[1] = sq;
-                }
-                const float mean = su / Gn.cnt;
-                s_stat[2 * pair] = mean;
-                s_stat[2 * pair + 1] = rsqrtf(fmaxf(sq / Gn.cnt - mean * mean, 0.f) + Gn.eps);
-            });
+            __syncthreads();
+            if (dbg && threadIdx.x == 0) dbg[7] = clock64();   // statistics done
+            // ---- phase 3: a = act((y - mean) rstd gamma + beta) from the registers of phase 1
+            if (valid) {
+                __nv_bfloat16* ap = Gn.a + (int64_t)n * Gn.a_sn + (int64_t)ho * Gn.a_sh + (int64_t)wo * Gn.a_sw + j0 + c0;
+                const float* st = s_stat + nl * IS;
 #pragma unroll
-            for (int c = 0; c < NT; c += 32) {
-                float v[32];
-                tmem_ld32(trow + (uint32_t)c, v);
-                tmem_ld_wait();
-                finalize(c, v, true);
-                GN_DISPATCH_W(cpg, gn_apply32<W>(v, s_stat + 2 * (nlc * GT + c / W), s_gb + c, s_gb + NT + c, Gn.silu));
-                if (valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(ap + c + i, v + i);
+                for (int i = 0; i < 32; ++i) {
+                    const int g = (c0 + i) >> sh;
+                    const float sc = st[2 * g + 1] * gam[i];
+                    v[i] = gn_act(fmaf(v[i], sc, bet[i] - st[2 * g] * sc), silu);
                 }
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(ap + i, v + i);
             }
         } else {
-            // backward: the accumulator is dy (gradient w.r.t. the normalised activation), rpre holds this row of x
-#pragma unroll
-            for (int c = 0; c < NT; c += 32) {
-                float v[32], xv[32], t1[32], t2[32];
-                tmem_ld32(trow + (uint32_t)c, v);
-                tmem_ld_wait();
-                finalize(c, v, false);
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) unpack_bf16x8(rpre[(c + i) >> 3], xv + i);
-                GN_DISPATCH_W(cpg, gn_bwd_pass1<W>(v, xv, s_mr + 2 * (nlc * GT + c / W), s_gb + c, s_gb + NT + c, Gn.silu, t1, t2, my_part + 2 * (c / W)));
-                const float c1 = warp_transpose_sum(t1, lane), c2 = warp_transpose_sum(t2, lane);
-                s_col[(warp * NT + c + lane) * 2] = c1;
-                s_col[(warp * NT + c + lane) * 2 + 1] = c2;
+            // A = sum gamma du, B = sum gamma du xhat per (image, group)
+            for (int it = 0; it < pair_rounds; ++it) {
+                const int pr = pair + it * pair_stride;
+                float A, B;
+                pair_sum(pr, [&](int o, int ch, float& a, float& b) { const float gd = s_gb[ch] * tileV[o]; a += gd; b = fmaf(gd, tileX[o], b); }, A, B);
+                if (part == 0 && pr < npairs) {
+                    const int img = pr / GT, g = pr - img * GT;
+                    s_stat[img * IS + 2 * g] = A * inv_cnt; s_stat[img * IS + 2 * g + 1] = B * inv_cnt;
+                }
             }
-            reduce_pairs([&](int pair, int, int, float A, float B) {
-                s_stat[2 * pair] = A / Gn.cnt;
-                s_stat[2 * pair + 1] = B / Gn.cnt;
-            });
-            // per-tile channel sums for the affine-parameter gradients (folded over the tiles by dmu_gn_param_grads)
-            for (int e = threadIdx.x; e < NT * 2; e += 128)
-                Gn.red[((int64_t)tile * Gn.C + j0) * 2 + e] = (s_col[e] + s_col[NT * 2 + e]) + (s_col[2 * NT * 2 + e] + s_col[3 * NT * 2 + e]);
-            __nv_bfloat16* dxp = Gn.dx + (int64_t)n * Gn.dx_sn + (int64_t)ho * Gn.dx_sh + (int64_t)wo * Gn.dx_sw + j0;
-            const __nv_bfloat16* a0p = (Gn.add0 && valid) ? Gn.add0 + (int64_t)n * Gn.a0_sn + (int64_t)ho * Gn.a0_sh + (int64_t)wo * Gn.a0_sw + j0 : nullptr;
-            const __nv_bfloat16* a1p = (Gn.add1 && valid) ? Gn.add1 + (int64_t)n * Gn.a1_sn + (int64_t)ho * Gn.a1_sh + (int64_t)wo * Gn.a1_sw + j0 : nullptr;
+            // per-tile channel sums (sum du, sum du xhat) for the affine-parameter gradients: thread = (channel, quarter of the rows)
+            {
+                const int c = tid & (NT - 1), q4 = tid / NT;        // NT = 64: four quarters of 32 rows
+                float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int r = q4 * 32; r < q4 * 32 + 32; r += 4) {
 #pragma unroll
-            for (int c = 0; c < NT; c += 32) {
-                float v[32], xv[32], o[32];
+                    for (int q = 0; q < 4; ++q) { const float du = tileV[(r + q) * TS + c]; a[q] += du; b[q] = fmaf(du, tileX[(r + q) * TS + c], b[q]); }
+                }
+                s_tmp[(q4 * NT + c) * 2] = (a[0] + a[1]) + (a[2] + a[3]); s_tmp[(q4 * NT + c) * 2 + 1] = (b[0] + b[1]) + (b[2] + b[3]);
+            }
+            __syncthreads();
+            for (int e = tid; e < NT * 2; e += 256)
+                Gn.red[((int64_t)tile * Gn.C + j0) * 2 + e] = (s_tmp[e] + s_tmp[NT * 2 + e]) + (s_tmp[2 * NT * 2 + e] + s_tmp[3 * NT * 2 + e]);
+            if (dbg && threadIdx.x == 0) dbg[7] = clock64();   // reductions done
+            // ---- phase 3: dx = rstd (gamma du - A - xhat B) + add0 + add1 from the registers of phase 1
+            if (valid) {
+                const int64_t px = (int64_t)j0 + c0;
+                __nv_bfloat16* dxp = Gn.dx + (int64_t)n * Gn.dx_sn + (int64_t)ho * Gn.dx_sh + (int64_t)wo * Gn.dx_sw + px;
+                const __nv_bfloat16* a0p = Gn.add0 ? Gn.add0 + (int64_t)n * Gn.a0_sn + (int64_t)ho * Gn.a0_sh + (int64_t)wo * Gn.a0_sw + px : nullptr;
+                const __nv_bfloat16* a1p = Gn.add1 ? Gn.add1 + (int64_t)n * Gn.a1_sn + (int64_t)ho * Gn.a1_sh + (int64_t)wo * Gn.a1_sw + px : nullptr;
+                const float* mr = s_mr + nl * IS;
+                const float* ab = s_stat + nl * IS;
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                 uint4 r0[4], r1[4];
-                if (a0p) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) r0[i] = *reinterpret_cast<const uint4*>(a0p + c + i * 8);
+                for (int i = 0; i < 4; ++i) {
+                    r0[i] = a0p ? *reinterpret_cast<const uint4*>(a0p + i * 8) : z;
+                    r1[i] = a1p ? *reinterpret_cast<const uint4*>(a1p + i * 8) : z;
                 }
-                if (a1p) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) r1[i] = *reinterpret_cast<const uint4*>(a1p + c + i * 8);
+                for (int i = 0; i < 32; ++i) {
+                    const int g = (c0 + i) >> sh;
+                    v[i] = mr[2 * g + 1] * (gam[i] * v[i] - ab[2 * g] - xh[i] * ab[2 * g + 1]);
                 }
-                tmem_ld32(trow + (uint32_t)c, v);
-                tmem_ld_wait();
-                finalize(c, v, false);
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) unpack_bf16x8(rpre[(c + i) >> 3], xv + i);
-                GN_DISPATCH_W(cpg, gn_bwd_pass2<W>(v, xv, s_mr + 2 * (nlc * GT + c / W), s_stat + 2 * (nlc * GT + c / W), s_gb + c, s_gb + NT + c, Gn.silu, o));
-                if (a0p) {
+                for (int i = 0; i < 4; ++i) {
+                    float t0[8], t1[8];
+                    unpack_bf16x8(r0[i], t0);
+                    unpack_bf16x8(r1[i], t1);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { float t[8]; unpack_bf16x8(r0[i], t);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) o[i * 8 + k] += t[k]; }
-                }
-                if (a1p) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { float t[8]; unpack_bf16x8(r1[i], t);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) o[i * 8 + k] += t[k]; }
-                }
-                if (valid) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(dxp + c + i, o + i);
+                    for (int k = 0; k < 8; ++k) v[i * 8 + k] += t0[k] + t1[k];
+                    store_vec<__nv_bfloat16>(dxp + i * 8, v + i * 8);
                 }
             }
         }
+        if (dbg && threadIdx.x == 0) dbg[5] = clock64();   // epilogue stores issued
         tc_fence_before();
         __syncthreads();
         if (warp == 1) tmem_dealloc(tmem, NT);
@@ -973,7 +944,7 @@ static int conv_prepare(const dmu_conv_params* p, Maps* maps, ConvArgs& A, ConvG
     A.stages = max_stages;
     // mode-2 GroupNorm statistics are staged while the pipeline runs, in a region behind the ring that comes out of the ring's budget
     int gn_pre = 0;
-    if (gn && p->gn_fuse_mode == 2) gn_pre = (b.BN * (NT / (gn->C / gn->G)) * 2 * 4 + 1023) / 1024 * 1024;
+    if (gn && p->gn_fuse_mode == 2) gn_pre = (b.BN * (2 * (NT / (gn->C / gn->G)) + 1) * 4 + 1023) / 1024 * 1024;
     if (deep) {
         A.stages = (ring_kb * 1024 - gn_pre) / A.stage_bytes;
         if (A.stages > max_stages) A.stages = max_stages;
@@ -996,7 +967,9 @@ static int conv_prepare(const dmu_conv_params* p, Maps* maps, ConvArgs& A, ConvG
                  (!gn->add0.ptr || gn_tensor_ok(gn->add0)) && (!gn->add1.ptr || gn_tensor_ok(gn->add1));
         if (ok) {
             const int GT = NT / cpg;
-            const size_t need = ((size_t)128 * (2 * GT + 1) + (size_t)b.BN * GT * 2 + (size_t)4 * NT * 2) * 4;
+            // two [128][NT + 1] tiles, the per-(image, group) results, the partials of the reductions (<= 256 pairs x 2 or the channel sums)
+            const size_t npairs = (size_t)b.BN * GT;
+            const size_t need = ((size_t)2 * 128 * (NT + 1) + (size_t)b.BN * (2 * GT + 1) + 2 * (npairs > 256 ? npairs : 256)) * 4;
             ok = need <= ring;
         }
         if (!ok) return -1;      // not an error by itself: dmu_conv2d_gn_fuse_supported reports 0, dmu_conv2d fails loudly
@@ -1042,17 +1015,20 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         cudaFuncSetAttribute(conv_tc_kernel<128, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 0>::kSmem);
         cudaFuncSetAttribute(conv_tc_kernel<64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 1>::kSmem);
         cudaFuncSetAttribute(conv_tc_kernel<128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 1>::kSmem);
-        cudaFuncSetAttribute(conv_tc_kernel<64, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 0>::kSmem + 32 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 1>::kSmem + 32 * 1024);
+        // the GroupNorm variants never exceed ring (<= 128 KB, its statistics region included) + slack: conv_prepare sizes them
+        cudaFuncSetAttribute(conv_tc_kernel<64, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (cudaError_t ae = cudaGetLastError(); ae != cudaSuccess) return fail("dmu_conv2d/tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ae));
         attr_done = true;
     }
     const dim3 cluster(1, 1, (unsigned)A.splits);
     const dim3 grid = G.grid;
     const size_t smem = G.smem;
+    DMU_REQUIRE(!A.gn.mode || smem <= 160 * 1024, "dmu_conv2d/tc: GroupNorm epilogue launch needs %zu bytes of shared memory", smem);
     const bool deep = G.deep;
     cudaError_t e;
-    if (A.gn.mode) e = deep ? launch_pdl(conv_tc_kernel<64, 1, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
-                            : launch_pdl(conv_tc_kernel<64, 0, 1>, grid, dim3(128), smem, stream, cluster, maps, A);
+    if (A.gn.mode) e = deep ? launch_pdl(conv_tc_kernel<64, 1, 1>, grid, dim3(256), smem, stream, cluster, maps, A)
+                            : launch_pdl(conv_tc_kernel<64, 0, 1>, grid, dim3(256), smem, stream, cluster, maps, A);
     else if (G.NT == 64) e = deep ? launch_pdl(conv_tc_kernel<64, 1, 0>, grid, dim3(128), smem, stream, cluster, maps, A)
                                   : launch_pdl(conv_tc_kernel<64, 0, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
     else e = deep ? launch_pdl(conv_tc_kernel<128, 1, 0>, grid, dim3(128), smem, stream, cluster, maps, A)

@@ -222,6 +222,41 @@ struct ScaleAdd {
     }
 };
 
+// ------------------------------------------------------------------ 'snr' time weights (utils/losses.py:144-181)
+// One CTA: the [B]-sized weight vector of a step.  The reference builds cumprod(1 - linspace(1e-4, 2e-2, t_max + 1)) for the
+// batch's t_max on the host side of a .item() sync; here `table` holds that vector for EVERY possible t_max (row tm, built once
+// with the reference's own torch calls), so the kernel only gathers and replays the element-wise arithmetic in the
+// reference's order with explicit IEEE operations (no FMA contraction): bit-identical weights, no host sync, one launch
+// instead of ~25.
+__device__ __forceinline__ float block_reduce_max(float v, float* s_red) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = s_red[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, s_red[i]);
+    return r;
+}
+__global__ void __launch_bounds__(256) snr_weights_kernel(const int64_t* __restrict__ t, const float* __restrict__ table, int64_t T, int64_t B,
+                                                          float lo, float span, float* __restrict__ w) {
+    __shared__ float s_red[8];
+    float tm = 0.f;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) tm = fmaxf(tm, (float)t[b]);       // timesteps < 2^24: exact in fp32
+    const int64_t tmax = (int64_t)block_reduce_max(tm, s_red);
+    const float* row = table + tmax * T;
+    auto snr_of = [&](int64_t b) { const float a = row[t[b]]; return DIV(a, SUB(1.f, a)); };
+    float m = -INFINITY;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) m = fmaxf(m, snr_of(b));
+    const float smax = block_reduce_max(m, s_red);
+    auto v_of = [&](int64_t b) { return fmaxf(DIV(snr_of(b), smax), 1e-5f); };
+    float vmx = -INFINITY, vmn = -INFINITY;      // min as max of the negation
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) { const float v = v_of(b); vmx = fmaxf(vmx, v); vmn = fmaxf(vmn, -v); }
+    const float wmax = block_reduce_max(vmx, s_red);
+    const float wmin = -block_reduce_max(vmn, s_red);
+    const float den = ADD(SUB(wmax, wmin), 1e-5f);
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) w[b] = ADD(lo, MUL(span, DIV(SUB(v_of(b), wmin), den)));
+}
+
 template <class F>
 static int launch_per_sample(const F& f, int64_t batch, int64_t inner, cudaStream_t s, const char* what) {
     if (batch * inner == 0) return 0;
@@ -379,6 +414,14 @@ int dmu_scale_add(const float* x, const float* z, const float* a, const float* c
     DMU_REQUIRE(aligned16(x) && aligned16(z) && aligned16(out), "dmu_scale_add: buffers must be 16-byte aligned");
     ScaleAdd f{x, z, a, c, out};
     return launch_per_sample(f, batch, inner, as_stream(stream), "dmu_scale_add");
+}
+
+int dmu_snr_time_weights(const int64_t* t, const float* table, int64_t num_timesteps, int64_t batch, float min_weight, float weight_span,
+                         float* w, dmu_stream_t stream) {
+    if (batch == 0) return 0;
+    DMU_REQUIRE(t && table && w && num_timesteps >= 1 && batch > 0, "dmu_snr_time_weights: bad arguments");
+    snr_weights_kernel<<<1, 256, 0, as_stream(stream)>>>(t, table, num_timesteps, batch, min_weight, weight_span, w);
+    return check_launch("dmu_snr_time_weights");
 }
 
 int64_t dmu_loss_workspace_floats(int64_t numel) { return (int64_t)loss_grid(numel > 0 ? numel : 1); }

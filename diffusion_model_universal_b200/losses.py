@@ -52,6 +52,22 @@ class DiffusionLoss:
         raise ValueError(f"Unsupported single loss type: {self.loss_type}")  # 'hybrid' without use_hybrid, losses.py:113-114
 
     max_t = None   # upper bound on the timesteps (set by the owning model): enables the host-sync-free 'snr' weights
+    _snr_tables = None     # device -> fp32 [max_t, max_t]: row tm = cumprod(1 - linspace(1e-4, 2e-2, tm + 1)) (dmu_snr_time_weights)
+
+    def _snr_table(self, device) -> torch.Tensor:
+        """Every table the reference could build at losses.py:150-157, one per possible t_max, made once per device with the
+        reference's own calls (so each row is bit-identical to what it computes there).  4 MB at 1000 timesteps."""
+        if self._snr_tables is None:
+            self._snr_tables = {}
+        key = (str(device), int(self.max_t))
+        tab = self._snr_tables.get(key)
+        if tab is None:
+            T = int(self.max_t)
+            tab = torch.zeros(T, T, device=device, dtype=torch.float32)
+            for tm in range(T):
+                tab[tm, :tm + 1] = torch.cumprod(1 - torch.linspace(1e-4, 2e-2, tm + 1, device=device), dim=0)
+            self._snr_tables[key] = tab
+        return tab
 
     def _snr_alphas_cumprod(self, timesteps: torch.Tensor) -> torch.Tensor:
         """losses.py:150-157: ``cumprod(1 - linspace(1e-4, 2e-2, t_max + 1))[t]``.  The reference reads ``t_max`` back to the
@@ -77,6 +93,11 @@ class DiffusionLoss:
         """The [B] weights this loss would apply for ``timesteps`` (None = unweighted)."""
         if not self.use_time_weighting or timesteps is None:
             return None
+        if (self.time_weight_type == "snr" and self.max_t is not None and timesteps.is_cuda and timesteps.dtype == torch.int64
+                and timesteps.dim() == 1 and timesteps.is_contiguous()):
+            # one launch, no host sync (the torch-op formulation below stays as the general path and as the test's comparator)
+            return ops.snr_time_weights(timesteps, self._snr_table(timesteps.device), self.time_weight_params["min_weight"],
+                                        self.time_weight_params["max_weight"])
         return self._get_time_weights(timesteps).float().contiguous()
 
     def _get_time_weights(self, timesteps: torch.Tensor) -> torch.Tensor:

@@ -78,13 +78,25 @@ def t4_rows(t: torch.Tensor) -> Tensor4:
 
 
 # ------------------------------------------------------------------ process updates
-def q_sample(x0, t, noise, alphas_cumprod):
+def snr_time_weights(t, table, min_weight: float, max_weight: float):
+    """utils/losses.py:144-181 ('snr'): the [B] weight vector in one launch, t_max kept on the device.  table: fp32 [T, T]."""
+    _need_cuda(t, table)
+    _index_vec(t, t.shape[0], "t")
+    _f32c(table, "table")
+    w = torch.empty(t.shape[0], device=t.device, dtype=torch.float32)
+    _launched()
+    check(_abi.lib().dmu_snr_time_weights(t.data_ptr(), table.data_ptr(), table.shape[0], t.shape[0], float(min_weight),
+                                          float(max_weight - min_weight), w.data_ptr(), _stream()), "snr_time_weights")
+    return w
+
+
+def q_sample(x0, t, noise, alphas_cumprod, out=None):
     """models/ddpm.py:286-296."""
     _need_cuda(x0, t, noise, alphas_cumprod)
     x0, noise = _f32c(x0, "x0"), _f32c(noise, "noise")
     _index_vec(t, x0.shape[0], "t")
     _f32c(alphas_cumprod, "alphas_cumprod")
-    out = torch.empty_like(x0)
+    out = torch.empty_like(x0) if out is None else _f32c(out, "out")
     b = x0.shape[0]
     _launched()
     check(_abi.lib().dmu_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), alphas_cumprod.data_ptr(), out.data_ptr(),
@@ -92,7 +104,7 @@ def q_sample(x0, t, noise, alphas_cumprod):
     return out
 
 
-def ingest_u8(img, mean=None, std=None, layout="NCHW", t=None, noise=None, alphas_cumprod=None, want_x0=True):
+def ingest_u8(img, mean=None, std=None, layout="NCHW", t=None, noise=None, alphas_cumprod=None, want_x0=True, xt_out=None):
     """datasets/dataset_utils.py:58-61 (ToTensor + Normalize) on the device, optionally fused with q_sample
     (models/ddpm.py:286-296).  img: uint8 [B,C,H,W] (layout "NCHW") or [B,H,W,C] ("NHWC"); mean / std: fp32 [C] device
     tensors or None.  Returns (x0, xt) as fp32 [B,C,H,W]; x0 is None when want_x0 is False, xt is None without noise."""
@@ -120,7 +132,7 @@ def ingest_u8(img, mean=None, std=None, layout="NCHW", t=None, noise=None, alpha
     elif not want_x0:
         raise ValueError("nothing to compute: want_x0 is False and no noise was given")
     x0 = torch.empty((b, c, h, w), device=img.device, dtype=torch.float32) if want_x0 else None
-    xt = torch.empty((b, c, h, w), device=img.device, dtype=torch.float32) if fused else None
+    xt = (torch.empty((b, c, h, w), device=img.device, dtype=torch.float32) if xt_out is None else _f32c(xt_out, "xt_out")) if fused else None
     ptr = lambda v: v.data_ptr() if v is not None else None
     _launched()
     check(_abi.lib().dmu_ingest_u8(img.data_ptr(), 1 if layout == "NHWC" else 0, ptr(mean), ptr(std), ptr(noise),
@@ -245,14 +257,15 @@ def scale_add(x, z, a, c, out=None):
     return out
 
 
-def diffusion_loss(pred, target, w, wm, wl, wh, delta, want_grad: bool):
-    """utils/losses.py:74-131 given per-sample weights w [B] (or None).  Returns (loss 0-dim, dpred or None)."""
+def diffusion_loss(pred, target, w, wm, wl, wh, delta, want_grad: bool, dpred_out=None):
+    """utils/losses.py:74-131 given per-sample weights w [B] (or None).  Returns (loss 0-dim, dpred or None); dpred_out = an
+    existing fp32 tensor of pred's shape to receive the gradient (the engine's static upstream-gradient buffer)."""
     _need_cuda(pred, target, w)
     pred, target = _f32c(pred, "pred"), _f32c(target, "target")
     b = pred.shape[0]
     n = pred.numel()
     loss = torch.empty((), device=pred.device, dtype=torch.float32)
-    dpred = torch.empty_like(pred) if want_grad else None
+    dpred = (torch.empty_like(pred) if dpred_out is None else _f32c(dpred_out, "dpred_out")) if want_grad else None
     part = torch.empty(_abi.lib().dmu_loss_workspace_floats(n), device=pred.device, dtype=torch.float32)
     _launched(2)
     check(_abi.lib().dmu_diffusion_loss(pred.data_ptr(), target.data_ptr(), w.data_ptr() if w is not None else None,

@@ -98,6 +98,7 @@ class TrainStep:
         self.group = group
         self._synced = False
         self._stage = None
+        self._side = None      # side stream of the step's front (filter-cache refresh next to the RNG draws)
         self._works = None
         # Single-GPU DDPM steps replay ONE CUDA graph of everything between the input batch and the gradient arena (RNG draws,
         # time weights, q_sample, forward, loss, three-part backward): ~30 small eager launches and four graph launches per step
@@ -220,28 +221,41 @@ class TrainStep:
         return loss
 
     def _ddpm_front(self, images: torch.Tensor):
-        """RNG draws, time weights, q_sample, forward, loss and dL/d(eps)."""
+        """RNG draws, time weights, q_sample, forward, loss and dL/d(eps).  No staging copies: q_sample writes the network's
+        static input buffer, the loss reads its static output and writes the static upstream-gradient buffer; the refresh of
+        the bf16 filter caches (dmu_repack_weights, ~60 us) runs on a side stream next to the RNG / weight / q_sample front."""
         m = self.model
         eng = m.model.engine
-        t = torch.randint(0, m.num_timesteps, (images.shape[0],), device=images.device)
-        if images.dtype == torch.uint8:        # decoded bytes: ToTensor + Normalize + q_sample in one launch
+        eng.prepare(images.device)
+        if images.dtype == torch.uint8:
             b, d1, d2, d3 = images.shape
             shape = (b, d3, d1, d2) if self.input_layout == "NHWC" else (b, d1, d2, d3)
-            noise = torch.randn(shape, device=images.device, dtype=torch.float32)
         else:
-            noise = torch.randn_like(images)
-        w = m.loss_fn.time_weights(t)          # [B]-sized torch ops, issued before the forward so nothing waits on them later
-        if images.dtype == torch.uint8:
-            _, xt = ops.ingest_u8(images, self._norm_dev[0], self._norm_dev[1], self.input_layout, t, noise, m.alphas_cumprod,
-                                  want_x0=False)
+            shape = tuple(images.shape)
+        plan = eng.get_plan(shape, True)
+        cur = torch.cuda.current_stream(images.device) if images.is_cuda else None
+        side = None
+        if cur is not None and not eng.frozen:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=images.device)
+            side = self._side
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                eng.repack(ops._stream())
+        t = torch.randint(0, m.num_timesteps, (shape[0],), device=images.device)
+        noise = torch.randn(shape, device=images.device, dtype=torch.float32) if images.dtype == torch.uint8 else torch.randn_like(images)
+        w = m.loss_fn.time_weights(t)          # [B]-sized, issued before the forward so nothing waits on it later
+        if images.dtype == torch.uint8:        # decoded bytes: ToTensor + Normalize + q_sample in one launch
+            ops.ingest_u8(images, self._norm_dev[0], self._norm_dev[1], self.input_layout, t, noise, m.alphas_cumprod,
+                          want_x0=False, xt_out=plan.x_in)
         else:
-            xt = m._add_noise(images, t, noise)
-        eng.prepare(images.device)
-        plan = eng.get_plan(xt.shape, True)
-        eps = eng.run_forward(xt, t, plan)
+            ops.q_sample(images.contiguous(), t, noise, m.alphas_cumprod, out=plan.x_in)
+        if side is not None:
+            cur.wait_stream(side)
+        eps = eng.run_forward(None, t, plan, repacked=side is not None, clone=False)
         wm, wl, wh = m.loss_fn.coefficients()
-        loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True)
-        return loss, dpred, plan
+        loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True, dpred_out=plan.dout)
+        return loss, None, plan       # dL/d(eps) already sits in plan.dout
 
     def _ddpm_back(self, plan, dpred):
         eng = self.model.model.engine

@@ -528,13 +528,17 @@ class Engine:
         g.replay()
         ops.LAUNCHES += plan.nlaunch[which]
 
-    def run_forward(self, x, t, plan: Plan) -> torch.Tensor:
-        if not self.frozen:
+    def run_forward(self, x, t, plan: Plan, repacked: bool = False, clone: bool = True) -> torch.Tensor:
+        """x = None: the caller has already written the network input into plan.x_in (TrainStep's q_sample does).
+        repacked: the filter caches are already current (refreshed on a side stream).  clone=False returns the plan's static
+        output buffer itself (overwritten by the next execution)."""
+        if not (self.frozen or repacked):
             self.repack(ops._stream())
-        plan.x_in.copy_(x)
+        if x is not None:
+            plan.x_in.copy_(x)
         plan.t_in.copy_(t)       # int64 timesteps are cast to fp32 here exactly like embeddings.py:35 promotes them
         self._execute(plan, "fwd")
-        return plan.out.clone()
+        return plan.out.clone() if clone else plan.out
 
     def run_backward(self, plan: Plan, dout, between=None):
         """Fills the gradient arena; returns it (flat fp32, same offsets as the parameter arena).  ``between(lo, hi)`` is
@@ -546,7 +550,8 @@ class Engine:
         for p in self.named.values():
             if p.grad is not None and lo <= p.grad.data_ptr() < hi:
                 p.grad = p.grad.clone()
-        plan.dout.copy_(dout)
+        if dout is not None:      # None: the caller wrote the upstream gradient straight into plan.dout
+            plan.dout.copy_(dout)
         if between is None:
             self._execute(plan, "bwd")
         else:

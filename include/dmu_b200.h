@@ -91,6 +91,14 @@ int dmu_energy_renoise(const float* x, const float* noise, const float* alphas_c
 int dmu_scale_add(const float* x, const float* z, const float* a, const float* c, float* out,
                   int64_t batch, int64_t inner, dmu_stream_t stream);
 
+/* utils/losses.py:144-181 `_get_time_weights`, time_weight_type 'snr', without the reference's timesteps.max().item() sync:
+ *   acp = cumprod(1 - linspace(1e-4, 2e-2, t_max + 1))[t];  snr = acp / (1 - acp);  v = clamp(snr / max(snr), 1e-5);
+ *   w = min_weight + weight_span * (v - min(v)) / (max(v) - min(v) + 1e-5)          (weight_span = max_weight - min_weight)
+ * `table` is fp32 [num_timesteps][num_timesteps]: row tm = that cumprod vector for t_max = tm (entries past tm unused), built
+ * once by the host with the reference's own torch calls; t int64 [batch] with values < num_timesteps; one launch. */
+int dmu_snr_time_weights(const int64_t* t, const float* table, int64_t num_timesteps, int64_t batch, float min_weight, float weight_span,
+                         float* w, dmu_stream_t stream);
+
 /* utils/losses.py:74-131 `DiffusionLoss.__call__` minus the [B]-sized time
  * weights (computed by the host with the reference's own torch ops and passed
  * as `w`, NULL = unweighted):

@@ -269,3 +269,27 @@ def test_trainstep_with_energy_model(dev):
     assert ts2.opt.ema is not None and torch.isfinite(ts2.opt.ema).all()
     ck = ts2.checkpoint(epoch=1)
     assert set(ck["model_state_dict"]) == set(b.state_dict())
+
+
+def test_snr_time_weights_kernel_matches_reference_formula(dev):
+    """dmu_snr_time_weights (one launch, t_max on the device) against utils/losses.py:144-181 evaluated with the reference's own
+    torch calls on the same device (host-synchronising .item() included): same IEEE operations in the same order."""
+    from diffusion_model_universal_b200.losses import DiffusionLoss
+    cfg = {"use_time_weighting": True, "time_weight_type": "snr", "time_weight_params": {"min_weight": 0.1, "max_weight": 1.0}}
+    fused = DiffusionLoss("mse", dict(cfg))
+    fused.max_t = 1000
+    plain = DiffusionLoss("mse", dict(cfg))          # max_t None: linspace(1e-4, 2e-2, t.max().item() + 1) like the reference
+    g = torch.Generator().manual_seed(3)
+    cases = [torch.randint(0, 1000, (128,), generator=g), torch.randint(0, 10, (16,), generator=g), torch.zeros(4, dtype=torch.long),
+             torch.tensor([1, 0, 1]), torch.tensor([999]), torch.tensor([5, 5, 5, 5]), torch.arange(0, 1000, 37),
+             torch.randint(0, 1000, (1000,), generator=g)]
+    worst = 0.0
+    for t in cases:
+        td = t.to(dev)
+        a, b = fused.time_weights(td), plain.time_weights(td)
+        assert a.shape == b.shape and a.dtype == torch.float32
+        worst = max(worst, float((a - b).abs().max()))
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (t, a, b)
+        ref = L.time_weights(t, "snr", 0.1, 1.0).reshape(-1)          # the oracle on the CPU (its cumprod rounds differently from the GPU's scan)
+        assert torch.allclose(a.cpu(), ref, rtol=1e-4, atol=2e-6), float((a.cpu() - ref).abs().max())
+    print(f"snr time weights: largest |kernel - torch ops| = {worst:.3e}")
