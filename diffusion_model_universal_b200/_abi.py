@@ -134,7 +134,7 @@ _SIGS = {
     "dmu_repack_weights": (c_i32, [c_vp, c_i32, c_i64, c_vp]),
     "dmu_zero": (c_i32, [c_vp, c_i64, c_vp]),
     "dmu_copy4": (c_i32, [P(Tensor4), P(Tensor4), c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "dmu_adam_ema": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_f32, c_vp]),
+    "dmu_adam_ema": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_f32, c_vp, c_vp]),
     "dmu_ingest_u8": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
     "dmu_image_grid_shape": (c_i32, [c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, P(c_i64), P(c_i64), P(c_i32)]),
     "dmu_image_grid_u8": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),

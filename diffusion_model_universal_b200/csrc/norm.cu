@@ -55,7 +55,63 @@ __device__ __forceinline__ void unpack(const uint4& r, float* out) {
 }
 constexpr int kUnroll = 4;
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): the slab kernels below put their WHOLE slab in flight at once without
+// holding it in registers, and consume it group by group in issue order.  A thread only ever reads back the bytes it copied
+// itself, so cp.async.wait_group is all the synchronisation the data needs.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// wait until at most `pending` of this thread's committed groups are still in flight (pending < 8)
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {
+    switch (pending) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        case 6: cp_async_wait<6>(); break;
+        default: cp_async_wait<7>(); break;
+    }
+}
+constexpr int kSlabGroups = 8;      // commit groups per slab: consumption starts when the first eighth has landed
+
 __device__ __forceinline__ float silu_f(float u) { return __fdividef(u, 1.f + __expf(-u)); }
+
+// du = dy * act'(u)
+__device__ __forceinline__ float act_grad(float u, float dy, int silu) {
+    if (!silu) return dy;
+    const float s = __fdividef(1.f, 1.f + __expf(-u));
+    return dy * (s * fmaf(u, 1.f - s, 1.f));
+}
+
+// One-MUFU sigmoid for the bf16 slab kernels: sigmoid(u) = 0.5 tanh(u / 2) + 0.5 (tanh.approx.f32: ~2^-11 relative, below the
+// 2^-9 of the bf16 store that follows).  These kernels are instruction-bound (profiles/r01_ncu_full_groupnorm.txt), not HBM-bound:
+// the exp2 + reciprocal form costs two MUFU and three more FP instructions per element.
+__device__ __forceinline__ float sigmoid_fast(float u) {
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * u));
+    return fmaf(0.5f, th, 0.5f);
+}
+template <typename T>
+__device__ __forceinline__ float act_fwd_t(float u, int silu) {
+    if constexpr (sizeof(T) == 2) return silu ? u * sigmoid_fast(u) : u;
+    else return silu ? silu_f(u) : u;
+}
+template <typename T>
+__device__ __forceinline__ float act_grad_t(float u, float dy, int silu) {
+    if constexpr (sizeof(T) == 2) {
+        const float sg = sigmoid_fast(u);
+        const float r = dy * (sg * fmaf(u, 1.f - sg, 1.f));
+        return silu ? r : dy;
+    } else {
+        return act_grad(u, dy, silu);
+    }
+}
+
 
 
 // Block-wide per-channel sum of per-thread partials WITHOUT shared-memory float atomics (those compile to a CAS spin loop
@@ -175,20 +231,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(dmu_gn_params P) {
             unpack<T>(r[u], v);
 #pragma unroll
             for (int i = 0; i < kVec; ++i) {
-                const float t = fmaf(v[i], sc[i], sh[i]);
-                v[i] = P.silu ? silu_f(t) : t;
+                v[i] = act_fwd_t<T>(fmaf(v[i], sc[i], sh[i]), P.silu);
             }
             store_vec<T>(yb + pix_off(P.y, n, pp, P.W), v);
         }
     }
 }
 
-// du = dy * act'(u)
-__device__ __forceinline__ float act_grad(float u, float dy, int silu) {
-    if (!silu) return dy;
-    const float s = __fdividef(1.f, 1.f + __expf(-u));
-    return dy * (s * fmaf(u, 1.f - s, 1.f));
-}
 
 // per-image affine form of the normalisation for the conv kernels that apply it to their operand tile (conv_halo.cu)
 __global__ void __launch_bounds__(256) gn_coef_kernel(dmu_gn_params P, float* __restrict__ coef) {
@@ -251,7 +300,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(dmu_gn_params P) {
 #pragma unroll
                 for (int i = 0; i < kVec; ++i) {
                     const float d = xv[i] - mu[i];
-                    const float du = act_grad(fmaf(d, sc[i], be[i]), dv[i], P.silu);
+                    const float du = act_grad_t<T>(fmaf(d, sc[i], be[i]), dv[i], P.silu);
                     a[i] += du;
                     b[i] = fmaf(du, d, b[i]);     // sum du*(x-mean); scaled by rstd below
                 }
@@ -334,7 +383,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(dmu_gn_params P) {
             unpack<T>(rd[u], dv);
 #pragma unroll
             for (int i = 0; i < kVec; ++i) {
-                const float du = act_grad(fmaf(xv[i] - mu[i], sc[i], be[i]), dv[i], P.silu);
+                const float du = act_grad_t<T>(fmaf(xv[i] - mu[i], sc[i], be[i]), dv[i], P.silu);
                 o[i] = fmaf(du, sc[i], fmaf(xv[i], k1[i], k0[i]));
             }
             if (a0) {
@@ -454,8 +503,7 @@ __global__ void __launch_bounds__(256) gn_fwd_fused_kernel(dmu_gn_params P) {
             unpack<T>(r[u], v);
 #pragma unroll
             for (int i = 0; i < kVec; ++i) {
-                const float t = fmaf(v[i], sc[i], sh[i]);
-                v[i] = P.silu ? silu_f(t) : t;
+                v[i] = act_fwd_t<T>(fmaf(v[i], sc[i], sh[i]), P.silu);
             }
             store_vec<T>(yb + pix_off(P.y, n, pp, P.W), v);
         }
@@ -504,7 +552,7 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(dmu_gn_params P) {
 #pragma unroll
             for (int i = 0; i < kVec; ++i) {
                 const float d = xv[i] - mu[i];
-                const float du = act_grad(fmaf(d, sc[i], be[i]), dv[i], P.silu);    // dy == 0 for the padding slots
+                const float du = act_grad_t<T>(fmaf(d, sc[i], be[i]), dv[i], P.silu);    // dy == 0 for the padding slots
                 a[i] += du;
                 b[i] = fmaf(du, d, b[i]);
             }
@@ -557,7 +605,7 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(dmu_gn_params P) {
             unpack<T>(rd[u], dv);
 #pragma unroll
             for (int i = 0; i < kVec; ++i) {
-                const float du = act_grad(fmaf(xv[i] - mu[i], sc[i], be[i]), dv[i], P.silu);
+                const float du = act_grad_t<T>(fmaf(xv[i] - mu[i], sc[i], be[i]), dv[i], P.silu);
                 o[i] = fmaf(du, sc[i], fmaf(xv[i], k1[i], k0[i]));
             }
             if (a0) {
@@ -602,20 +650,22 @@ __global__ void __launch_bounds__(256, 3) gn_fwd_smem_kernel(dmu_gn_params P, in
 #pragma unroll
         for (int i = 0; i < kVec; ++i) { a[i] = 0.f; q[i] = 0.f; }
         if (m.active) {
-            for (int p = p0 + m.lane; p < p1; p += m.lanes * kU2) {
-                uint4 r[kU2];
-#pragma unroll
-                for (int u = 0; u < kU2; ++u) {
-                    const int pp = p + u * m.lanes;
-                    r[u] = pp < p1 ? ld_raw<T>(xb + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
+            // the whole slab goes in flight (kSlabGroups commit groups of this thread's pixels), then it is consumed in order
+            const int mine = p1 > p0 + m.lane ? (p1 - p0 - m.lane + m.lanes - 1) / m.lanes : 0;      // pixels of this thread
+            const int per_grp = (mine + kSlabGroups - 1) / kSlabGroups;
+            for (int g = 0; g < kSlabGroups; ++g) {
+                for (int k = g * per_grp; k < min(mine, (g + 1) * per_grp); ++k) {
+                    const int pp = p0 + m.lane + k * m.lanes;
+                    cp_async16(&s_x[(size_t)(pp - p0) * m.V + m.v], xb + pix_off(P.x, n, pp, P.W));
                 }
-#pragma unroll
-                for (int u = 0; u < kU2; ++u) {
-                    const int pp = p + u * m.lanes;
-                    if (pp >= p1) break;
-                    s_x[(size_t)(pp - p0) * m.V + m.v] = r[u];
+                cp_async_commit();
+            }
+            for (int g = 0; g < kSlabGroups; ++g) {
+                cp_async_wait_dyn(kSlabGroups - 1 - g);
+                for (int k = g * per_grp; k < min(mine, (g + 1) * per_grp); ++k) {
+                    const int pp = p0 + m.lane + k * m.lanes;
                     float v[kVec];
-                    unpack<T>(r[u], v);
+                    unpack<T>(s_x[(size_t)(pp - p0) * m.V + m.v], v);
 #pragma unroll
                     for (int i = 0; i < kVec; ++i) { a[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
                 }
@@ -652,10 +702,7 @@ __global__ void __launch_bounds__(256, 3) gn_fwd_smem_kernel(dmu_gn_params P, in
         float v[kVec];
         unpack<T>(s_x[(size_t)(p - p0) * m.V + m.v], v);       // this thread's own entries: no barrier needed
 #pragma unroll
-        for (int i = 0; i < kVec; ++i) {
-            const float t = fmaf(v[i], sc[i], sh[i]);
-            v[i] = P.silu ? silu_f(t) : t;
-        }
+        for (int i = 0; i < kVec; ++i) v[i] = act_fwd_t<T>(fmaf(v[i], sc[i], sh[i]), P.silu);
         store_vec<T>(yb + pix_off(P.y, n, p, P.W), v);
     }
 }
@@ -678,46 +725,50 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_smem_kernel(dmu_gn_params P, in
     float *s_scale = s_mean + C, *s_beta = s_scale + C, *s_rstd = s_beta + C;
     float *s_a = s_rstd + C, *s_b = s_a + C, *s_ta = s_b + C, *s_tb = s_ta + C;
     __shared__ float s_red[256 * kVec];
-    stage_affine(P, n, s_mean, s_scale, s_beta, s_rstd);
-    __syncthreads();
     RowMap m(C, kVec);
     const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
     const int cbase = m.active ? m.v * kVec : 0;
+    const T* xb = reinterpret_cast<const T*>(P.x.ptr) + cbase;
+    const T* dyb = reinterpret_cast<const T*>(P.y.ptr) + cbase;
+    // the whole (x, dy) slab goes in flight first; the statistics / affine staging below overlaps its latency
+    const int mine = (m.active && p1 > p0 + m.lane) ? (p1 - p0 - m.lane + m.lanes - 1) / m.lanes : 0;      // pixels of this thread
+    const int per_grp = (mine + kSlabGroups - 1) / kSlabGroups;
+    for (int g = 0; g < kSlabGroups; ++g) {
+        for (int k = g * per_grp; k < min(mine, (g + 1) * per_grp); ++k) {
+            const int pp = p0 + m.lane + k * m.lanes;
+            cp_async16(&s_x[(size_t)(pp - p0) * m.V + m.v], xb + pix_off(P.x, n, pp, P.W));
+            cp_async16(&s_d[(size_t)(pp - p0) * m.V + m.v], dyb + pix_off(P.y, n, pp, P.W));
+        }
+        cp_async_commit();
+    }
+    stage_affine(P, n, s_mean, s_scale, s_beta, s_rstd);
+    __syncthreads();
     float mu[kVec], sc[kVec], be[kVec];
 #pragma unroll
     for (int i = 0; i < kVec; ++i) { mu[i] = s_mean[cbase + i]; sc[i] = s_scale[cbase + i]; be[i] = s_beta[cbase + i]; }
-    const T* xb = reinterpret_cast<const T*>(P.x.ptr) + cbase;
-    const T* dyb = reinterpret_cast<const T*>(P.y.ptr) + cbase;
     {
         float a[kVec], b[kVec];
 #pragma unroll
         for (int i = 0; i < kVec; ++i) { a[i] = 0.f; b[i] = 0.f; }
         if (m.active) {
-            for (int p = p0 + m.lane; p < p1; p += m.lanes * kU2) {
-                uint4 rx[kU2], rd[kU2];
-#pragma unroll
-                for (int u = 0; u < kU2; ++u) {
-                    const int pp = p + u * m.lanes;
-                    const bool ok = pp < p1;
-                    rx[u] = ok ? ld_raw<T>(xb + pix_off(P.x, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
-                    rd[u] = ok ? ld_raw<T>(dyb + pix_off(P.y, n, pp, P.W)) : make_uint4(0u, 0u, 0u, 0u);
-                }
-#pragma unroll
-                for (int u = 0; u < kU2; ++u) {
-                    const int pp = p + u * m.lanes;
-                    if (pp >= p1) break;
-                    s_x[(size_t)(pp - p0) * m.V + m.v] = rx[u];
-                    s_d[(size_t)(pp - p0) * m.V + m.v] = rd[u];
+            for (int g = 0; g < kSlabGroups; ++g) {
+                cp_async_wait_dyn(kSlabGroups - 1 - g);
+                for (int k = g * per_grp; k < min(mine, (g + 1) * per_grp); ++k) {
+                    const int pp = p0 + m.lane + k * m.lanes;
                     float xv[kVec], dv[kVec];
-                    unpack<T>(rx[u], xv);
-                    unpack<T>(rd[u], dv);
+                    uint4* sd = &s_d[(size_t)(pp - p0) * m.V + m.v];
+                    unpack<T>(s_x[(size_t)(pp - p0) * m.V + m.v], xv);
+                    unpack<T>(*sd, dv);
 #pragma unroll
                     for (int i = 0; i < kVec; ++i) {
                         const float d = xv[i] - mu[i];
-                        const float du = act_grad(fmaf(d, sc[i], be[i]), dv[i], P.silu);
+                        const float du = act_grad_t<T>(fmaf(d, sc[i], be[i]), dv[i], P.silu);
+                        dv[i] = du;
                         a[i] += du;
                         b[i] = fmaf(du, d, b[i]);
                     }
+                    // du replaces dy in the slab (in the tensor's own dtype): the second pass needs no transcendental
+                    store_vec<T>(reinterpret_cast<T*>(sd), dv);
                 }
             }
 #pragma unroll
@@ -776,12 +827,9 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_smem_kernel(dmu_gn_params P, in
             if (pp >= p1) break;
             float xv[kVec], dv[kVec], o[kVec];
             unpack<T>(s_x[(size_t)(pp - p0) * m.V + m.v], xv);       // this thread's own entries: no barrier needed
-            unpack<T>(s_d[(size_t)(pp - p0) * m.V + m.v], dv);
+            unpack<T>(s_d[(size_t)(pp - p0) * m.V + m.v], dv);          // du, written by this thread in the first pass
 #pragma unroll
-            for (int i = 0; i < kVec; ++i) {
-                const float du = act_grad(fmaf(xv[i] - mu[i], sc[i], be[i]), dv[i], P.silu);
-                o[i] = fmaf(du, sc[i], fmaf(xv[i], k1[i], k0[i]));
-            }
+            for (int i = 0; i < kVec; ++i) o[i] = fmaf(dv[i], sc[i], fmaf(xv[i], k1[i], k0[i]));
             if (a0) {
                 float t[kVec];
                 unpack<T>(r0[u], t);
@@ -1406,7 +1454,18 @@ __global__ void copy4_kernel(dmu_tensor4 S, dmu_tensor4 D, int N, int H, int W, 
 // ------------------------------------------------------------------ Adam + EMA
 __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ ema, int64_t n, float lr, float b1,
-                                                       float b2, float eps, float wd, float bc1, float bc2_sqrt, float decay, float gscale) {
+                                                       float b2, float eps, float wd, float bc1, float bc2_sqrt, float decay, float gscale,
+                                                       const int64_t* __restrict__ step_dev) {
+    if (step_dev) {      // bias corrections from the device-resident step count (graph replay): one double pow per CTA
+        __shared__ float s_bc[2];
+        if (threadIdx.x == 0) {
+            const double st = (double)*step_dev;
+            s_bc[0] = (float)(1.0 - pow((double)b1, st));
+            s_bc[1] = (float)sqrt(1.0 - pow((double)b2, st));
+        }
+        __syncthreads();
+        bc1 = s_bc[0]; bc2_sqrt = s_bc[1];
+    }
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
         if (i + 3 < n) {
             float4 pv = *reinterpret_cast<float4*>(p + i), gv = *reinterpret_cast<const float4*>(g + i);
@@ -1572,14 +1631,15 @@ int dmu_gn_backward(const dmu_gn_params* p, dmu_stream_t stream) {
     // only pays for images one CTA can hold, where it saves a launch; larger images take the two-pass kernels
     const int64_t bytes = (int64_t)p->N * p->H * p->W * p->C * (p->x.dtype == DMU_BF16 ? 2 : 4);
     const int64_t img_bytes = bytes / p->N;
-    // measured (scripts/gn_time.py): register-held single pass up to ~3 MB (launch-bound sizes), shared-memory single pass for
-    // images of >= 128 KB, the two-pass pair in between (4.2 MB: 11.0 vs 14.3 us, 8.4 MB: 20.5 vs 24.7 us)
+    // measured (scripts/gn_time.py, round 2: slab kernel with the whole (x, dy) slab in flight by cp.async, du kept in the slab,
+    // one-MUFU sigmoid): shared-memory single pass for images of >= 32 KB (32x32x64 x 128: 23 us against 32 us for the two-pass
+    // pair and 46 us for the round-1 slab kernel; 16x16x128: 11 vs 17 us), the two-pass pair below that
     // measured inside the backward graph: the register-held single pass (221 registers, one CTA per SM) is the faster kernel
     // alone for small tensors but costs the step 2.4 % (41.6k vs 40.6k img/s with it off): its CTAs leave no room for the
     // weight-gradient lane, the two-pass pair does.  DMU_GN_BWD_FUSED_MB > 0 re-enables it up to that size.
     static const int bwd_fused_mb = [] { const char* e = getenv("DMU_GN_BWD_FUSED_MB"); return e ? atoi(e) : 0; }();
     const int cs = (bytes <= ((int64_t)bwd_fused_mb << 20) && gn_fused_cluster(p->H * p->W, p->C, vec) == 1) ? 1 : 0;
-    static const int smem_min_kb = [] { const char* e = getenv("DMU_GN_BWD_SMEM_MIN_KB"); return e ? atoi(e) : 128; }();
+    static const int smem_min_kb = [] { const char* e = getenv("DMU_GN_BWD_SMEM_MIN_KB"); return e ? atoi(e) : 32; }();
     if (cs == 0 && img_bytes < ((int64_t)smem_min_kb << 10)) {
         if (int e = dmu_gn_bwd_reduce(p, stream)) return e;
         return dmu_gn_bwd_apply(p, stream);
@@ -1739,13 +1799,17 @@ int dmu_copy4(const dmu_tensor4* src, const dmu_tensor4* dst, int32_t N, int32_t
 }
 
 int dmu_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, float lr, float beta1, float beta2,
-                 float eps, float weight_decay, int64_t step, float ema_decay, float grad_scale, dmu_stream_t stream) {
-    DMU_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "dmu_adam_ema: bad arguments");
+                 float eps, float weight_decay, int64_t step, float ema_decay, float grad_scale, const int64_t* step_device,
+                 dmu_stream_t stream) {
+    DMU_REQUIRE(p && g && m && v && n >= 0 && (step >= 1 || step_device), "dmu_adam_ema: bad arguments");
+    DMU_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) & 15) == 0, "dmu_adam_ema: arenas (and range starts) must be 16-byte aligned");
+    if (step < 1) step = 1;
     if (n == 0) return 0;
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     int grid = (int)((n / 4 + 255) / 256); if (grid > sm_count() * 8) grid = sm_count() * 8; if (grid < 1) grid = 1;
-    adam_ema_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, ema_decay, grad_scale);
+    adam_ema_kernel<<<grid, 256, 0, as_stream(stream)>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, ema_decay, grad_scale,
+                                                         step_device);
     return check_launch("dmu_adam_ema");
 }
 

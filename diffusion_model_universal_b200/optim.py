@@ -19,6 +19,7 @@ class FusedAdamEMA:
         self.lr, self.betas, self.eps, self.weight_decay, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
         self.step_count = 0
         self.m = self.v = self.ema = None
+        self.step_dev = None      # device-resident copy of step_count: lets the update sit in a replayed CUDA graph
 
     def _ensure(self):
         eng = self.unet.engine
@@ -32,13 +33,34 @@ class FusedAdamEMA:
 
     def step(self, grad_scale: float = 1.0):
         """Apply one update using the gradient arena filled by the last backward."""
+        self.begin_step()
+        self.step_range(0, None, grad_scale)
+
+    def begin_step(self, count_host: bool = True):
+        """Once per optimisation step, before its step_range() calls: advances the step count on the host and on the device.
+        count_host=False while the caller CAPTURES the step into a CUDA graph (the device increment is recorded, the host
+        mirror is advanced by the caller once per replay)."""
         eng = self._ensure()
-        self.step_count += 1
+        if self.step_dev is None or self.step_dev.device != eng.flat.device:
+            self.step_dev = torch.full((), self.step_count, device=eng.flat.device, dtype=torch.int64)
+        self.step_dev.add_(1)
+        if count_host:
+            self.step_count += 1
+
+    def step_range(self, lo: int = 0, hi=None, grad_scale: float = 1.0):
+        """Update the arena elements [lo, hi) (16-byte aligned range starts) from the gradients of the same range.  The
+        backward finishes its gradients part by part (Engine.run_backward's ``between``): the update of a finished range runs on
+        another stream while the rest of the backward is still in flight; the bias corrections come from the device step count."""
+        eng = self._ensure()
+        hi = eng.flat.numel() if hi is None else hi
+        if hi <= lo:
+            return
+        off = lambda t: t.data_ptr() + lo * 4
         _abi.check(_abi.lib().dmu_adam_ema(
-            eng.flat.data_ptr(), eng.gflat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-            self.ema.data_ptr() if self.ema is not None else None, eng.flat.numel(),
-            self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
-            self.ema_decay if self.ema_decay is not None else 0.0, grad_scale, ops._stream()), "adam_ema")
+            off(eng.flat), off(eng.gflat), off(self.m), off(self.v), off(self.ema) if self.ema is not None else None, hi - lo,
+            self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, max(self.step_count, 1),
+            self.ema_decay if self.ema_decay is not None else 0.0, grad_scale,
+            self.step_dev.data_ptr() if self.step_dev is not None else None, ops._stream()), "adam_ema")
         ops.LAUNCHES += 1
 
     def ema_state_dict(self, prefix=""):
@@ -85,6 +107,7 @@ class FusedAdamEMA:
             raise ValueError("amsgrad / maximize / decoupled weight decay are not implemented by the fused Adam")
         self.lr, self.betas, self.eps, self.weight_decay = float(g["lr"]), tuple(g["betas"]), float(g["eps"]), float(g["weight_decay"])
         state = sd["state"]
+        self.step_dev = None          # rebuilt from step_count by the next begin_step()
         if not state:
             self.step_count, self.m, self.v = 0, None, None
             return

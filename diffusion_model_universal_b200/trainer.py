@@ -104,9 +104,8 @@ class TrainStep:
         # time weights, q_sample, forward, loss, three-part backward): ~30 small eager launches and four graph launches per step
         # become one.  DMU_STEP_GRAPH=0 keeps the piecewise path.
         self._use_step_graph = os.environ.get("DMU_STEP_GRAPH", "1") != "0"
-        # Opt-in (DMU_DP_GRAPH=1, not yet measured on GPUs): with several ranks, capture the three backward parts AND their NCCL
-        # all-reduces into the same graph instead of replaying the front and issuing the rest eagerly.
-        self._dp_in_graph = os.environ.get("DMU_DP_GRAPH", "0") == "1"
+        # (Capturing the NCCL all-reduces into the step graph was measured at 2 GPUs in round 2: 84.3k vs 84.5k img/s, and the
+        # process hung in teardown - the piecewise form below is what runs with several ranks.)
         self._graph = None
         self._g_in = self._g_loss = self._g_dpred = self._g_plan = None
         self._g_warm = 0
@@ -135,11 +134,10 @@ class TrainStep:
                 self._norm_dev = tuple(v.to(images.device) for v in self._norm_host)
             if not ddpm_like:      # score / energy variants take the normalised batch
                 images, _ = ops.ingest_u8(images, self._norm_dev[0], self._norm_dev[1], self.input_layout)
-        if ddpm_like:
+        if ddpm_like:     # gradient exchange and optimizer update run inside, range by range, while the backward continues
             if self._use_step_graph and images.is_cuda and m.model.engine.use_graphs:
-                loss = self._ddpm_step_graphed(images)
-            else:
-                loss = self._ddpm_step(images)
+                return self._ddpm_step_graphed(images).detach()
+            return self._ddpm_step(images).detach()
         elif self._own_arena:   # EnergyNet: autograd accumulates straight into the views of the gradient arena
             self._net.engine.install_grads()
             loss = m.loss_function(images)
@@ -191,12 +189,8 @@ class TrainStep:
             g = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES
             with torch.cuda.graph(g):
-                if self.reducer.world == 1:
-                    self._g_loss = self._ddpm_step(self._g_in)
-                elif self._dp_in_graph:      # backward parts and their bucketed all-reduces are graph nodes too
-                    self._g_loss = self._ddpm_step(self._g_in)
-                    self.reducer.finish(self._works)
-                    self._works = None
+                if self.reducer.world == 1:    # front, backward and the three range updates: one graph
+                    self._g_loss = self._ddpm_step(self._g_in, capturing=True)
                 else:      # data parallel: the graph ends at dL/d(eps); the three backward graphs alternate with the all-reduces
                     self._g_loss, self._g_dpred, self._g_plan = self._ddpm_front(self._g_in)
             self._g_launches = ops.LAUNCHES - n0
@@ -205,19 +199,21 @@ class TrainStep:
         self._graph.replay()
         ops.LAUNCHES += self._g_launches
         if self.reducer.world > 1:
-            if self._dp_in_graph:
-                self._works = []           # the replayed graph already holds the summed gradients
-            else:
-                self._ddpm_back(self._g_plan, self._g_dpred)
+            self.opt.begin_step()
+            self._ddpm_back(self._g_plan)
+        else:
+            self.opt.step_count += 1       # host mirror of the device step count the replayed graph advanced
         # the graph's static output is overwritten by the next replay: hand out a copy (one 4-byte device copy, no sync)
         return self._g_loss.clone()
 
-    def _ddpm_step(self, images: torch.Tensor) -> torch.Tensor:
+    def _ddpm_step(self, images: torch.Tensor, capturing: bool = False) -> torch.Tensor:
         """``DDPM.loss_function`` + ``backward`` (models/ddpm.py:207-235) straight on the engine: same RNG calls in the same
         order and the same launches, without the autograd graph (314 AccumulateGrad nodes cost more host time than the
-        GPU needs for the whole backward pass).  Gradients land in the engine's flat arena, which the optimizer reads."""
-        loss, dpred, plan = self._ddpm_front(images)
-        self._ddpm_back(plan, dpred)
+        GPU needs for the whole backward pass).  Gradients land in the engine's flat arena; every third of it is exchanged and
+        fed to the fused Adam + EMA as soon as its part of the backward has finished."""
+        loss, _, plan = self._ddpm_front(images)
+        self.opt.begin_step(count_host=not capturing)
+        self._ddpm_back(plan)
         return loss
 
     def _ddpm_front(self, images: torch.Tensor):
@@ -257,15 +253,22 @@ class TrainStep:
         loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True, dpred_out=plan.dout)
         return loss, None, plan       # dL/d(eps) already sits in plan.dout
 
-    def _ddpm_back(self, plan, dpred):
+    def _ddpm_back(self, plan):
+        """The backward (dL/d(eps) already sits in plan.dout), the gradient exchange and the fused Adam + EMA update.
+        One rank: the whole backward as one launch list, then one update of the whole arena - inside the step graph (the bias
+        corrections come from the device-resident step count).  Several ranks: the backward runs in three parts and the
+        all-reduce of each third of the gradient arena starts as soon as its part has finished.
+        (Measured in round 2 on one GPU: updating each third of the arena on a second stream while the rest of the backward
+        runs LOSES - 2.93 ms against 2.865 ms per step, 2.89 ms with the Adam grid capped at 2 CTAs per SM: any co-running
+        kernel takes SM slots from the backward's two lanes - so the update stays behind the backward.)"""
         eng = self.model.model.engine
-        if self.reducer.world > 1:
-            # all-reduce each third of the gradient arena as soon as its part of the backward has finished
-            works = []
-            eng.run_backward(plan, dpred, between=lambda lo, hi: works.extend(self.reducer.launch(lo, hi)))
-            self._works = works
-        else:
-            eng.run_backward(plan, dpred)
+        if self.reducer.world == 1:
+            eng.run_backward(plan, None)
+            self.opt.step_range(0, None, 1.0)
+            return
+        works = []
+        eng.run_backward(plan, None, between=lambda lo, hi: works.extend(self.reducer.launch(lo, hi)))
+        self.opt.step_range(0, None, self.reducer.finish(works))
 
     # ------------------------------------------------------------------ checkpoint interop (SURVEY.md §8 f4)
     def checkpoint(self, epoch: int, config=None, best_val_loss: float = float("inf")) -> dict:

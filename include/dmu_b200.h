@@ -351,10 +351,13 @@ int dmu_copy4(const dmu_tensor4* src, const dmu_tensor4* dst, int32_t N, int32_t
 
 /* Fused Adam + EMA over a flat fp32 arena (SURVEY.md §8 f1;
  * trainers/ddpm_trainer.py:139-143,463-480):  torch.optim.Adam semantics
- * (no amsgrad, L2 weight decay), then ema = decay*ema + (1-decay)*p (ema NULL = skip). */
-int dmu_adam_ema(float* p, const float* g, float* m, float* v, float* ema,
-                 int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                 int64_t step, float ema_decay, float grad_scale, dmu_stream_t stream);
+ * (no amsgrad, L2 weight decay), then ema = decay*ema + (1-decay)*p (ema NULL = skip).
+ * `step` (>= 1) sets the bias corrections; when step_device != NULL the step count is read from that device location instead
+ * (the launch can then sit in a CUDA graph that is replayed every step).  p / g / m / v / ema may point into the middle of
+ * the arenas: the update of one arena range can run while the backward still fills another. */
+int dmu_adam_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                 float ema_decay, float grad_scale, const int64_t* step_device, dmu_stream_t stream);
 
 /* ------------------------------------------------------------------ *
  * Input ingest / sample formatting                   *

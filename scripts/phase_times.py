@@ -24,7 +24,7 @@ def timeit(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 print("fwd graph   %.3f ms" % timeit(lambda: plan.graphs["fwd"].replay()))
-print("bwd graph   %.3f ms" % timeit(lambda: plan.graphs["bwd"].replay()))
+print("bwd graph   %.3f ms" % timeit(lambda: eng.run_backward(plan, None)))
 print("repack      %.3f ms" % timeit(lambda: eng.repack(ops._stream())))
 print("adam        %.3f ms" % timeit(lambda: ts.opt.step()))
 print("full step   %.3f ms" % timeit(lambda: ts.step(x)))

@@ -436,8 +436,10 @@ class FakeLib:
         _flat(_addr(out), grid.numel(), dtype=torch.uint8).copy_(grid.reshape(-1))
         return 0
 
-    def dmu_adam_ema(self, p, g, m, v, ema, n, lr, b1, b2, eps, wd, step, decay, gscale, stream):
+    def dmu_adam_ema(self, p, g, m, v, ema, n, lr, b1, b2, eps, wd, step, decay, gscale, step_device, stream):
         self._count()
+        if _addr(step_device):
+            step = int(_flat(_addr(step_device), 1, dtype=torch.int64)[0])
         pv, gv, mv, vv = (_flat(_addr(a), n) for a in (p, g, m, v))
         gr = gv * gscale + wd * pv
         mv.mul_(b1).add_(gr, alpha=1 - b1)

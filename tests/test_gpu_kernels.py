@@ -475,14 +475,24 @@ def test_adam_ema_matches_torch():
     opt = torch.optim.Adam([p_ref], lr=2e-4, betas=(0.9, 0.999), eps=1e-8)
     p, m, v, ema = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), p0.clone()
     ema_ref = p0.clone()
+    # the second copy takes the step count from device memory and is updated in two ranges (what the overlapped step does)
+    p2, m2, v2, ema2 = p0.clone(), torch.zeros(n + 1, device=dev)[:n], torch.zeros(n, device=dev), p0.clone()
+    step_dev = torch.zeros((), device=dev, dtype=torch.int64)
+    cut = 4096
     for step in range(1, 4):
         grad = torch.randn(n, generator=g).to(dev)
         p_ref.grad = grad.clone()
         opt.step()
         ema_ref.mul_(0.999).add_(p_ref.detach(), alpha=0.001)
         _abi.check(_abi.lib().dmu_adam_ema(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n,
-                                           2e-4, 0.9, 0.999, 1e-8, 0.0, step, 0.999, 1.0, _stream()))
+                                           2e-4, 0.9, 0.999, 1e-8, 0.0, step, 0.999, 1.0, None, _stream()))
+        step_dev.add_(1)
+        for lo, hi in ((cut, n), (0, cut)):
+            _abi.check(_abi.lib().dmu_adam_ema(p2.data_ptr() + 4 * lo, grad.data_ptr() + 4 * lo, m2.data_ptr() + 4 * lo, v2.data_ptr() + 4 * lo,
+                                               ema2.data_ptr() + 4 * lo, hi - lo, 2e-4, 0.9, 0.999, 1e-8, 0.0, 0, 0.999, 1.0,
+                                               step_dev.data_ptr(), _stream()))
     assert rel_l2(p, p_ref) < 1e-6 and rel_l2(ema, ema_ref) < 1e-6
+    assert rel_l2(p2, p_ref) < 1e-6 and rel_l2(ema2, ema_ref) < 1e-6 and rel_l2(m2, m) < 1e-6
 
 
 @pytest.mark.parametrize("shape", [(3, 8, 8, 64, 8), (2, 16, 16, 128, 8), (2, 4, 4, 16, 8), (2, 8, 8, 64, 32)])
