@@ -2,6 +2,7 @@
 library is a plain C-ABI shared object (include/dmu_b200.h)."""
 
 import concurrent.futures
+import hashlib
 import os
 import shutil
 import subprocess
@@ -22,11 +23,23 @@ def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def _stale(target, deps):
-    if not os.path.exists(target):
+def _digest(paths, extra=""):
+    """sha256 over the CONTENTS of a source, every header it may include and the compiler flags: what decides whether an
+    object file is current (modification times do not survive a checkout or the copy to the GPU box)."""
+    h = hashlib.sha256(extra.encode())
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target, digest):
+    """True when `target` is missing or was built from other contents than `digest` says (recorded next to it in .sha)."""
+    if not os.path.exists(target) or not os.path.exists(target + ".sha"):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(target + ".sha") as f:
+        return f.read().strip() != digest
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -34,10 +47,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG), "include", "dmu_b200.h"))
     jobs = []
+    digests = {}
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OUT_DIR, s.replace(".cu", ".o"))
-        if force or _stale(obj, [src] + headers):
+        digests[obj] = _digest([src] + headers, " ".join(NVCC_FLAGS))
+        if force or _stale(obj, digests[obj]):
             jobs.append((src, obj))
 
     def compile_one(job):
@@ -48,7 +63,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(log, "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
+            if os.path.exists(obj + ".sha"):
+                os.remove(obj + ".sha")
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        with open(obj + ".sha", "w") as f:
+            f.write(digests[obj])
         return r.stderr
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
@@ -56,12 +75,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 print(out)
     objs = [os.path.join(OUT_DIR, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
+    lib_digest = hashlib.sha256("".join(digests[o] for o in objs).encode()).hexdigest()
+    if force or jobs or _stale(LIB, lib_digest):
         cmd = [_nvcc(), "-shared", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        with open(LIB + ".sha", "w") as f:
+            f.write(lib_digest)
     return LIB
+
+
+def is_current() -> bool:
+    """Does the shared library on disk correspond to the sources on disk?  (No compiler needed: used by the GPU-side checks.)"""
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(PKG), "include", "dmu_b200.h"))
+    ds = [_digest([os.path.join(CSRC, s)] + headers, " ".join(NVCC_FLAGS)) for s in SOURCES]
+    return not _stale(LIB, hashlib.sha256("".join(ds).encode()).hexdigest())
 
 
 if __name__ == "__main__":

@@ -16,11 +16,14 @@
 //     N = up to 128 channels of P; split over pixel ranges (blockIdx.z), fp32 atomics into the OIHW gradient.
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
 namespace dmu {
 namespace tc {
+
+template <int V> using IntC = std::integral_constant<int, V>;
 
 // ------------------------------------------------------------------------------------------------ host helpers
 EncodeTiledFn encode_tiled_fn() {
@@ -186,13 +189,20 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& r, float* out) {
 }
 // The GroupNorm epilogue runs on the four warps of one CTA: every loop below is latency-bound, so the activations are
 // branch-free (a select, not a jump: eight independent elements stay interleaved) and the loops carry 4-8 independent chains.
+// One-MUFU sigmoid, sigmoid(u) = 0.5 tanh(u / 2) + 0.5 - the arithmetic of norm.cu's bf16 kernels (sigmoid_fast), so that the fused
+// and the stand-alone GroupNorm agree; tanh.approx.f32 is ~2^-11 relative, below the 2^-9 of the bf16 store that follows.
+__device__ __forceinline__ float gn_sigmoid(float u) {
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * u));
+    return fmaf(0.5f, th, 0.5f);
+}
 __device__ __forceinline__ float gn_act(float u, int silu) {
-    const float v = __fdividef(u, 1.f + __expf(-u));
+    const float v = u * gn_sigmoid(u);
     return silu ? v : u;
 }
-// du = dy * act'(u)   (same arithmetic as norm.cu's act_grad: the fused and the stand-alone GroupNorm must agree)
+// du = dy * act'(u)
 __device__ __forceinline__ float gn_act_grad(float u, float dy, int silu) {
-    const float sg = __fdividef(1.f, 1.f + __expf(-u));
+    const float sg = gn_sigmoid(u);
     const float r = dy * (sg * fmaf(u, 1.f - sg, 1.f));
     return silu ? r : dy;
 }
@@ -212,7 +222,7 @@ struct ConvCfg {
 // The GN = 1 kernels run 256 threads: warps 4-7 idle through the pipeline and then take the upper 32 channels of every tile row in the
 // epilogue (a warp reads the TMEM lane quarter warp % 4), which halves every latency-bound phase of the norm.
 template <int NT, int DEEP, int GN>
-__global__ void __launch_bounds__(GN ? 256 : 128) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
+__global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
     using Cfg = ConvCfg<NT, DEEP>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -221,6 +231,8 @@ __global__ void __launch_bounds__(GN ? 256 : 128) conv_tc_kernel(const __grid_co
     __shared__ uint32_t s_tmem, s_issued;
     __shared__ __align__(16) float s_bt[kBtImgs * NT];     // bias + temb[n] of the (<= kBtImgs) images this tile touches
     __shared__ __align__(16) float s_gb[GN ? 2 * NT : 4];  // GroupNorm gamma | beta of this CTA's channels
+    __shared__ float s_x[GN ? 8 * 32 : 1];                 // GroupNorm: (image, group) sums handed between the two warps of a 64-row image
+    __shared__ float s_red[GN ? 8 * 64 : 1];               // GroupNorm backward: per-warp channel sums
 
     const int split = (int)blockIdx.z % P.splits;
     const Phase ph = P.phases[blockIdx.z / P.splits];
@@ -428,211 +440,224 @@ __global__ void __launch_bounds__(GN ? 256 : 128) conv_tc_kernel(const __grid_co
     const bool have_acc = *reinterpret_cast<volatile uint32_t*>(&s_issued) != 0;
     if constexpr (GN) {
         // ------------------------------------------------ fused GroupNorm epilogue (splits == 1, whole images per tile)
-        // The finished tile is parked in shared memory (the pipeline ring is idle: every MMA has retired) and the norm runs over
-        // it in ROLLED loops with their own thread mappings, 256 threads.  (A first version kept the TMEM-lane mapping in
-        // registers and unrolled per channels-per-group case: 411 KB of SASS per kernel and +14 us per launch.)
-        //   tileV [128][TS] fp32: conv output y (forward) | dy, then du (backward);   tileX [128][TS]: x, then xhat (backward)
-        //   s_stat [BN][IS]: (mean, rstd) per group forward | (A, B) / cnt backward;   s_tmp: partial sums of the reductions
+        // The norm runs out of REGISTERS: a thread holds 32 channels (= 32 >> SH whole groups) of one tile row, the rows of one
+        // image are HWt consecutive TMEM lanes (HWt = BH * BW, a power of two <= 64), so the (image, group) sums are a butterfly
+        // over min(HWt, 32) adjacent lanes - plus one exchange between the two warps of an image when HWt = 64 - and nothing is
+        // parked in shared memory.  (The first version staged the tile in shared memory and ran three 256-thread phases with
+        // two barriers: 6.7k clk forward / 10.2k clk backward per launch against 2.2k for the plain epilogue,
+        // scripts/gn_epi_timeline.py.)  One instantiation per channels-per-group value (2, 4, 8, 16, 32), chosen at run time.
         const GnEpi& Gn = P.gn;
-        constexpr int TS = NT + 1;
-        const int cpg = Gn.cpg, sh = 31 - __clz(cpg), GT = NT >> sh, IS = 2 * GT + 1, HWt = P.BH * P.BW, npairs = P.BN * GT;
-        float* tileV = reinterpret_cast<float*>(smem);
-        float* tileX = tileV + 128 * TS;
-        float* s_stat = tileX + 128 * TS;
-        float* s_tmp = s_stat + P.BN * IS;
-        const float* s_mr = reinterpret_cast<const float*>(smem + Gn.epi_off);
-        const int tid = threadIdx.x;
+        const int HWt = P.BH * P.BW;
+        const int seg = HWt < 32 ? HWt : 32;
         const int silu = Gn.silu;
         const float inv_cnt = 1.f / Gn.cnt;
-        float* myV = tileV + row * TS + c0;
-        float* myX = tileX + row * TS + c0;
         const float* gam = s_gb + c0;
         const float* bet = s_gb + NT + c0;
-        // Few phases, few barriers (every phase of a 256-thread CTA costs ~1-2k cycles of latency whatever its size):
-        //   1. this thread's 32 channels of its row -> registers: finalised conv output (forward) or du / xhat (backward), parked
-        //      in the shared tiles for the cross-row sums;                                              barrier
-        //   2. (image, group) sums - the threads of one pair are adjacent lanes, combined by shuffles - and, backward, the
-        //      per-tile channel sums;                                                                     barrier
-        //   3. the result from the registers of phase 1.
-        float v[32], xh[32];
+        float v[32];
         tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
         tmem_ld_wait();
         if (!have_acc || !valid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (valid) {
-            if (stage_bt) {
+        // sum over the rows of an image inside the warp (all 32 lanes take part; rows outside the problem carry zeros)
+        auto seg_allreduce = [&](auto& a) {
+            constexpr int NV = sizeof(a) / sizeof(float);
+            for (int o = seg >> 1; o > 0; o >>= 1) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(&s_bt[nl * NT + c0 + i]);
-                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                for (int i = 0; i < NV; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+            }
+            if (HWt == 64) {      // the image's other half sits in the neighbouring warp
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) s_x[warp * 32 + i] = a[i];
                 }
-            } else {
-                if (P.bias) {
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < NV; ++i) a[i] += s_x[(warp ^ 1) * 32 + i];
+            }
+        };
+        if (Gn.mode == 1) {
+            // ---- forward: y = conv (+ bias + temb + residual), a = act(GroupNorm(y))
+            if (valid) {
+                if (stage_bt) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c0 + i));
+                        const float4 b = *reinterpret_cast<const float4*>(&s_bt[nl * NT + c0 + i]);
                         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
                     }
-                }
-                if (P.temb) {
-                    const float* tp = P.temb + (int64_t)n * P.temb_pitch + j0 + c0;
+                } else {
+                    if (P.bias) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(tp + i));
-                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c0 + i));
+                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                        }
+                    }
+                    if (P.temb) {
+                        const float* tp = P.temb + (int64_t)n * P.temb_pitch + j0 + c0;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(tp + i));
+                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                        }
                     }
                 }
-            }
-            if (Gn.mode == 1 && rp) {
+                if (rp) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float r8[8];
-                    unpack_bf16x8(rpre[i], r8);
+                    for (int i = 0; i < 4; ++i) {
+                        float r8[8];
+                        unpack_bf16x8(rpre[i], r8);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) v[i * 8 + k] += r8[k];
+                        for (int k = 0; k < 8; ++k) v[i * 8 + k] += r8[k];
+                    }
                 }
-            }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
-            if (Gn.mode == 1) {
+                for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
                 __nv_bfloat16* yp1 = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0 + c0;
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp1 + i, v + i);
             }
-        }
-        if (Gn.mode == 2) {
-            // du = dy act'(u), xhat: rpre holds this thread's part of row x (zeros, like dy, for rows outside the problem)
-            const float* mr = s_mr + (valid ? nl : 0) * IS;
+            auto fwd = [&](auto shc) {
+                constexpr int SH = decltype(shc)::value, CPG = 1 << SH, NG = 32 >> SH;
+                float st[2 * NG];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) unpack_bf16x8(rpre[i], xh + i * 8);
+                for (int g = 0; g < NG; ++g) {
+                    float s = 0.f, q = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int g = (c0 + i) >> sh;
-                const float mean = mr[2 * g], rstd = mr[2 * g + 1];
-                const float d = xh[i] - mean;
-                v[i] = gn_act_grad(fmaf(d, rstd * gam[i], bet[i]), v[i], silu);
-                xh[i] = d * rstd;
-                myX[i] = xh[i];
-            }
-        }
+                    for (int k = 0; k < CPG; ++k) { const float t = v[g * CPG + k]; s += t; q = fmaf(t, t, q); }
+                    st[2 * g] = s; st[2 * g + 1] = q;
+                }
+                seg_allreduce(st);
+                if (valid) {
+                    // raw (sum, sum of squares) for the backward: the image's first row writes (of the first warp when it spans two)
+                    if ((lane & (seg - 1)) == 0 && (HWt < 64 || (warp & 1) == 0)) {
+                        float2* sp = reinterpret_cast<float2*>(Gn.sums + ((int64_t)n * Gn.G + ((j0 + c0) >> SH)) * 2);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) myV[i] = v[i];
-        if (dbg && threadIdx.x == 0) dbg[6] = clock64();   // (GroupNorm epilogue) tile parked in shared memory
-        __syncthreads();
-        // ---- phase 2: `parts` adjacent lanes share one (image, group) pair, rows interleaved
-        int parts = 1;
-        while (parts < 32 && parts * 2 * npairs <= 256 && parts * 2 <= HWt) parts *= 2;
-        const int pair = tid / parts, part = tid - pair * parts;
-        // f(offset into the tiles, channel of the group, two accumulators); two independent accumulator pairs (even / odd channels)
-        auto pair_sum = [&](int pr, auto&& f, float& r0, float& r1) {
-            const int img = pr / GT, g = pr - img * GT;
-            float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-            if (pr < npairs) {
-                for (int r = part; r < HWt; r += parts) {
-                    const int off = (img * HWt + r) * TS + (g << sh);
-#pragma unroll 2
-                    for (int k = 0; k < cpg; k += 2) {
-                        f(off + k, (g << sh) + k, a0, b0);
-                        f(off + k + 1, (g << sh) + k + 1, a1, b1);
+                        for (int g = 0; g < NG; ++g) sp[g] = make_float2(st[2 * g], st[2 * g + 1]);
                     }
-                }
-            }
-            r0 = a0 + a1; r1 = b0 + b1;
-            for (int o = parts >> 1; o > 0; o >>= 1) {        // the pair's threads are `parts` adjacent lanes (parts divides 32)
-                r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-                r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-            }
-        };
-        const int pair_stride = 256 / parts;
-        const int pair_rounds = (npairs + pair_stride - 1) / pair_stride;      // uniform trip count: the shuffles need whole warps
-        if (Gn.mode == 1) {
-            for (int it = 0; it < pair_rounds; ++it) {
-                const int pr = pair + it * pair_stride;
-                float su, sq;
-                pair_sum(pr, [&](int o, int, float& a, float& b) { const float t = tileV[o]; a += t; b = fmaf(t, t, b); }, su, sq);
-                if (part == 0 && pr < npairs) {
-                    const int img = pr / GT, g = pr - img * GT;
-                    if (n0 + img < P.N) {
-                        float* sp = Gn.sums + ((int64_t)(n0 + img) * Gn.G + (j0 >> sh) + g) * 2;
-                        sp[0] = su; sp[1] = sq;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const float mean = st[2 * g] * inv_cnt;
+                        const float rstd = rsqrtf(fmaxf(fmaf(st[2 * g + 1], inv_cnt, -mean * mean), 0.f) + Gn.eps);
+#pragma unroll
+                        for (int k = 0; k < CPG; ++k) {
+                            const int i = g * CPG + k;
+                            const float sc = rstd * gam[i];
+                            v[i] = gn_act(fmaf(v[i], sc, bet[i] - mean * sc), silu);
+                        }
                     }
-                    const float mean = su * inv_cnt;
-                    s_stat[img * IS + 2 * g] = mean;
-                    s_stat[img * IS + 2 * g + 1] = rsqrtf(fmaxf(fmaf(sq, inv_cnt, -mean * mean), 0.f) + Gn.eps);
-                }
-            }
-            __syncthreads();
-            if (dbg && threadIdx.x == 0) dbg[7] = clock64();   // statistics done
-            // ---- phase 3: a = act((y - mean) rstd gamma + beta) from the registers of phase 1
-            if (valid) {
-                __nv_bfloat16* ap = Gn.a + (int64_t)n * Gn.a_sn + (int64_t)ho * Gn.a_sh + (int64_t)wo * Gn.a_sw + j0 + c0;
-                const float* st = s_stat + nl * IS;
+                    __nv_bfloat16* ap = Gn.a + (int64_t)n * Gn.a_sn + (int64_t)ho * Gn.a_sh + (int64_t)wo * Gn.a_sw + j0 + c0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int g = (c0 + i) >> sh;
-                    const float sc = st[2 * g + 1] * gam[i];
-                    v[i] = gn_act(fmaf(v[i], sc, bet[i] - st[2 * g] * sc), silu);
+                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(ap + i, v + i);
                 }
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(ap + i, v + i);
+            };
+            switch (Gn.cpg) {
+                case 2: fwd(IntC<1>{}); break;
+                case 4: fwd(IntC<2>{}); break;
+                case 8: fwd(IntC<3>{}); break;
+                case 16: fwd(IntC<4>{}); break;
+                default: fwd(IntC<5>{}); break;
             }
         } else {
-            // A = sum gamma du, B = sum gamma du xhat per (image, group)
-            for (int it = 0; it < pair_rounds; ++it) {
-                const int pr = pair + it * pair_stride;
-                float A, B;
-                pair_sum(pr, [&](int o, int ch, float& a, float& b) { const float gd = s_gb[ch] * tileV[o]; a += gd; b = fmaf(gd, tileX[o], b); }, A, B);
-                if (part == 0 && pr < npairs) {
-                    const int img = pr / GT, g = pr - img * GT;
-                    s_stat[img * IS + 2 * g] = A * inv_cnt; s_stat[img * IS + 2 * g + 1] = B * inv_cnt;
-                }
+            // ---- backward: the accumulator is dy of the norm's output; rpre holds this thread's part of row x (zeros, like dy, for rows
+            //      outside the problem);  du = dy act'(u),  dx = rstd (gamma du - A - xhat B) + add0 + add1  with
+            //      A = mean_group(gamma du), B = mean_group(gamma du xhat);  per-tile channel sums (sum du, sum du xhat) for dgamma / dbeta
+            float xh[32];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) unpack_bf16x8(rpre[i], xh + i * 8);
+            const int64_t px = (int64_t)j0 + c0;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            uint4 r0[4], r1[4];      // the addends fly while the sums are formed
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { r0[i] = z; r1[i] = z; }
+            if (valid && Gn.add0) {
+                const __nv_bfloat16* a0p = Gn.add0 + (int64_t)n * Gn.a0_sn + (int64_t)ho * Gn.a0_sh + (int64_t)wo * Gn.a0_sw + px;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r0[i] = *reinterpret_cast<const uint4*>(a0p + i * 8);
             }
-            // per-tile channel sums (sum du, sum du xhat) for the affine-parameter gradients: thread = (channel, quarter of the rows)
+            if (valid && Gn.add1) {
+                const __nv_bfloat16* a1p = Gn.add1 + (int64_t)n * Gn.a1_sn + (int64_t)ho * Gn.a1_sh + (int64_t)wo * Gn.a1_sw + px;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r1[i] = *reinterpret_cast<const uint4*>(a1p + i * 8);
+            }
+            auto bwd = [&](auto shc) {
+                constexpr int SH = decltype(shc)::value, CPG = 1 << SH, NG = 32 >> SH;
+                const int IS = 2 * (NT >> SH) + 1;
+                const float* mr = reinterpret_cast<const float*>(smem + Gn.epi_off) + (valid ? nl : 0) * IS + 2 * (c0 >> SH);
+                float ab[2 * NG];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const float mean = mr[2 * g], rstd = mr[2 * g + 1];
+                    float A = 0.f, B = 0.f;
+#pragma unroll
+                    for (int k = 0; k < CPG; ++k) {
+                        const int i = g * CPG + k;
+                        const float d = xh[i] - mean;
+                        const float du = gn_act_grad(fmaf(d, rstd * gam[i], bet[i]), v[i], silu);
+                        const float xn = d * rstd;
+                        const float gd = gam[i] * du;
+                        v[i] = du; xh[i] = xn;
+                        A += gd; B = fmaf(gd, xn, B);
+                    }
+                    ab[2 * g] = A; ab[2 * g + 1] = B;
+                }
+                seg_allreduce(ab);
+                if (valid) {
+                    float o[32];
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const float rstd = mr[2 * g + 1], A = ab[2 * g] * inv_cnt, B = ab[2 * g + 1] * inv_cnt;
+#pragma unroll
+                        for (int k = 0; k < CPG; ++k) {
+                            const int i = g * CPG + k;
+                            o[i] = rstd * (gam[i] * v[i] - A - xh[i] * B);
+                        }
+                    }
+                    __nv_bfloat16* dxp = Gn.dx + (int64_t)n * Gn.dx_sn + (int64_t)ho * Gn.dx_sh + (int64_t)wo * Gn.dx_sw + px;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float t0[8], t1[8];
+                        unpack_bf16x8(r0[i], t0);
+                        unpack_bf16x8(r1[i], t1);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[i * 8 + k] += t0[k] + t1[k];
+                        store_vec<__nv_bfloat16>(dxp + i * 8, o + i * 8);
+                    }
+                }
+            };
+            switch (Gn.cpg) {
+                case 2: bwd(IntC<1>{}); break;
+                case 4: bwd(IntC<2>{}); break;
+                case 8: bwd(IntC<3>{}); break;
+                case 16: bwd(IntC<4>{}); break;
+                default: bwd(IntC<5>{}); break;
+            }
+            // per-tile channel sums over the warp's 32 rows: a transposing butterfly - at offset o a lane keeps the half of its values its
+            // bit o selects and adds the partner's copy of that half - leaves lane L with channel c0 + L: (sum du, sum du xhat)
+            float w0, w1;
             {
-                const int c = tid & (NT - 1), q4 = tid / NT;        // NT = 64: four quarters of 32 rows
-                float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int r = q4 * 32; r < q4 * 32 + 32; r += 4) {
+                float w[64];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const float du = tileV[(r + q) * TS + c]; a[q] += du; b[q] = fmaf(du, tileX[(r + q) * TS + c], b[q]); }
+                for (int i = 0; i < 32; ++i) { w[2 * i] = v[i]; w[2 * i + 1] = v[i] * xh[i]; }
+#pragma unroll
+                for (int half = 32; half >= 2; half >>= 1) {
+                    const bool up = (lane & (half >> 1)) != 0;
+#pragma unroll
+                    for (int i = 0; i < half; ++i) {
+                        const float keep = up ? w[half + i] : w[i];
+                        const float send = up ? w[i] : w[half + i];
+                        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, half >> 1);
+                    }
                 }
-                s_tmp[(q4 * NT + c) * 2] = (a[0] + a[1]) + (a[2] + a[3]); s_tmp[(q4 * NT + c) * 2 + 1] = (b[0] + b[1]) + (b[2] + b[3]);
+                w0 = w[0]; w1 = w[1];
             }
+            s_red[warp * 64 + 2 * lane] = w0; s_red[warp * 64 + 2 * lane + 1] = w1;
             __syncthreads();
-            for (int e = tid; e < NT * 2; e += 256)
-                Gn.red[((int64_t)tile * Gn.C + j0) * 2 + e] = (s_tmp[e] + s_tmp[NT * 2 + e]) + (s_tmp[2 * NT * 2 + e] + s_tmp[3 * NT * 2 + e]);
-            if (dbg && threadIdx.x == 0) dbg[7] = clock64();   // reductions done
-            // ---- phase 3: dx = rstd (gamma du - A - xhat B) + add0 + add1 from the registers of phase 1
-            if (valid) {
-                const int64_t px = (int64_t)j0 + c0;
-                __nv_bfloat16* dxp = Gn.dx + (int64_t)n * Gn.dx_sn + (int64_t)ho * Gn.dx_sh + (int64_t)wo * Gn.dx_sw + px;
-                const __nv_bfloat16* a0p = Gn.add0 ? Gn.add0 + (int64_t)n * Gn.a0_sn + (int64_t)ho * Gn.a0_sh + (int64_t)wo * Gn.a0_sw + px : nullptr;
-                const __nv_bfloat16* a1p = Gn.add1 ? Gn.add1 + (int64_t)n * Gn.a1_sn + (int64_t)ho * Gn.a1_sh + (int64_t)wo * Gn.a1_sw + px : nullptr;
-                const float* mr = s_mr + nl * IS;
-                const float* ab = s_stat + nl * IS;
-                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                uint4 r0[4], r1[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    r0[i] = a0p ? *reinterpret_cast<const uint4*>(a0p + i * 8) : z;
-                    r1[i] = a1p ? *reinterpret_cast<const uint4*>(a1p + i * 8) : z;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int g = (c0 + i) >> sh;
-                    v[i] = mr[2 * g + 1] * (gam[i] * v[i] - ab[2 * g] - xh[i] * ab[2 * g + 1]);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float t0[8], t1[8];
-                    unpack_bf16x8(r0[i], t0);
-                    unpack_bf16x8(r1[i], t1);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v[i * 8 + k] += t0[k] + t1[k];
-                    store_vec<__nv_bfloat16>(dxp + i * 8, v + i * 8);
-                }
+            if (threadIdx.x < 2 * NT) {       // (channel, which sum): the four warps that share a channel half
+                const int e = threadIdx.x, hf = e >> 6, r = e & 63;
+                const float* sp = s_red + hf * 4 * 64 + r;
+                Gn.red[((int64_t)tile * Gn.C + j0) * 2 + e] = (sp[0] + sp[64]) + (sp[128] + sp[192]);
             }
         }
         if (dbg && threadIdx.x == 0) dbg[5] = clock64();   // epilogue stores issued

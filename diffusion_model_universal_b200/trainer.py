@@ -99,6 +99,7 @@ class TrainStep:
         self._synced = False
         self._stage = None
         self._side = None      # side stream of the step's front (filter-cache refresh next to the RNG draws)
+        self._side2 = None     # branch of the backward's memsets (next to the whole forward)
         self._works = None
         # Single-GPU DDPM steps replay ONE CUDA graph of everything between the input batch and the gradient arena (RNG draws,
         # time weights, q_sample, forward, loss, three-part backward): ~30 small eager launches and four graph launches per step
@@ -231,7 +232,20 @@ class TrainStep:
         plan = eng.get_plan(shape, True)
         cur = torch.cuda.current_stream(images.device) if images.is_cuda else None
         side = None
-        if cur is not None and not eng.frozen:
+        if cur is not None:
+            # the memsets the backward needs (gradient arena, filter-gradient staging: 2 x 64 MB) run on a branch of their own
+            # that only rejoins after the forward
+            if self._side2 is None:
+                self._side2 = torch.cuda.Stream(device=images.device)
+            self._side2.wait_stream(cur)
+            with torch.cuda.stream(self._side2):
+                eng.zero_backward_buffers(plan, ops._stream())
+        else:
+            eng.zero_backward_buffers(plan)
+        repack_main = os.environ.get("DMU_REPACK_LANE", "side") == "main"      # A/B aid
+        if repack_main and not eng.frozen:
+            eng.repack(ops._stream())
+        elif cur is not None and not eng.frozen:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=images.device)
             side = self._side
@@ -248,9 +262,11 @@ class TrainStep:
             ops.q_sample(images.contiguous(), t, noise, m.alphas_cumprod, out=plan.x_in)
         if side is not None:
             cur.wait_stream(side)
-        eps = eng.run_forward(None, t, plan, repacked=side is not None, clone=False)
+        eps = eng.run_forward(None, t, plan, repacked=(side is not None) or repack_main, clone=False)
         wm, wl, wh = m.loss_fn.coefficients()
         loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True, dpred_out=plan.dout)
+        if cur is not None:
+            cur.wait_stream(self._side2)
         return loss, None, plan       # dL/d(eps) already sits in plan.dout
 
     def _ddpm_back(self, plan):
@@ -263,11 +279,11 @@ class TrainStep:
         kernel takes SM slots from the backward's two lanes - so the update stays behind the backward.)"""
         eng = self.model.model.engine
         if self.reducer.world == 1:
-            eng.run_backward(plan, None)
+            eng.run_backward(plan, None, prezeroed=True)
             self.opt.step_range(0, None, 1.0)
             return
         works = []
-        eng.run_backward(plan, None, between=lambda lo, hi: works.extend(self.reducer.launch(lo, hi)))
+        eng.run_backward(plan, None, between=lambda lo, hi: works.extend(self.reducer.launch(lo, hi)), prezeroed=True)
         self.opt.step_range(0, None, self.reducer.finish(works))
 
     # ------------------------------------------------------------------ checkpoint interop (SURVEY.md §8 f4)

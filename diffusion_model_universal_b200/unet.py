@@ -20,6 +20,7 @@ Data layout in HBM:
 import ctypes as C
 import math
 import os
+import warnings
 from collections import OrderedDict
 
 import torch
@@ -27,6 +28,9 @@ import torch.nn as nn
 
 from . import _abi, ops
 from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, RepackDesc, GnPgDesc, ColsumDesc
+
+
+AUX = 1000      # lane id of micro-batch k's auxiliary chain: AUX + k (Engine._run_forked)
 
 
 def gn_groups(channels: int, num_groups: int = 32) -> int:
@@ -222,6 +226,8 @@ class Plan:
         self.out = None         # fp32 [N,Cout,H,W] written by the head conv
         self.dout = None        # fp32 [N,Cout,H,W] upstream gradient (training plans)
         self.ws = None          # split-K scratch of the tensor-core convs (zero between launches)
+        self.zero_ops = []      # memsets of everything a backward accumulates into (Engine.zero_backward_buffers)
+        self.zero_red = None    # (sub-plan) the GroupNorm / time-projection accumulators' memset
         self.graphs = {}        # "fwd"/"bwd" -> torch.cuda.CUDAGraph
         self.runs = {}          # "fwd"/"bwd" -> eager executions so far (the first one is the warm-up before capture)
         self.nlaunch = {}       # "fwd"/"bwd" -> kernels per replay
@@ -230,12 +236,19 @@ class Plan:
 
 class Engine:
     """Builds and runs launch plans for one UNet instance."""
+    _warned_fp32 = False
 
     def __init__(self, net: UNet):
         self.net = net
         self.code = BF16 if net.precision == "bf16" else F32
         if net.precision not in ("fp32", "bf16"):
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {net.precision!r}")
+        if net.precision == "fp32" and not Engine._warned_fp32:
+            # measured on B200 (bench.py extra.fp32_mode_train): ~4.0k img/s against ~44k img/s in bf16 mode
+            Engine._warned_fp32 = True
+            warnings.warn("diffusion_model_universal_b200: precision 'fp32' (the default, reference numerics: eps rel-L2 <= 1e-3) runs the "
+                          "convolutions on fp32 SIMT kernels; add `precision: bf16` to model_config for the tcgen05 tensor-core path "
+                          "(~11x faster, eps rel-L2 <= 2e-2).", stacklevel=3)
         self.tdtype = torch.bfloat16 if self.code == BF16 else torch.float32
         self.esize = 2 if self.code == BF16 else 4
         self.flat = None
@@ -256,6 +269,9 @@ class Engine:
         # gradient (backward): the <= 8x8 stages, where one output tile holds whole images (dmu_conv_params.gn_fuse).  The library
         # decides per layer (dmu_conv2d_gn_fuse_supported); DMU_GN_EPI=0 keeps every GroupNorm a launch of its own (A/B aid).
         self.fuse_gn_epi = os.environ.get("DMU_GN_EPI", "1") != "0"
+        # ResBlock shortcut convolutions (forward and dgrad) on an auxiliary graph branch instead of inside the main chain
+        # (DMU_AUX_LANES=0: A/B aid)
+        self.aux_lanes = os.environ.get("DMU_AUX_LANES", "1") != "0"
         self._lib = None
 
     # ------------------------------------------------------------------ parameters
@@ -445,19 +461,26 @@ class Engine:
     def _run_forked(self, oplist):
         """Capture-time execution over lanes.  Lane 0 is the capturing stream; lane 2k is the main chain of micro-batch k,
         lane 2k+1 its side chain (weight gradients, bias / time-projection column sums: they only read finished tensors and
-        accumulate into their own outputs).  Markers: (None, (), -2) = fork point (main lanes start after everything issued
-        on lane 0 so far), (None, (), 2k) = side lane 2k+1 joins main lane 2k, (None, (), -1) = every lane joins lane 0.
-        An op on a side lane depends on everything issued on its main lane before it."""
+        accumulate into their own outputs), lane AUX+k its auxiliary chain (an independent branch of the layer graph that
+        rejoins: a ResBlock's 1x1 shortcut convolution next to its conv1 -> norm2 chain).  Markers: (None, (), -2) = fork
+        point (main lanes start after everything issued on lane 0 so far), (None, (), 2k) = side lane 2k+1 joins main lane 2k,
+        (None, (), AUX+k) = the auxiliary lane joins main lane 2k, (None, (), -1) = every lane joins lane 0.  An op on a side
+        or auxiliary lane depends on everything issued on its main lane before it."""
         main = torch.cuda.current_stream()
         streams, ptrs, started, dirty = {0: main}, {}, {0}, set()
         fork = None
+
+        def main_of(lane):
+            if lane >= AUX:
+                return 2 * (lane - AUX)
+            return lane - 1 if lane % 2 == 1 else lane
 
         def lane_stream(lane):
             if lane not in streams:
                 streams[lane] = torch.cuda.Stream(device=self.device)
             if lane not in started:
                 started.add(lane)
-                if lane % 2 == 0:
+                if main_of(lane) == lane:
                     if fork is not None:
                         streams[lane].wait_event(fork)
                     else:
@@ -473,13 +496,18 @@ class Engine:
                     fork = torch.cuda.Event()
                     fork.record(main)
                 elif lane == -1:
-                    for l in sorted(dirty, reverse=True):      # sides into their mains first, then mains into lane 0
-                        tgt = l - 1 if l % 2 == 1 else 0
+                    for l in sorted(dirty, reverse=True):      # sides / auxiliaries into their mains first, then mains into lane 0
+                        tgt = main_of(l) if main_of(l) != l else 0
                         if l != 0:
                             lane_stream(tgt).wait_stream(streams[l])
                             if tgt != 0:
                                 dirty.add(tgt)
                     dirty.clear()
+                elif lane >= AUX:
+                    if lane in dirty:
+                        lane_stream(main_of(lane)).wait_stream(streams[lane])
+                        dirty.discard(lane)
+                        dirty.add(main_of(lane))
                 else:
                     if lane + 1 in dirty:
                         lane_stream(lane).wait_stream(streams[lane + 1])
@@ -487,8 +515,8 @@ class Engine:
                         dirty.add(lane)
                 continue
             st = lane_stream(lane)
-            if lane % 2 == 1:
-                st.wait_stream(lane_stream(lane - 1))
+            if main_of(lane) != lane:
+                st.wait_stream(lane_stream(main_of(lane)))
             ops.LAUNCHES += 1
             rc = op[0](*op[1], ptrs[lane])
             if rc != 0:
@@ -540,9 +568,15 @@ class Engine:
         self._execute(plan, "fwd")
         return plan.out.clone() if clone else plan.out
 
-    def run_backward(self, plan: Plan, dout, between=None):
+    def zero_backward_buffers(self, plan: Plan, stream=None):
+        """The memsets a backward of `plan` needs beforehand (gradient arena, filter-gradient staging, GroupNorm / time-projection
+        accumulators); anything between the previous optimizer update and this plan's backward is early enough."""
+        self._run(plan.zero_ops, stream if stream is not None else ops._stream())
+
+    def run_backward(self, plan: Plan, dout, between=None, prezeroed=False):
         """Fills the gradient arena; returns it (flat fp32, same offsets as the parameter arena).  ``between(lo, hi)`` is
-        called after each of the three parts of the backward with the arena range that just became final."""
+        called after each of the three parts of the backward with the arena range that just became final.  prezeroed: the caller
+        has already run zero_backward_buffers(plan) since the last update."""
         g = self.gflat
         # param.grad tensors handed out by an earlier backward are views of this arena.  If any is still installed
         # (gradient accumulation, zero_grad(set_to_none=False)) detach it first so autograd's `grad += new` stays correct.
@@ -552,6 +586,8 @@ class Engine:
                 p.grad = p.grad.clone()
         if dout is not None:      # None: the caller wrote the upstream gradient straight into plan.dout
             plan.dout.copy_(dout)
+        if not prezeroed:
+            self.zero_backward_buffers(plan)
         if between is None:
             self._execute(plan, "bwd")
         else:
@@ -601,12 +637,14 @@ class Engine:
             gn_pg += sub.gn_pg
 
         def retag(ops_, k):
+            """sub-plan tags (none = main chain, 1 = side chain, 2 = auxiliary chain) -> lane ids of micro-batch k"""
             out = []
             for op in ops_:
+                tag = op[2] if len(op) == 3 else 0
                 if op[0] is None:
-                    out.append((None, (), 2 * k))                        # join this sub-plan's side lane into its main lane
+                    out.append((None, (), AUX + k if tag == 2 else 2 * k))   # join the auxiliary / side lane into the main lane
                 else:
-                    out.append((op[0], op[1], 2 * k + (1 if len(op) == 3 else 0)))
+                    out.append((op[0], op[1], 2 * k if tag == 0 else 2 * k + 1 if tag == 1 else AUX + k))
             return out
 
         lib = self._lib
@@ -630,8 +668,12 @@ class Engine:
                 g0, g1 = sub.gn_pg_split
                 pg[0].extend(sub.gn_pg[:g0]); pg[1].extend(sub.gn_pg[g0:g1]); pg[2].extend(sub.gn_pg[g1:])
             plan.gn_pg_tables = []
-            plan.bwd_parts = [[(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4), 0),
-                               (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4), 0)], [], []]
+            # what a backward accumulates into (filter-gradient staging, gradient arena, GroupNorm / time-projection sums):
+            # zeroed by Engine.zero_backward_buffers - at the start of run_backward, or earlier by the caller (TrainStep does it
+            # on a branch next to the forward)
+            plan.zero_ops = [(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4)),
+                             (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4))] + [sub.plan.zero_red for sub in subs]
+            plan.bwd_parts = [[], [], []]
             tails = ([], [], [])       # per part: batch fold of the GroupNorm parameter gradients + staging unpack
             for h, lst in enumerate(plan.bwd_parts):
                 lst.append((None, (), -2))
@@ -655,10 +697,7 @@ class Engine:
             for h in range(3):
                 body = plan.bwd_parts[h][:len(plan.bwd_parts[h]) - len(tails[h])]
                 if h == 0:
-                    # the two arena memsets (128 MB) also move to the side lane: only weight gradients / column sums (side
-                    # lane, same stream order) and the tails accumulate into them before the lanes join
-                    i = body.index((None, (), -2)) + 1
-                    plan.bwd += [body[i - 1]] + [(fn, args, 1) for fn, args, _ in body[:i - 1]] + body[i:]
+                    plan.bwd += body
                 else:
                     i = body.index((None, (), -2)) + 1
                     plan.bwd += body[:i] + [(fn, args, 1) for fn, args, _ in tails[h - 1]] + body[i:]
@@ -667,6 +706,8 @@ class Engine:
             joins = [i for i, op in enumerate(plan.bwd) if op[0] is None and op[2] == 0]
             if len(joins) >= 2 and K == 1:
                 i = joins[-2] + 1
+                while plan.bwd[i][0] is not None and plan.bwd[i][2] == 1:     # the stem's weight gradient follows that join on the
+                    i += 1                                                    # side lane: the unpack reads what it writes
                 plan.bwd[i:i] = [(fn, args, 1) for fn, args, _ in tails[2]]
             else:
                 plan.bwd += tails[2]
@@ -788,7 +829,7 @@ class _PlanBuilder:
         self.cs_pending = []
 
     def conv(self, lst, x: Tensor4, y: Tensor4, w, w_strides, w_code, dims, geom, bias=None, temb=None, temb_pitch=0, res=None, gather=0,
-             gn_coef=None, gn_silu=0, a_out=None, emit=True):
+             gn_coef=None, gn_silu=0, a_out=None, emit=True, lane=0):
         N, Hi, Wi, Ck, Ho, Wo, Cj = dims
         R, S, stride, pad = geom
         p = ConvParams(x, y, res if res is not None else _null_t4(), w, w_strides[0], w_strides[1], w_strides[2], bias, temb, temb_pitch,
@@ -799,9 +840,9 @@ class _PlanBuilder:
             if temb is not None and self.temb_join_pending and lst is self.plan.fwd:
                 lst.append((None, ()))       # the time-embedding lane joins before the first launch that reads its projections
                 self.temb_join_pending = False
-            lst.append((self.lib.dmu_conv2d, (C.byref(p),)))
+            lst.append((self.lib.dmu_conv2d, (C.byref(p),), lane) if lane else (self.lib.dmu_conv2d, (C.byref(p),)))
             self.plan.keep.append(p)
-            if lst is self.plan.fwd and gn_coef is None:
+            if lst is self.plan.fwd and gn_coef is None and not lane:
                 self.prod[(y.ptr, y.sw, Cj)] = p
         return p
 
@@ -900,20 +941,20 @@ class _PlanBuilder:
             self.plan.bwd.append((self.lib.dmu_gn_backward, (C.byref(p),)))
 
     # ---- conv layer helpers (filters repacked [O][R][S][I])
-    def conv_layer(self, x: Buf, y: Buf, wname, bname, R, stride, pad, temb=None, temb_pitch=0, res: Buf = None):
+    def conv_layer(self, x: Buf, y: Buf, wname, bname, R, stride, pad, temb=None, temb_pitch=0, res: Buf = None, lane=0):
         Ci, Co = x.C, y.C
         self.conv(self.plan.fwd, x.t4(), y.t4(), self.e.waddr(wname), (R * R * Ci, 1, Ci), self.code,
                   (self.N, x.H, x.W, Ci, y.H, y.W, Co), (R, R, stride, pad), bias=self.e.paddr(bname), temb=temb, temb_pitch=temb_pitch,
-                  res=res.t4() if res is not None else None)
+                  res=res.t4() if res is not None else None, lane=lane)
 
-    def conv_layer_bwd(self, x: Buf, y: Buf, wname, bname, R, stride, pad, dx: Buf, need_dx=True, gn=None):
+    def conv_layer_bwd(self, x: Buf, y: Buf, wname, bname, R, stride, pad, dx: Buf, need_dx=True, gn=None, lane=0):
         """dgrad into dx (plain write) and wgrad/dbias into the arena.  dy = y.grad.  gn = (rec, out, add0, add1): x is the output
         of the GroupNorm `rec`, whose backward follows immediately (into `out`) - in the dgrad's epilogue where possible."""
         Ci, Co = x.C, y.C
         dy = y.grad
         # dx[n,hi,wi,ci] = sum dy[n,(hi+pad-r)/s,..,co] w[co][r][s][ci]
         dgrad = lambda emit: self.conv(self.plan.bwd, dy.t4(), dx.t4(), self.e.waddr_t(wname), (R * R * Co, 1, Co), self.code,
-                                       (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad), gather=1, emit=emit)
+                                       (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad), gather=1, emit=emit, lane=lane)
         wgrad = lambda: self.wgrad(dy.t4(), x.t4(), self.e.gsaddr(wname), (R * R * Ci, 1, Ci), self.gp(bname),
                                    (self.N, y.H, y.W, Co, x.H, x.W, Ci), (R, R, stride, pad))
         if gn is not None:
@@ -943,13 +984,19 @@ class _PlanBuilder:
         e = self.e
         Ci, Co = x.C, y.C
         h = self.act(x.H, x.W, Co)
+        has_sc = Ci != Co
+        aux = 2 if (has_sc and e.aux_lanes) else 0
+        if aux:     # the 1x1 shortcut only needs x: it runs on the auxiliary lane next to norm1 -> conv1 -> norm2 and rejoins before conv2
+            sc = self.tmp(x.H, x.W, Co)
+            self.conv_layer(x, sc, pfx + "shortcut.weight", pfx + "shortcut.bias", 1, 1, 0, lane=aux)
         a1, rec1 = self.gn_conv(x, gn_groups(Ci), pfx + "norm1.weight", pfx + "norm1.bias", True, h.t4(), e.waddr(pfx + "conv1.weight"),
                                 (9 * Ci, 1, Ci), (self.N, x.H, x.W, Ci, h.H, h.W, Co), (3, 3, 1, 1), bias=e.paddr(pfx + "conv1.bias"),
                                 temb=tp_addr, temb_pitch=tp_pitch)
-        has_sc = Ci != Co
-        if has_sc:
+        if has_sc and not aux:
             sc = self.tmp(x.H, x.W, Co)
             self.conv_layer(x, sc, pfx + "shortcut.weight", pfx + "shortcut.bias", 1, 1, 0)
+        if aux:
+            self.plan.fwd.append((None, (), 2))
         a2, rec2 = self.gn_conv(h, gn_groups(Co), pfx + "norm2.weight", pfx + "norm2.bias", True, y.t4(), e.waddr(pfx + "conv2.weight"),
                                 (9 * Co, 1, Co), (self.N, h.H, h.W, Co, y.H, y.W, Co), (3, 3, 1, 1), bias=e.paddr(pfx + "conv2.bias"),
                                 res=(sc if has_sc else x).t4())
@@ -957,18 +1004,24 @@ class _PlanBuilder:
             return
 
         def bwd():
-            # conv2, then norm2 + silu -> dh (in the dgrad's epilogue where one tile holds whole images)
-            self.conv_layer_bwd(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, a2.grad, gn=(rec2, h.grad, None, None))
-            # time projection: per-image channel sums of dh
-            self.colsum(h.grad.t4(), self.N, h.H, h.W, Co, self.dtproj + self.tp_off[pfx] * 4, self.tp_total, None)
-            # shortcut (before conv1: its input gradient is an addend of norm1's backward)
+            # shortcut: its input gradient is an addend of norm1's backward; the dgrad only needs dy, so it runs on the auxiliary
+            # lane next to conv2 / norm2 / conv1 and rejoins before norm1's backward
             if has_sc:
                 dxs = self.tmp(x.H, x.W, Ci)
                 scb = Buf(0, self.N, x.H, x.W, Co, Co, self.code)
                 scb.grad = y.grad
+                if aux:
+                    self.conv_layer_bwd(x, scb, pfx + "shortcut.weight", pfx + "shortcut.bias", 1, 1, 0, dxs, lane=aux)
+            # conv2, then norm2 + silu -> dh (in the dgrad's epilogue where one tile holds whole images)
+            self.conv_layer_bwd(a2, y, pfx + "conv2.weight", pfx + "conv2.bias", 3, 1, 1, a2.grad, gn=(rec2, h.grad, None, None))
+            # time projection: per-image channel sums of dh
+            self.colsum(h.grad.t4(), self.N, h.H, h.W, Co, self.dtproj + self.tp_off[pfx] * 4, self.tp_total, None)
+            if has_sc and not aux:
                 self.conv_layer_bwd(x, scb, pfx + "shortcut.weight", pfx + "shortcut.bias", 1, 1, 0, dxs)
-            else:
+            if not has_sc:
                 dxs = y.grad
+            if aux:
+                self.plan.bwd.append((None, (), 2))
             prev = x.grad if x.grad_written else None
             # conv1, then norm1 + silu (+ shortcut / skip gradients) -> dx
             self.conv_layer_bwd(a1, h, pfx + "conv1.weight", pfx + "conv1.bias", 3, 1, 1, a1.grad, gn=(rec1, x.grad, dxs, prev))
@@ -1174,13 +1227,14 @@ class _PlanBuilder:
                 plan.bwd.append(("split", ()))
                 self.gn_pg_split.append(len(self.gn_pg))
             self.tape[i]()
-        # stem: wgrad only (the network input needs no gradient on this path)
-        self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), e.gsaddr("initial_conv.weight"),
-                   (9 * net.in_channels, 1, net.in_channels), self.gp("initial_conv.bias"), (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
         # time projections (one GEMM for all 22 blocks), then the embedding MLP: they consume the per-image column sums the
-        # side lane produced, so the lanes join here
+        # side lane produced, so the lanes join here - BEFORE the stem's weight gradient (wgrad only: the network input needs
+        # no gradient on this path) is queued on the side lane: it runs next to the embedding backward instead of in front of it
+        self.colsum(h0.grad.t4(), N, H, W, Cm, None, 0, self.gp("initial_conv.bias"))
         self.flush_colsums()
         plan.bwd.append((None, ()))
+        self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), e.gsaddr("initial_conv.weight"),
+                   (9 * net.in_channels, 1, net.in_channels), None, (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
         self.side_lane = False
         dtemb = self.f32(N * T4)
         self.linear_bwd(_rows_t4(temb, T4), _rows_t4(self.dtproj, self.tp_total), _rows_t4(dtemb, T4), N, T4, self.tp_total,
@@ -1202,8 +1256,8 @@ class _PlanBuilder:
             plan.bwd.append((lib.dmu_act_bwd, (h1, dg1, dh1, N * Cm, 1)))
             self.linear_bwd(_rows_t4(ls, 1), _rows_t4(dh1, Cm), None, N, 1, Cm, e.paddr("time_embed.0.weight"),
                             self.gp("time_embed.0.weight"), self.gp("time_embed.0.bias"), need_dx=False)
-        # one launch zeroes every GroupNorm backward accumulator
-        plan.bwd.insert(0, (lib.dmu_zero, (self.red.base, max(self.red.off, 4))))
+        # one launch zeroes every GroupNorm backward accumulator (issued with the gradient-arena memsets: Engine._build)
+        plan.zero_red = (lib.dmu_zero, (self.red.base, max(self.red.off, 4)))
         plan.bwd.append((None, ()))      # side lane joins
         # (zeroing of the gradient arena / staging, the GroupNorm parameter-gradient fold and the staging unpack are
         #  emitted once for all micro-batch lanes by Engine._build)

