@@ -167,6 +167,7 @@ struct ConvArgs {
     int stage_bytes, a_off;   // stage stride and offset of the filter tile: a 64-pixel box only reserves 8 KB for the pixels
     int kps, kb_bytes;   // k-blocks per ring stage and bytes of one k-block (pixels + filters)
     int m64;             // 64-pixel tile computed by M = 64 MMAs
+    int pix256;          // GroupNorm launches: a 256-pixel box (one 16x16 image) computed as two M = 128 accumulators
     GnEpi gn;
 };
 
@@ -221,8 +222,8 @@ struct ConvCfg {
 // GN = 1: the instantiation with the fused GroupNorm epilogues (GnEpi); the plain kernels stay lean (registers / code size)
 // The GN = 1 kernels run 256 threads: warps 4-7 idle through the pipeline and then take the upper 32 channels of every tile row in the
 // epilogue (a warp reads the TMEM lane quarter warp % 4), which halves every latency-bound phase of the norm.
-template <int NT, int DEEP, int GN>
-__global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
+template <int NT, int DEEP, int GN, int TB2 = 0>      // TB2: GroupNorm launch on a 256-pixel box (two accumulators, ConvArgs::pix256)
+__device__ __forceinline__ void conv_tc_body(const Maps& maps, const ConvArgs& P) {
     using Cfg = ConvCfg<NT, DEEP>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(con
         s_issued = 0;
         tma_prefetch_desc(&maps.b);
     }
-    if (warp == 1) tmem_alloc(&s_tmem, NT);
+    if (warp == 1) tmem_alloc(&s_tmem, NT << TB2);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -294,14 +295,33 @@ __global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(con
     const bool stage_bt = P.prefetch && P.splits == 1 && P.BN <= kBtImgs && (P.bias || P.temb);
     const __nv_bfloat16* rp = (P.res && valid && P.splits == 1) ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
     uint4 rpre[NT / 8];
+    // GN, 256-pixel box (one 16x16 image): this thread's second row, r + 128, lives in the second accumulator
+    int ho2 = 0, wo2 = 0;
+    bool valid2 = false;
+    uint4 rpre2[GN ? 4 : 1];
     if constexpr (GN) {
         // backward mode: the same registers hold this row of the norm's input x (a dgrad has no residual)
         if (P.gn.mode == 2) rp = valid ? P.gn.x + (int64_t)n * P.gn.x_sn + (int64_t)ho * P.gn.x_sh + (int64_t)wo * P.gn.x_sw + j0 : nullptr;
 #pragma unroll
         for (int i = 0; i < NT / 8; ++i) rpre[i] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rpre2[i] = make_uint4(0u, 0u, 0u, 0u);
         if (rp) {      // this thread's 32 channels only
 #pragma unroll
             for (int i = 0; i < 4; ++i) rpre[i] = *reinterpret_cast<const uint4*>(rp + c0 + i * 8);
+        }
+        if constexpr (TB2 != 0) {
+            const int row2 = row + 128;
+            const int th2 = th0 + (row2 / P.BW) % P.BH, tw2 = tw0 + row2 % P.BW;
+            ho2 = th2 * P.os + ph.oph; wo2 = tw2 * P.os + ph.opw;
+            valid2 = n < P.N && th2 < ph.TH && tw2 < ph.TW && ho2 < P.Ho && wo2 < P.Wo;
+            const __nv_bfloat16* rp2 = nullptr;
+            if (valid2 && P.gn.mode == 2) rp2 = P.gn.x + (int64_t)n * P.gn.x_sn + (int64_t)ho2 * P.gn.x_sh + (int64_t)wo2 * P.gn.x_sw + j0;
+            else if (valid2 && P.res) rp2 = P.res + (int64_t)n * P.r_sn + (int64_t)ho2 * P.r_sh + (int64_t)wo2 * P.r_sw + j0;
+            if (rp2) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rpre2[i] = *reinterpret_cast<const uint4*>(rp2 + c0 + i * 8);
+            }
         }
     } else if (rp && P.prefetch) {
 #pragma unroll
@@ -418,6 +438,10 @@ __global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(con
 #pragma unroll
                     for (int k = 0; k < 4; ++k)   // 4 x K=16 inside the 128-byte swizzle row: +32 B per step
                         umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (g | j | k) != 0);
+                    if constexpr (TB2 != 0) {     // rows 128..255 of the box (16 KB further on) into the second accumulator
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem + NT, da + 1024 + 2 * k, db + 2 * k, idesc, (g | j | k) != 0);
+                    }
                 }
                 umma_commit(&empty_bar[st]);
                 d_stage += stage16;
@@ -441,115 +465,147 @@ __global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(con
     if constexpr (GN) {
         // ------------------------------------------------ fused GroupNorm epilogue (splits == 1, whole images per tile)
         // The norm runs out of REGISTERS: a thread holds 32 channels (= 32 >> SH whole groups) of one tile row, the rows of one
-        // image are HWt consecutive TMEM lanes (HWt = BH * BW, a power of two <= 64), so the (image, group) sums are a butterfly
-        // over min(HWt, 32) adjacent lanes - plus one exchange between the two warps of an image when HWt = 64 - and nothing is
+        // image are HWt consecutive TMEM lanes (HWt = BH * BW, a power of two), so the (image, group) sums are a butterfly over
+        // min(HWt, 32) adjacent lanes plus one exchange between the warps of an image when it spans several, and nothing is
         // parked in shared memory.  (The first version staged the tile in shared memory and ran three 256-thread phases with
         // two barriers: 6.7k clk forward / 10.2k clk backward per launch against 2.2k for the plain epilogue,
-        // scripts/gn_epi_timeline.py.)  One instantiation per channels-per-group value (2, 4, 8, 16, 32), chosen at run time.
+        // scripts/gn_epi_timeline.py.)  A 256-pixel box (16x16 images: P.pix256) is two accumulators of 128 rows; a thread then
+        // owns rows r and r + 128, sums over both and reads the accumulators a second time for the result instead of keeping
+        // both rows in registers.  One instantiation per channels-per-group value (2, 4, 8, 16, 32), chosen at run time.
         const GnEpi& Gn = P.gn;
+        constexpr int TB = 1 + TB2;
         const int HWt = P.BH * P.BW;
         const int seg = HWt < 32 ? HWt : 32;
+        const int wpi = HWt <= 32 ? 1 : (HWt == 64 ? 2 : 4);      // warps one image spans inside a 128-row accumulator
         const int silu = Gn.silu;
         const float inv_cnt = 1.f / Gn.cnt;
         const float* gam = s_gb + c0;
         const float* bet = s_gb + NT + c0;
         float v[32];
-        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (!have_acc || !valid) {
+        // accumulator `t` of this thread's row -> v (zeros for rows outside the problem)
+        auto load_acc = [&](int t, bool ok) {
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * NT + c0), v);
+            tmem_ld_wait();
+            if (!have_acc || !ok) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        // sum over the rows of an image inside the warp (all 32 lanes take part; rows outside the problem carry zeros)
-        auto seg_allreduce = [&](auto& a) {
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+        };
+        // sum over the rows of an image: lanes of the warp first (all 32 lanes take part; rows outside the problem carry zeros),
+        // then the warps the image spans
+        auto image_allreduce = [&](auto& a) {
             constexpr int NV = sizeof(a) / sizeof(float);
             for (int o = seg >> 1; o > 0; o >>= 1) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
             }
-            if (HWt == 64) {      // the image's other half sits in the neighbouring warp
+            if (wpi > 1) {
                 if (lane == 0) {
 #pragma unroll
                     for (int i = 0; i < NV; ++i) s_x[warp * 32 + i] = a[i];
                 }
                 __syncthreads();
+                const float* sp = s_x + (warp & ~(wpi - 1)) * 32;
 #pragma unroll
-                for (int i = 0; i < NV; ++i) a[i] += s_x[(warp ^ 1) * 32 + i];
+                for (int i = 0; i < NV; ++i) {
+                    float s = sp[i] + sp[32 + i];
+                    if (wpi == 4) s += sp[64 + i] + sp[96 + i];
+                    a[i] = s;
+                }
             }
         };
+        // One accumulator (TB == 1): a single step forms the sums, reduces them and writes the result from the same registers.
+        // Two (TB == 2): steps 0, 1 form the sums of rows r, r + 128, step 1 ends with the reduction, steps 2, 3 read the
+        // accumulators again (same arithmetic, same values) and write the results.  Every piece of code below exists once.
+        constexpr int nsteps = TB == 1 ? 1 : 4;
         if (Gn.mode == 1) {
             // ---- forward: y = conv (+ bias + temb + residual), a = act(GroupNorm(y))
-            if (valid) {
-                if (stage_bt) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(&s_bt[nl * NT + c0 + i]);
-                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                    }
-                } else {
-                    if (P.bias) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c0 + i));
-                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                        }
-                    }
-                    if (P.temb) {
-                        const float* tp = P.temb + (int64_t)n * P.temb_pitch + j0 + c0;
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(tp + i));
-                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                        }
-                    }
-                }
-                if (rp) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float r8[8];
-                        unpack_bf16x8(rpre[i], r8);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) v[i * 8 + k] += r8[k];
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
-                __nv_bfloat16* yp1 = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0 + c0;
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp1 + i, v + i);
-            }
             auto fwd = [&](auto shc) {
                 constexpr int SH = decltype(shc)::value, CPG = 1 << SH, NG = 32 >> SH;
                 float st[2 * NG];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    float s = 0.f, q = 0.f;
+                for (int i = 0; i < 2 * NG; ++i) st[i] = 0.f;
+#pragma unroll 1
+                for (int s = 0; s < nsteps; ++s) {
+                    const int t = s & 1;
+                    const bool second = s >= 2, vt = t ? valid2 : valid;
+                    const int hot = t ? ho2 : ho, wot = t ? wo2 : wo;
+                    load_acc(t, vt);
+                    if (vt) {
+                        if (stage_bt) {
 #pragma unroll
-                    for (int k = 0; k < CPG; ++k) { const float t = v[g * CPG + k]; s += t; q = fmaf(t, t, q); }
-                    st[2 * g] = s; st[2 * g + 1] = q;
-                }
-                seg_allreduce(st);
-                if (valid) {
-                    // raw (sum, sum of squares) for the backward: the image's first row writes (of the first warp when it spans two)
-                    if ((lane & (seg - 1)) == 0 && (HWt < 64 || (warp & 1) == 0)) {
-                        float2* sp = reinterpret_cast<float2*>(Gn.sums + ((int64_t)n * Gn.G + ((j0 + c0) >> SH)) * 2);
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 b = *reinterpret_cast<const float4*>(&s_bt[nl * NT + c0 + i]);
+                                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                            }
+                        } else {
+                            if (P.bias) {
 #pragma unroll
-                        for (int g = 0; g < NG; ++g) sp[g] = make_float2(st[2 * g], st[2 * g + 1]);
-                    }
+                                for (int i = 0; i < 32; i += 4) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + j0 + c0 + i));
+                                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                                }
+                            }
+                            if (P.temb) {
+                                const float* tp = P.temb + (int64_t)n * P.temb_pitch + j0 + c0;
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        const float mean = st[2 * g] * inv_cnt;
-                        const float rstd = rsqrtf(fmaxf(fmaf(st[2 * g + 1], inv_cnt, -mean * mean), 0.f) + Gn.eps);
+                                for (int i = 0; i < 32; i += 4) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(tp + i));
+                                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                                }
+                            }
+                        }
+                        if (P.res) {
 #pragma unroll
-                        for (int k = 0; k < CPG; ++k) {
-                            const int i = g * CPG + k;
-                            const float sc = rstd * gam[i];
-                            v[i] = gn_act(fmaf(v[i], sc, bet[i] - mean * sc), silu);
+                            for (int i = 0; i < 4; ++i) {
+                                float r8[8];
+                                unpack_bf16x8(t ? rpre2[i] : rpre[i], r8);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) v[i * 8 + k] += r8[k];
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+                        if (!second) {
+                            __nv_bfloat16* yp1 = P.y + (int64_t)n * P.y_sn + (int64_t)hot * P.y_sh + (int64_t)wot * P.y_sw + j0 + c0;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp1 + i, v + i);
                         }
                     }
-                    __nv_bfloat16* ap = Gn.a + (int64_t)n * Gn.a_sn + (int64_t)ho * Gn.a_sh + (int64_t)wo * Gn.a_sw + j0 + c0;
+                    if (!second) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(ap + i, v + i);
+                        for (int g = 0; g < NG; ++g) {
+                            float su = 0.f, q = 0.f;
+#pragma unroll
+                            for (int k = 0; k < CPG; ++k) { const float x = v[g * CPG + k]; su += x; q = fmaf(x, x, q); }
+                            st[2 * g] += su; st[2 * g + 1] += q;
+                        }
+                    }
+                    if (s == TB - 1) {
+                        image_allreduce(st);
+                        // raw (sum, sum of squares) for the backward: the image's first row writes (of the first warp when it spans several)
+                        if (valid && (lane & (seg - 1)) == 0 && (warp & (wpi - 1)) == 0) {
+                            float2* sp = reinterpret_cast<float2*>(Gn.sums + ((int64_t)n * Gn.G + ((j0 + c0) >> SH)) * 2);
+#pragma unroll
+                            for (int g = 0; g < NG; ++g) sp[g] = make_float2(st[2 * g], st[2 * g + 1]);
+                        }
+                    }
+                    if ((TB == 1 || second) && vt) {
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            const float mean = st[2 * g] * inv_cnt;
+                            const float rstd = rsqrtf(fmaxf(fmaf(st[2 * g + 1], inv_cnt, -mean * mean), 0.f) + Gn.eps);
+#pragma unroll
+                            for (int k = 0; k < CPG; ++k) {
+                                const int i = g * CPG + k;
+                                const float sc = rstd * gam[i];
+                                v[i] = gn_act(fmaf(v[i], sc, bet[i] - mean * sc), silu);
+                            }
+                        }
+                        __nv_bfloat16* ap = Gn.a + (int64_t)n * Gn.a_sn + (int64_t)hot * Gn.a_sh + (int64_t)wot * Gn.a_sw + j0 + c0;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(ap + i, v + i);
+                    }
                 }
             };
             switch (Gn.cpg) {
@@ -564,65 +620,99 @@ __global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(con
             //      outside the problem);  du = dy act'(u),  dx = rstd (gamma du - A - xhat B) + add0 + add1  with
             //      A = mean_group(gamma du), B = mean_group(gamma du xhat);  per-tile channel sums (sum du, sum du xhat) for dgamma / dbeta
             float xh[32];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) unpack_bf16x8(rpre[i], xh + i * 8);
             const int64_t px = (int64_t)j0 + c0;
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
             uint4 r0[4], r1[4];      // the addends fly while the sums are formed
+            auto load_adds = [&](bool ok, int hot, int wot) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { r0[i] = z; r1[i] = z; }
-            if (valid && Gn.add0) {
-                const __nv_bfloat16* a0p = Gn.add0 + (int64_t)n * Gn.a0_sn + (int64_t)ho * Gn.a0_sh + (int64_t)wo * Gn.a0_sw + px;
+                for (int i = 0; i < 4; ++i) { r0[i] = z; r1[i] = z; }
+                if (ok && Gn.add0) {
+                    const __nv_bfloat16* a0p = Gn.add0 + (int64_t)n * Gn.a0_sn + (int64_t)hot * Gn.a0_sh + (int64_t)wot * Gn.a0_sw + px;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) r0[i] = *reinterpret_cast<const uint4*>(a0p + i * 8);
-            }
-            if (valid && Gn.add1) {
-                const __nv_bfloat16* a1p = Gn.add1 + (int64_t)n * Gn.a1_sn + (int64_t)ho * Gn.a1_sh + (int64_t)wo * Gn.a1_sw + px;
+                    for (int i = 0; i < 4; ++i) r0[i] = *reinterpret_cast<const uint4*>(a0p + i * 8);
+                }
+                if (ok && Gn.add1) {
+                    const __nv_bfloat16* a1p = Gn.add1 + (int64_t)n * Gn.a1_sn + (int64_t)hot * Gn.a1_sh + (int64_t)wot * Gn.a1_sw + px;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) r1[i] = *reinterpret_cast<const uint4*>(a1p + i * 8);
-            }
+                    for (int i = 0; i < 4; ++i) r1[i] = *reinterpret_cast<const uint4*>(a1p + i * 8);
+                }
+            };
+            float w0 = 0.f, w1 = 0.f;      // this lane's channel (c0 + lane): sum du, sum du xhat over the warp's rows
             auto bwd = [&](auto shc) {
                 constexpr int SH = decltype(shc)::value, CPG = 1 << SH, NG = 32 >> SH;
                 const int IS = 2 * (NT >> SH) + 1;
                 const float* mr = reinterpret_cast<const float*>(smem + Gn.epi_off) + (valid ? nl : 0) * IS + 2 * (c0 >> SH);
                 float ab[2 * NG];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const float mean = mr[2 * g], rstd = mr[2 * g + 1];
-                    float A = 0.f, B = 0.f;
+                for (int i = 0; i < 2 * NG; ++i) ab[i] = 0.f;
+                load_adds(valid, ho, wo);
+#pragma unroll 1
+                for (int s = 0; s < nsteps; ++s) {
+                    const int t = s & 1;
+                    const bool second = s >= 2, vt = t ? valid2 : valid;
+                    const int hot = t ? ho2 : ho, wot = t ? wo2 : wo;
+                    if (second && t == 1) load_adds(vt, hot, wot);
+                    // v <- du, xh <- xhat of accumulator t
+                    load_acc(t, vt);
 #pragma unroll
-                    for (int k = 0; k < CPG; ++k) {
-                        const int i = g * CPG + k;
-                        const float d = xh[i] - mean;
-                        const float du = gn_act_grad(fmaf(d, rstd * gam[i], bet[i]), v[i], silu);
-                        const float xn = d * rstd;
-                        const float gd = gam[i] * du;
-                        v[i] = du; xh[i] = xn;
-                        A += gd; B = fmaf(gd, xn, B);
-                    }
-                    ab[2 * g] = A; ab[2 * g + 1] = B;
-                }
-                seg_allreduce(ab);
-                if (valid) {
-                    float o[32];
+                    for (int i = 0; i < 4; ++i) unpack_bf16x8(t ? rpre2[i] : rpre[i], xh + i * 8);
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        const float rstd = mr[2 * g + 1], A = ab[2 * g] * inv_cnt, B = ab[2 * g + 1] * inv_cnt;
+                        const float mean = mr[2 * g], rstd = mr[2 * g + 1];
+                        float A = 0.f, B = 0.f;
 #pragma unroll
                         for (int k = 0; k < CPG; ++k) {
                             const int i = g * CPG + k;
-                            o[i] = rstd * (gam[i] * v[i] - A - xh[i] * B);
+                            const float d = xh[i] - mean;
+                            const float du = gn_act_grad(fmaf(d, rstd * gam[i], bet[i]), v[i], silu);
+                            const float xn = d * rstd;
+                            const float gd = gam[i] * du;
+                            v[i] = du; xh[i] = xn;
+                            A += gd; B = fmaf(gd, xn, B);
                         }
+                        if (!second) { ab[2 * g] += A; ab[2 * g + 1] += B; }
                     }
-                    __nv_bfloat16* dxp = Gn.dx + (int64_t)n * Gn.dx_sn + (int64_t)ho * Gn.dx_sh + (int64_t)wo * Gn.dx_sw + px;
+                    if (s == TB - 1) image_allreduce(ab);
+                    if (TB == 1 || second) {
+                        // per-tile channel sums over the warp's 32 rows: a transposing butterfly - at offset o a lane keeps the half of
+                        // its values its bit o selects and adds the partner's copy of that half - leaves lane L with channel c0 + L
+                        {
+                            float w[64];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float t0[8], t1[8];
-                        unpack_bf16x8(r0[i], t0);
-                        unpack_bf16x8(r1[i], t1);
+                            for (int i = 0; i < 32; ++i) { w[2 * i] = v[i]; w[2 * i + 1] = v[i] * xh[i]; }
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) o[i * 8 + k] += t0[k] + t1[k];
-                        store_vec<__nv_bfloat16>(dxp + i * 8, o + i * 8);
+                            for (int half = 32; half >= 2; half >>= 1) {
+                                const bool up = (lane & (half >> 1)) != 0;
+#pragma unroll
+                                for (int i = 0; i < half; ++i) {
+                                    const float keep = up ? w[half + i] : w[i];
+                                    const float send = up ? w[i] : w[half + i];
+                                    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, half >> 1);
+                                }
+                            }
+                            w0 += w[0]; w1 += w[1];
+                        }
+                        if (vt) {
+#pragma unroll
+                            for (int g = 0; g < NG; ++g) {
+                                const float rstd = mr[2 * g + 1], A = ab[2 * g] * inv_cnt, B = ab[2 * g + 1] * inv_cnt;
+#pragma unroll
+                                for (int k = 0; k < CPG; ++k) {
+                                    const int i = g * CPG + k;
+                                    v[i] = rstd * (gam[i] * v[i] - A - xh[i] * B);
+                                }
+                            }
+                            __nv_bfloat16* dxp = Gn.dx + (int64_t)n * Gn.dx_sn + (int64_t)hot * Gn.dx_sh + (int64_t)wot * Gn.dx_sw + px;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float t0[8], t1[8];
+                                unpack_bf16x8(r0[i], t0);
+                                unpack_bf16x8(r1[i], t1);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) v[i * 8 + k] += t0[k] + t1[k];
+                                store_vec<__nv_bfloat16>(dxp + i * 8, v + i * 8);
+                            }
+                        }
                     }
                 }
             };
@@ -632,25 +722,6 @@ __global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(con
                 case 8: bwd(IntC<3>{}); break;
                 case 16: bwd(IntC<4>{}); break;
                 default: bwd(IntC<5>{}); break;
-            }
-            // per-tile channel sums over the warp's 32 rows: a transposing butterfly - at offset o a lane keeps the half of its values its
-            // bit o selects and adds the partner's copy of that half - leaves lane L with channel c0 + L: (sum du, sum du xhat)
-            float w0, w1;
-            {
-                float w[64];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) { w[2 * i] = v[i]; w[2 * i + 1] = v[i] * xh[i]; }
-#pragma unroll
-                for (int half = 32; half >= 2; half >>= 1) {
-                    const bool up = (lane & (half >> 1)) != 0;
-#pragma unroll
-                    for (int i = 0; i < half; ++i) {
-                        const float keep = up ? w[half + i] : w[i];
-                        const float send = up ? w[i] : w[half + i];
-                        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, half >> 1);
-                    }
-                }
-                w0 = w[0]; w1 = w[1];
             }
             s_red[warp * 64 + 2 * lane] = w0; s_red[warp * 64 + 2 * lane + 1] = w1;
             __syncthreads();
@@ -663,7 +734,7 @@ __global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(con
         if (dbg && threadIdx.x == 0) dbg[5] = clock64();   // epilogue stores issued
         tc_fence_before();
         __syncthreads();
-        if (warp == 1) tmem_dealloc(tmem, NT);
+        if (warp == 1) tmem_dealloc(tmem, NT << TB2);
         return;
     }
     if (P.splits > 1) {
@@ -780,6 +851,17 @@ __global__ void __launch_bounds__(GN ? 256 : 128, GN ? 1 : 0) conv_tc_kernel(con
     if (warp == 1) tmem_dealloc(tmem, NT);
 }
 
+template <int NT, int DEEP>
+__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
+    conv_tc_body<NT, DEEP, 0>(maps, P);
+}
+// The GroupNorm variants run 256 threads; the register cap keeps a weight-gradient CTA of the backward's other lane (128 threads
+// x 56 registers) resident on the same SM next to one of these.
+template <int DEEP, int TB2>
+__global__ void __maxnreg__(216) conv_tc_gn_kernel(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs P) {
+    conv_tc_body<64, DEEP, 1, TB2>(maps, P);
+}
+
 long long* g_debug_buffer = nullptr;
 
 // conv_halo.cu
@@ -866,6 +948,12 @@ static int conv_prepare(const dmu_conv_params* p, Maps* maps, ConvArgs& A, ConvG
         if (small_tiles && NT == 128 && ctas * 2 <= cap) { NT = 64; ctas *= 2; }
         if (small_tiles && ctas * 2 <= cap && (int64_t)p->N * THmax * TWmax > 64 && !(gn && img_rows > 64)) { pix = 64; ctas *= 2; }
         if (small_tiles >= 2 && pix == 64 && ctas * 2 <= cap && (int64_t)p->N * THmax * TWmax > 32 && !gn) pix = 32;
+        // GroupNorm epilogue on a 16x16 image: one 256-pixel box per CTA (two M = 128 accumulators), so that the tile still holds
+        // the whole image.  Sub-wave grids only: per SM it is the same k-loop traffic as two co-resident 128-pixel CTAs.
+        static const int pix256 = [] { const char* e = getenv("DMU_GN_PIX256"); return e ? atoi(e) : 1; }();       // A/B aid
+        if (gn && pix256 && img_rows == 256 && THmax == 16 && TWmax == 16 && nph == 1 && st == 1 &&
+            p->N * (p->Cj / 64) <= sm_count())
+            pix = 256;
     }
     const Box b = make_box(p->N, THmax, TWmax, pix);
     if (p->gather == 0) {
@@ -961,9 +1049,10 @@ static int conv_prepare(const dmu_conv_params* p, Maps* maps, ConvArgs& A, ConvG
     // measured: the k-loop of these launches is issue-bound (~100 clk per MMA whatever its shape), M = 64 buys nothing: opt-in
     static const int m64_env = [] { const char* e = getenv("DMU_CONV_M64"); return e ? atoi(e) : 0; }();
     A.m64 = (pix == 64 && A.splits == 1 && m64_env && !gn) ? 1 : 0;
+    A.pix256 = pix == 256 ? 1 : 0;
     A.a_off = pix * 128;
     A.kb_bytes = A.a_off + NT * 128;
-    A.kps = deep ? (kps_env < 1 ? 1 : kps_env) : 1;
+    A.kps = (deep && pix <= 128) ? (kps_env < 1 ? 1 : kps_env) : 1;
     A.stage_bytes = A.kps * A.kb_bytes;
     const int max_stages = NT == 64 ? (deep ? ConvCfg<64, 1>::kStages : ConvCfg<64, 0>::kStages) : (deep ? ConvCfg<128, 1>::kStages : ConvCfg<128, 0>::kStages);
     A.stages = max_stages;
@@ -976,7 +1065,7 @@ static int conv_prepare(const dmu_conv_params* p, Maps* maps, ConvArgs& A, ConvG
         if (A.stages < 2) A.stages = 2;
     }
     // + 1 KB alignment slack + the rows past a 64-pixel box that the M = 128 MMA of the last stage still reads
-    const size_t ring = (size_t)A.stages * A.stage_bytes + (128 * 128 - A.a_off);
+    const size_t ring = (size_t)A.stages * A.stage_bytes + (A.a_off < 128 * 128 ? 128 * 128 - A.a_off : 0);
     G.smem = ring + 1024 + gn_pre;
     G.NT = NT; G.pix = pix; G.nph = nph; G.b = b; G.gn_tiles = 0;
     if (gn) {
@@ -990,13 +1079,6 @@ static int conv_prepare(const dmu_conv_params* p, Maps* maps, ConvArgs& A, ConvG
         if (ok && p->gn_fuse_mode == 2)
             ok = gn_tensor_ok(gn->x) && gn_tensor_ok(gn->dx) && gn->red && !p->res.ptr && !p->bias && !p->temb &&
                  (!gn->add0.ptr || gn_tensor_ok(gn->add0)) && (!gn->add1.ptr || gn_tensor_ok(gn->add1));
-        if (ok) {
-            const int GT = NT / cpg;
-            // two [128][NT + 1] tiles, the per-(image, group) results, the partials of the reductions (<= 256 pairs x 2 or the channel sums)
-            const size_t npairs = (size_t)b.BN * GT;
-            const size_t need = ((size_t)2 * 128 * (NT + 1) + (size_t)b.BN * (2 * GT + 1) + 2 * (npairs > 256 ? npairs : 256)) * 4;
-            ok = need <= ring;
-        }
         if (!ok) return -1;      // not an error by itself: dmu_conv2d_gn_fuse_supported reports 0, dmu_conv2d fails loudly
         GnEpi& E = A.gn;
         E.mode = p->gn_fuse_mode; E.G = gn->G; E.cpg = cpg; E.silu = gn->silu; E.C = gn->C;
@@ -1036,13 +1118,14 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(conv_tc_kernel<64, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 0>::kSmem);
-        cudaFuncSetAttribute(conv_tc_kernel<128, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 0>::kSmem);
-        cudaFuncSetAttribute(conv_tc_kernel<64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 1>::kSmem);
-        cudaFuncSetAttribute(conv_tc_kernel<128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 1>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 0>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 0>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<64, 1>::kSmem);
+        cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<128, 1>::kSmem);
         // the GroupNorm variants never exceed ring (<= 128 KB, its statistics region included) + slack: conv_prepare sizes them
-        cudaFuncSetAttribute(conv_tc_kernel<64, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(conv_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv_tc_gn_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv_tc_gn_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv_tc_gn_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (cudaError_t ae = cudaGetLastError(); ae != cudaSuccess) return fail("dmu_conv2d/tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ae));
         attr_done = true;
     }
@@ -1052,12 +1135,15 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     DMU_REQUIRE(!A.gn.mode || smem <= 160 * 1024, "dmu_conv2d/tc: GroupNorm epilogue launch needs %zu bytes of shared memory", smem);
     const bool deep = G.deep;
     cudaError_t e;
-    if (A.gn.mode) e = deep ? launch_pdl(conv_tc_kernel<64, 1, 1>, grid, dim3(256), smem, stream, cluster, maps, A)
-                            : launch_pdl(conv_tc_kernel<64, 0, 1>, grid, dim3(256), smem, stream, cluster, maps, A);
-    else if (G.NT == 64) e = deep ? launch_pdl(conv_tc_kernel<64, 1, 0>, grid, dim3(128), smem, stream, cluster, maps, A)
-                                  : launch_pdl(conv_tc_kernel<64, 0, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
-    else e = deep ? launch_pdl(conv_tc_kernel<128, 1, 0>, grid, dim3(128), smem, stream, cluster, maps, A)
-                  : launch_pdl(conv_tc_kernel<128, 0, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
+    if (A.gn.mode && A.pix256) {
+        DMU_REQUIRE(deep, "dmu_conv2d/tc: 256-pixel GroupNorm launch outside a sub-wave grid");
+        e = launch_pdl(conv_tc_gn_kernel<1, 1>, grid, dim3(256), smem, stream, cluster, maps, A);
+    } else if (A.gn.mode) e = deep ? launch_pdl(conv_tc_gn_kernel<1, 0>, grid, dim3(256), smem, stream, cluster, maps, A)
+                                   : launch_pdl(conv_tc_gn_kernel<0, 0>, grid, dim3(256), smem, stream, cluster, maps, A);
+    else if (G.NT == 64) e = deep ? launch_pdl(conv_tc_kernel<64, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
+                                  : launch_pdl(conv_tc_kernel<64, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
+    else e = deep ? launch_pdl(conv_tc_kernel<128, 1>, grid, dim3(128), smem, stream, cluster, maps, A)
+                  : launch_pdl(conv_tc_kernel<128, 0>, grid, dim3(128), smem, stream, cluster, maps, A);
     if (e != cudaSuccess) return fail("dmu_conv2d/tc: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/tc");
 }

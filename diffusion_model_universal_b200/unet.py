@@ -30,7 +30,7 @@ from . import _abi, ops
 from ._abi import F32, BF16, Tensor4, ConvParams, WgradParams, GnParams, AttnParams, RepackDesc, GnPgDesc, ColsumDesc
 
 
-AUX = 1000      # lane id of micro-batch k's auxiliary chain: AUX + k (Engine._run_forked)
+AUX, AUXK = 1000, 16      # lane id of micro-batch k's auxiliary chain j (sub-plan tag 2 + j): AUX + j * AUXK + k (Engine._run_forked)
 
 
 def gn_groups(channels: int, num_groups: int = 32) -> int:
@@ -472,7 +472,7 @@ class Engine:
 
         def main_of(lane):
             if lane >= AUX:
-                return 2 * (lane - AUX)
+                return 2 * ((lane - AUX) % AUXK)
             return lane - 1 if lane % 2 == 1 else lane
 
         def lane_stream(lane):
@@ -637,14 +637,14 @@ class Engine:
             gn_pg += sub.gn_pg
 
         def retag(ops_, k):
-            """sub-plan tags (none = main chain, 1 = side chain, 2 = auxiliary chain) -> lane ids of micro-batch k"""
+            """sub-plan tags (none = main chain, 1 = side chain, 2 + j = auxiliary chain j) -> lane ids of micro-batch k"""
             out = []
             for op in ops_:
                 tag = op[2] if len(op) == 3 else 0
                 if op[0] is None:
-                    out.append((None, (), AUX + k if tag == 2 else 2 * k))   # join the auxiliary / side lane into the main lane
+                    out.append((None, (), AUX + (tag - 2) * AUXK + k if tag >= 2 else 2 * k))   # join an auxiliary / the side lane into the main lane
                 else:
-                    out.append((op[0], op[1], 2 * k if tag == 0 else 2 * k + 1 if tag == 1 else AUX + k))
+                    out.append((op[0], op[1], 2 * k if tag == 0 else 2 * k + 1 if tag == 1 else AUX + (tag - 2) * AUXK + k))
             return out
 
         lib = self._lib
@@ -701,16 +701,15 @@ class Engine:
                 else:
                     i = body.index((None, (), -2)) + 1
                     plan.bwd += body[:i] + [(fn, args, 1) for fn, args, _ in tails[h - 1]] + body[i:]
-            # the last tail runs next to the time-embedding backward (both only need the lanes joined): it goes on the side lane
-            # right after the join that precedes those launches (the second-to-last join marker of the part)
-            joins = [i for i, op in enumerate(plan.bwd) if op[0] is None and op[2] == 0]
-            if len(joins) >= 2 and K == 1:
-                i = joins[-2] + 1
-                while plan.bwd[i][0] is not None and plan.bwd[i][2] == 1:     # the stem's weight gradient follows that join on the
-                    i += 1                                                    # side lane: the unpack reads what it writes
-                plan.bwd[i:i] = [(fn, args, 1) for fn, args, _ in tails[2]]
+            # the last tail runs next to the time-embedding backward: on the side lane, behind the stem's weight gradient (the unpack
+            # reads what that writes) - where the sub-plan left its "tails" marker
+            marks = [i for i, op in enumerate(plan.bwd) if op[0] == "tails"]
+            if K == 1 and len(marks) == 1:
+                i = marks[0]
+                plan.bwd[i:i + 1] = [(fn, args, 1) for fn, args, _ in tails[2]]
             else:
-                plan.bwd += tails[2]
+                plan.bwd = [op for op in plan.bwd if op[0] != "tails"] + tails[2]
+            plan.bwd_parts = [[op for op in lst if op[0] != "tails"] for lst in plan.bwd_parts]
         plan.arena = arena
         plan.nbytes = nbytes
         plan.lanes = K
@@ -774,6 +773,7 @@ class _PlanBuilder:
         self.gn_pg = []         # (red, dgamma, dbeta, C) of every GroupNorm backward: folded by one launch at the end
         self.gn_pg_split = []   # len(gn_pg) at each split marker of the backward
         self.side_lane = True   # weight-gradient / column-sum launches of the backward go to the graph's second branch
+        self.leaf_tag = 0
         self.cs_pending = []    # column sums (bias gradients, time-projection sums) batched into one launch per backward part
         self.temb_join_pending = False
         self.prod = {}          # output address -> ConvParams of the forward conv that writes it (candidates for a fused GroupNorm)
@@ -825,7 +825,9 @@ class _PlanBuilder:
         dev = self.e.device
         tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self.plan.keep.append(tab)
-        self.plan.bwd.append((self.lib.dmu_colsum_multi, (tab.data_ptr(), len(self.cs_pending), cta, self.code), 1))
+        # its own auxiliary chain (not the weight-gradient lane's queue): the sums only need finished main-lane tensors, and the
+        # embedding backward at the very end of the step waits for the last batch of them
+        self.plan.bwd.append((self.lib.dmu_colsum_multi, (tab.data_ptr(), len(self.cs_pending), cta, self.code), 3 if self.e.aux_lanes else 1))
         self.cs_pending = []
 
     def conv(self, lst, x: Tensor4, y: Tensor4, w, w_strides, w_code, dims, geom, bias=None, temb=None, temb_pitch=0, res=None, gather=0,
@@ -893,7 +895,8 @@ class _PlanBuilder:
         batched = dbias is not None and self.side_lane and p4.sc == 1 and p4.dtype == self.code
         p = WgradParams(p4, q4, dw, dw_strides[0], dw_strides[1], dw_strides[2], None if batched else dbias, N, Hp, Wp, Ca, Hq, Wq, Cb, R, S, stride, pad,
                         self.e.impl)
-        self.plan.bwd.append((self.lib.dmu_conv2d_wgrad, (C.byref(p),), 1) if self.side_lane else (self.lib.dmu_conv2d_wgrad, (C.byref(p),)))
+        tag = 1 if self.side_lane else self.leaf_tag      # leaf_tag: where weight gradients go once the side lane is closed
+        self.plan.bwd.append((self.lib.dmu_conv2d_wgrad, (C.byref(p),), tag) if tag else (self.lib.dmu_conv2d_wgrad, (C.byref(p),)))
         self.plan.keep.append(p)
         if batched:
             self.colsum(p4, N, Hp, Wp, Ca, None, 0, dbias)
@@ -1232,10 +1235,14 @@ class _PlanBuilder:
         # no gradient on this path) is queued on the side lane: it runs next to the embedding backward instead of in front of it
         self.colsum(h0.grad.t4(), N, H, W, Cm, None, 0, self.gp("initial_conv.bias"))
         self.flush_colsums()
-        plan.bwd.append((None, ()))
+        plan.bwd.append((None, (), 3) if e.aux_lanes else (None, ()))      # the column sums are in: join their chain
         self.wgrad(h0.grad.t4(), _nchw_t4(x_ptr, net.in_channels, H, W), e.gsaddr("initial_conv.weight"),
                    (9 * net.in_channels, 1, net.in_channels), None, (N, H, W, Cm, H, W, net.in_channels), (3, 3, 1, 1))
+        plan.bwd.append(("tails", ()))      # Engine._build puts the last part's tail (parameter-gradient fold, staging unpack) here, on the side lane
         self.side_lane = False
+        # the embedding backward is a chain dtemb -> dg1 -> dh1 with three weight gradients hanging off it: those leaves go to the
+        # (now idle) column-sum chain instead of standing in the chain
+        self.leaf_tag = 3 if e.aux_lanes else 0
         dtemb = self.f32(N * T4)
         self.linear_bwd(_rows_t4(temb, T4), _rows_t4(self.dtproj, self.tp_total), _rows_t4(dtemb, T4), N, T4, self.tp_total,
                         e.paddr(first + "time_mlp.weight"), self.gp(first + "time_mlp.weight"), self.gp(first + "time_mlp.bias"))

@@ -575,6 +575,9 @@ GN_EPI_CASES = [
     (9, 4, 4, 128, 128, 1, 1, 32, True),      # attention final projection (+ x) followed by its post-norm
     (8, 1, 1, 256, 512, 3, 1, 32, False),     # cpg 16
     (4, 8, 8, 64, 64, 3, 1, 2, False),        # cpg 32
+    (128, 16, 16, 64, 64, 3, 1, 32, True),    # the bench's 16x16 stage: one 256-pixel box (two accumulators) per image, cpg 2
+    (5, 16, 16, 64, 128, 3, 1, 32, True),     # the same with two channel tiles, cpg 4
+    (3, 16, 16, 128, 256, 3, 1, 32, False),   # cpg 8
 ]
 
 
