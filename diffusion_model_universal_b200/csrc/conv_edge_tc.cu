@@ -1,19 +1,21 @@
 // Weight gradients of the two 3-channel boundary layers on the tensor cores (stem 3 -> C, head C -> 3; models/ddpm.py:49,90):
 //   out[c][tap][j] += sum_pix wide[pix, c] * narrow[pix + sgn * (tap - pad), j]         (same contract as narrow_wgrad_kernel)
-// OPT-IN (DMU_EDGE_WGRAD_TC=1): written at the end of round 1 after the GPU budget was spent; it compiles for sm_100a but has
-// not run on a B200 yet.  The SIMT kernel in conv_edge.cu stays the default until tests/test_gpu_kernels.py passes with the
-// switch on.
+// Default for the bf16 path since round 2 (DMU_EDGE_WGRAD_TC=0 falls back to the SIMT kernel in conv_edge.cu): measured inside the
+// training step it is not faster alone (29 - 59 us next to the other lane's kernels) but it runs 128 threads x 56 registers,
+// where the SIMT kernel's two 256-thread x 125-register CTAs per SM fill the register file for ~45 us and stall everything queued
+// beside it - the embedding backward at the end of the step, the first dgrads at its start (48.4k vs 47.7k img/s).
 //
 // Shape: the pixels are the contraction axis.  Per 64-pixel k-block
 //   B operand  = wide[64 pixels][64 channels] straight from NHWC by one TMA box (MN-major, as the per-tap wgrad kernel uses it),
 //   A operand  = the im2col rows of the narrow tensor, [m = tap * Cn + j][64 pixels] K-major SWIZZLE_128B, written by the CTA's
-//                threads (rows 9 * Cn .. 127 stay zero; row 9 * Cn holds ones, so D[9 * Cn][c] = sum_pix wide[pix, c] = the bias
-//                gradient of the conv whose output gradient is `wide`, for free),
+//                threads: rows 0 .. 9 Cn - 1 hold the bf16 value, rows 9 Cn + 1 .. 18 Cn the bf16 remainder of an fp32 narrow
+//                tensor (x - bf16(x): the pair carries ~16 mantissa bits, so the network input / dL/d(eps) are not rounded to
+//                bf16 here; both rows are added into the same output), row 9 Cn holds ones, so D[9 Cn][c] = sum_pix wide[pix, c]
+//                = the bias gradient of the conv whose output gradient is `wide`, for free; the remaining rows stay zero,
 //   D[128 x 64] += A * B with four M = 128, N = 64, K = 16 tcgen05.mma.
 // Only descriptor / instruction configurations that other kernels of this library already run are used: K-major M = 128 A
 // (conv_stem.cu), MN-major N = 64 B (wgrad_tc_kernel).  Each CTA reduces a contiguous range of k-blocks and ends with one pass of
-// (9 * Cn + 1) x 64 atomics.  wide is read once (16.8 MB at B = 128, 32 x 32, C = 64: 2.6 us of HBM); the narrow operand is
-// rounded to bf16 like every activation of the bf16 path.
+// (18 * Cn + 1) x 64 atomics.  wide is read once (16.8 MB at B = 128, 32 x 32, C = 64: 2.6 us of HBM).
 #include <stdlib.h>
 #include <string.h>
 
@@ -76,6 +78,8 @@ __global__ void __launch_bounds__(128) edge_wgrad_tc_kernel(const __grid_constan
     const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);     // A K-major, B MN-major
     float nsum[4] = {0.f, 0.f, 0.f, 0.f};
 
+    // (measured: fetching the narrow values one k-block ahead does not shorten the launch and doubles its registers - the loop is
+    // bound by the barrier + MMA round trip per k-block, not by the gather)
     for (int i = 0; i < nblk; ++i) {
         const int st = i & 1;
         uint8_t* s_a = smem + st * kEwStage;
@@ -108,7 +112,12 @@ __global__ void __launch_bounds__(128) edge_wgrad_tc_kernel(const __grid_constan
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (j < P.Cn) *reinterpret_cast<__nv_bfloat16*>(s_a + ew_sw128_off(t * P.Cn + j, p)) = __float2bfloat16_rn(v[j]);
+                if (j < P.Cn) {
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+                    *reinterpret_cast<__nv_bfloat16*>(s_a + ew_sw128_off(t * P.Cn + j, p)) = hi;
+                    if constexpr (sizeof(TN) == 4)
+                        *reinterpret_cast<__nv_bfloat16*>(s_a + ew_sw128_off(rows + 1 + t * P.Cn + j, p)) = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+                }
         }
         if (half == 1) *reinterpret_cast<__nv_bfloat16*>(s_a + ew_sw128_off(rows, p)) = __float2bfloat16_rn(valid ? 1.f : 0.f);
         fence_proxy_async();       // generic-proxy writes of the im2col tile -> visible to the tensor core's async proxy
@@ -129,19 +138,21 @@ __global__ void __launch_bounds__(128) edge_wgrad_tc_kernel(const __grid_constan
     }
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
-    // ---- epilogue: accumulator row m sits in TMEM lane m; rows 0 .. rows are all in warp 0's quadrant (rows + 1 <= 32)
-    if (warp == 0) {
+    // ---- epilogue: accumulator row m sits in TMEM lane m; rows 0 .. 2 * rows live in the quadrants of warps 0 and 1 (2 * rows + 1 <= 64)
+    if (warp < 2) {
+        const int L = warp * 32 + lane;
+        const int m = L < rows ? L : ((L > rows && L <= 2 * rows) ? L - rows - 1 : -1);     // value row | remainder row of the same (tap, j)
 #pragma unroll 1
         for (int c = 0; c < 64; c += 32) {
             float v[32];
-            tmem_ld32(tmem + (uint32_t)c, v);
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
             tmem_ld_wait();
-            if (lane < rows) {
-                const int tap = lane / P.Cn, j = lane - tap * P.Cn;
+            if (m >= 0) {
+                const int tap = m / P.Cn, j = m - tap * P.Cn;
                 float* o = P.out + (int64_t)tap * P.o_t + (int64_t)j * P.o_j;
 #pragma unroll
                 for (int q = 0; q < 32; ++q) atomicAdd(o + (int64_t)(c0 + c + q) * P.o_c, v[q]);
-            } else if (lane == rows && P.dbias) {
+            } else if (L == rows && P.dbias) {
 #pragma unroll
                 for (int q = 0; q < 32; ++q) atomicAdd(P.dbias + c0 + c + q, v[q]);
             }
@@ -162,14 +173,14 @@ __global__ void __launch_bounds__(128) edge_wgrad_tc_kernel(const __grid_constan
 }
 
 static bool edge_wgrad_tc_enabled() {
-    static const int v = [] { const char* e = getenv("DMU_EDGE_WGRAD_TC"); return e ? atoi(e) : 0; }();
+    static const int v = [] { const char* e = getenv("DMU_EDGE_WGRAD_TC"); return e ? atoi(e) : 1; }();
     return v != 0;
 }
 
-// wide: bf16 NHWC, pixel-contiguous (one 2-D map), Cw % 64 == 0; narrow: 1..3 channels (9 * Cn + 1 <= 32), fp32 or bf16, any strides
+// wide: bf16 NHWC, pixel-contiguous (one 2-D map), Cw % 64 == 0; narrow: 1..3 channels (18 * Cn + 1 <= 64), fp32 or bf16, any strides
 int edge_wgrad_tc_supported(const dmu_tensor4* wide, const dmu_tensor4* narrow, int N, int H, int W, int Cw, int Cn) {
     if (!edge_wgrad_tc_enabled() || !wide || !narrow || !wide->ptr || !narrow->ptr) return 0;
-    if (Cn < 1 || 9 * Cn + 1 > 32 || Cw % 64 != 0 || Cw < 64) return 0;
+    if (Cn < 1 || 18 * Cn + 1 > 64 || Cw % 64 != 0 || Cw < 64) return 0;
     if (wide->dtype != DMU_BF16 || wide->sc != 1 || wide->sw % 8 || (reinterpret_cast<uintptr_t>(wide->ptr) & 15)) return 0;
     if (wide->sh != (int64_t)W * wide->sw || wide->sn != (int64_t)H * wide->sh) return 0;
     if (narrow->dtype != DMU_F32 && narrow->dtype != DMU_BF16) return 0;

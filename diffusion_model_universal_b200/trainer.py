@@ -98,8 +98,6 @@ class TrainStep:
         self.group = group
         self._synced = False
         self._stage = None
-        self._side = None      # side stream of the step's front (filter-cache refresh next to the RNG draws)
-        self._side2 = None     # branch of the backward's memsets (next to the whole forward)
         self._works = None
         # Single-GPU DDPM steps replay ONE CUDA graph of everything between the input batch and the gradient arena (RNG draws,
         # time weights, q_sample, forward, loss, three-part backward): ~30 small eager launches and four graph launches per step
@@ -220,7 +218,8 @@ class TrainStep:
     def _ddpm_front(self, images: torch.Tensor):
         """RNG draws, time weights, q_sample, forward, loss and dL/d(eps).  No staging copies: q_sample writes the network's
         static input buffer, the loss reads its static output and writes the static upstream-gradient buffer; the refresh of
-        the bf16 filter caches (dmu_repack_weights, ~60 us) runs on a side stream next to the RNG / weight / q_sample front."""
+        the bf16 filter caches (dmu_repack_weights, ~60 us) comes first; the memsets the backward needs ride beside the forward's
+        latency-bound stages (Engine.run_forward(zero_backward=True))."""
         m = self.model
         eng = m.model.engine
         eng.prepare(images.device)
@@ -230,28 +229,11 @@ class TrainStep:
         else:
             shape = tuple(images.shape)
         plan = eng.get_plan(shape, True)
-        cur = torch.cuda.current_stream(images.device) if images.is_cuda else None
-        side = None
-        if cur is not None:
-            # the memsets the backward needs (gradient arena, filter-gradient staging: 2 x 64 MB) run on a branch of their own
-            # that only rejoins after the forward
-            if self._side2 is None:
-                self._side2 = torch.cuda.Stream(device=images.device)
-            self._side2.wait_stream(cur)
-            with torch.cuda.stream(self._side2):
-                eng.zero_backward_buffers(plan, ops._stream())
-        else:
-            eng.zero_backward_buffers(plan)
-        repack_main = os.environ.get("DMU_REPACK_LANE", "side") == "main"      # A/B aid
-        if repack_main and not eng.frozen:
+        # The refresh of the bf16 filter caches leads the step on the same stream as everything else.  (Measured in round 2 inside the
+        # step graph, 2.645 - 2.657 ms whichever way: the refresh on a side branch next to the draws, the draws on a high-priority
+        # branch next to the refresh - the 9344-CTA permutation fills the machine, a concurrent branch only queues behind it.)
+        if not eng.frozen:
             eng.repack(ops._stream())
-        elif cur is not None and not eng.frozen:
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=images.device)
-            side = self._side
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                eng.repack(ops._stream())
         t = torch.randint(0, m.num_timesteps, (shape[0],), device=images.device)
         noise = torch.randn(shape, device=images.device, dtype=torch.float32) if images.dtype == torch.uint8 else torch.randn_like(images)
         w = m.loss_fn.time_weights(t)          # [B]-sized, issued before the forward so nothing waits on it later
@@ -260,13 +242,9 @@ class TrainStep:
                           want_x0=False, xt_out=plan.x_in)
         else:
             ops.q_sample(images.contiguous(), t, noise, m.alphas_cumprod, out=plan.x_in)
-        if side is not None:
-            cur.wait_stream(side)
-        eps = eng.run_forward(None, t, plan, repacked=(side is not None) or repack_main, clone=False)
+        eps = eng.run_forward(None, t, plan, repacked=True, clone=False, zero_backward=True)
         wm, wl, wh = m.loss_fn.coefficients()
         loss, dpred = ops.diffusion_loss(eps, noise, w, wm, wl, wh, float(m.loss_fn.huber_delta), True, dpred_out=plan.dout)
-        if cur is not None:
-            cur.wait_stream(self._side2)
         return loss, None, plan       # dL/d(eps) already sits in plan.dout
 
     def _ddpm_back(self, plan):

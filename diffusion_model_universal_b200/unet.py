@@ -227,6 +227,7 @@ class Plan:
         self.dout = None        # fp32 [N,Cout,H,W] upstream gradient (training plans)
         self.ws = None          # split-K scratch of the tensor-core convs (zero between launches)
         self.zero_ops = []      # memsets of everything a backward accumulates into (Engine.zero_backward_buffers)
+        self.fwd_z = None       # training plans: fwd with zero_ops riding on an auxiliary chain (run_forward(zero_backward=True))
         self.zero_red = None    # (sub-plan) the GroupNorm / time-projection accumulators' memset
         self.graphs = {}        # "fwd"/"bwd" -> torch.cuda.CUDAGraph
         self.runs = {}          # "fwd"/"bwd" -> eager executions so far (the first one is the warm-up before capture)
@@ -466,6 +467,8 @@ class Engine:
         point (main lanes start after everything issued on lane 0 so far), (None, (), 2k) = side lane 2k+1 joins main lane 2k,
         (None, (), AUX+k) = the auxiliary lane joins main lane 2k, (None, (), -1) = every lane joins lane 0.  An op on a side
         or auxiliary lane depends on everything issued on its main lane before it."""
+        # (Measured in round 2: capturing the main chain on a high-priority stream, so that its CTAs are placed before the weight-
+        # gradient lane's, LOSES 100 us per step - 2.78 vs 2.68 ms: the starved lane becomes the critical path at the part ends.)
         main = torch.cuda.current_stream()
         streams, ptrs, started, dirty = {0: main}, {}, {0}, set()
         fork = None
@@ -530,7 +533,7 @@ class Engine:
     def _execute(self, plan: Plan, which: str):
         """Run plan.fwd / plan.bwd: eagerly the first time (warms every lazy one-time initialisation), then captured once
         into a CUDA graph and replayed — ~250 launches (and their tensor-map encodes) become one host call."""
-        oplist = plan.fwd if which == "fwd" else plan.bwd if which == "bwd" else plan.bwd_parts[int(which[3:])]
+        oplist = plan.fwd if which == "fwd" else plan.fwd_z if which == "fwd_z" else plan.bwd if which == "bwd" else plan.bwd_parts[int(which[3:])]
         if self.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
             # the caller is capturing (TrainStep's whole-step graph): record the launches, lanes included, into ITS graph
             self._run_forked(oplist)
@@ -556,16 +559,20 @@ class Engine:
         g.replay()
         ops.LAUNCHES += plan.nlaunch[which]
 
-    def run_forward(self, x, t, plan: Plan, repacked: bool = False, clone: bool = True) -> torch.Tensor:
+    def run_forward(self, x, t, plan: Plan, repacked: bool = False, clone: bool = True, zero_backward: bool = False) -> torch.Tensor:
         """x = None: the caller has already written the network input into plan.x_in (TrainStep's q_sample does).
         repacked: the filter caches are already current (refreshed on a side stream).  clone=False returns the plan's static
-        output buffer itself (overwritten by the next execution)."""
+        output buffer itself (overwritten by the next execution).  zero_backward: also run zero_backward_buffers(plan), beside the
+        latency-bound stages of this forward (the caller then passes prezeroed=True to run_backward; only for a caller that owns
+        the whole step: the memsets wipe the gradient arena)."""
         if not (self.frozen or repacked):
             self.repack(ops._stream())
         if x is not None:
             plan.x_in.copy_(x)
         plan.t_in.copy_(t)       # int64 timesteps are cast to fp32 here exactly like embeddings.py:35 promotes them
-        self._execute(plan, "fwd")
+        if zero_backward and plan.fwd_z is None:
+            self.zero_backward_buffers(plan)
+        self._execute(plan, "fwd_z" if (zero_backward and plan.fwd_z is not None) else "fwd")
         return plan.out.clone() if clone else plan.out
 
     def zero_backward_buffers(self, plan: Plan, stream=None):
@@ -652,6 +659,8 @@ class Engine:
         for k, sub in enumerate(subs):
             plan.fwd += retag(sub.plan.fwd, k)
         plan.fwd.append((None, (), -1))                                  # join all lanes
+        fwd_marked = plan.fwd
+        plan.fwd = [op for op in fwd_marked if op[0] != "zero_here"]
         if train:
             # one zeroing of the gradient arena / staging for all lanes, then the lanes, then the batch-folded tails
             # Three parts (see Engine._flatten): after part i the arena range ranges[i] is final, so a data-parallel step can
@@ -674,6 +683,19 @@ class Engine:
             plan.zero_ops = [(lib.dmu_zero, (self.gstage.data_ptr(), self.gstage.numel() * 4)),
                              (lib.dmu_zero, (self.gflat.data_ptr(), self.gflat.numel() * 4))] + [sub.plan.zero_red for sub in subs]
             plan.bwd_parts = [[], [], []]
+            # forward of a training step that zeroes them on the way: the memsets (2 x 64 MB, ~25 us of the whole GPU) hang off the
+            # first lane's chain where the <= 4x4 stages begin - those launches are latency-bound and leave most SMs idle - on an
+            # auxiliary chain of their own, joined with everything else at the end of the forward
+            plan.fwd_z, placed = [], False
+            for op in fwd_marked:
+                if op[0] == "zero_here":
+                    if not placed:
+                        plan.fwd_z += [(fn, args, AUX + 2 * AUXK) for fn, args in plan.zero_ops]
+                        placed = True
+                else:
+                    plan.fwd_z.append(op)
+            if not placed:
+                plan.fwd_z = None
             tails = ([], [], [])       # per part: batch fold of the GroupNorm parameter gradients + staging unpack
             for h, lst in enumerate(plan.bwd_parts):
                 lst.append((None, (), -2))
@@ -1156,6 +1178,7 @@ class _PlanBuilder:
             pfx = f"down_blocks.{i}."
             if i == 3:
                 down3_tape_start = len(self.tape)
+                plan.fwd.append(("zero_here", ()))     # Engine._build: where a training step may hang the backward's memsets (latency-bound stages follow)
             y = self.stage(pfx, attn, x, co)
             kcat = 4 - i
             hpart = uplan[kcat][1] - co
