@@ -46,6 +46,9 @@ struct HaloArgs {
     // for the backward (weight gradient operand)
     const float* gn_coef; int gn_silu;
     __nv_bfloat16* a_out; int64_t a_sn, a_sh, a_sw;
+    // GroupNorm statistics of the OUTPUT (dmu_conv_params.gn_fuse_mode 3): raw (sum, sum of squares) of the stored values, added to
+    // st_sums[n][g][0..1]; st_sh = log2(channels per group)
+    float* st_sums; int st_G, st_sh;
 };
 
 constexpr int kMaxAStages = 4, kMaxWStages = 8;
@@ -84,6 +87,15 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j0 = blockIdx.y * NT;
     const int kblocks = 9 * P.chunks;
+    // tile schedule of this CTA: round-robin over the grid, or - when the epilogue accumulates GroupNorm statistics - one contiguous
+    // run of tiles, so that a thread's consecutive tiles stay inside one image for plane / 128 tiles
+    int t_first = blockIdx.x, t_step = gridDim.x, t_count = ((int)P.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (P.st_sums) {
+        const int per = (P.tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+        t_first = blockIdx.x * per; t_step = 1;
+        t_count = min(per, P.tiles - t_first);
+    }
+    if (t_count < 0) t_count = 0;
 
     pdl_trigger();
     if (threadIdx.x == 0) {
@@ -116,7 +128,8 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         __syncwarp();
         int sa = 0, pa = 1, sw = 0, pw = 1;
         const uint32_t a_bytes = (uint32_t)(P.NR * P.PW) * 128u;
-        for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        for (int ti = 0; ti < t_count; ++ti) {
+            const int tile = t_first + ti * t_step;
             const int L0 = floordiv_dev(tile * 128 - P.PW - 1, P.PW);
             for (int c = 0; c < P.chunks; ++c) {
                 mbar_wait(&a_empty[sa], pa);
@@ -149,7 +162,8 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
         if (P.resident) mbar_wait(&w_full[0], 0);
         int sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
-        for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
+        for (; it < t_count; ++it) {
+            const int tile = t_first + it * t_step;
             const int buf = it & 1;
             long long* dbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && lane == 0) ? P.dbg + 8 * it : nullptr;
             if (dbg) dbg[0] = clock64();
@@ -219,13 +233,14 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         int sa = 0, pa = 0;
         int coef_key = -1;
         float sc[8], sh[8];
-        for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        for (int ti = 0; ti < t_count; ++ti) {
+            const int tile = t_first + ti * t_step;
             const int Q0 = tile * 128;
             const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
             const int own0 = Q0 - L0 * P.PW;              // tile rows [own0, own0 + 128) are this tile's own output positions
             for (int c = 0; c < P.chunks; ++c) {
-                long long* tdbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tw == 0 && lane == 0 && (tile - (int)blockIdx.x) / (int)gridDim.x < 64)
-                                      ? P.dbg + 8 * 64 + 8 * ((tile - (int)blockIdx.x) / (int)gridDim.x) : nullptr;
+                long long* tdbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tw == 0 && lane == 0 && ti < 64)
+                                      ? P.dbg + 8 * 64 + 8 * ti : nullptr;
                 if (tdbg) tdbg[0] = clock64();
                 mbar_wait(&a_full[sa], pa);
                 if (tdbg) tdbg[1] = clock64();
@@ -293,14 +308,67 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         // ---------------------------------------------------- epilogue warps 0..3: thread = one output position (TMEM lane)
         const int row = threadIdx.x;          // 0..127
         const int plane = P.PH * P.PW;
+        // GroupNorm statistics of the output (st_sums, NT = 64): every thread keeps the sums of its rows per channel PAIR (a group is
+        // >= 2 channels) for the image it is in; only when some lane of the warp moves on to another image - every plane / 128
+        // tiles, the CTA's tiles being one contiguous run - are the warp's sums reduced and added to st_sums.  (Reducing every tile
+        // cost the 64 x 64 layers 40 us each: the four epilogue warps then no longer keep up with the MMA stream.)
+        float acc_s[(NT == 64 && !GN) ? 32 : 1], acc_q[(NT == 64 && !GN) ? 32 : 1];
+        int acc_img = -1;
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(acc_s) / sizeof(float)); ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+        auto stats_flush = [&]() {
+            if constexpr (NT == 64 && !GN) {
+                // the warp's lanes hold sums of at most two images.  A transposing butterfly - at offset o a lane keeps the half of
+                // its values its bit o selects and adds the partner's copy of that half - leaves lane L with channel pair L's
+                // (sum, sum of squares) over the warp; the lanes of a group then combine and one of them adds to st_sums.
+                const int nA = __reduce_min_sync(0xffffffffu, acc_img >= 0 ? acc_img : 0x7fffffff);
+                const int nB = __reduce_max_sync(0xffffffffu, acc_img);
+#pragma unroll 1
+                for (int im = nA; im <= nB && nB >= 0; ++im) {
+                    const bool mine = acc_img == im;
+                    float w[64];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { w[2 * i] = mine ? acc_s[i] : 0.f; w[2 * i + 1] = mine ? acc_q[i] : 0.f; }
+#pragma unroll
+                    for (int half = 32; half >= 2; half >>= 1) {
+                        const bool up = (lane & (half >> 1)) != 0;
+#pragma unroll
+                        for (int i = 0; i < half; ++i) {
+                            const float keep = up ? w[half + i] : w[i];
+                            const float send = up ? w[i] : w[half + i];
+                            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, half >> 1);
+                        }
+                    }
+                    float su = w[0], sq = w[1];
+                    const int ppg = 1 << (P.st_sh - 1);          // channel pairs per group
+                    for (int o = 1; o < ppg; o <<= 1) {
+                        su += __shfl_xor_sync(0xffffffffu, su, o);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    }
+                    if ((lane & (ppg - 1)) == 0) {
+                        float* sp = P.st_sums + ((int64_t)im * P.st_G + ((j0 + 2 * lane) >> P.st_sh)) * 2;
+                        atomicAdd(sp, su);
+                        atomicAdd(sp + 1, sq);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+                acc_img = -1;
+            }
+        };
         int it = 0;
-        for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
+        for (; it < t_count; ++it) {
+            const int tile = t_first + it * t_step;
             const int buf = it & 1;
             const int Q = tile * 128 + row;
             const int n = Q / plane, rem = Q - n * plane;
             const int hp = rem / P.PW, wp = rem - hp * P.PW;
             const bool valid = n < P.N && hp >= 1 && hp <= P.H && wp >= 1 && wp <= P.W;
             const int ho = hp - 1, wo = wp - 1;
+            if (P.st_sums) {
+                if (__any_sync(0xffffffffu, valid && acc_img >= 0 && acc_img != n)) stats_flush();
+                if (valid) acc_img = n;
+            }
             __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0;
             const __nv_bfloat16* rp = (P.res && valid) ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
             const float* tp = (P.temb && valid) ? P.temb + (int64_t)n * P.temb_pitch + j0 : nullptr;
@@ -360,13 +428,25 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
                         }
                     }
 #pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));      // what the store below writes
+#pragma unroll
                     for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp + c + i, v + i);
+                }
+                if constexpr (NT == 64 && !GN) {
+                    if (P.st_sums && valid) {      // this row's pair sums of the stored values (flushed when the warp moves on to another image)
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            acc_s[(c + i) >> 1] += v[i] + v[i + 1];
+                            acc_q[(c + i) >> 1] = fmaf(v[i], v[i], fmaf(v[i + 1], v[i + 1], acc_q[(c + i) >> 1]));
+                        }
+                    }
                 }
             }
             if (dbg) dbg[6] = clock64();
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);      // 128 arrivals release the accumulator to the MMA warp
         }
+        if (P.st_sums) stats_flush();
     }
     tc_fence_before();
     __syncthreads();
@@ -424,6 +504,19 @@ int halo_supported(const dmu_conv_params* p, int force) {
     return 1;
 }
 
+// gn_fuse_mode 3: can the halo kernel (chosen by its own heuristics) add the output's GroupNorm sums in its epilogue?
+int halo_stats_supported(const dmu_conv_params* p) {
+    const dmu_gn_params* gn = reinterpret_cast<const dmu_gn_params*>(p->gn_fuse);
+    if (!gn || !gn->sums || gn->G <= 0 || gn->C != p->Cj || gn->C % gn->G != 0) return 0;
+    if (gn->N != p->N || gn->H != p->Ho || gn->W != p->Wo) return 0;
+    const int cpg = gn->C / gn->G;
+    if (cpg < 2 || cpg > 32 || (cpg & (cpg - 1)) != 0 || p->Cj <= 4 || p->Cj % 128 == 0 || p->gn_coef) return 0;     // 64-channel tiles, pairs
+    if ((p->Hi + 2) * (p->Wi + 2) < 128) return 0;          // a warp's 32 rows must lie in at most two images
+    dmu_conv_params q = *p;
+    q.gn_fuse = nullptr; q.gn_fuse_mode = 0;
+    return halo_supported(&q, 0);
+}
+
 int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
     HaloMaps maps;
     HaloArgs A;
@@ -451,6 +544,13 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
     A.res = reinterpret_cast<const __nv_bfloat16*>(p->res.ptr); A.r_sn = p->res.sn; A.r_sh = p->res.sh; A.r_sw = p->res.sw;
     A.bias = p->bias; A.temb = p->temb; A.temb_pitch = p->temb_pitch;
     A.dbg = g_debug_buffer;
+    if (p->gn_fuse_mode == 3) {
+        const dmu_gn_params* gn = reinterpret_cast<const dmu_gn_params*>(p->gn_fuse);
+        DMU_REQUIRE(halo_stats_supported(p), "dmu_conv2d/halo: this launch cannot accumulate the GroupNorm statistics of gn_fuse (ask dmu_conv2d_gn_fuse_supported first)");
+        const int cpg = gn->C / gn->G;
+        A.st_sums = gn->sums; A.st_G = gn->G; A.st_sh = 0;
+        while ((1 << A.st_sh) < cpg) ++A.st_sh;
+    }
     const int ntiles_n = narrow ? 1 : p->Cj / NT;
     int gx = sm_count() / ntiles_n;
     if (gx < 1) gx = 1;

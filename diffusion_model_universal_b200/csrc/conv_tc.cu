@@ -866,6 +866,7 @@ long long* g_debug_buffer = nullptr;
 
 // conv_halo.cu
 int halo_supported(const dmu_conv_params* p, int force);
+int halo_stats_supported(const dmu_conv_params* p);
 int halo_launch(const dmu_conv_params* p, cudaStream_t stream);
 // conv_stem.cu: few-channel input (stem fprop, head dgrad)
 int stem_supported(const dmu_conv_params* p);
@@ -1099,6 +1100,7 @@ static int conv_prepare(const dmu_conv_params* p, Maps* maps, ConvArgs& A, ConvG
 static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     // 3x3 stride-1 layers of 8x8 pixels and up: the persistent halo kernel (each input pixel fetched once per CTA);
     // impl 4 forces the per-tap kernel below
+    if (p->gn_fuse_mode == 3) return halo_launch(p, stream);      // statistics of the output in the halo kernel's epilogue
     if (!p->gn_fuse_mode) {
         if (p->impl == 5) {
             DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3, stride 1, pad 1, >= 8x8)");
@@ -1150,6 +1152,13 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
 
 // what dmu_conv2d_gn_fuse_supported answers: would dmu_conv2d run this layer on the per-tap kernel with the norm in its epilogue?
 static int conv_gn_fuse_tiles(const dmu_conv_params* p) {
+    if (p && p->gn_fuse && p->gn_fuse_mode == 3) {
+        if (p->impl == 1 || p->impl == 3 || p->impl == 4 || !halo_enabled()) return 0;
+        if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y) || (p->res.ptr && !nhwc_bf16_ok(p->res))) return 0;
+        if (p->Ck % 64 != 0 || p->Cj % 64 != 0 || encode_tiled_fn() == nullptr) return 0;
+        if (p->w_sk != 1 || p->w_st != p->Ck || p->w_sn != (int64_t)9 * p->Ck || !aligned16(p->w)) return 0;
+        return halo_stats_supported(p) ? 1 : 0;
+    }
     if (!p || !p->gn_fuse || (p->gn_fuse_mode != 1 && p->gn_fuse_mode != 2)) return 0;
     if (p->impl == 1 || p->impl == 3 || p->impl == 5 || p->gn_coef) return 0;
     if (p->w_dtype != DMU_BF16 || !nhwc_bf16_ok(p->x) || !nhwc_bf16_ok(p->y)) return 0;

@@ -273,6 +273,8 @@ class Engine:
         # ResBlock shortcut convolutions (forward and dgrad) on an auxiliary graph branch instead of inside the main chain
         # (DMU_AUX_LANES=0: A/B aid)
         self.aux_lanes = os.environ.get("DMU_AUX_LANES", "1") != "0"
+        # GroupNorm statistics of the large layers accumulated by the producing conv (dmu_conv_params.gn_fuse_mode 3); DMU_GN_STATS=0: A/B aid
+        self.fuse_gn_stats = os.environ.get("DMU_GN_STATS", "1") != "0"
         self._lib = None
 
     # ------------------------------------------------------------------ parameters
@@ -800,6 +802,7 @@ class _PlanBuilder:
         self.temb_join_pending = False
         self.prod = {}          # output address -> ConvParams of the forward conv that writes it (candidates for a fused GroupNorm)
         self.n_gn_fused = [0, 0]   # GroupNorms that ride in a conv epilogue: [forward, backward]
+        self.n_gn_stats = 0        # GroupNorms whose statistics the producing conv accumulates (the apply pass stays a launch)
 
     # ---- allocation helpers
     def act(self, H, W, Cc, want_grad=True) -> Buf:
@@ -935,6 +938,10 @@ class _PlanBuilder:
         prod = self.prod.pop((x.addr, x.pitch, x.C), None)
         if prod is not None and self._try_fuse(prod, p, 1):
             self.n_gn_fused[0] += 1
+        elif prod is not None and self.e.fuse_gn_stats and self._try_fuse(prod, p, 3):
+            # the large layers (persistent 3x3 kernel): the producer adds the raw sums in its epilogue, the norm is the apply pass alone
+            self.n_gn_stats += 1
+            self.plan.fwd.append((self.lib.dmu_gn_apply, (C.byref(p),)))
         else:
             self.plan.fwd.append((self.lib.dmu_gn_forward, (C.byref(p),)))
         return y, (x, y, sums, G, gamma_name, beta_name, silu)

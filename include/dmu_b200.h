@@ -173,6 +173,10 @@ typedef struct {
      *     beta) + add0 + add1, and gn->red receives PER-TILE channel sums [tiles][C][2] = (sum du, sum du*xhat) over the
      *     images of each pixel tile (tiles = the return value of dmu_conv2d_gn_fuse_supported; fold them with
      *     dmu_gn_param_grads, desc.count = tiles).  res / bias / temb must be NULL; gn->y is ignored.
+     *   gn_fuse_mode 3, statistics only (the large layers of the persistent 3x3 kernel, where an image spans many tiles): y is
+     *     written as usual and the raw sums of the stored (rounded) output are ADDED to gn->sums[n, g, 0..1] with atomics
+     *     (caller zeroes them, like dmu_gn_stats); the next layer's norm is then dmu_gn_apply alone - its statistics pass over
+     *     the tensor is gone.  Only gn->sums, N, H, W, C, G are read.
      * Any shape dmu_conv2d_gn_fuse_supported rejects is an error with gn_fuse set. */
     const void* gn_fuse;
     int32_t gn_fuse_mode;

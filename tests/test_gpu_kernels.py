@@ -713,3 +713,54 @@ def test_conv_gn_epilogue_backward(case, adds, silu):
     assert rel_l2(dg1, gq.grad) < 1e-2 and rel_l2(db1, bq.grad) < 1e-2
     # the fused path forms du from the fp32 accumulator, the stand-alone norm from the bf16-rounded dgrad output: 2e-3 apart at most
     assert rel_l2(dg1, dg0) < 4e-3 and rel_l2(db1, db0) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm statistics in the halo conv's epilogue
+@pytest.mark.parametrize("case", [(128, 32, 32, 64, 64, True, True), (32, 64, 64, 64, 64, False, True), (128, 32, 32, 64, 128, True, False),
+                                  (129, 32, 32, 64, 64, True, False)])
+def test_conv_gn_statistics_epilogue(case):
+    """dmu_conv_params.gn_fuse mode 3: the persistent 3x3 kernel adds the raw GroupNorm sums of its stored output to gn->sums; the
+    conv output is unchanged and dmu_gn_apply on those sums equals dmu_gn_forward (statistics pass + apply) and ATen."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams, GnParams
+    dev = torch.device("cuda:0")
+    dtype = torch.bfloat16
+    N, H, W, Ci, Co, has_res, has_temb = case
+    G = 32
+    g = torch.Generator().manual_seed(N + H + Co)
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev)
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / math.sqrt(Ci * 9)).to(dev)
+    bias = torch.randn(Co, generator=g).to(dev)
+    temb = torch.randn(N, Co, generator=g).to(dev) if has_temb else None
+    res = torch.randn(N, H, W, Co, generator=g).to(dev).to(dtype) if has_res else None
+    gamma, beta = (1 + 0.2 * torch.randn(Co, generator=g)).to(dev), (0.1 * torch.randn(Co, generator=g)).to(dev)
+    xh = ops.nchw_to_nhwc(x, dtype)
+    wk = _repack(w, False, dtype)
+    code = ops.dtype_code(xh)
+    lib = _abi.lib()
+
+    def run(fused):
+        y = torch.zeros(N, H, W, Co, device=dev, dtype=dtype)
+        a = torch.zeros(N, H, W, Co, device=dev, dtype=dtype)
+        sums = torch.zeros(N, G, 2, device=dev)
+        gp = GnParams(ops.t4_nhwc(y), ops.t4_nhwc(a), _null(), _null(), _null(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                      None, None, None, N, H, W, Co, G, 1, 1e-5, 0)
+        p = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(y), ops.t4_nhwc(res) if has_res else _null(), wk.data_ptr(), 9 * Ci, 1, Ci,
+                       bias.data_ptr(), temb.data_ptr() if has_temb else None, Co if has_temb else 0, N, H, W, Ci, H, W, Co, 3, 3, 1, 1, 0, code, 0, 0, None, 0)
+        if fused:
+            p.gn_fuse = C.cast(C.pointer(gp), C.c_void_p)
+            p.gn_fuse_mode = 3
+            if lib.dmu_conv2d_gn_fuse_supported(C.byref(p)) <= 0:
+                pytest.skip("the persistent 3x3 kernel does not take this layer by its own heuristics")
+        ops.conv2d_raw(p)
+        _abi.check((lib.dmu_gn_apply if fused else lib.dmu_gn_forward)(C.byref(gp), _stream()))
+        torch.cuda.synchronize()
+        return y, a, sums
+    y1, a1, s1 = run(True)
+    y0, a0, s0 = run(False)
+    assert torch.equal(y1, y0), "the conv output must not change"
+    assert rel_l2(s1, s0) < 1e-5, "raw sums"
+    yq = y1.float().permute(0, 3, 1, 2)
+    aref = F.silu(F.group_norm(yq, G, gamma, beta, eps=1e-5))
+    assert rel_l2(a1.float().permute(0, 3, 1, 2), aref) < TOL[dtype]
+    assert rel_l2(a1, a0) < 2e-3
