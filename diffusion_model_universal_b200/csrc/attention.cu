@@ -260,6 +260,11 @@ static int attn_launch(const dmu_attn_params* p, cudaStream_t s, bool bwd) {
     return check_launch(bwd ? "dmu_attn_bwd" : "dmu_attn_fwd");
 }
 
+namespace tc {      // attention_tc.cu
+int attn_tc_supported(const dmu_attn_params* p);
+int attn_tc_launch(const dmu_attn_params* p, cudaStream_t stream);
+}  // namespace tc
+
 }  // namespace dmu
 
 using namespace dmu;
@@ -268,6 +273,8 @@ extern "C" {
 
 int dmu_attn_fwd(const dmu_attn_params* p, dmu_stream_t stream) {
     if (int e = attn_check(p, "dmu_attn_fwd", false)) return e;
+    // bf16, head dim 32 / 64, S | 128: scores and probabilities on the tensor cores (attention_tc.cu)
+    if (tc::attn_tc_supported(p)) return tc::attn_tc_launch(p, as_stream(stream));
     return p->dtype == DMU_BF16 ? attn_launch<__nv_bfloat16>(p, as_stream(stream), false) : attn_launch<float>(p, as_stream(stream), false);
 }
 int dmu_attn_bwd(const dmu_attn_params* p, dmu_stream_t stream) {

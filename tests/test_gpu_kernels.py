@@ -403,7 +403,8 @@ def _groupnorm_case(N, H, W, C_, G, dtype, silu, one_call):
     assert rel_l2(dgam, gq.grad) < 1e-4 and rel_l2(dbet, bq.grad) < 1e-4
 
 
-@pytest.mark.parametrize("N,S,C_,heads", [(3, 16, 128, 4), (2, 64, 128, 4), (5, 1, 256, 4), (4, 4, 128, 4), (2, 16, 64, 4), (3, 4, 32, 4)])
+@pytest.mark.parametrize("N,S,C_,heads", [(3, 16, 128, 4), (2, 64, 128, 4), (5, 1, 256, 4), (4, 4, 128, 4), (2, 16, 64, 4), (3, 4, 32, 4),
+                                          (9, 64, 128, 4), (130, 1, 256, 4), (64, 4, 256, 4), (128, 16, 128, 4), (1, 128, 64, 2)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_attention_core(N, S, C_, heads, dtype):
     ops, _abi = _mods()
