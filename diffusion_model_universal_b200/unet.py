@@ -218,6 +218,7 @@ class Plan:
     def __init__(self):
         self.fwd, self.bwd = [], []
         self.bwd_parts = []     # bwd cut in three (head + up | bottleneck + down 4,3 | rest), for overlapping the DP all-reduce
+        self.bwd_tails = []     # per part: GroupNorm parameter-gradient fold + staging unpack (what completes the part's arena range)
         self.ranges = []        # gradient-arena range that is final after each part
         self.arena = None       # torch uint8 tensor keeping all plan buffers alive
         # static I/O buffers: every pointer in the recorded launches is fixed, so a plan can be replayed as a CUDA graph
@@ -275,6 +276,7 @@ class Engine:
         self.aux_lanes = os.environ.get("DMU_AUX_LANES", "1") != "0"
         # GroupNorm statistics of the large layers accumulated by the producing conv (dmu_conv_params.gn_fuse_mode 3); DMU_GN_STATS=0: A/B aid
         self.fuse_gn_stats = os.environ.get("DMU_GN_STATS", "1") != "0"
+        self._tail_stream = None
         self._lib = None
 
     # ------------------------------------------------------------------ parameters
@@ -535,7 +537,8 @@ class Engine:
     def _execute(self, plan: Plan, which: str):
         """Run plan.fwd / plan.bwd: eagerly the first time (warms every lazy one-time initialisation), then captured once
         into a CUDA graph and replayed — ~250 launches (and their tensor-map encodes) become one host call."""
-        oplist = plan.fwd if which == "fwd" else plan.fwd_z if which == "fwd_z" else plan.bwd if which == "bwd" else plan.bwd_parts[int(which[3:])]
+        oplist = (plan.fwd if which == "fwd" else plan.fwd_z if which == "fwd_z" else plan.bwd if which == "bwd" else
+                  plan.bwd_tails[int(which[4:])] if which.startswith("tail") else plan.bwd_parts[int(which[3:])])
         if self.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
             # the caller is capturing (TrainStep's whole-step graph): record the launches, lanes included, into ITS graph
             self._run_forked(oplist)
@@ -599,10 +602,27 @@ class Engine:
             self.zero_backward_buffers(plan)
         if between is None:
             self._execute(plan, "bwd")
-        else:
+        elif self.device.type != "cuda":
             for i in range(len(plan.bwd_parts)):
                 self._execute(plan, "bwd%d" % i)
+                if plan.bwd_tails[i]:
+                    self._execute(plan, "tail%d" % i)
                 between(*plan.ranges[i])      # gflat[lo:hi] is final: e.g. start its all-reduce while the next part runs
+        else:
+            # the tail of part i (GroupNorm parameter-gradient fold, staging unpack: ~45 us) and the caller's hook (the all-reduce of the
+            # range that tail completes) go to a second stream; the main stream continues with part i + 1 at once
+            cur = torch.cuda.current_stream(self.device)
+            if self._tail_stream is None:
+                self._tail_stream = torch.cuda.Stream(device=self.device)
+            ts = self._tail_stream
+            for i in range(len(plan.bwd_parts)):
+                self._execute(plan, "bwd%d" % i)
+                ts.wait_stream(cur)
+                with torch.cuda.stream(ts):
+                    if plan.bwd_tails[i]:
+                        self._execute(plan, "tail%d" % i)
+                    between(*plan.ranges[i])      # gflat[lo:hi] is final: e.g. start its all-reduce while the next part runs
+            cur.wait_stream(ts)
         return g
 
     # ------------------------------------------------------------------ plan construction
@@ -712,14 +732,16 @@ class Engine:
                 tab, n_un = self.unpack_tables[h]
                 if n_un:
                     tails[h].append((lib.dmu_repack_weights, (tab.data_ptr(), n_un, self.repack_max), 0))
-                lst.extend(tails[h])
+            # the parts form (data parallel): the tail of part h runs on a stream of its own, in front of that part's all-reduce,
+            # while the main stream already replays part h + 1 (Engine.run_backward)
+            plan.bwd_tails = [list(t) for t in tails]
             total = self.gflat.numel()
             plan.ranges = [(self.cuts[0], total), (self.cuts[1], self.cuts[0]), (0, self.cuts[1])]
             # One-graph form (no all-reduce between the parts): the tail of part h only touches part h's gradients, so it rides
             # on the side lane at the start of part h + 1 instead of standing between the two parts on lane 0.
             plan.bwd = []
             for h in range(3):
-                body = plan.bwd_parts[h][:len(plan.bwd_parts[h]) - len(tails[h])]
+                body = plan.bwd_parts[h]
                 if h == 0:
                     plan.bwd += body
                 else:
@@ -733,6 +755,13 @@ class Engine:
                 plan.bwd[i:i + 1] = [(fn, args, 1) for fn, args, _ in tails[2]]
             else:
                 plan.bwd = [op for op in plan.bwd if op[0] != "tails"] + tails[2]
+            # parts form: the last part's tail rides on its side lane in the same place (next to the embedding backward) instead of
+            # following the part on the tail stream; the other parts' tails stay in bwd_tails
+            marks = [i for i, op in enumerate(plan.bwd_parts[2]) if op[0] == "tails"]
+            if K == 1 and len(marks) == 1:
+                i = marks[0]
+                plan.bwd_parts[2][i:i + 1] = [(fn, args, 1) for fn, args, _ in tails[2]]
+                plan.bwd_tails[2] = []
             plan.bwd_parts = [[op for op in lst if op[0] != "tails"] for lst in plan.bwd_parts]
         plan.arena = arena
         plan.nbytes = nbytes
