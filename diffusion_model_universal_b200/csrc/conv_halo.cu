@@ -49,11 +49,18 @@ struct HaloArgs {
     // GroupNorm statistics of the OUTPUT (dmu_conv_params.gn_fuse_mode 3): raw (sum, sum of squares) of the stored values, added to
     // st_sums[n][g][0..1]; st_sh = log2(channels per group)
     float* st_sums; int st_G, st_sh;
+    int run, run_sh;     // tile schedule: runs of `run` = 1 << run_sh consecutive tiles per CTA, dealt round-robin
+    uint32_t pw_magic;   // floor(2^32 / PW) + 1 when every padded position * PW stays below 2^32 (floordiv_magic), else 0
 };
 
 constexpr int kMaxAStages = 4, kMaxWStages = 8;
 
 __device__ __forceinline__ int floordiv_dev(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+// floor(a / d) for a >= -2 d by one multiply: magic = floor(2^32 / d) + 1, exact while (a + 2 d) * d < 2^32 (checked by the host;
+// the per-tile integer divisions sat on the MMA warp's path between two tiles: ~150 clk each of a ~2.7k clk tile)
+__device__ __forceinline__ int floordiv_magic(int a, int d, uint32_t magic) {
+    return (int)(((uint64_t)(uint32_t)(a + 2 * d) * magic) >> 32) - 2;
+}
 
 // x * sigmoid(x) with one MUFU: sigmoid(x) = 0.5 * (1 + tanh(x / 2))
 __device__ __forceinline__ float silu_tanh(float t) {
@@ -87,15 +94,14 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j0 = blockIdx.y * NT;
     const int kblocks = 9 * P.chunks;
-    // tile schedule of this CTA: round-robin over the grid, or - when the epilogue accumulates GroupNorm statistics - one contiguous
-    // run of tiles, so that a thread's consecutive tiles stay inside one image for plane / 128 tiles
-    int t_first = blockIdx.x, t_step = gridDim.x, t_count = ((int)P.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    if (P.st_sums) {
-        const int per = (P.tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-        t_first = blockIdx.x * per; t_step = 1;
-        t_count = min(per, P.tiles - t_first);
-    }
-    if (t_count < 0) t_count = 0;
+    // tile schedule of this CTA: runs of P.run consecutive tiles, the runs dealt round-robin over the grid (run = 1: plain
+    // round-robin).  With GroupNorm statistics in the epilogue a thread's consecutive tiles should stay inside one image (the sums
+    // are flushed when the image changes), while the CTAs should still walk the tensor side by side (one contiguous range per CTA
+    // measured 15 % slower at 64 x 64: 148 distant DRAM streams).
+    const int run = P.run, run_sh = P.run_sh;
+    int t_count = 0;
+    for (int base = (int)blockIdx.x * run; base < P.tiles; base += (int)gridDim.x * run) t_count += min(run, P.tiles - base);
+    auto tile_at = [&](int i) { return (((i >> run_sh) * (int)gridDim.x + (int)blockIdx.x) << run_sh) + (i & (run - 1)); };
 
     pdl_trigger();
     if (threadIdx.x == 0) {
@@ -129,8 +135,8 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         int sa = 0, pa = 1, sw = 0, pw = 1;
         const uint32_t a_bytes = (uint32_t)(P.NR * P.PW) * 128u;
         for (int ti = 0; ti < t_count; ++ti) {
-            const int tile = t_first + ti * t_step;
-            const int L0 = floordiv_dev(tile * 128 - P.PW - 1, P.PW);
+            const int tile = tile_at(ti);
+            const int L0 = P.pw_magic ? floordiv_magic(tile * 128 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(tile * 128 - P.PW - 1, P.PW);
             for (int c = 0; c < P.chunks; ++c) {
                 mbar_wait(&a_empty[sa], pa);
                 if (elect_one()) {
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         if (P.resident) mbar_wait(&w_full[0], 0);
         int sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
         for (; it < t_count; ++it) {
-            const int tile = t_first + it * t_step;
+            const int tile = tile_at(it);
             const int buf = it & 1;
             long long* dbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && lane == 0) ? P.dbg + 8 * it : nullptr;
             if (dbg) dbg[0] = clock64();
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
             if (dbg) dbg[1] = clock64();
             const uint32_t d_tmem = tmem + (uint32_t)(buf * NT);
             const int Q0 = tile * 128;
-            const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
+            const int L0 = P.pw_magic ? floordiv_magic(Q0 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(Q0 - P.PW - 1, P.PW);
             const int base_off = Q0 - P.PW - 1 - L0 * P.PW;       // smem row of padded position (Q0 - PW - 1)
             for (int c = 0; c < P.chunks; ++c) {
                 mbar_wait(GN ? &a_ready[sa] : &a_full[sa], pa);
@@ -234,9 +240,9 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         int coef_key = -1;
         float sc[8], sh[8];
         for (int ti = 0; ti < t_count; ++ti) {
-            const int tile = t_first + ti * t_step;
+            const int tile = tile_at(ti);
             const int Q0 = tile * 128;
-            const int L0 = floordiv_dev(Q0 - P.PW - 1, P.PW);
+            const int L0 = P.pw_magic ? floordiv_magic(Q0 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(Q0 - P.PW - 1, P.PW);
             const int own0 = Q0 - L0 * P.PW;              // tile rows [own0, own0 + 128) are this tile's own output positions
             for (int c = 0; c < P.chunks; ++c) {
                 long long* tdbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tw == 0 && lane == 0 && ti < 64)
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         };
         int it = 0;
         for (; it < t_count; ++it) {
-            const int tile = t_first + it * t_step;
+            const int tile = tile_at(it);
             const int buf = it & 1;
             const int Q = tile * 128 + row;
             const int n = Q / plane, rem = Q - n * plane;
@@ -558,6 +564,17 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
     // even out the tail: every CTA gets the same number of tiles (+-1)
     const int rounds = (A.tiles + gx - 1) / gx;
     gx = (A.tiles + rounds - 1) / rounds;
+    if (A.st_sums) {
+        // runs of up to 8 consecutive tiles per CTA (the statistics are flushed when a thread's image changes), the longest run that
+        // keeps the busiest CTA within 4 % of the average
+        static const int run_max = [] { const char* e = getenv("DMU_HALO_STATS_RUN_SH"); return e ? atoi(e) : 3; }();      // A/B aid
+        for (int sh = run_max; sh >= 0; --sh) {
+            const int run = 1 << sh, runs = (A.tiles + run - 1) / run, per = (runs + gx - 1) / gx * run;
+            if ((int64_t)per * gx * 100 <= (int64_t)A.tiles * 104 || sh == 0) { A.run_sh = sh; break; }
+        }
+    }
+    A.run = 1 << A.run_sh;
+    if (((int64_t)A.N * A.PH * A.PW + 2 * A.PW + 256) * A.PW < (1ll << 32)) A.pw_magic = (uint32_t)((1ull << 32) / (uint64_t)A.PW) + 1u;
     dim3 grid(gx, ntiles_n);
     static bool attr_done = false;
     if (!attr_done) {
