@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(OUT_DIR, "libdmu_b200.so")
-SOURCES = ["process.cu", "norm.cu", "conv_simt.cu", "attention.cu", "attention_tc.cu", "conv_tc.cu", "conv_halo.cu", "conv_edge.cu", "conv_stem.cu", "conv_edge_tc.cu", "pipeline.cu"]
+SOURCES = ["process.cu", "norm.cu", "conv_simt.cu", "attention.cu", "attention_tc.cu", "conv_tc.cu", "conv_halo.cu", "conv_wgrad_halo.cu", "conv_edge.cu", "conv_stem.cu", "conv_edge_tc.cu", "pipeline.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -13,8 +13,8 @@
 //   * the kernel is persistent (one CTA per SM, static round-robin over tiles); when the whole filter bank of the CTA's
 //     output-channel tile fits (9 x Ck x NT bf16 <= ~144 KB) it is loaded once and stays resident, otherwise it streams
 //     through its own mbarrier ring.
-//   * warp roles: 4 epilogue warps, 1 TMA warp, 1 MMA warp; two TMEM accumulators so the epilogue of tile i overlaps the
-//     MMAs of tile i+1.
+//   * warp roles: 8 epilogue warps (two per TMEM lane quarter, half of the tile's channels each), 1 TMA warp, 1 MMA warp; two
+//     TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Positions of the padded space that are padding themselves are computed and dropped (efficiency H*W/((H+2)(W+2)): 89 %
 // at 32x32, 79 % at 16x16, 64 % at 8x8); below 8x8 the per-tap kernel (with split-K) is used instead.
 #include <stdlib.h>
@@ -78,8 +78,13 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// Epilogue warps: 8 in the plain kernel - warp w and warp w + 4 share the TMEM lane quarter w % 4 and each takes half of the tile's
+// channels.  Measured (ncu, 64->64 at 256x64x64): with 4 warps the epilogue of a tile (~1070 instructions per warp, one warp per
+// scheduler) took ~4.3k clk against ~2.0k clk of MMA issue, i.e. the kernel was bound by its epilogue, tensor pipe 30 %.
+template <bool GN> struct HaloCfg { static constexpr int kEpiWarps = GN ? 4 : 8; static constexpr int kThreads = (kEpiWarps + 2 + (GN ? 8 : 0)) * 32; };
+
 template <int NT, bool GN>
-__global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloArgs P) {
+__global__ void __launch_bounds__(HaloCfg<GN>::kThreads, 1) conv3x3_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloArgs P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t a_full[kMaxAStages], a_empty[kMaxAStages], w_full[kMaxWStages], w_empty[kMaxWStages];
@@ -89,6 +94,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
     __shared__ float s_bias[NT];
 
     constexpr int kWTile = NT * 128;                       // one (tap, chunk) weight block: NT rows x 64 bf16
+    constexpr int kEpiWarps = HaloCfg<GN>::kEpiWarps, kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kXformWarp0 = kEpiWarps + 2;
     uint8_t* smem_a = smem;
     uint8_t* smem_w = smem + (size_t)P.a_stages * P.a_stage_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,13 +113,13 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps * 32); }
         for (int i = 0; i < kMaxAStages; ++i) mbar_init(&a_ready[i], 8);
         fence_mbar_init();
         tma_prefetch_desc(&maps.a);
         tma_prefetch_desc(&maps.b);
     }
-    if (warp == 5) tmem_alloc(&s_tmem, 2 * NT);
+    if (warp == kMmaWarp) tmem_alloc(&s_tmem, 2 * NT);
     for (int i = threadIdx.x; i < NT; i += blockDim.x)       // parameters: not produced by the previous launch
         s_bias[i] = (P.bias && j0 + i < P.Cj) ? P.bias[j0 + i] : 0.f;
     tc_fence_before();
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
     pdl_wait();
 
     // TMA and MMA roles run as whole converged warps; the asynchronous instructions sit under elect_one() (tc_common.cuh)
-    if (warp == 4) {
+    if (warp == kTmaWarp) {
         // ------------------------------------------------ TMA producer
         if (P.resident && elect_one()) {
             mbar_arrive_expect_tx(&w_full[0], (uint32_t)(kblocks * kWTile));
@@ -138,7 +144,10 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
             const int tile = tile_at(ti);
             const int L0 = P.pw_magic ? floordiv_magic(tile * 128 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(tile * 128 - P.PW - 1, P.PW);
             for (int c = 0; c < P.chunks; ++c) {
+                long long* pdbg = (!GN && P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ti < 64 && c == 0 && lane == 0) ? P.dbg + 8 * 64 + 8 * ti : nullptr;
+                if (pdbg) pdbg[1] = clock64();
                 mbar_wait(&a_empty[sa], pa);
+                if (pdbg) pdbg[2] = clock64();
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&a_full[sa], a_bytes);
                     uint8_t* dst = smem_a + (size_t)sa * P.a_stage_bytes;
@@ -149,6 +158,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
                     }
                 }
                 __syncwarp();
+                if (pdbg) pdbg[3] = clock64();
                 if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
                 if (!P.resident) {
                     for (int t = 0; t < 9; ++t) {
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         // ------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
         if (P.resident) mbar_wait(&w_full[0], 0);
@@ -181,6 +191,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
             const int L0 = P.pw_magic ? floordiv_magic(Q0 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(Q0 - P.PW - 1, P.PW);
             const int base_off = Q0 - P.PW - 1 - L0 * P.PW;       // smem row of padded position (Q0 - PW - 1)
             for (int c = 0; c < P.chunks; ++c) {
+                if (!GN && dbg && c == 0) dbg[8 * 64] = clock64();      // (the slots of the transform warps are free in the plain kernel)
                 mbar_wait(GN ? &a_ready[sa] : &a_full[sa], pa);
                 tc_fence_after();
                 if (dbg && c == 0) dbg[2] = clock64();
@@ -224,8 +235,8 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
             __syncwarp();
             if (dbg) dbg[3] = clock64();
         }
-    } else if (GN && warp >= 6) {
-        // ------------------------------------------------ GroupNorm(+SiLU) transform warps 6..13
+    } else if (GN && warp >= kXformWarp0) {
+        // ------------------------------------------------ GroupNorm(+SiLU) transform warps (the eight after the MMA warp)
         // Tile row r is padded-flat position L0 * PW + r.  Rows that are padding (TMA zero fill) stay zero; every other row is
         // normalised in place: thread = one 16-byte chunk (8 channels) of one pixel, the chunk's logical position follows the
         // 128-byte swizzle (physical chunk ^ (row & 7); the stage base is 1024-byte aligned).
@@ -234,7 +245,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
         // flight.  The transform of a tile is a latency chain (LDS -> affine -> SiLU -> STS) that the MMA warp waits for, so it
         // is spread over rows and unrolled rather than made instruction-lean only.  The affine part runs in fp32, SiLU on the
         // bf16x2-rounded pair: 0.5 t (1 + tanh(0.5 t)) = HMUL2 + MUFU + HFMA2.
-        const int tw = warp - 6;                          // 0..7
+        const int tw = warp - kXformWarp0;                // 0..7
         const int j = lane & 7, pp = lane >> 3;           // logical chunk, pixel phase 0..3
         int sa = 0, pa = 0;
         int coef_key = -1;
@@ -311,32 +322,38 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
             }
         }
     } else {
-        // ---------------------------------------------------- epilogue warps 0..3: thread = one output position (TMEM lane)
-        const int row = threadIdx.x;          // 0..127
+        // ---------------------------------------------------- epilogue warps: thread = one output position (TMEM lane) x CH channels
+        constexpr int CH = NT / (kEpiWarps / 4);             // channels per thread: the tile's channels split over warp w and warp w + 4
+        constexpr int kPre = CH < 64 ? CH : 64;               // residual channels prefetched into registers
+        const int row = threadIdx.x & 127;
+        const int cb = (int)(threadIdx.x >> 7) * CH;          // this thread's first channel inside the tile
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const int plane = P.PH * P.PW;
         // GroupNorm statistics of the output (st_sums, NT = 64): every thread keeps the sums of its rows per channel PAIR (a group is
         // >= 2 channels) for the image it is in; only when some lane of the warp moves on to another image - every plane / 128
         // tiles, the CTA's tiles being one contiguous run - are the warp's sums reduced and added to st_sums.  (Reducing every tile
-        // cost the 64 x 64 layers 40 us each: the four epilogue warps then no longer keep up with the MMA stream.)
-        float acc_s[(NT == 64 && !GN) ? 32 : 1], acc_q[(NT == 64 && !GN) ? 32 : 1];
+        // cost the 64 x 64 layers 40 us each: the epilogue warps then no longer keep up with the MMA stream.)
+        constexpr int kPairs = (NT == 64 && !GN) ? CH / 2 : 1;
+        float acc_s[kPairs], acc_q[kPairs];
         int acc_img = -1;
 #pragma unroll
-        for (int i = 0; i < (int)(sizeof(acc_s) / sizeof(float)); ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+        for (int i = 0; i < kPairs; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
         auto stats_flush = [&]() {
             if constexpr (NT == 64 && !GN) {
                 // the warp's lanes hold sums of at most two images.  A transposing butterfly - at offset o a lane keeps the half of
-                // its values its bit o selects and adds the partner's copy of that half - leaves lane L with channel pair L's
-                // (sum, sum of squares) over the warp; the lanes of a group then combine and one of them adds to st_sums.
+                // its values its bit o selects and adds the partner's copy of that half - leaves lane L with channel pair
+                // L % kPairs's (sum, sum of squares) over the lanes that differ from L in the bits walked (all of them once the
+                // halves of the warp are added, kPairs < 32); the lanes of a group then combine and one of them adds to st_sums.
                 const int nA = __reduce_min_sync(0xffffffffu, acc_img >= 0 ? acc_img : 0x7fffffff);
                 const int nB = __reduce_max_sync(0xffffffffu, acc_img);
 #pragma unroll 1
                 for (int im = nA; im <= nB && nB >= 0; ++im) {
                     const bool mine = acc_img == im;
-                    float w[64];
+                    float w[2 * kPairs];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { w[2 * i] = mine ? acc_s[i] : 0.f; w[2 * i + 1] = mine ? acc_q[i] : 0.f; }
+                    for (int i = 0; i < kPairs; ++i) { w[2 * i] = mine ? acc_s[i] : 0.f; w[2 * i + 1] = mine ? acc_q[i] : 0.f; }
 #pragma unroll
-                    for (int half = 32; half >= 2; half >>= 1) {
+                    for (int half = kPairs; half >= 2; half >>= 1) {
                         const bool up = (lane & (half >> 1)) != 0;
 #pragma unroll
                         for (int i = 0; i < half; ++i) {
@@ -346,19 +363,24 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
                         }
                     }
                     float su = w[0], sq = w[1];
+#pragma unroll
+                    for (int o = kPairs; o < 32; o <<= 1) {      // lanes that hold the same pair
+                        su += __shfl_xor_sync(0xffffffffu, su, o);
+                        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    }
                     const int ppg = 1 << (P.st_sh - 1);          // channel pairs per group
                     for (int o = 1; o < ppg; o <<= 1) {
                         su += __shfl_xor_sync(0xffffffffu, su, o);
                         sq += __shfl_xor_sync(0xffffffffu, sq, o);
                     }
-                    if ((lane & (ppg - 1)) == 0) {
-                        float* sp = P.st_sums + ((int64_t)im * P.st_G + ((j0 + 2 * lane) >> P.st_sh)) * 2;
+                    if ((lane & (ppg - 1)) == 0 && lane < kPairs) {
+                        float* sp = P.st_sums + ((int64_t)im * P.st_G + ((j0 + cb + 2 * lane) >> P.st_sh)) * 2;
                         atomicAdd(sp, su);
                         atomicAdd(sp + 1, sq);
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+                for (int i = 0; i < kPairs; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
                 acc_img = -1;
             }
         };
@@ -375,14 +397,14 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
                 if (__any_sync(0xffffffffu, valid && acc_img >= 0 && acc_img != n)) stats_flush();
                 if (valid) acc_img = n;
             }
-            __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0;
-            const __nv_bfloat16* rp = (P.res && valid) ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 : nullptr;
-            const float* tp = (P.temb && valid) ? P.temb + (int64_t)n * P.temb_pitch + j0 : nullptr;
-            // prefetch the first 64 channels of the residual (the loads fly while the MMAs of this tile run)
-            uint4 rpre[8];
+            __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)ho * P.y_sh + (int64_t)wo * P.y_sw + j0 + cb;
+            const __nv_bfloat16* rp = (P.res && valid) ? P.res + (int64_t)n * P.r_sn + (int64_t)ho * P.r_sh + (int64_t)wo * P.r_sw + j0 + cb : nullptr;
+            const float* tp = (P.temb && valid) ? P.temb + (int64_t)n * P.temb_pitch + j0 + cb : nullptr;
+            // prefetch this thread's (first 64) residual channels: the loads fly while the MMAs of this tile run
+            uint4 rpre[kPre / 8];
             if (rp) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) rpre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+                for (int i = 0; i < kPre / 8; ++i) rpre[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
             }
             long long* dbg = (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && threadIdx.x == 0) ? P.dbg + 8 * it : nullptr;
             if (dbg) dbg[4] = clock64();
@@ -390,27 +412,29 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
             tc_fence_after();
             if (dbg) dbg[5] = clock64();
             if (P.narrow) {
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * NT), v);
-                tmem_ld_wait();
-                if (valid) {
-                    float* op = P.yn + (int64_t)n * P.n_sn + (int64_t)ho * P.n_sh + (int64_t)wo * P.n_sw;
+                if (cb == 0) {
+                    float v[32];
+                    tmem_ld32(tmem + lane_base + (uint32_t)(buf * NT), v);
+                    tmem_ld_wait();
+                    if (valid) {
+                        float* op = P.yn + (int64_t)n * P.n_sn + (int64_t)ho * P.n_sh + (int64_t)wo * P.n_sw;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < P.narrow) op[(int64_t)j * P.n_sc] = v[j] + s_bias[j];
+                        for (int j = 0; j < 4; ++j)
+                            if (j < P.narrow) op[(int64_t)j * P.n_sc] = v[j] + s_bias[j];
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[buf]);
                 continue;
             }
 #pragma unroll
-            for (int c = 0; c < NT; c += 32) {
+            for (int c = 0; c < CH; c += 32) {
                 float v[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * NT + c), v);
+                tmem_ld32(tmem + lane_base + (uint32_t)(buf * NT + cb + c), v);
                 tmem_ld_wait();
                 if (valid) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += s_bias[c + i];
+                    for (int i = 0; i < 32; ++i) v[i] += s_bias[cb + c + i];
                     if (tp) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
@@ -422,7 +446,7 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
                             float r8[8];
-                            if (c < 64) {
+                            if (c < kPre) {
                                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rpre[(c + i) >> 3]);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h2[k]); r8[2 * k] = f.x; r8[2 * k + 1] = f.y; }
@@ -450,13 +474,230 @@ __global__ void __launch_bounds__(GN ? 448 : 192, 1) conv3x3_halo_kernel(const _
             }
             if (dbg) dbg[6] = clock64();
             tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);      // 128 arrivals release the accumulator to the MMA warp
+            mbar_arrive(&acc_empty[buf]);      // every epilogue thread arrives: the accumulator goes back to the MMA warp
         }
         if (P.st_sums) stats_flush();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, 2 * NT);
+    if (warp == kMmaWarp) tmem_dealloc(tmem, 2 * NT);
+}
+
+// ================================================================================================ 4x4 stride-2 transposed gather
+// ConvTranspose2d(k = 4, s = 2, p = 1) and the input gradient of Conv2d(k = 4, s = 2, p = 1) (dmu_conv_params.gather = 1):
+//   y[n, 2 th + a, 2 tw + b, :] = sum over the four taps (r, s) with r = 1 - a (mod 2), s = 1 - b (mod 2) of x[n, th + dh, tw + dw, :] W[r][s],
+//   dh = (a + 1 - r) / 2 in {-1, 0, 1}.
+// The per-tap kernel runs this as four launches' worth of CTAs (one per output parity class) whose k-loops are 4 k-blocks long: at
+// 256x32x32 -> 64x64 that is 8192 CTAs bound by their fixed cost (190 us, 0.13 of the tensor peak).  Here the tile is 128 consecutive
+// positions of the zero-padded flat INPUT space, in which the nine (dh, dw) are pure shifts of ONE halo tile (as in the 3x3 kernel
+// above), the sixteen 64 x 64 filter blocks stay resident in shared memory, and the four parity classes are four TMEM accumulators
+// of the same tile: 64 MMAs per 128 input positions = 512 output pixels, every input pixel fetched once per CTA.
+// Epilogue: thread = input position x output row parity a; it writes the two horizontally adjacent output pixels (b = 0, 1).
+struct HaloTArgs {
+    int N, H, W, Ck, Cj;            // H, W: input extent (output 2H x 2W)
+    int PW, PH, NR, tiles;
+    int a_stage_bytes, a_stages;
+    __nv_bfloat16* y; int64_t y_sn, y_sh, y_sw;
+    const float* bias;
+    uint32_t pw_magic;
+};
+
+__global__ void __launch_bounds__(320, 1) conv4x4t_halo_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloTArgs P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t a_full[kMaxAStages], a_empty[kMaxAStages], w_full, acc_full[2], acc_empty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_bias[64];
+    constexpr int kWTile = 64 * 128, kEpiWarps = 8, kTmaWarp = 8, kMmaWarp = 9;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_w = smem + (size_t)P.a_stages * P.a_stage_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j0 = blockIdx.y * 64;
+    int t_count = 0;
+    for (int t = blockIdx.x; t < P.tiles; t += gridDim.x) ++t_count;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        mbar_init(&w_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps * 32); }
+        fence_mbar_init();
+        tma_prefetch_desc(&maps.a);
+        tma_prefetch_desc(&maps.b);
+    }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bias[i] = (P.bias && j0 + i < P.Cj) ? P.bias[j0 + i] : 0.f;
+    // This kernel takes ALL 512 TMEM columns of its SM (2 buffers x 4 parity classes x 64).  Under programmatic dependent launch a
+    // CTA of the previous kernel may still be on the SM and may not have allocated yet, and a CTA of the next kernel may arrive and
+    // allocate before this one: either would leave two CTAs waiting for each other.  So: allocate only once the previous grid has
+    // completed (its columns are free), and let the dependents in only after the allocation.
+    pdl_wait();
+    if (warp == kMmaWarp) tmem_alloc(&s_tmem, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    pdl_trigger();
+
+    if (warp == kTmaWarp) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&w_full, (uint32_t)(16 * kWTile));
+            for (int t = 0; t < 16; ++t) tma_load_2d(smem_w + (size_t)t * kWTile, &maps.b, &w_full, t * P.Ck, j0);
+            int sa = 0, pa = 1;
+            const uint32_t a_bytes = (uint32_t)(P.NR * P.PW) * 128u;
+            for (int ti = 0; ti < t_count; ++ti) {
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const int L0 = P.pw_magic ? floordiv_magic(tile * 128 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(tile * 128 - P.PW - 1, P.PW);
+                mbar_wait(&a_empty[sa], pa);
+                mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+                uint8_t* dst = smem_a + (size_t)sa * P.a_stage_bytes;
+                int n = floordiv_dev(L0, P.PH), hp = L0 - n * P.PH;
+                for (int i = 0; i < P.NR; ++i) {
+                    tma_load_4d(dst + (size_t)i * P.PW * 128, &maps.a, &a_full[sa], 0, -1, hp - 1, n);
+                    if (++hp == P.PH) { hp = 0; ++n; }
+                }
+                if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kMmaWarp) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+            mbar_wait(&w_full, 0);
+            const uint32_t w_base = smem_u32(smem_w);
+            int sa = 0, pa = 0;
+            for (int it = 0; it < t_count; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int buf = it & 1;
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                const int Q0 = tile * 128;
+                const int L0 = P.pw_magic ? floordiv_magic(Q0 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(Q0 - P.PW - 1, P.PW);
+                const int base_off = Q0 - P.PW - 1 - L0 * P.PW;       // halo row of the (dh, dw) = (-1, -1) neighbour of position Q0
+                mbar_wait(&a_full[sa], pa);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes) + (uint32_t)base_off * 128u;
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph) {
+                    const int a = ph >> 1, b = ph & 1;
+                    const uint32_t d_tmem = tmem + (uint32_t)(buf * 256 + ph * 64);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        // parity 0: r = 1 (dh = 0), r = 3 (dh = -1); parity 1: r = 0 (dh = +1), r = 2 (dh = 0)
+                        const int r = (a ? 0 : 1) + 2 * (q >> 1), sx = (b ? 0 : 1) + 2 * (q & 1);
+                        const int dh = (a + 1 - r) / 2, dw = (b + 1 - sx) / 2;      // exact: the numerators are even
+                        const uint64_t da = smem_desc_sw128(a_base + (uint32_t)((dh + 1) * P.PW + (dw + 1)) * 128u, 16, 1024);
+                        const uint64_t db = smem_desc_sw128(w_base + (uint32_t)((r * 4 + sx) * kWTile), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (q | k) != 0);
+                    }
+                }
+                umma_commit(&a_empty[sa]);
+                umma_commit(&acc_full[buf]);
+                if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------- epilogue warps 0..7: thread = input position x output row parity
+        const int row = threadIdx.x & 127, a = (int)(threadIdx.x >> 7);
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int plane = P.PH * P.PW;
+        for (int it = 0; it < t_count; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int buf = it & 1;
+            const int Q = tile * 128 + row;
+            const int n = Q / plane, rem = Q - n * plane;
+            const int hp = rem / P.PW, wp = rem - hp * P.PW;
+            const bool valid = n < P.N && hp >= 1 && hp <= P.H && wp >= 1 && wp <= P.W;
+            // the two output pixels (2 th + a, 2 tw), (2 th + a, 2 tw + 1)
+            __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)(2 * (hp - 1) + a) * P.y_sh + (int64_t)(2 * (wp - 1)) * P.y_sw + j0;
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 128; c += 32) {        // columns: parity class (a, b = c / 64) x 64 channels
+                float v[32];
+                tmem_ld32(tmem + lane_base + (uint32_t)(buf * 256 + a * 128 + c), v);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += s_bias[(c & 63) + i];
+                    __nv_bfloat16* op = yp + (int64_t)(c >> 6) * P.y_sw + (c & 63);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(op + i, v + i);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem, 512);
+}
+
+static int halo_t_geometry(const dmu_conv_params* p, HaloTArgs& A) {
+    memset(&A, 0, sizeof(A));
+    A.N = p->N; A.H = p->Hi; A.W = p->Wi; A.Ck = p->Ck; A.Cj = p->Cj;
+    A.PW = A.W + 2; A.PH = A.H + 2;
+    A.NR = 3 + (129 + A.PW - 1) / A.PW;
+    A.tiles = (int)(((int64_t)A.N * A.PH * A.PW + 127) / 128);
+    A.a_stage_bytes = ((A.NR * A.PW * 128) + 1023) / 1024 * 1024;
+    const int budget = 214 * 1024, wbytes = 16 * 64 * 128;
+    A.a_stages = (budget - wbytes) / A.a_stage_bytes;
+    if (A.a_stages > kMaxAStages) A.a_stages = kMaxAStages;
+    if (A.a_stages < 2) return -1;
+    return A.a_stages * A.a_stage_bytes + wbytes + 1024;
+}
+
+int halo_t_supported(const dmu_conv_params* p, int force) {
+    if (p->gather != 1 || p->R != 4 || p->S != 4 || p->stride != 2 || p->pad != 1) return 0;
+    if (p->Ho != 2 * p->Hi || p->Wo != 2 * p->Wi) return 0;
+    if (p->Hi < 4 || p->Wi < 4 || p->Wi + 2 > 256) return 0;
+    if (p->Ck != 64 || p->Cj % 64 != 0) return 0;             // the sixteen filter blocks of one 64-channel chunk stay resident
+    if (p->res.ptr || p->temb || p->gn_coef || p->gn_fuse_mode) return 0;
+    if (p->w_sk != 1 || p->w_st != p->Ck || p->w_sn != (int64_t)16 * p->Ck) return 0;
+    if ((int64_t)p->N * (p->Hi + 2) * (p->Wi + 2) >= (1ll << 31) - 4096) return 0;
+    HaloTArgs A;
+    if (halo_t_geometry(p, A) <= 0) return 0;
+    if (force) return 1;
+    static const int enabled = [] { const char* e = getenv("DMU_HALO_T"); return e ? atoi(e) : 1; }();
+    // a CTA loads 128 KB of filters before its first tile: measured worth it from about two tiles per CTA (training step: 324 tiles yes, 100 no)
+    static const int min_tiles = [] { const char* e = getenv("DMU_HALO_T_MIN_TILES"); return e ? atoi(e) : 300; }();
+    return enabled && A.tiles >= min_tiles ? 1 : 0;
+}
+
+int halo_t_launch(const dmu_conv_params* p, cudaStream_t stream) {
+    HaloMaps maps;
+    HaloTArgs A;
+    const int smem = halo_t_geometry(p, A);
+    DMU_REQUIRE(smem > 0 && smem <= 224 * 1024, "dmu_conv2d/halo_t: tile does not fit shared memory");
+    {
+        const uint64_t dims[4] = {(uint64_t)p->Ck, (uint64_t)p->Wi, (uint64_t)p->Hi, (uint64_t)p->N};
+        const uint64_t str[4] = {1, (uint64_t)p->x.sw, (uint64_t)p->x.sh, (uint64_t)p->x.sn};
+        const uint32_t box[4] = {64, (uint32_t)A.PW, 1, 1};
+        if (int rc = make_map_bf16(&maps.a, p->x.ptr, 4, dims, str, box, "dmu_conv2d/halo_t")) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)16 * p->Ck, (uint64_t)p->Cj};
+        const uint64_t str[2] = {1, (uint64_t)p->w_sn};
+        const uint32_t box[2] = {64, 64};
+        if (int rc = make_map_bf16(&maps.b, p->w, 2, dims, str, box, "dmu_conv2d/halo_t weights")) return rc;
+    }
+    A.y = reinterpret_cast<__nv_bfloat16*>(p->y.ptr); A.y_sn = p->y.sn; A.y_sh = p->y.sh; A.y_sw = p->y.sw;
+    A.bias = p->bias;
+    if (((int64_t)A.N * A.PH * A.PW + 2 * A.PW + 256) * A.PW < (1ll << 32)) A.pw_magic = (uint32_t)((1ull << 32) / (uint64_t)A.PW) + 1u;
+    const int ny = p->Cj / 64;
+    int gx = sm_count() / ny;
+    if (gx < 1) gx = 1;
+    if (gx > A.tiles) gx = A.tiles;
+    const int rounds = (A.tiles + gx - 1) / gx;
+    gx = (A.tiles + rounds - 1) / rounds;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv4x4t_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        attr_done = true;
+    }
+    cudaError_t e = launch_pdl(conv4x4t_halo_kernel, dim3(gx, ny), dim3(320), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
+    if (e != cudaSuccess) return fail("dmu_conv2d/halo_t: launch failed: %s", cudaGetErrorString(e));
+    return check_launch("dmu_conv2d/halo_t");
 }
 
 static int pick_smem(const dmu_conv_params* p, int NT, HaloArgs& A) {
@@ -588,11 +829,11 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
     if (p->gn_coef) {
         A.gn_coef = p->gn_coef; A.gn_silu = p->gn_silu;
         A.a_out = reinterpret_cast<__nv_bfloat16*>(p->a_out.ptr); A.a_sn = p->a_out.sn; A.a_sh = p->a_out.sh; A.a_sw = p->a_out.sw;
-        e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64, true>, grid, dim3(448), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
-                     : launch_pdl(conv3x3_halo_kernel<128, true>, grid, dim3(448), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
+        e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64, true>, grid, dim3(HaloCfg<true>::kThreads), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
+                     : launch_pdl(conv3x3_halo_kernel<128, true>, grid, dim3(HaloCfg<true>::kThreads), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
     } else {
-        e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64, false>, grid, dim3(192), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
-                     : launch_pdl(conv3x3_halo_kernel<128, false>, grid, dim3(192), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
+        e = NT == 64 ? launch_pdl(conv3x3_halo_kernel<64, false>, grid, dim3(HaloCfg<false>::kThreads), (size_t)smem, stream, dim3(1, 1, 1), maps, A)
+                     : launch_pdl(conv3x3_halo_kernel<128, false>, grid, dim3(HaloCfg<false>::kThreads), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
     }
     if (e != cudaSuccess) return fail("dmu_conv2d/halo: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/halo");

@@ -561,7 +561,7 @@ int dmu_conv2d_wgrad(const dmu_wgrad_params* p, dmu_stream_t stream) {
     DMU_REQUIRE(p->p.ptr && p->q.ptr && p->dw, "dmu_conv2d_wgrad: null pointer");
     DMU_REQUIRE(p->N > 0 && p->Hp > 0 && p->Wp > 0 && p->Ca > 0 && p->Hq > 0 && p->Wq > 0 && p->Cb > 0, "dmu_conv2d_wgrad: non-positive dims");
     DMU_REQUIRE(p->R > 0 && p->S > 0 && p->stride > 0 && p->pad >= 0, "dmu_conv2d_wgrad: bad filter geometry");
-    if (p->impl == 2) {
+    if (p->impl == 2 || p->impl == 5) {      // 5: the halo weight-gradient kernel wherever its geometry allows (tests), else as 2
         DMU_REQUIRE(dmu_wgrad_tc_supported(p), "dmu_conv2d_wgrad: impl=tcgen05 requested for an unsupported shape");
         return dmu_wgrad_tc(p, stream);
     }

@@ -868,6 +868,9 @@ long long* g_debug_buffer = nullptr;
 int halo_supported(const dmu_conv_params* p, int force);
 int halo_stats_supported(const dmu_conv_params* p);
 int halo_launch(const dmu_conv_params* p, cudaStream_t stream);
+// conv_halo.cu: 4x4 stride-2 transposed gather (ConvTranspose2d upsampling, input gradient of the 4x4 stride-2 downsampling conv)
+int halo_t_supported(const dmu_conv_params* p, int force);
+int halo_t_launch(const dmu_conv_params* p, cudaStream_t stream);
 // conv_stem.cu: few-channel input (stem fprop, head dgrad)
 int stem_supported(const dmu_conv_params* p);
 int stem_launch(const dmu_conv_params* p, cudaStream_t stream);
@@ -1103,13 +1106,15 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     if (p->gn_fuse_mode == 3) return halo_launch(p, stream);      // statistics of the output in the halo kernel's epilogue
     if (!p->gn_fuse_mode) {
         if (p->impl == 5) {
-            DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3, stride 1, pad 1, >= 8x8)");
+            if (nhwc_bf16_ok(p->x) && nhwc_bf16_ok(p->y) && p->w_dtype == DMU_BF16 && aligned16(p->w) && halo_t_supported(p, 1)) return halo_t_launch(p, stream);
+            DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3 stride 1 pad 1 of >= 8x8, or 4x4 stride 2 pad 1 transposed with 64 input channels)");
             return halo_launch(p, stream);
         }
         if (narrow_head_supported(p)) return halo_launch(p, stream);
         if (p->gn_coef) return halo_launch(p, stream);
         if (p->impl != 4 && stem_supported(p)) return stem_launch(p, stream);
         if (p->impl != 4 && halo_enabled() && halo_supported(p, 0)) return halo_launch(p, stream);
+        if (p->impl != 4 && halo_enabled() && halo_t_supported(p, 0)) return halo_t_launch(p, stream);
     }
     Maps maps;
     ConvArgs A;
@@ -1330,7 +1335,12 @@ static int wgrad_supported(const dmu_wgrad_params* p) {
     return 1;
 }
 
+// conv_wgrad_halo.cu: 3x3 stride-1 layers with many position tiles (both operands read once per tap group)
+int wgrad_halo_supported(const dmu_wgrad_params* p, int force);
+int wgrad_halo_launch(const dmu_wgrad_params* p, cudaStream_t stream);
+
 static int wgrad_launch(const dmu_wgrad_params* p, cudaStream_t stream) {
+    if (wgrad_halo_supported(p, p->impl == 5 ? 1 : 0)) return wgrad_halo_launch(p, stream);
     Maps maps;
     WgradArgs A;
     memset(&A, 0, sizeof(A));

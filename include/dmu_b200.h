@@ -197,7 +197,10 @@ int64_t dmu_conv2d_workspace_bytes(void);
  *   dw[a*dw_sa + b*dw_sb + (r*S+s)*dw_st] += sum_{n,po,qo} p[n,po,qo,a] * q[n, po*stride-pad+r, qo*stride-pad+s, b]
  * p = tensor on the strided (small) grid, q = gathered tensor.  fp32 output,
  * accumulated with atomics (caller zeroes dw).  Optionally also
- * dbias[a] += sum p[.,.,.,a]. */
+ * dbias[a] += sum p[.,.,.,a].
+ * impl: 0 = auto, 1 = SIMT, 2 = tcgen05 (auto between the per-tap kernel and, for 3x3 stride-1 layers with many pixel
+ * tiles, the halo kernel that reads p and q once per tap group), 3 = narrow-operand (3-channel) kernels, 5 = tcgen05 with the
+ * halo kernel wherever its geometry allows. */
 typedef struct {
     dmu_tensor4 p;
     dmu_tensor4 q;

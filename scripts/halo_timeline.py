@@ -21,5 +21,9 @@ def run(N, H, Ci, Co, res=False, gn=False):
     print(f"--- N={N} H={H} {Ci}->{Co} res={res}: tiles of CTA 0 = {len(d)}")
     print("tile  mma:start  acc_empty_ok  a_full_ok  mmas_issued | epi:start_wait  acc_full_ok  stores_done")
     for i in range(len(d)):
-        print(f"{i:4d} " + " ".join(f"{int(v) - t0:10d}" for v in d[i, :7]) + ("   | transform: wait_start a_full_ok body_done arrived " + " ".join(f"{int(v) - t0:8d}" for v in tr[i, :4]) if i < len(tr) else ""))
-run(128, 32, 64, 64); run(128, 32, 64, 64, gn=True); run(256, 64, 64, 64, gn=True)
+        print(f"{i:4d} " + " ".join(f"{int(v) - t0:10d}" for v in d[i, :7]) + ("   | mma:before_a_full_wait  tma:wait_a_empty a_empty_ok loads_issued " + " ".join(f"{int(v) - t0:8d}" for v in tr[i, :4]) if i < len(tr) else ""))
+cases = sys.argv[1] if len(sys.argv) > 1 else "gn"
+if cases == "gn":
+    run(128, 32, 64, 64); run(128, 32, 64, 64, gn=True); run(256, 64, 64, 64, gn=True)
+else:
+    run(128, 32, 64, 64); run(256, 64, 64, 64); run(256, 64, 64, 64, res=True)

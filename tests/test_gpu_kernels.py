@@ -205,6 +205,91 @@ def _conv_case(case, dtype, impl, ws=None):
         assert rel_l2(db - 1, dyq.sum(dim=(0, 2, 3))) < 5e-5, "dbias"
 
 
+HALO_T_CASES = [
+    # N, H, W (input), Co
+    (256, 16, 16, 64),     # 648 tiles: several per CTA
+    (128, 16, 16, 64),     # the training step's up4 / down0-dgrad shape
+    (3, 32, 32, 64),       # tiles straddle images
+    (5, 8, 8, 128),        # two output-channel tiles
+    (1, 4, 12, 64),        # non-square, one partial tile
+]
+
+
+@pytest.mark.parametrize("case", HALO_T_CASES)
+def test_conv_transposed_halo(case):
+    """impl 5 on a 4x4 stride-2 pad-1 transposed gather with 64 input channels = the halo kernel of that read pattern (input
+    positions of the padded flat space as the tile, four output parity classes as four accumulators), in both of its uses:
+    nn.ConvTranspose2d forward (+bias) and the input gradient of the 4x4 stride-2 nn.Conv2d; against ATen on the same bf16
+    operands, and against the per-tap kernel (impl 4)."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams
+    N, H, W, Co = case
+    Ci = 64
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(N * 100 + H + Co)
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev)
+    xh = ops.nchw_to_nhwc(x, torch.bfloat16)
+    xq = xh.float().permute(0, 3, 1, 2)
+    code = ops.dtype_code(xh)
+    # (a) ConvTranspose2d: weight [Ci][Co][4][4]
+    wt = (torch.randn(Ci, Co, 4, 4, generator=g) / math.sqrt(Ci * 4)).to(dev)
+    bias = torch.randn(Co, generator=g).to(dev)
+    wk = _repack(wt, True, torch.bfloat16)
+    ref = F.conv_transpose2d(xq, wt.to(torch.bfloat16).float(), bias, stride=2, padding=1)
+    outs = {}
+    for impl in (5, 4):
+        y_full = torch.zeros(N, 2 * H, 2 * W, Co + 16, device=dev, dtype=torch.bfloat16)      # written into a channel slice
+        p = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(y_full, 8, Co), _null(), wk.data_ptr(), 16 * Ci, 1, Ci, bias.data_ptr(), None, 0,
+                       N, H, W, Ci, 2 * H, 2 * W, Co, 4, 4, 2, 1, 1, code, impl, 0, None, 0)
+        ops.conv2d_raw(p)
+        got = y_full[..., 8:8 + Co].float().permute(0, 3, 1, 2)
+        assert rel_l2(got, ref) < TOL[torch.bfloat16], f"conv_transpose2d impl {impl}"
+        assert y_full[..., :8].abs().max() == 0 and y_full[..., 8 + Co:].abs().max() == 0, "wrote outside its channel slice"
+        outs[impl] = got
+    assert rel_l2(outs[5], outs[4]) < 1e-3      # same products, fp32 accumulation in a different order, one bf16 rounding
+    # (b) input gradient of Conv2d(Co' = 64 -> ..., k 4, s 2, p 1): dy on the small grid [N, Ci=64 channels], w [64(out)][Co(in)][4][4]
+    w = (torch.randn(Ci, Co, 4, 4, generator=g) / math.sqrt(Co * 16)).to(dev)      # Conv2d weight [out = 64][in = Co]
+    wkt = _repack(w, False, torch.bfloat16, dgrad=True)
+    dx = torch.empty(N, 2 * H, 2 * W, Co, device=dev, dtype=torch.bfloat16)
+    p2 = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(dx), _null(), wkt.data_ptr(), 16 * Ci, 1, Ci, None, None, 0,
+                    N, H, W, Ci, 2 * H, 2 * W, Co, 4, 4, 2, 1, 1, code, 5, 0, None, 0)
+    ops.conv2d_raw(p2)
+    dref = torch.nn.grad.conv2d_input((N, Co, 2 * H, 2 * W), w.to(torch.bfloat16).float(), xq, stride=2, padding=1)
+    assert rel_l2(dx.float().permute(0, 3, 1, 2), dref) < TOL[torch.bfloat16], "dgrad of the strided conv"
+
+
+WGRAD_HALO_CASES = [
+    (128, 32, 32, 64, 64),     # the bench layer: 1156 position tiles, both tap groups, 85 + 63 CTAs
+    (3, 32, 32, 128, 64),      # two 64-channel chunks of q
+    (5, 16, 16, 64, 128),      # two 64-channel tiles of p
+    (2, 64, 64, 64, 64),       # 64x64: three padded rows per p tile
+    (7, 8, 8, 192, 64),        # tiles straddle images, three chunks
+    (1, 8, 24, 64, 64),        # non-square, fewer tiles than CTAs asked for
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_HALO_CASES)
+def test_wgrad_halo(case):
+    """impl 5 = the halo weight-gradient kernel (3x3 stride 1: padded-flat position tiles, taps as shifted MN-major windows of one
+    shared-memory tile, two taps per M = 128 instruction) against ATen's convolution_backward on the same bf16 operands, written
+    through the engine's staging layout [a][r][s][b] and accumulated onto existing content; the per-tap kernel (impl 2 with the
+    halo kernel's size threshold not met) must agree with it."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import WgradParams
+    N, H, W, Ci, Co = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + H + Ci)
+    xh = torch.randn(N, H, W, Ci, generator=g).to(dev).to(torch.bfloat16)
+    dyh = torch.randn(N, H, W, Co, generator=g).to(dev).to(torch.bfloat16)
+    wref = torch.nn.grad.conv2d_weight(xh.float().permute(0, 3, 1, 2), (Co, Ci, 3, 3), dyh.float().permute(0, 3, 1, 2), stride=1, padding=1)
+    for impl in (5, 2):
+        dw = torch.ones(Co, 3, 3, Ci, device=dev)
+        db = torch.ones(Co, device=dev)
+        ops.wgrad_raw(WgradParams(ops.t4_nhwc(dyh), ops.t4_nhwc(xh), dw.data_ptr(), 9 * Ci, 1, Ci, db.data_ptr(), N, H, W, Co, H, W, Ci, 3, 3, 1, 1, impl))
+        assert rel_l2((dw - 1).permute(0, 3, 1, 2), wref) < 5e-5, f"wgrad impl {impl}"
+        assert rel_l2(db - 1, dyh.float().sum(dim=(0, 1, 2))) < 5e-5, f"dbias impl {impl}"
+
+
 @pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_stem_and_head_layouts(dtype, impl):
