@@ -81,6 +81,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 // Epilogue warps: 8 in the plain kernel - warp w and warp w + 4 share the TMEM lane quarter w % 4 and each takes half of the tile's
 // channels.  Measured (ncu, 64->64 at 256x64x64): with 4 warps the epilogue of a tile (~1070 instructions per warp, one warp per
 // scheduler) took ~4.3k clk against ~2.0k clk of MMA issue, i.e. the kernel was bound by its epilogue, tensor pipe 30 %.
+// What the ~2650 clk of a 128-position tile are (scripts/halo_timeline.py, 64 -> 64): ~2050 clk in which the 36 MMAs issue at the pace
+// of the SM's shared-memory bandwidth (36 x 6 KB of operand reads plus the 30-42 KB TMA write of a later tile at 128 B/clk), and
+// ~450-600 clk between the last MMA of a tile and the first of the next (two commits, the accumulator / halo barrier waits with their
+// tcgen05 fences, tile arithmetic).  Measured and dropped: a second MMA warp taking every other tile (its own accumulator and its own
+// half of the halo ring) - the second issuer still starts ~270 clk after the first one's last MMA, whether it waits with try_wait or
+// polls with test_wait, and DDIM-50 stayed at 1.80k img/s.
 template <bool GN> struct HaloCfg { static constexpr int kEpiWarps = GN ? 4 : 8; static constexpr int kThreads = (kEpiWarps + 2 + (GN ? 8 : 0)) * 32; };
 
 template <int NT, bool GN>
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(HaloCfg<GN>::kThreads, 1) conv3x3_halo_kernel(
             for (int c = 0; c < P.chunks; ++c) {
                 if (!GN && dbg && c == 0) dbg[8 * 64] = clock64();      // (the slots of the transform warps are free in the plain kernel)
                 mbar_wait(GN ? &a_ready[sa] : &a_full[sa], pa);
-                tc_fence_after();
+                if (GN) tc_fence_after();      // (a TMA fill needs no tcgen05 fence: the mbarrier's complete_tx orders it before the MMAs)
                 if (dbg && c == 0) dbg[2] = clock64();
                 const uint32_t a_base = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes) + (uint32_t)base_off * 128u;
                 if (P.resident) {
@@ -698,6 +704,218 @@ int halo_t_launch(const dmu_conv_params* p, cudaStream_t stream) {
     cudaError_t e = launch_pdl(conv4x4t_halo_kernel, dim3(gx, ny), dim3(320), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
     if (e != cudaSuccess) return fail("dmu_conv2d/halo_t: launch failed: %s", cudaGetErrorString(e));
     return check_launch("dmu_conv2d/halo_t");
+}
+
+// ================================================================================================ 4x4 stride-2 convolution
+// Conv2d(k = 4, s = 2, p = 1) (the learned downsampling) and the input gradient of ConvTranspose2d(k = 4, s = 2, p = 1)
+// (dmu_conv_params.gather = 0):  y[n, ho, wo, :] = sum_{r, s} x[n, 2 ho - 1 + r, 2 wo - 1 + s, :] W[r][s].
+// Row 2 ho - 1 + r lies on the parity sub-lattice ph = (r + 1) mod 2 of the input at index ho + dh, dh = floor((r - 1) / 2): on each of
+// the four sub-lattices X[ph][pw][n, i, j] = x[n, 2 i + ph, 2 j + pw] (a strided tensor map) the layer is a 2 x 2 convolution
+// whose taps are pure shifts in the zero-padded flat space of the OUTPUT grid.  The kernel walks the four sub-lattices like the
+// 3x3 kernel walks 64-channel chunks: one halo tile per sub-lattice and output tile (a ring stage), four taps each, all sixteen
+// filter blocks resident, one accumulator per tile.  The per-tap kernel pulls sixteen 16 KB boxes per tile through the SM's L2
+// port instead of four ~25 KB halo tiles (measured at 256x64x64 -> 32x32: 90 us, 0.27 of the tensor peak).
+struct HaloSMaps { CUtensorMap a[4]; CUtensorMap b; };
+struct HaloSArgs {
+    int N, H, W, Ck, Cj;            // H, W: OUTPUT extent (input 2H x 2W)
+    int PW, PH, NR, tiles;
+    int a_stage_bytes, a_stages;
+    __nv_bfloat16* y; int64_t y_sn, y_sh, y_sw;
+    const float* bias;
+    uint32_t pw_magic;
+};
+
+__global__ void __launch_bounds__(320, 1) conv4x4s2_halo_kernel(const __grid_constant__ HaloSMaps maps, const __grid_constant__ HaloSArgs P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t a_full[kMaxAStages], a_empty[kMaxAStages], w_full, acc_full[2], acc_empty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_bias[64];
+    constexpr int kWTile = 64 * 128, kEpiWarps = 8, kTmaWarp = 8, kMmaWarp = 9;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_w = smem + (size_t)P.a_stages * P.a_stage_bytes;
+    const int warp = threadIdx.x >> 5;
+    const int j0 = blockIdx.y * 64;
+    int t_count = 0;
+    for (int t = blockIdx.x; t < P.tiles; t += gridDim.x) ++t_count;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        mbar_init(&w_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps * 32); }
+        fence_mbar_init();
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
+        tma_prefetch_desc(&maps.b);
+    }
+    if (warp == kMmaWarp) tmem_alloc(&s_tmem, 128);          // 2 buffers x 64 columns
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bias[i] = (P.bias && j0 + i < P.Cj) ? P.bias[j0 + i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    pdl_wait();
+
+    if (warp == kTmaWarp) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&w_full, (uint32_t)(16 * kWTile));
+            for (int t = 0; t < 16; ++t) tma_load_2d(smem_w + (size_t)t * kWTile, &maps.b, &w_full, t * P.Ck, j0);
+            int sa = 0, pa = 1;
+            const uint32_t a_bytes = (uint32_t)(P.NR * P.PW) * 128u;
+            for (int ti = 0; ti < t_count; ++ti) {
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const int L0 = P.pw_magic ? floordiv_magic(tile * 128 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(tile * 128 - P.PW - 1, P.PW);
+                const int n0 = floordiv_dev(L0, P.PH), hp0 = L0 - n0 * P.PH;
+                for (int sub = 0; sub < 4; ++sub) {
+                    mbar_wait(&a_empty[sa], pa);
+                    mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+                    uint8_t* dst = smem_a + (size_t)sa * P.a_stage_bytes;
+                    int n = n0, hp = hp0;
+                    for (int i = 0; i < P.NR; ++i) {
+                        tma_load_4d(dst + (size_t)i * P.PW * 128, &maps.a[sub], &a_full[sa], 0, -1, hp - 1, n);
+                        if (++hp == P.PH) { hp = 0; ++n; }
+                    }
+                    if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kMmaWarp) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+            mbar_wait(&w_full, 0);
+            const uint32_t w_base = smem_u32(smem_w);
+            int sa = 0, pa = 0;
+            for (int it = 0; it < t_count; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int buf = it & 1;
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                const uint32_t d_tmem = tmem + (uint32_t)(buf * 64);
+                const int Q0 = tile * 128;
+                const int L0 = P.pw_magic ? floordiv_magic(Q0 - P.PW - 1, P.PW, P.pw_magic) : floordiv_dev(Q0 - P.PW - 1, P.PW);
+                const int base_off = Q0 - P.PW - 1 - L0 * P.PW;       // halo row of the (dh, dw) = (-1, -1) neighbour of position Q0
+#pragma unroll
+                for (int sub = 0; sub < 4; ++sub) {
+                    const int ph = sub >> 1, pw = sub & 1;
+                    mbar_wait(&a_full[sa], pa);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem_a + (size_t)sa * P.a_stage_bytes) + (uint32_t)base_off * 128u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        // even sub-lattice: r = 1 (dh = 0), r = 3 (dh = +1); odd sub-lattice: r = 0 (dh = -1), r = 2 (dh = 0)
+                        const int r = (ph ? 0 : 1) + 2 * (q >> 1), sx = (pw ? 0 : 1) + 2 * (q & 1);
+                        const int dh = (r - 1 - ph) / 2, dw = (sx - 1 - pw) / 2;      // exact: the numerators are even
+                        const uint64_t da = smem_desc_sw128(a_base + (uint32_t)((dh + 1) * P.PW + (dw + 1)) * 128u, 16, 1024);
+                        const uint64_t db = smem_desc_sw128(w_base + (uint32_t)((r * 4 + sx) * kWTile), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (sub | q | k) != 0);
+                    }
+                    umma_commit(&a_empty[sa]);
+                    if (++sa == P.a_stages) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------- epilogue warps 0..7: thread = output position x 32 channels
+        const int row = threadIdx.x & 127, cb = (int)(threadIdx.x >> 7) * 32;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int plane = P.PH * P.PW;
+        for (int it = 0; it < t_count; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int buf = it & 1;
+            const int Q = tile * 128 + row;
+            const int n = Q / plane, rem = Q - n * plane;
+            const int hp = rem / P.PW, wp = rem - hp * P.PW;
+            const bool valid = n < P.N && hp >= 1 && hp <= P.H && wp >= 1 && wp <= P.W;
+            __nv_bfloat16* yp = P.y + (int64_t)n * P.y_sn + (int64_t)(hp - 1) * P.y_sh + (int64_t)(wp - 1) * P.y_sw + j0 + cb;
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(tmem + lane_base + (uint32_t)(buf * 64 + cb), v);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);      // the values are in registers: the accumulator goes back before the stores
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += s_bias[cb + i];
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) store_vec<__nv_bfloat16>(yp + i, v + i);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem, 128);
+}
+
+static int halo_s_geometry(const dmu_conv_params* p, HaloSArgs& A) {
+    memset(&A, 0, sizeof(A));
+    A.N = p->N; A.H = p->Ho; A.W = p->Wo; A.Ck = p->Ck; A.Cj = p->Cj;
+    A.PW = A.W + 2; A.PH = A.H + 2;
+    A.NR = 3 + (129 + A.PW - 1) / A.PW;
+    A.tiles = (int)(((int64_t)A.N * A.PH * A.PW + 127) / 128);
+    A.a_stage_bytes = ((A.NR * A.PW * 128) + 1023) / 1024 * 1024;
+    const int budget = 214 * 1024, wbytes = 16 * 64 * 128;
+    A.a_stages = (budget - wbytes) / A.a_stage_bytes;
+    if (A.a_stages > kMaxAStages) A.a_stages = kMaxAStages;
+    if (A.a_stages < 2) return -1;
+    return A.a_stages * A.a_stage_bytes + wbytes + 1024;
+}
+
+int halo_s_supported(const dmu_conv_params* p, int force) {
+    if (p->gather != 0 || p->R != 4 || p->S != 4 || p->stride != 2 || p->pad != 1) return 0;
+    if (p->Hi != 2 * p->Ho || p->Wi != 2 * p->Wo) return 0;
+    if (p->Ho < 4 || p->Wo < 4 || p->Wo + 2 > 256) return 0;
+    if (p->Ck != 64 || p->Cj % 64 != 0) return 0;             // the sixteen filter blocks of one 64-channel chunk stay resident
+    if (p->res.ptr || p->temb || p->gn_coef || p->gn_fuse_mode) return 0;
+    if (p->w_sk != 1 || p->w_st != p->Ck || p->w_sn != (int64_t)16 * p->Ck) return 0;
+    if ((int64_t)p->N * (p->Ho + 2) * (p->Wo + 2) >= (1ll << 31) - 4096) return 0;
+    HaloSArgs A;
+    if (halo_s_geometry(p, A) <= 0) return 0;
+    if (force) return 1;
+    static const int enabled = [] { const char* e = getenv("DMU_HALO_S"); return e ? atoi(e) : 1; }();
+    static const int min_tiles = [] { const char* e = getenv("DMU_HALO_S_MIN_TILES"); return e ? atoi(e) : 300; }();
+    return enabled && A.tiles >= min_tiles ? 1 : 0;
+}
+
+int halo_s_launch(const dmu_conv_params* p, cudaStream_t stream) {
+    HaloSMaps maps;
+    HaloSArgs A;
+    const int smem = halo_s_geometry(p, A);
+    DMU_REQUIRE(smem > 0 && smem <= 224 * 1024, "dmu_conv2d/halo_s: tile does not fit shared memory");
+    for (int sub = 0; sub < 4; ++sub) {      // parity sub-lattice (ph, pw) of the input: [N][Ho][Wo] at twice the strides
+        const int ph = sub >> 1, pw = sub & 1;
+        const uint64_t dims[4] = {(uint64_t)p->Ck, (uint64_t)p->Wo, (uint64_t)p->Ho, (uint64_t)p->N};
+        const uint64_t str[4] = {1, (uint64_t)p->x.sw * 2, (uint64_t)p->x.sh * 2, (uint64_t)p->x.sn};
+        const uint32_t box[4] = {64, (uint32_t)A.PW, 1, 1};
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(p->x.ptr) + (int64_t)ph * p->x.sh + (int64_t)pw * p->x.sw;
+        if (int rc = make_map_bf16(&maps.a[sub], base, 4, dims, str, box, "dmu_conv2d/halo_s")) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)16 * p->Ck, (uint64_t)p->Cj};
+        const uint64_t str[2] = {1, (uint64_t)p->w_sn};
+        const uint32_t box[2] = {64, 64};
+        if (int rc = make_map_bf16(&maps.b, p->w, 2, dims, str, box, "dmu_conv2d/halo_s weights")) return rc;
+    }
+    A.y = reinterpret_cast<__nv_bfloat16*>(p->y.ptr); A.y_sn = p->y.sn; A.y_sh = p->y.sh; A.y_sw = p->y.sw;
+    A.bias = p->bias;
+    if (((int64_t)A.N * A.PH * A.PW + 2 * A.PW + 256) * A.PW < (1ll << 32)) A.pw_magic = (uint32_t)((1ull << 32) / (uint64_t)A.PW) + 1u;
+    const int ny = p->Cj / 64;
+    int gx = sm_count() / ny;
+    if (gx < 1) gx = 1;
+    if (gx > A.tiles) gx = A.tiles;
+    const int rounds = (A.tiles + gx - 1) / gx;
+    gx = (A.tiles + rounds - 1) / rounds;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv4x4s2_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        attr_done = true;
+    }
+    cudaError_t e = launch_pdl(conv4x4s2_halo_kernel, dim3(gx, ny), dim3(320), (size_t)smem, stream, dim3(1, 1, 1), maps, A);
+    if (e != cudaSuccess) return fail("dmu_conv2d/halo_s: launch failed: %s", cudaGetErrorString(e));
+    return check_launch("dmu_conv2d/halo_s");
 }
 
 static int pick_smem(const dmu_conv_params* p, int NT, HaloArgs& A) {

@@ -871,6 +871,9 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream);
 // conv_halo.cu: 4x4 stride-2 transposed gather (ConvTranspose2d upsampling, input gradient of the 4x4 stride-2 downsampling conv)
 int halo_t_supported(const dmu_conv_params* p, int force);
 int halo_t_launch(const dmu_conv_params* p, cudaStream_t stream);
+// conv_halo.cu: 4x4 stride-2 convolution (learned downsampling, input gradient of the ConvTranspose2d upsampling)
+int halo_s_supported(const dmu_conv_params* p, int force);
+int halo_s_launch(const dmu_conv_params* p, cudaStream_t stream);
 // conv_stem.cu: few-channel input (stem fprop, head dgrad)
 int stem_supported(const dmu_conv_params* p);
 int stem_launch(const dmu_conv_params* p, cudaStream_t stream);
@@ -1107,7 +1110,8 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
     if (!p->gn_fuse_mode) {
         if (p->impl == 5) {
             if (nhwc_bf16_ok(p->x) && nhwc_bf16_ok(p->y) && p->w_dtype == DMU_BF16 && aligned16(p->w) && halo_t_supported(p, 1)) return halo_t_launch(p, stream);
-            DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3 stride 1 pad 1 of >= 8x8, or 4x4 stride 2 pad 1 transposed with 64 input channels)");
+            if (nhwc_bf16_ok(p->x) && nhwc_bf16_ok(p->y) && p->w_dtype == DMU_BF16 && aligned16(p->w) && halo_s_supported(p, 1)) return halo_s_launch(p, stream);
+            DMU_REQUIRE(halo_supported(p, 1), "dmu_conv2d: impl=halo requested for an unsupported shape (3x3 stride 1 pad 1 of >= 8x8, or 4x4 stride 2 pad 1 with 64 input channels)");
             return halo_launch(p, stream);
         }
         if (narrow_head_supported(p)) return halo_launch(p, stream);
@@ -1115,6 +1119,7 @@ static int conv_launch(const dmu_conv_params* p, cudaStream_t stream) {
         if (p->impl != 4 && stem_supported(p)) return stem_launch(p, stream);
         if (p->impl != 4 && halo_enabled() && halo_supported(p, 0)) return halo_launch(p, stream);
         if (p->impl != 4 && halo_enabled() && halo_t_supported(p, 0)) return halo_t_launch(p, stream);
+        if (p->impl != 4 && halo_enabled() && halo_s_supported(p, 0)) return halo_s_launch(p, stream);
     }
     Maps maps;
     ConvArgs A;

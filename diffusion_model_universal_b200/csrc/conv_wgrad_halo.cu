@@ -175,7 +175,7 @@ static int wh_geometry(const dmu_wgrad_params* p, WHaloArgs& A) {
     A.q_bytes = (A.NRq * A.PW * 128 + 1023) / 1024 * 1024;
     const int p_bytes = (A.NRp * A.PW * 128 + 1023) / 1024 * 1024;
     A.stage_bytes = A.q_bytes + p_bytes;
-    static const int want = [] { const char* e = getenv("DMU_WGRAD_HALO_STAGES"); const int v = e ? atoi(e) : 2; return v < 2 ? 2 : (v > kWhMaxStages ? kWhMaxStages : v); }();
+    static const int want = [] { const char* e = getenv("DMU_WGRAD_HALO_STAGES"); const int v = e ? atoi(e) : 3; return v < 2 ? 2 : (v > kWhMaxStages ? kWhMaxStages : v); }();
     A.stages = want;
     while (A.stages > 2 && A.stages * A.stage_bytes + 1024 > 200 * 1024) --A.stages;
     if (A.stages * A.stage_bytes + 1024 > 220 * 1024) return -1;

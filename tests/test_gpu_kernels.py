@@ -258,6 +258,58 @@ def test_conv_transposed_halo(case):
     assert rel_l2(dx.float().permute(0, 3, 1, 2), dref) < TOL[torch.bfloat16], "dgrad of the strided conv"
 
 
+HALO_S_CASES = [
+    # N, Ho, Wo (output), Co
+    (256, 16, 16, 64),     # 648 tiles: several per CTA, three ring stages
+    (128, 16, 16, 64),     # the training step's down0 / up4-dgrad shape
+    (3, 32, 32, 64),       # two ring stages, tiles straddle images
+    (5, 8, 8, 128),        # two output-channel tiles
+    (1, 4, 12, 64),        # non-square, one partial tile
+]
+
+
+@pytest.mark.parametrize("case", HALO_S_CASES)
+def test_conv_strided_halo(case):
+    """impl 5 on a 4x4 stride-2 pad-1 convolution with 64 input channels = the halo kernel of that read pattern (the four parity
+    sub-lattices of the input as four halo tiles per output tile), in both of its uses: nn.Conv2d downsampling forward (+bias) and
+    the input gradient of nn.ConvTranspose2d; against ATen on the same bf16 operands, and against the per-tap kernel (impl 4)."""
+    ops, _abi = _mods()
+    from diffusion_model_universal_b200._abi import ConvParams
+    N, Ho, Wo, Co = case
+    Ci, H, W = 64, 2 * Ho, 2 * Wo
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(N * 100 + Ho + Co)
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev)
+    xh = ops.nchw_to_nhwc(x, torch.bfloat16)
+    xq = xh.float().permute(0, 3, 1, 2)
+    code = ops.dtype_code(xh)
+    # (a) Conv2d: weight [Co][Ci][4][4]
+    w = (torch.randn(Co, Ci, 4, 4, generator=g) / math.sqrt(Ci * 16)).to(dev)
+    bias = torch.randn(Co, generator=g).to(dev)
+    wk = _repack(w, False, torch.bfloat16)
+    ref = F.conv2d(xq, w.to(torch.bfloat16).float(), bias, stride=2, padding=1)
+    outs = {}
+    for impl in (5, 4):
+        y_full = torch.zeros(N, Ho, Wo, Co + 16, device=dev, dtype=torch.bfloat16)      # written into a channel slice
+        p = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(y_full, 8, Co), _null(), wk.data_ptr(), 16 * Ci, 1, Ci, bias.data_ptr(), None, 0,
+                       N, H, W, Ci, Ho, Wo, Co, 4, 4, 2, 1, 0, code, impl, 0, None, 0)
+        ops.conv2d_raw(p)
+        got = y_full[..., 8:8 + Co].float().permute(0, 3, 1, 2)
+        assert rel_l2(got, ref) < TOL[torch.bfloat16], f"conv2d impl {impl}"
+        assert y_full[..., :8].abs().max() == 0 and y_full[..., 8 + Co:].abs().max() == 0, "wrote outside its channel slice"
+        outs[impl] = got
+    assert rel_l2(outs[5], outs[4]) < 1e-3      # same products, fp32 accumulation in a different order, one bf16 rounding
+    # (b) input gradient of ConvTranspose2d(Co -> 64, k 4, s 2, p 1): dy = x on the big grid (64 channels), weight [Co(in)][64(out)][4][4]
+    wt = (torch.randn(Co, Ci, 4, 4, generator=g) / math.sqrt(Ci * 4)).to(dev)
+    wkt = _repack(wt, True, torch.bfloat16, dgrad=True)
+    dx = torch.empty(N, Ho, Wo, Co, device=dev, dtype=torch.bfloat16)
+    p2 = ConvParams(ops.t4_nhwc(xh), ops.t4_nhwc(dx), _null(), wkt.data_ptr(), 16 * Ci, 1, Ci, None, None, 0,
+                    N, H, W, Ci, Ho, Wo, Co, 4, 4, 2, 1, 0, code, 5, 0, None, 0)
+    ops.conv2d_raw(p2)
+    dref = F.conv2d(xq, wt.to(torch.bfloat16).float(), stride=2, padding=1)
+    assert rel_l2(dx.float().permute(0, 3, 1, 2), dref) < TOL[torch.bfloat16], "dgrad of the transposed conv"
+
+
 WGRAD_HALO_CASES = [
     (128, 32, 32, 64, 64),     # the bench layer: 1156 position tiles, both tap groups, 85 + 63 CTAs
     (3, 32, 32, 128, 64),      # two 64-channel chunks of q
