@@ -86,7 +86,8 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 // ~450-600 clk between the last MMA of a tile and the first of the next (two commits, the accumulator / halo barrier waits with their
 // tcgen05 fences, tile arithmetic).  Measured and dropped: a second MMA warp taking every other tile (its own accumulator and its own
 // half of the halo ring) - the second issuer still starts ~270 clk after the first one's last MMA, whether it waits with try_wait or
-// polls with test_wait, and DDIM-50 stayed at 1.80k img/s.
+// polls with test_wait, and DDIM-50 stayed at 1.80k img/s; the whole issue loop as one elected thread with the next tile's two barrier
+// waits polled after the sixth tap (a tile 2.69k -> 2.57k clk in the timeline, the time moves into the two commits; 1.80k img/s).
 template <bool GN> struct HaloCfg { static constexpr int kEpiWarps = GN ? 4 : 8; static constexpr int kThreads = (kEpiWarps + 2 + (GN ? 8 : 0)) * 32; };
 
 template <int NT, bool GN>
