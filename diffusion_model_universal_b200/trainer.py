@@ -231,7 +231,9 @@ class TrainStep:
         plan = eng.get_plan(shape, True)
         # The refresh of the bf16 filter caches leads the step on the same stream as everything else.  (Measured in round 2 inside the
         # step graph, 2.645 - 2.657 ms whichever way: the refresh on a side branch next to the draws, the draws on a high-priority
-        # branch next to the refresh - the 9344-CTA permutation fills the machine, a concurrent branch only queues behind it.)
+        # branch next to the refresh - the 9344-CTA permutation fills the machine, a concurrent branch only queues behind it; and the
+        # refresh split by consumer - the forward's [O][R][S][I] copies first, the backward's [I][R][S][O] copies on a second stream
+        # beside the forward - LOSES 1.1 %: 48.04k against 48.58k img/s, the co-running half slows the forward by more than it saves.)
         if not eng.frozen:
             eng.repack(ops._stream())
         t = torch.randint(0, m.num_timesteps, (shape[0],), device=images.device)
