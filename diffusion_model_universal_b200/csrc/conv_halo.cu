@@ -667,8 +667,7 @@ int halo_t_supported(const dmu_conv_params* p, int force) {
     if (force) return 1;
     static const int enabled = [] { const char* e = getenv("DMU_HALO_T"); return e ? atoi(e) : 1; }();
     // a CTA loads 128 KB of filters before its first tile: measured worth it from about two tiles per CTA (training step: 324 tiles yes, 100 no)
-    static const int min_tiles = [] { const char* e = getenv("DMU_HALO_T_MIN_TILES"); return e ? atoi(e) : 300; }();
-    return enabled && A.tiles >= min_tiles ? 1 : 0;
+    return enabled && A.tiles >= 300 ? 1 : 0;
 }
 
 int halo_t_launch(const dmu_conv_params* p, cudaStream_t stream) {
@@ -877,8 +876,7 @@ int halo_s_supported(const dmu_conv_params* p, int force) {
     if (halo_s_geometry(p, A) <= 0) return 0;
     if (force) return 1;
     static const int enabled = [] { const char* e = getenv("DMU_HALO_S"); return e ? atoi(e) : 1; }();
-    static const int min_tiles = [] { const char* e = getenv("DMU_HALO_S_MIN_TILES"); return e ? atoi(e) : 300; }();
-    return enabled && A.tiles >= min_tiles ? 1 : 0;
+    return enabled && A.tiles >= 300 ? 1 : 0;      // as for the transposed kernel
 }
 
 int halo_s_launch(const dmu_conv_params* p, cudaStream_t stream) {

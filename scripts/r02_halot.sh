@@ -5,7 +5,7 @@ timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "transpos
 {
 run DMU_HALO_T=0
 run DMU_HALO_T=1
-run DMU_HALO_T_MIN_TILES=300
+
 rund DMU_HALO_T=0
 rund DMU_HALO_T=1
 } 2>&1 | tee gpurun_out/r02p8/ab.txt
