@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [os.path.join(OUT_DIR, s.replace(".cu", ".o")) for s in SOURCES]
     lib_digest = hashlib.sha256("".join(digests[o] for o in objs).encode()).hexdigest()
     if force or jobs or _stale(LIB, lib_digest):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs      # (without the arch the link step adds an empty sm_52 stub cubin)
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
