@@ -615,6 +615,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # the package's NCCL defaults (diffusion_model_universal_b200/parallel.py: NCCL_MAX_CTAS) must be in the environment before the
+        # communicator exists
+        import diffusion_model_universal_b200.parallel  # noqa: F401
         dist.init_process_group("nccl", device_id=dev)
     from diffusion_model_universal_b200 import ops, _abi
     _abi.lib()   # fail loudly if the CUDA extension is missing

@@ -10,10 +10,18 @@ order, so buckets are issued from the arena's tail towards its head and the
 first bucket (time MLP gradients, completed last) goes out at the very end.
 """
 
+import os
 from typing import List, Tuple
 
 import torch
 import torch.distributed as dist
+
+# The all-reduces run BESIDE the backward's two lanes, whose kernels are sized to share every SM: with NCCL's default of 32 CTAs per
+# collective the ring kernels take SM slots from them.  Measured on B200s (bench.py, 128 img / GPU): 16 CTAs carry the 16 MB buckets
+# just as well - 2 GPUs 92.8k -> 94.2k img/s (0.950 -> 0.964 of linear), 8 GPUs 362.0k -> 371.5k img/s (0.926 -> 0.951); 8 and 4
+# CTAs lose (91.4k / 90.8k at 2 GPUs: the last, exposed all-reduce gets slower).  Read by NCCL when the communicator is created, so
+# this module must be imported before torch.distributed.init_process_group(..., device_id=...); a value set by the user wins.
+os.environ.setdefault("NCCL_MAX_CTAS", "16")
 
 
 def bucket_ranges(total: int, bucket_elems: int) -> List[Tuple[int, int]]:

@@ -262,9 +262,13 @@ class TrainStep:
             eng.run_backward(plan, None, prezeroed=True)
             self.opt.step_range(0, None, 1.0)
             return
-        works = []
-        eng.run_backward(plan, None, between=lambda lo, hi: works.extend(self.reducer.launch(lo, hi)), prezeroed=True)
-        self.opt.step_range(0, None, self.reducer.finish(works))
+        # The all-reduces of the first two ranges are long done when the backward ends; the last range (the gradients the backward
+        # completes last, ~9.5 MB) is still on the wire for ~50 us.  The update therefore runs range by range in arrival order: Adam + EMA
+        # of the first two ranges (85 % of the arena, HBM-bound) overlaps the last all-reduce (NVLink-bound) instead of waiting for it.
+        parts = []
+        eng.run_backward(plan, None, between=lambda lo, hi: parts.append((lo, hi, self.reducer.launch(lo, hi))), prezeroed=True)
+        for lo, hi, works in parts:
+            self.opt.step_range(lo, hi, self.reducer.finish(works))
 
     # ------------------------------------------------------------------ checkpoint interop
     def checkpoint(self, epoch: int, config=None, best_val_loss: float = float("inf")) -> dict:
