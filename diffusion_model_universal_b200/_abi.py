@@ -52,8 +52,11 @@ class GnParams(C.Structure):
         ("x", Tensor4), ("y", Tensor4), ("dx", Tensor4), ("add0", Tensor4), ("add1", Tensor4),
         ("sums", c_vp), ("gamma", c_vp), ("beta", c_vp), ("red", c_vp), ("dgamma", c_vp), ("dbeta", c_vp),
         ("N", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32), ("G", c_i32),
-        ("silu", c_i32), ("eps", c_f32), ("_pad", c_i32),
+        ("silu", c_i32), ("eps", c_f32), ("flags", c_i32),      # flags: GN_FIXED_SUMS
     ]
+
+
+GN_FIXED_SUMS = 1      # include/dmu_b200.h DMU_GN_FIXED_SUMS: int64 fixed-point accumulators behind the float sums
 
 
 class GnBwd2Params(C.Structure):

@@ -96,6 +96,15 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 
 inline bool is_nhwc(const dmu_tensor4& t) { return t.sc == 1; }
 
+// DMU_GN_FIXED_SUMS (include/dmu_b200.h): GroupNorm raw sums accumulated as 64-bit fixed-point integers (value * 2^20) in the int64
+// array behind the float array - integer atomics commute, the statistics are bit-identical from run to run.
+__device__ __forceinline__ unsigned long long* gn_fixed_sums(float* sums, int N, int G) {
+    return reinterpret_cast<unsigned long long*>(sums + (int64_t)N * G * 2);
+}
+__device__ __forceinline__ unsigned long long gn_to_fixed(float v) { return (unsigned long long)__float2ll_rn(v * 1048576.f); }
+__device__ __forceinline__ float gn_from_fixed(unsigned long long v) { return (float)((double)(long long)v * (1.0 / 1048576.0)); }
+
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
 // A recorded plan is a chain of hundreds of short dependent kernels; with the launch attribute below the next kernel's CTAs
 // are scheduled (and run their prologue) while the previous kernel drains, and block in pdl_wait() until that kernel's

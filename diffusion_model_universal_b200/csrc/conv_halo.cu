@@ -49,6 +49,7 @@ struct HaloArgs {
     // GroupNorm statistics of the OUTPUT (dmu_conv_params.gn_fuse_mode 3): raw (sum, sum of squares) of the stored values, added to
     // st_sums[n][g][0..1]; st_sh = log2(channels per group)
     float* st_sums; int st_G, st_sh;
+    unsigned long long* st_fixed;      // DMU_GN_FIXED_SUMS: the int64 fixed-point accumulators behind st_sums (order-independent)
     int run, run_sh;     // tile schedule: runs of `run` = 1 << run_sh consecutive tiles per CTA, dealt round-robin
     uint32_t pw_magic;   // floor(2^32 / PW) + 1 when every padded position * PW stays below 2^32 (floordiv_magic), else 0
 };
@@ -381,9 +382,14 @@ __global__ void __launch_bounds__(HaloCfg<GN>::kThreads, 1) conv3x3_halo_kernel(
                         sq += __shfl_xor_sync(0xffffffffu, sq, o);
                     }
                     if ((lane & (ppg - 1)) == 0 && lane < kPairs) {
-                        float* sp = P.st_sums + ((int64_t)im * P.st_G + ((j0 + cb + 2 * lane) >> P.st_sh)) * 2;
-                        atomicAdd(sp, su);
-                        atomicAdd(sp + 1, sq);
+                        const int64_t si = ((int64_t)im * P.st_G + ((j0 + cb + 2 * lane) >> P.st_sh)) * 2;
+                        if (P.st_fixed) {
+                            atomicAdd(P.st_fixed + si, gn_to_fixed(su));
+                            atomicAdd(P.st_fixed + si + 1, gn_to_fixed(sq));
+                        } else {
+                            atomicAdd(P.st_sums + si, su);
+                            atomicAdd(P.st_sums + si + 1, sq);
+                        }
                     }
                 }
 #pragma unroll
@@ -1013,6 +1019,7 @@ int halo_launch(const dmu_conv_params* p, cudaStream_t stream) {
         DMU_REQUIRE(halo_stats_supported(p), "dmu_conv2d/halo: this launch cannot accumulate the GroupNorm statistics of gn_fuse (ask dmu_conv2d_gn_fuse_supported first)");
         const int cpg = gn->C / gn->G;
         A.st_sums = gn->sums; A.st_G = gn->G; A.st_sh = 0;
+        A.st_fixed = (gn->flags & DMU_GN_FIXED_SUMS) ? reinterpret_cast<unsigned long long*>(gn->sums + (int64_t)gn->N * gn->G * 2) : nullptr;
         while ((1 << A.st_sh) < cpg) ++A.st_sh;
     }
     const int ntiles_n = narrow ? 1 : p->Cj / NT;

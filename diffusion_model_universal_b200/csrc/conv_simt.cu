@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(128) linear_splitk_kernel(dmu_conv_params P, i
                 if (P.bias) v += P.bias[jc];
                 if (P.res.ptr) v += ld_as_float(P.res.ptr, (int64_t)m * P.res.sn + (int64_t)jc * P.res.sc, P.res.dtype);
             }
-            atomicAdd(&y[(int64_t)m * P.y.sn + jc], v);
+            if (gridDim.z == 1) y[(int64_t)m * P.y.sn + jc] = v;      // unsplit contraction: plain store, deterministic
+            else atomicAdd(&y[(int64_t)m * P.y.sn + jc], v);
         }
     }
 }
@@ -533,11 +534,16 @@ int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream) {
         ((M + BM - 1) / BM) * ((p->Cj + BN - 1) / BN) < sm_count() / 2 && (int64_t)M * p->Cj * K >= (1 << 18)) {
         dim3 grid((M + LM - 1) / LM, (p->Cj + LN - 1) / LN, 1);
         int splits = (2 * sm_count() + grid.x * grid.y - 1) / (grid.x * grid.y);
+        // Contractions of up to 256 (every Linear of the FORWARD: the time-embedding MLP and the 22-way time projection) run unsplit
+        // with plain stores: fp32 atomics would make the forward differ from run to run in its last bits, which a bf16 network
+        // amplifies to ~1e-2 (tests/test_gpu_unet.py::test_bf16_forward_is_bit_identical_from_run_to_run).  The long contractions of
+        // the backward (K = 3328 of the projection's input gradient) keep the split.
+        if (K <= 256) splits = 1;
         int per = (K + splits - 1) / splits;
         per = ((per + LK - 1) / LK) * LK;
         if (per < 2 * LK) per = 2 * LK;
         grid.z = (K + per - 1) / per;
-        if (cudaMemsetAsync(p->y.ptr, 0, (size_t)M * p->Cj * sizeof(float), as_stream(stream)) != cudaSuccess) return check_launch("dmu_conv2d/linear zero");
+        if (grid.z > 1 && cudaMemsetAsync(p->y.ptr, 0, (size_t)M * p->Cj * sizeof(float), as_stream(stream)) != cudaSuccess) return check_launch("dmu_conv2d/linear zero");
         linear_splitk_kernel<<<grid, 128, 0, as_stream(stream)>>>(*p, per);
         return check_launch("dmu_conv2d/linear_splitk");
     }

@@ -170,19 +170,33 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(dmu_gn_params P) {
     for (int g = threadIdx.x; g < P.G; g += blockDim.x) {
         float a = 0.f, q = 0.f;
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += s_sum[c]; q += s_sq[c]; }
-        atomicAdd(&P.sums[((int64_t)n * P.G + g) * 2 + 0], a);
-        atomicAdd(&P.sums[((int64_t)n * P.G + g) * 2 + 1], q);
+        if (P.flags & DMU_GN_FIXED_SUMS) {
+            unsigned long long* fx = gn_fixed_sums(P.sums, P.N, P.G) + ((int64_t)n * P.G + g) * 2;
+            atomicAdd(fx, gn_to_fixed(a));
+            atomicAdd(fx + 1, gn_to_fixed(q));
+        } else {
+            atomicAdd(&P.sums[((int64_t)n * P.G + g) * 2 + 0], a);
+            atomicAdd(&P.sums[((int64_t)n * P.G + g) * 2 + 1], q);
+        }
     }
 }
 
 // per-channel mean / rstd*gamma / beta staged in smem for image n
+// fixed: read the statistics from the int64 fixed-point accumulators behind P.sums (DMU_GN_FIXED_SUMS; only the apply pass that
+// directly follows the accumulating launch does - it also publishes their float value in P.sums, see gn_apply_kernel)
 __device__ __forceinline__ void stage_affine(const dmu_gn_params& P, int n, float* s_mean, float* s_scale, float* s_beta, float* s_rstd,
-                                             float* s_gamma = nullptr) {
+                                             float* s_gamma = nullptr, bool fixed = false) {
     const int cpg = P.C / P.G;
     const float cnt = (float)cpg * (float)P.H * (float)P.W;
     for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
         const int g = c / cpg;
-        const float su = P.sums[((int64_t)n * P.G + g) * 2 + 0], sq = P.sums[((int64_t)n * P.G + g) * 2 + 1];
+        float su, sq;
+        if (fixed) {
+            const unsigned long long* fx = gn_fixed_sums(P.sums, P.N, P.G) + ((int64_t)n * P.G + g) * 2;
+            su = gn_from_fixed(fx[0]); sq = gn_from_fixed(fx[1]);
+        } else {
+            su = P.sums[((int64_t)n * P.G + g) * 2 + 0]; sq = P.sums[((int64_t)n * P.G + g) * 2 + 1];
+        }
         const float mean = su / cnt;
         const float var = fmaxf(sq / cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + P.eps);
@@ -203,7 +217,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(dmu_gn_params P) {
     constexpr int kVec = Elem<T>::kVec;
     __shared__ float s_mean[kMaxC], s_scale[kMaxC], s_beta[kMaxC];
     const int n = blockIdx.y, HW = P.H * P.W;
-    stage_affine(P, n, s_mean, s_scale, s_beta, nullptr);
+    const bool fixed = (P.flags & DMU_GN_FIXED_SUMS) != 0;
+    stage_affine(P, n, s_mean, s_scale, s_beta, nullptr, nullptr, fixed);
+    if (fixed && blockIdx.x == 0) {      // the float view of the order-independent sums, for the backward of this norm
+        const unsigned long long* fx = gn_fixed_sums(P.sums, P.N, P.G) + (int64_t)n * P.G * 2;
+        for (int i = threadIdx.x; i < P.G * 2; i += blockDim.x) P.sums[(int64_t)n * P.G * 2 + i] = gn_from_fixed(fx[i]);
+    }
     __syncthreads();
     RowMap m(P.C, kVec);
     if (!m.active) return;

@@ -274,6 +274,7 @@ class Engine:
         # ResBlock shortcut convolutions (forward and dgrad) on an auxiliary graph branch instead of inside the main chain
         # (DMU_AUX_LANES=0: A/B aid)
         self.aux_lanes = os.environ.get("DMU_AUX_LANES", "1") != "0"
+        self.fixed_sums = os.environ.get("DMU_GN_FIXED_SUMS", "1") != "0"     # order-independent GroupNorm statistics (0: float atomics, A/B aid)
         # GroupNorm statistics of the large layers accumulated by the producing conv (dmu_conv_params.gn_fuse_mode 3); DMU_GN_STATS=0: A/B aid
         self.fuse_gn_stats = os.environ.get("DMU_GN_STATS", "1") != "0"
         self._tail_stream = None
@@ -958,10 +959,13 @@ class _PlanBuilder:
 
     def gn(self, x: Buf, G, gamma_name, beta_name, silu: bool, out: Buf = None):
         """Forward GroupNorm(+SiLU): returns (y, gn-record)."""
-        sums = self.stats.take(self.N * G * 2 * 4, 16)
+        # [N][G][2] float sums, followed by the int64 fixed-point accumulators of the launches that add statistics with atomics
+        # (GN_FIXED_SUMS: integer atomics commute, the bf16 forward is bit-identical from run to run)
+        fixed = self.e.fixed_sums
+        sums = self.stats.take(self.N * G * 2 * 4 * (3 if fixed else 1), 16)
         y = out if out is not None else self.act(x.H, x.W, x.C)
         p = GnParams(x.t4(), y.t4(), _null_t4(), _null_t4(), _null_t4(), sums, self.e.paddr(gamma_name), self.e.paddr(beta_name),
-                     None, None, None, self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, 0)
+                     None, None, None, self.N, x.H, x.W, x.C, G, 1 if silu else 0, 1e-5, _abi.GN_FIXED_SUMS if fixed else 0)
         self.plan.keep.append(p)
         # the conv that wrote x (and nothing else has normalised yet) may carry this norm in its epilogue: no launch then
         prod = self.prod.pop((x.addr, x.pitch, x.C), None)

@@ -235,8 +235,15 @@ typedef struct {
     int32_t N, H, W, C, G;
     int32_t silu;
     float eps;
-    int32_t _pad;
+    int32_t flags;       /* DMU_GN_FIXED_SUMS (1): order-independent statistics - see below */
 } dmu_gn_params;
+/* flags & DMU_GN_FIXED_SUMS: the launches that ACCUMULATE raw sums with atomics (dmu_gn_stats, a dmu_conv2d with gn_fuse_mode 3)
+ * add them as 64-bit fixed-point integers (value * 2^20, two's complement) into the [N, G, 2] int64 array that FOLLOWS the float
+ * array (at sums + N*G*2, 8-byte aligned, zeroed by the caller like sums), and dmu_gn_apply / the apply half of dmu_gn_forward read
+ * that array and store its float value into sums[n, g, 0..1] for every later consumer (the backward).  Integer addition is
+ * associative, so the statistics - and with them a bf16 forward - are bit-identical from run to run; float atomics are not
+ * (two runs of a bf16 UNet differ by ~1e-2 rel-L2 once the network has amplified a few different roundings). */
+#define DMU_GN_FIXED_SUMS 1
 /* One-call forms: forward = stats + apply (sums must NOT be pre-zeroed: they are overwritten when the single-pass
  * cluster kernel runs and accumulated by the two-pass fallback, so zero them as for dmu_gn_stats), backward =
  * bwd_reduce + bwd_apply.  An image that fits the registers of at most 8 CTAs (a thread-block cluster, partial sums

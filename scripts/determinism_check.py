@@ -16,7 +16,8 @@ for precision in ("fp32", "bf16"):
     wsd = W.make_state_dict(W.unet_param_spec(64, 3, "model."), 1)
     sd = m.state_dict(); sd.update(wsd); m.load_state_dict(sd); m.cuda()
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(8, 3, 32, 32, generator=g).cuda(); t = torch.randint(0, 1000, (8,), generator=g).cuda()
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 128      # 128: the batch at which the statistics ride in the persistent 3x3 kernel
+    x = torch.randn(B, 3, 32, 32, generator=g).cuda(); t = torch.randint(0, 1000, (B,), generator=g).cuda()
     eng = m.model.engine
     with torch.no_grad():
         eng.use_graphs = False

@@ -573,3 +573,30 @@ def test_ddim50_full_chain_golden(precision):
     # the public loop from the same seed on the device draws its own noise: shape / finiteness only
     s2 = m.generate_samples(2, torch.device("cuda"))
     assert s2.shape == (2, 3, 64, 64) and torch.isfinite(s2).all()
+
+
+@pytest.mark.parametrize("size,batch", [(32, 128), (64, 64)])
+def test_bf16_forward_is_bit_identical_from_run_to_run(size, batch):
+    """The launches that add GroupNorm statistics with atomics (the persistent 3x3 kernel's statistics epilogue, the two-pass
+    statistics kernel) accumulate 64-bit fixed-point integers (DMU_GN_FIXED_SUMS): integer addition commutes, so two runs of the
+    same bf16 forward - eager launches and graph replays alike - give the same bits.  With float atomics they differ by ~1e-2
+    rel-L2 (a few different bf16 roundings, amplified by the network), which would hide a kernel regression of that size.
+    Sizes at which those launches are what the engine picks (many position tiles per SM)."""
+    import diffusion_model_universal_b200 as D
+    m = _bench_model(D.DDPM if size == 32 else D.DDIM, size, "bf16")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(batch, 3, size, size, generator=g).cuda()
+    t = torch.randint(0, 1000, (batch,), generator=g).cuda()
+    eng = m.model.engine
+    with torch.no_grad():
+        eng.use_graphs = False
+        a = m.forward(x, t).clone()
+        b = m.forward(x, t).clone()
+        eng.use_graphs = True
+        c = m.forward(x, t).clone()      # eager (first run of the plan), then captured and replayed
+        d = m.forward(x, t).clone()
+        e = m.forward(x, t).clone()
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b), f"eager vs eager: {rel_l2(b, a):.3e}"
+    assert torch.equal(c, d) and torch.equal(d, e), f"graph replays: {rel_l2(e, d):.3e}"
+    assert torch.equal(a, e), f"eager vs graph: {rel_l2(e, a):.3e}"
