@@ -4,6 +4,7 @@
 // path for the layers the tcgen05 kernels do not take (3-channel stem/head,
 // Linear layers with tiny M).  One gather-GEMM covers Conv2d / ConvTranspose2d
 // / Linear fprop and dgrad through the weight strides (see dmu_conv_params).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dmu {
@@ -247,7 +248,10 @@ __global__ void __launch_bounds__(128) conv_small_n_kernel(dmu_conv_params P) {
 // (time-embedding MLP, the 22-way time projection and their input gradients: M = batch, K up to 3328).
 //   y[m, j] (+)= bias[j] + res[m, j] + sum_k x[m, k] * w[j*w_sn + k*w_sk]      fp32 output, pre-zeroed, fp32 atomics
 constexpr int LM = 32, LN = 64, LK = 32;
-__global__ void __launch_bounds__(128) linear_splitk_kernel(dmu_conv_params P, int k_per_split) {
+// ordered = 1: the splits of one output tile form a thread-block cluster along z; every CTA parks its partial tile in shared memory
+// and CTA 0 adds them in the order z = 1, 2, ... through DSMEM and stores the tile - no atomics, no zeroing, and the same bits
+// on every run (the forward's Linear layers: fp32 atomics would make a bf16 forward differ from run to run by ~1e-2).
+__global__ void __launch_bounds__(128) linear_splitk_kernel(dmu_conv_params P, int k_per_split, int ordered) {
     __shared__ float As[LK][LM + 1];
     __shared__ __align__(16) float Bs[LK][LN + 4];
     const int tid = threadIdx.x;
@@ -334,6 +338,31 @@ __global__ void __launch_bounds__(128) linear_splitk_kernel(dmu_conv_params P, i
         }
         __syncthreads();
     }
+    if (ordered && gridDim.z > 1) {
+        float* part = &Bs[0][0];      // LM x LN floats fit the filter tile's LK x (LN + 4) (the k-loop is over: the last __syncthreads passed)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) part[(ty * 4 + i) * LN + tx * 4 + j] = acc[i][j];
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (blockIdx.z == 0) {
+            for (unsigned z = 1; z < gridDim.z; ++z) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t ra;
+                        float v;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((uint32_t)__cvta_generic_to_shared(&part[(ty * 4 + i) * LN + tx * 4 + j])), "r"(z));
+                        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+                        acc[i][j] += v;
+                    }
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");      // nobody leaves while CTA 0 still reads
+        if (blockIdx.z != 0) return;
+    }
+    const bool plain = gridDim.z == 1 || ordered;
     float* y = reinterpret_cast<float*>(P.y.ptr);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -348,7 +377,7 @@ __global__ void __launch_bounds__(128) linear_splitk_kernel(dmu_conv_params P, i
                 if (P.bias) v += P.bias[jc];
                 if (P.res.ptr) v += ld_as_float(P.res.ptr, (int64_t)m * P.res.sn + (int64_t)jc * P.res.sc, P.res.dtype);
             }
-            if (gridDim.z == 1) y[(int64_t)m * P.y.sn + jc] = v;      // unsplit contraction: plain store, deterministic
+            if (plain) y[(int64_t)m * P.y.sn + jc] = v;
             else atomicAdd(&y[(int64_t)m * P.y.sn + jc], v);
         }
     }
@@ -538,13 +567,26 @@ int dmu_conv2d(const dmu_conv_params* p, dmu_stream_t stream) {
         // with plain stores: fp32 atomics would make the forward differ from run to run in its last bits, which a bf16 network
         // amplifies to ~1e-2 (tests/test_gpu_unet.py::test_bf16_forward_is_bit_identical_from_run_to_run).  The long contractions of
         // the backward (K = 3328 of the projection's input gradient) keep the split.
-        if (K <= 256) splits = 1;
         int per = (K + splits - 1) / splits;
         per = ((per + LK - 1) / LK) * LK;
         if (per < 2 * LK) per = 2 * LK;
         grid.z = (K + per - 1) / per;
+        // Up to 8 splits (every Linear of the FORWARD: K <= 256) are reduced in a fixed order inside a cluster; the long contractions
+        // of the backward (K = 3328 of the projection's input gradient: 16 splits and more) keep the fp32 atomics.
+        static const int ordered = [] { const char* e = getenv("DMU_LINEAR_ORDERED"); return e ? atoi(e) : 1; }();      // A/B aid (0: atomics)
+        if (ordered && grid.z > 1 && grid.z <= 8) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = as_stream(stream);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = grid.z;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, linear_splitk_kernel, *p, per, 1);
+            if (e != cudaSuccess) return fail("dmu_conv2d/linear_splitk: cluster launch failed: %s", cudaGetErrorString(e));
+            return check_launch("dmu_conv2d/linear_splitk");
+        }
         if (grid.z > 1 && cudaMemsetAsync(p->y.ptr, 0, (size_t)M * p->Cj * sizeof(float), as_stream(stream)) != cudaSuccess) return check_launch("dmu_conv2d/linear zero");
-        linear_splitk_kernel<<<grid, 128, 0, as_stream(stream)>>>(*p, per);
+        linear_splitk_kernel<<<grid, 128, 0, as_stream(stream)>>>(*p, per, 0);
         return check_launch("dmu_conv2d/linear_splitk");
     }
     if (p->Cj <= 4 && K <= kSmallMaxK) {
