@@ -128,8 +128,9 @@ int dmu_diffusion_loss(const float* pred, const float* target, const float* w,
  * With the weight strides this one contraction covers fprop and dgrad of
  * both layer kinds.  impl: 0 = auto, 1 = generic SIMT fp32-FMA kernel, 2 = tcgen05 (bf16, channels % 64 == 0),
  * 3 = the direct kernels for the 3-channel boundary layers (at most 4 channels on one side, stride 1),
- * 4 = tcgen05 per-tap kernel only, 5 = tcgen05 persistent halo kernel only (3x3 stride 1 pad 1, >= 8x8); impl 2 picks
- * between the two by measured shape heuristics.
+ * 4 = tcgen05 per-tap kernel only, 5 = tcgen05 halo kernels only (3x3 stride 1 pad 1 of >= 8x8; 4x4 stride 2 pad 1 with 64 input
+ * channels, conv or transposed gather: an error for any other shape); impl 2 picks between the two families by measured shape
+ * heuristics.
  */
 typedef struct {
     dmu_tensor4 x;       /* gathered input, channels K = Ck */
