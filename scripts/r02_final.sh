@@ -1,6 +1,6 @@
 # Final state of round 2: GPU test suite, the five bench workloads, smoke, run-to-run spread
 set -u
-O=gpurun_out/r02n; mkdir -p $O
+O=gpurun_out/r02r; mkdir -p $O
 timeout 400 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?"; tail -2 $O/pytest_gpu.log
 timeout 400 python bench.py --steps 50 --warmup 10 > $O/bench_train.json 2> $O/bench_train.err; echo "bench rc=$?"; cut -c1-300 $O/bench_train.json
 for w in ddim ddpm_sample score energy; do
