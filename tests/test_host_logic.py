@@ -197,3 +197,44 @@ def test_groupnorm_epilogue_fusion_plan_equals_unfused(monkeypatch):
     assert rel_l2(outs[1][0], outs[0][0]) < 1e-6
     for k, g0 in outs[0][1].items():
         assert rel_l2(outs[1][1][k], g0) < 1e-5 or g0.norm() < 1e-9, k
+
+
+def test_nccl_cta_cap_is_a_default_not_an_override():
+    """parallel.py caps NCCL at 16 CTAs per collective (the all-reduces run beside the backward's kernels) unless the user has set
+    the variable: run in fresh interpreters, because the environment is read at import."""
+    import os, subprocess, sys
+    code = "import os, diffusion_model_universal_b200.parallel; print(os.environ['NCCL_MAX_CTAS'])"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k != "NCCL_MAX_CTAS"}
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "16"
+    env["NCCL_MAX_CTAS"] = "8"
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "8"
+
+
+def test_forward_norms_ask_for_order_independent_statistics(monkeypatch):
+    """Every GroupNorm of a forward plan carries DMU_GN_FIXED_SUMS and reserves the int64 accumulators behind its float sums (three
+    times the bytes), so that the launches which add statistics with atomics stay bit-reproducible; DMU_GN_FIXED_SUMS=0 restores
+    float atomics and the old footprint."""
+    import diffusion_model_universal_b200 as D
+    from diffusion_model_universal_b200 import _abi
+    fake_device.install(monkeypatch)
+    f = load_golden("unet_forward.pt")["c32_r32"]
+    sizes = {}
+    for fixed in ("1", "0"):
+        monkeypatch.setenv("DMU_GN_FIXED_SUMS", fixed)
+        net = D.UNet(3, f["C"], 3)
+        net.load_state_dict(W.make_state_dict(W.unet_param_spec(f["C"], 3, ""), f["seed"]))
+        with torch.no_grad():
+            y = net(f["x"], f["t"])
+        assert rel_l2(y, f["eps"]) < 1e-4
+        plan = net.engine.get_plan(tuple(f["x"].shape), False)
+        flags = [p.flags for sub in plan.keep for p in getattr(sub, "keep", []) if isinstance(p, _abi.GnParams)]
+        assert len(flags) >= 50, "GroupNorm parameter blocks of the forward plan"
+        assert all(fl == (_abi.GN_FIXED_SUMS if fixed == "1" else 0) for fl in flags)
+        sizes[fixed] = plan.nbytes
+    assert sizes["1"] > sizes["0"]
