@@ -205,6 +205,32 @@ def _conv_case(case, dtype, impl, ws=None):
         assert rel_l2(db - 1, dyq.sum(dim=(0, 2, 3))) < 5e-5, "dbias"
 
 
+# Every distinct implicit-GEMM shape of the C = 64 UNet at 32 x 32 input (M = B Ho Wo, N = C_out, K = C_in kh kw),
+# at the benchmark's batch: 3x3 layers incl. the eight concatenated inputs of the up path, 4x4 stride-2 down- and up-sampling, 1x1 shortcuts.
+# (The two 3-channel boundary layers have their own test: test_stem_and_head_layouts.)
+UNET_SHAPES = [
+    (128, 32, 32, 64, 64, 3, 1, 1, "conv"), (128, 16, 16, 64, 64, 3, 1, 1, "conv"), (128, 16, 16, 128, 64, 3, 1, 1, "conv"),
+    (128, 8, 8, 128, 128, 3, 1, 1, "conv"), (128, 8, 8, 192, 64, 3, 1, 1, "conv"), (128, 8, 8, 64, 64, 3, 1, 1, "conv"),
+    (128, 8, 8, 64, 128, 3, 1, 1, "conv"), (128, 4, 4, 128, 128, 3, 1, 1, "conv"), (128, 4, 4, 256, 128, 3, 1, 1, "conv"),
+    (128, 2, 2, 256, 256, 3, 1, 1, "conv"), (128, 2, 2, 384, 128, 3, 1, 1, "conv"), (128, 2, 2, 128, 128, 3, 1, 1, "conv"),
+    (128, 2, 2, 128, 256, 3, 1, 1, "conv"), (128, 1, 1, 256, 256, 3, 1, 1, "conv"), (128, 1, 1, 512, 256, 3, 1, 1, "conv"),
+    (128, 32, 32, 64, 64, 4, 2, 1, "conv"), (128, 16, 16, 64, 64, 4, 2, 1, "conv"), (128, 8, 8, 128, 128, 4, 2, 1, "conv"),
+    (128, 4, 4, 128, 128, 4, 2, 1, "conv"), (128, 2, 2, 256, 256, 4, 2, 1, "conv"),
+    (128, 1, 1, 256, 256, 4, 2, 1, "convT"), (128, 2, 2, 128, 128, 4, 2, 1, "convT"), (128, 4, 4, 128, 128, 4, 2, 1, "convT"),
+    (128, 8, 8, 64, 64, 4, 2, 1, "convT"), (128, 16, 16, 64, 64, 4, 2, 1, "convT"),
+    (128, 16, 16, 128, 64, 1, 1, 0, "conv"), (128, 8, 8, 192, 64, 1, 1, 0, "conv"), (128, 8, 8, 64, 128, 1, 1, 0, "conv"),
+    (128, 4, 4, 256, 128, 1, 1, 0, "conv"), (128, 2, 2, 384, 128, 1, 1, 0, "conv"), (128, 2, 2, 128, 256, 1, 1, 0, "conv"),
+    (128, 1, 1, 512, 256, 1, 1, 0, "conv"),
+]
+
+
+@pytest.mark.parametrize("case", UNET_SHAPES)
+def test_every_unet_gemm_shape_at_the_bench_batch(case):
+    """fprop (+bias +temb +residual), dgrad and wgrad of every layer shape of the network at B = 128, through the kernels the engine's
+    own dispatch picks (impl 2), against ATen fp32 on the same bf16-rounded operands."""
+    _conv_case(case, torch.bfloat16, 2)
+
+
 HALO_T_CASES = [
     # N, H, W (input), Co
     (256, 16, 16, 64),     # 648 tiles: several per CTA
