@@ -55,7 +55,9 @@ def test_ddpm_train_step_golden(precision):
     loss.backward()
     params = dict(m.named_parameters())
     scale = max(f["grad_norm"].values())
-    gtol = 2e-3 if precision == "fp32" else 1e-1   # stated: per-tensor gradient rel-L2 vs the fp32 reference <= 2e-3 (fp32), <= 1e-1 (bf16)
+    # stated: per-tensor gradient rel-L2 vs the fp32 reference <= 1e-4 (fp32; measured 8.4e-6), <= 1e-1 (bf16; measured 8.2e-2 on the
+    # worst small tensor, 2e-2 on the large ones)
+    gtol = 1e-4 if precision == "fp32" else 1e-1
     worst = 0.0
     bad = []
     for k, p in params.items():
